@@ -1,0 +1,182 @@
+/*
+ * include/qtipsim.h -- C ABI of libqtipsim, the B200-native tandem-read simulator.
+ *
+ * This is the drop-in boundary for the one data-parallel stage of Qtip: everything the
+ * reference does between `StreamingSimulator ss(...)` and the seven fclose() calls in
+ * qtip_parse.cpp:1825-1867.  The reference has no FFI layer for this path (it is a C++
+ * class consumed by one caller); the entry points below are what a binding for it
+ * would bind, one per reference interface, cited on each declaration.  src/ holds the
+ * header-compatible C++ shim (simplesim.h, input_model.h, ...) that forwards the
+ * reference's own class interface to these calls, so the unchanged qtip_parse.cpp
+ * compiles and links against it.
+ *
+ * Plain pointers and sizes only: no C++ or torch types cross this line.  Every call
+ * returns QTIPSIM_OK (0) or a negative error code; qtipsim_last_error() gives the text.
+ * There is no CPU fallback: qtipsim_create fails with QTIPSIM_ENODEVICE when no CUDA
+ * device (sm_100) is usable.
+ */
+#ifndef QTIPSIM_H
+#define QTIPSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QTIPSIM_ABI_VERSION 1
+
+enum {
+	QTIPSIM_OK = 0,
+	QTIPSIM_EINVAL = -1,    /* bad argument */
+	QTIPSIM_ENODEVICE = -2, /* no usable CUDA device / driver */
+	QTIPSIM_ECUDA = -3,     /* CUDA runtime error (text in last_error) */
+	QTIPSIM_EIO = -4,       /* FASTA unreadable: reference `throw 1`, fasta.cpp:54-58,83-85 */
+	QTIPSIM_EXSCRIPT = -5,  /* unknown edit op / length mismatch: simplesim.cpp:58-63 */
+	QTIPSIM_ERANGE = -6,    /* chunksz <= olap (fasta.h:41), empty model with target, seed out of range */
+	QTIPSIM_ESTATE = -7,    /* call order violated (no genome, no run yet, ...) */
+	QTIPSIM_ENOMEM = -8
+};
+
+/* read categories, in the order the reference simulates them per window
+ * (simplesim.cpp:242, :279, :340-341) */
+enum { QTIPSIM_CAT_U = 0, QTIPSIM_CAT_B = 1, QTIPSIM_CAT_C = 2, QTIPSIM_CAT_D = 3 };
+
+/* output streams, in the reference's file order (qtip_parse.cpp:1831-1837):
+ * _reads_u, _reads_b_1, _reads_b_2, _reads_c_1, _reads_c_2, _reads_d_1, _reads_d_2 */
+enum {
+	QTIPSIM_OUT_U = 0, QTIPSIM_OUT_B1 = 1, QTIPSIM_OUT_B2 = 2, QTIPSIM_OUT_C1 = 3,
+	QTIPSIM_OUT_C2 = 4, QTIPSIM_OUT_D1 = 5, QTIPSIM_OUT_D2 = 6, QTIPSIM_NOUT = 7
+};
+
+/* simplesim.h:197-201 */
+enum { QTIPSIM_FUNC_LINEAR = 1, QTIPSIM_FUNC_SQRT = 2, QTIPSIM_FUNC_CONST = 3 };
+
+/* Where the random draws come from.
+ * REPLAY : consumes the reference's rnglib/ranlib stream (L'Ecuyer-Cote combined MLCG,
+ *          rnglib.cpp:573-683, ranlib.cpp:1094-1389) draw for draw; output is
+ *          byte-identical to the reference for the same model, FASTA and RNG state.
+ * PHILOX : counter-based Philox4x32-10 keyed by (seed, read index); same sampling
+ *          model, different stream; fully parallel. */
+enum { QTIPSIM_RNG_REPLAY = 0, QTIPSIM_RNG_PHILOX = 1 };
+
+/* One unpaired / bad-end template.  Mirrors TemplateUnpaired, template.h:97-104.
+ * qual and xscript are NUL-terminated and only read during the call. */
+typedef struct {
+	int32_t best_score;
+	int32_t len;
+	char fw_flag;   /* 'T' = forward strand */
+	char mate_flag; /* '0', '1' or '2' */
+	int32_t opp_len;
+	const char *qual;
+	const char *xscript; /* ops = X I D S, reference-forward orientation */
+} qtipsim_tmpl_unp;
+
+/* One concordant / discordant pair template.  Mirrors TemplatePaired, template.h:218-230. */
+typedef struct {
+	int32_t score_12;
+	int32_t score_1;
+	int32_t len_1;
+	char fw_flag_1;
+	const char *qual_1;
+	const char *xscript_1;
+	int32_t score_2;
+	int32_t len_2;
+	char fw_flag_2;
+	const char *qual_2;
+	const char *xscript_2;
+	int32_t upstream1; /* bool */
+	uint64_t fraglen;
+} qtipsim_tmpl_pair;
+
+/* Arguments of StreamingSimulator::simulate_batch (simplesim.h:251-257; note the
+ * reference's order u, c, d, b) plus the state the reference keeps in globals. */
+typedef struct {
+	uint64_t chunksz;  /* rolling FASTA window, qtip_parse.cpp:1840 passes 128*1024 */
+	float fraction;    /* sim-factor */
+	int32_t function;  /* QTIPSIM_FUNC_* */
+	uint64_t min_u, min_c, min_d, min_b;
+	int32_t rng_mode;  /* QTIPSIM_RNG_* */
+	int32_t cg1, cg2;  /* REPLAY: rnglib state at entry (get_state, rnglib.cpp:516); the
+	                      state at exit is written back here */
+	uint64_t philox_seed; /* PHILOX */
+	/* sharding across GPUs: this handle simulates the windows whose index i satisfies
+	 * shard_rank*nwin/shard_count <= i < (shard_rank+1)*nwin/shard_count.  {0,1} = all. */
+	uint32_t shard_rank, shard_count;
+} qtipsim_run_params;
+
+typedef struct {
+	uint64_t wrote[4];          /* u, b, c, d reads / pairs written (simplesim.cpp:399-406) */
+	uint64_t target[4];         /* u, b, c, d targets after apply_function (simplesim.cpp:205-208) */
+	uint64_t bytes[QTIPSIM_NOUT]; /* FASTQ bytes per output stream */
+	uint64_t draws;             /* REPLAY: rnglib draws consumed */
+	uint64_t algorithmic_bytes; /* sum over reads of (FASTQ bytes written + ceil(rflen/4)) */
+	uint32_t kernel_launches;   /* kernels launched by the call */
+	float ms_pack;              /* device time, FASTA pack kernels (0 if genome was already resident) */
+	float ms_plan;              /* device/host time, window table + draw-chain resolution + offsets */
+	float ms_simulate;          /* device time, simulate+emit kernel(s) */
+	float ms_total;             /* device time for the whole run call */
+} qtipsim_stats;
+
+typedef struct qtipsim qtipsim_t;
+
+int qtipsim_abi_version(void);
+
+/* Handle bound to one CUDA device.  device < 0 picks the current device. */
+int qtipsim_create(qtipsim_t **out, int device);
+void qtipsim_destroy(qtipsim_t *h);
+const char *qtipsim_last_error(const qtipsim_t *h); /* h may be NULL: last create error */
+
+/* Genome: replaces FastaChunkwiseParser (fasta.h:24-105, fasta.cpp:42-127) and
+ * estimate_fasta_length (simplesim.h:272-286).  Loads (multi-)FASTA, upper-cases,
+ * maps non-ACGT to N (fasta.cpp:18-35), packs to 2 bit/base + 1 bit/base N mask in HBM.
+ * Only the first path of a multi-file list has defined behaviour in the reference
+ * (SURVEY Q13); more than one path is rejected with QTIPSIM_EINVAL. */
+int qtipsim_load_fasta(qtipsim_t *h, const char *const *paths, size_t npaths);
+/* Same, from FASTA text already in host memory (pinned or pageable). */
+int qtipsim_load_fasta_bytes(qtipsim_t *h, const void *bytes, size_t nbytes);
+/* size_t num_estimated_bases() const, simplesim.h:263-265 (= FASTA file bytes) */
+uint64_t qtipsim_num_estimated_bases(const qtipsim_t *h);
+uint64_t qtipsim_num_records(const qtipsim_t *h);
+
+/* Packed genome exchange for multi-GPU replication: rank 0 packs, the
+ * caller broadcasts these device buffers (NCCL over NVLink), other ranks adopt them.
+ * Buffers: 0 = 2-bit bases (u32 words), 1 = N mask (u32 words), 2 = record table
+ * (host-side blob; small).  export gives pointer+size; adopt takes ownership of
+ * nothing -- it copies (device-to-device for 0/1). */
+int qtipsim_genome_export(qtipsim_t *h, int which, void **ptr, uint64_t *nbytes, int *is_device);
+int qtipsim_genome_adopt(qtipsim_t *h, const void *blob, uint64_t blob_bytes,
+                         const void *d_bases, uint64_t bases_bytes,
+                         const void *d_nmask, uint64_t nmask_bytes);
+
+/* Input model: replaces InputModelUnpaired / InputModelPaired (input_model.h:26-42,
+ * :100-116).  kept = templates in v[], added = alignments seen (num_added(), :68-70). */
+int qtipsim_set_templates_unpaired(qtipsim_t *h, int cat /* U or B */,
+                                   const qtipsim_tmpl_unp *v, size_t kept, uint64_t added);
+int qtipsim_set_templates_paired(qtipsim_t *h, int cat /* C or D */,
+                                 const qtipsim_tmpl_pair *v, size_t kept, uint64_t added);
+/* olap_ (simplesim.h:228-230): max over models of max reference length / fragment length */
+uint64_t qtipsim_olap(const qtipsim_t *h);
+
+/* StreamingSimulator::simulate_batch (simplesim.cpp:195-407): plan + simulate + emit on
+ * the device.  FASTQ bytes stay in HBM until fetched. */
+int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats);
+
+/* Results of the last run.  copy: device-to-host into dst (cap >= bytes[stream]).
+ * device_ptr: the HBM buffer itself (valid until the next run / destroy). */
+int qtipsim_result_copy(qtipsim_t *h, int stream, void *dst, uint64_t cap);
+int qtipsim_result_device_ptr(qtipsim_t *h, int stream, const void **ptr, uint64_t *nbytes);
+/* Appends each stream to an open file descriptor (the shim passes fileno() of the
+ * caller's FILE* after fflush; SimulatedRead::write/write_pair, simplesim.cpp:102-171). */
+int qtipsim_result_write_fds(qtipsim_t *h, const int fds[QTIPSIM_NOUT]);
+
+/* Host-buffer convenience for end-to-end use: FASTA text + templates must already be
+ * set; runs, then copies all seven streams into caller buffers dst[i] (cap[i] bytes). */
+int qtipsim_run_to_host(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats,
+                        void *const dst[QTIPSIM_NOUT], const uint64_t cap[QTIPSIM_NOUT]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QTIPSIM_H */

@@ -1,0 +1,641 @@
+// api.cu -- the C ABI of libqtipsim (include/qtipsim.h): handle, genome upload, template
+// upload, run orchestration (plan -> lengths -> scan -> simulate), result access.
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <chrono>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/qtipsim.h"
+#include "common.h"
+#include "genome.h"
+#include "kernels.cuh"
+#include "lecuyer.h"
+#include "philox.h"
+#include "planner.h"
+#include "templates.h"
+
+using namespace qt;
+
+namespace {
+
+std::string g_create_err;
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+	cudaError_t ensure(size_t n) {
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+		size_t want = n + n / 8 + 256;
+		cudaError_t e = cudaMalloc(&p, want);
+		if (e != cudaSuccess) {
+			cudaGetLastError();
+			want = n;
+			e = cudaMalloc(&p, want);
+		}
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() {
+		if (p) cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+	template <class T>
+	T *as() const { return (T *)p; }
+};
+
+double now_ms() {
+	using namespace std::chrono;
+	return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+struct qtipsim {
+	int device = 0;
+	cudaStream_t st = nullptr;
+	std::string err;
+
+	HostGenome hg;
+	bool have_genome = false;
+	bool host_packed = false;  // hg.bases/nmask valid on the host (needed by the host planner)
+	DevBuf d_bases, d_nmask, d_recs, d_names;
+	float ms_pack_pending = 0;
+
+	TemplateStore ts;
+	bool tmpl_dirty[NCAT] = {true, true, true, true};
+	DevBuf d_t[NCAT], d_qual[NCAT], d_xs[NCAT];
+
+	DevBuf d_jt1, d_jt2;
+	bool have_jt = false;
+
+	DevBuf d_win, d_ncount, d_cum;
+	DevBuf d_plan[NCAT], d_len0, d_len1, d_off0[NCAT], d_off1[NCAT], d_scan_tmp, d_small;
+	DevBuf d_out[NOUT];
+	uint64_t out_bytes[NOUT] = {0, 0, 0, 0, 0, 0, 0};
+	bool have_result = false;
+
+	void *h_stage = nullptr;  // pinned staging for fd writes
+	size_t h_stage_cap = 0;
+
+	int fail(int code, const std::string &m) {
+		err = m;
+		return code;
+	}
+	int cuda_fail(cudaError_t e, const char *what) {
+		err = std::string(what) + ": " + cudaGetErrorString(e);
+		cudaGetLastError();
+		return QTIPSIM_ECUDA;
+	}
+};
+
+#define CK(call)                                                 \
+	do {                                                         \
+		cudaError_t e__ = (call);                                \
+		if (e__ != cudaSuccess) return h->cuda_fail(e__, #call); \
+	} while (0)
+
+extern "C" {
+
+int qtipsim_abi_version(void) { return QTIPSIM_ABI_VERSION; }
+
+int qtipsim_create(qtipsim_t **out, int device) {
+	if (!out) return QTIPSIM_EINVAL;
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) {
+		g_create_err = std::string("no usable CUDA device: ") +
+		               (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+		               " (libqtipsim has no CPU fallback)";
+		cudaGetLastError();
+		return QTIPSIM_ENODEVICE;
+	}
+	if (device < 0) {
+		if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+	}
+	if (device >= ndev) {
+		g_create_err = "device index out of range";
+		return QTIPSIM_EINVAL;
+	}
+	e = cudaSetDevice(device);
+	if (e != cudaSuccess) {
+		g_create_err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+		return QTIPSIM_ENODEVICE;
+	}
+	qtipsim *h = new qtipsim();
+	h->device = device;
+	e = cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+	if (e != cudaSuccess) {
+		g_create_err = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+		delete h;
+		return QTIPSIM_ECUDA;
+	}
+	*out = h;
+	return QTIPSIM_OK;
+}
+
+void qtipsim_destroy(qtipsim_t *h) {
+	if (!h) return;
+	cudaSetDevice(h->device);
+	cudaStreamSynchronize(h->st);
+	DevBuf *all[] = {&h->d_bases, &h->d_nmask, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
+	                 &h->d_ncount, &h->d_cum, &h->d_len0, &h->d_len1, &h->d_scan_tmp, &h->d_small};
+	for (DevBuf *b : all) b->release();
+	for (int c = 0; c < NCAT; c++) {
+		h->d_t[c].release();
+		h->d_qual[c].release();
+		h->d_xs[c].release();
+		h->d_plan[c].release();
+		h->d_off0[c].release();
+		h->d_off1[c].release();
+	}
+	for (int s = 0; s < NOUT; s++) h->d_out[s].release();
+	if (h->h_stage) cudaFreeHost(h->h_stage);
+	cudaStreamDestroy(h->st);
+	delete h;
+}
+
+const char *qtipsim_last_error(const qtipsim_t *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+static int upload_genome(qtipsim *h) {
+	CK(cudaSetDevice(h->device));
+	const HostGenome &g = h->hg;
+	CK(h->d_bases.ensure(g.bases.size() * 4));
+	CK(h->d_nmask.ensure(g.nmask.size() * 4));
+	CK(h->d_recs.ensure(g.recs.size() * sizeof(RecDev) + 16));
+	CK(h->d_names.ensure(g.names.size() + 16));
+	CK(cudaMemcpyAsync(h->d_bases.p, g.bases.data(), g.bases.size() * 4, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemcpyAsync(h->d_nmask.p, g.nmask.data(), g.nmask.size() * 4, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemcpyAsync(h->d_recs.p, g.recs.data(), g.recs.size() * sizeof(RecDev), cudaMemcpyHostToDevice, h->st));
+	if (!g.names.empty())
+		CK(cudaMemcpyAsync(h->d_names.p, g.names.data(), g.names.size(), cudaMemcpyHostToDevice, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	h->have_genome = true;
+	h->host_packed = true;
+	h->have_result = false;
+	return QTIPSIM_OK;
+}
+
+int qtipsim_load_fasta_bytes(qtipsim_t *h, const void *bytes, size_t nbytes) {
+	if (!h || (!bytes && nbytes)) return QTIPSIM_EINVAL;
+	h->hg.parse((const uint8_t *)bytes, nbytes);
+	return upload_genome(h);
+}
+
+int qtipsim_load_fasta(qtipsim_t *h, const char *const *paths, size_t npaths) {
+	if (!h || !paths) return QTIPSIM_EINVAL;
+	if (npaths != 1)
+		return h->fail(QTIPSIM_EINVAL, "exactly one FASTA file is supported (the reference crashes on more, SURVEY Q13)");
+	FILE *fh = fopen(paths[0], "rb");
+	if (!fh) return h->fail(QTIPSIM_EIO, std::string("Could not open FASTA file \"") + paths[0] + "\"");
+	std::vector<uint8_t> buf;
+	if (fseek(fh, 0, SEEK_END) == 0) {
+		long sz = ftell(fh);
+		fseek(fh, 0, SEEK_SET);
+		if (sz > 0) buf.resize((size_t)sz);
+	}
+	size_t got = buf.empty() ? 0 : fread(buf.data(), 1, buf.size(), fh);
+	const bool bad = ferror(fh) || got != buf.size();
+	fclose(fh);
+	if (bad) return h->fail(QTIPSIM_EIO, std::string("read error on FASTA file \"") + paths[0] + "\"");
+	h->hg.parse(buf.data(), buf.size());
+	return upload_genome(h);
+}
+
+uint64_t qtipsim_num_estimated_bases(const qtipsim_t *h) { return h ? h->hg.file_bytes : 0; }
+uint64_t qtipsim_num_records(const qtipsim_t *h) { return h ? h->hg.recs.size() : 0; }
+
+int qtipsim_genome_export(qtipsim_t *h, int which, void **ptr, uint64_t *nbytes, int *is_device) {
+	if (!h || !ptr || !nbytes) return QTIPSIM_EINVAL;
+	if (!h->have_genome) return h->fail(QTIPSIM_ESTATE, "no genome loaded");
+	static thread_local std::string blob;
+	switch (which) {
+	case 0:
+		*ptr = h->d_bases.p;
+		*nbytes = (h->hg.total_bases + 15) / 16 * 4 + 16;
+		if (is_device) *is_device = 1;
+		return QTIPSIM_OK;
+	case 1:
+		*ptr = h->d_nmask.p;
+		*nbytes = (h->hg.total_bases + 31) / 32 * 4 + 16;
+		if (is_device) *is_device = 1;
+		return QTIPSIM_OK;
+	case 2:
+		blob = h->hg.blob();
+		*ptr = (void *)blob.data();
+		*nbytes = blob.size();
+		if (is_device) *is_device = 0;
+		return QTIPSIM_OK;
+	}
+	return QTIPSIM_EINVAL;
+}
+
+int qtipsim_genome_adopt(qtipsim_t *h, const void *blob, uint64_t blob_bytes, const void *d_bases,
+                         uint64_t bases_bytes, const void *d_nmask, uint64_t nmask_bytes) {
+	if (!h || !blob || !d_bases || !d_nmask) return QTIPSIM_EINVAL;
+	CK(cudaSetDevice(h->device));
+	if (!h->hg.from_blob(blob, blob_bytes)) return h->fail(QTIPSIM_EINVAL, "bad genome blob");
+	const uint64_t need_b = (h->hg.total_bases + 15) / 16 * 4 + 16, need_n = (h->hg.total_bases + 31) / 32 * 4 + 16;
+	if (bases_bytes < need_b || nmask_bytes < need_n) return h->fail(QTIPSIM_EINVAL, "packed genome buffers too small");
+	CK(h->d_bases.ensure(need_b));
+	CK(h->d_nmask.ensure(need_n));
+	CK(h->d_recs.ensure(h->hg.recs.size() * sizeof(RecDev) + 16));
+	CK(h->d_names.ensure(h->hg.names.size() + 16));
+	CK(cudaMemcpyAsync(h->d_bases.p, d_bases, need_b, cudaMemcpyDeviceToDevice, h->st));
+	CK(cudaMemcpyAsync(h->d_nmask.p, d_nmask, need_n, cudaMemcpyDeviceToDevice, h->st));
+	CK(cudaMemcpyAsync(h->d_recs.p, h->hg.recs.data(), h->hg.recs.size() * sizeof(RecDev), cudaMemcpyHostToDevice, h->st));
+	if (!h->hg.names.empty())
+		CK(cudaMemcpyAsync(h->d_names.p, h->hg.names.data(), h->hg.names.size(), cudaMemcpyHostToDevice, h->st));
+	// the host replay planner reads reference bases at X positions: keep a host copy too
+	h->hg.bases.resize((size_t)(need_b / 4));
+	h->hg.nmask.resize((size_t)(need_n / 4));
+	CK(cudaMemcpyAsync(h->hg.bases.data(), h->d_bases.p, need_b, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(h->hg.nmask.data(), h->d_nmask.p, need_n, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	h->have_genome = true;
+	h->host_packed = true;
+	h->have_result = false;
+	return QTIPSIM_OK;
+}
+
+int qtipsim_set_templates_unpaired(qtipsim_t *h, int cat, const qtipsim_tmpl_unp *v, size_t kept, uint64_t added) {
+	if (!h || (!v && kept)) return QTIPSIM_EINVAL;
+	int rc = h->ts.set_unpaired(cat, v, kept, added, h->err);
+	if (rc == QTIPSIM_OK) h->tmpl_dirty[cat] = true;
+	return rc;
+}
+
+int qtipsim_set_templates_paired(qtipsim_t *h, int cat, const qtipsim_tmpl_pair *v, size_t kept, uint64_t added) {
+	if (!h || (!v && kept)) return QTIPSIM_EINVAL;
+	int rc = h->ts.set_paired(cat, v, kept, added, h->err);
+	if (rc == QTIPSIM_OK) h->tmpl_dirty[cat] = true;
+	return rc;
+}
+
+uint64_t qtipsim_olap(const qtipsim_t *h) { return h ? h->ts.olap() : 0; }
+
+static int upload_templates(qtipsim *h) {
+	for (int c = 0; c < NCAT; c++) {
+		if (!h->tmpl_dirty[c]) continue;
+		const Category &cg = h->ts.cat[c];
+		CK(h->d_t[c].ensure(cg.t.size() * sizeof(TmplDesc) + 16));
+		CK(h->d_qual[c].ensure(cg.qual.size() + 16));
+		CK(h->d_xs[c].ensure(cg.xs.size() + 16));
+		if (!cg.t.empty()) {
+			CK(cudaMemcpyAsync(h->d_t[c].p, cg.t.data(), cg.t.size() * sizeof(TmplDesc), cudaMemcpyHostToDevice, h->st));
+			CK(cudaMemcpyAsync(h->d_qual[c].p, cg.qual.data(), cg.qual.size(), cudaMemcpyHostToDevice, h->st));
+			CK(cudaMemcpyAsync(h->d_xs[c].p, cg.xs.data(), cg.xs.size(), cudaMemcpyHostToDevice, h->st));
+		}
+		h->tmpl_dirty[c] = false;
+	}
+	if (!h->have_jt) {
+		std::vector<uint32_t> j1(JUMP_TBL), j2(JUMP_TBL);
+		j1[0] = j2[0] = 1;
+		for (int i = 1; i < JUMP_TBL; i++) {
+			j1[i] = mulmod1(j1[i - 1], LA1);
+			j2[i] = mulmod2(j2[i - 1], LA2);
+		}
+		CK(h->d_jt1.ensure(JUMP_TBL * 4));
+		CK(h->d_jt2.ensure(JUMP_TBL * 4));
+		CK(cudaMemcpyAsync(h->d_jt1.p, j1.data(), JUMP_TBL * 4, cudaMemcpyHostToDevice, h->st));
+		CK(cudaMemcpyAsync(h->d_jt2.p, j2.data(), JUMP_TBL * 4, cudaMemcpyHostToDevice, h->st));
+		CK(cudaStreamSynchronize(h->st));  // j1/j2 are stack-lifetime
+		h->have_jt = true;
+	}
+	return QTIPSIM_OK;
+}
+
+// PHILOX mode: per-window counts ~ Binomial(target, p_window), the same model as the
+// reference (simplesim.cpp:224-226,242,279,340-341), drawn from a Philox stream keyed
+// by (seed, window, category).
+static uint64_t philox_window_count(const BinomSetup &bs, uint64_t seed, uint32_t win, int cat) {
+	uint32_t ctr = 0;
+	uint32_t have = 0;
+	Philox4 blk{};
+	auto nx = [&]() -> float {
+		if (!have) {
+			blk = philox4x32(win, 0u, ctr++, PHILOX_DOM_WINDOW | (uint32_t)cat, (uint32_t)seed, (uint32_t)(seed >> 32));
+			have = 4;
+		}
+		const uint32_t x = blk.v[4 - have];
+		have--;
+		return (float)((x >> 8) + 1u) * (1.0f / 16777216.0f);  // (0, 1]
+	};
+	return (uint64_t)binom_sample(bs, nx);
+}
+
+int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
+	if (!h || !p) return QTIPSIM_EINVAL;
+	if (!h->have_genome) return h->fail(QTIPSIM_ESTATE, "qtipsim_run: no genome loaded");
+	CK(cudaSetDevice(h->device));
+	const int launches0 = kernels_launch_count();
+	const uint64_t olap = h->ts.olap();
+	// assert(chunksz > olap), fasta.h:41
+	if (!(p->chunksz > olap)) return h->fail(QTIPSIM_ERANGE, "chunksz must exceed the longest template / fragment (fasta.h:41)");
+	if (p->chunksz > 0x7fffffffu) return h->fail(QTIPSIM_EINVAL, "chunksz too large");
+	if (p->rng_mode != QTIPSIM_RNG_REPLAY && p->rng_mode != QTIPSIM_RNG_PHILOX) return h->fail(QTIPSIM_EINVAL, "bad rng_mode");
+	if (p->shard_count == 0) p->shard_count = 1;
+	if (p->shard_rank >= p->shard_count) return h->fail(QTIPSIM_EINVAL, "shard_rank >= shard_count");
+
+	PlanParams pp;
+	pp.chunksz = p->chunksz;
+	pp.olap = olap;
+	pp.tot_fasta_len = h->hg.file_bytes;
+	// simplesim.cpp:205-208 (argument order u, c, d, b at the call site)
+	pp.target[CAT_U] = apply_function(p->fraction, p->function, p->min_u, h->ts.cat[CAT_U].added);
+	pp.target[CAT_B] = apply_function(p->fraction, p->function, p->min_b, h->ts.cat[CAT_B].added);
+	pp.target[CAT_C] = apply_function(p->fraction, p->function, p->min_c, h->ts.cat[CAT_C].added);
+	pp.target[CAT_D] = apply_function(p->fraction, p->function, p->min_d, h->ts.cat[CAT_D].added);
+	uint64_t tsum = 0;
+	for (int c = 0; c < NCAT; c++) {
+		tsum += pp.target[c];
+		if (pp.target[c] > 0x7fffffffull) return h->fail(QTIPSIM_ERANGE, "per-category target exceeds int range (draw_binomial casts to int)");
+		if (pp.target[c] && h->ts.cat[c].t.empty())
+			return h->fail(QTIPSIM_ERANGE, "non-zero target for a category with no templates (assert(!empty()), input_model.h:50)");
+		if (pp.target[c] && !h->ts.cat[c].valid) return h->fail(QTIPSIM_EXSCRIPT, h->ts.cat[c].why);
+	}
+	if (tsum == 0) return h->fail(QTIPSIM_ERANGE, "nothing to simulate (assert(nu+nb+nc+nd > 0), simplesim.cpp:209)");
+	if (p->rng_mode == QTIPSIM_RNG_REPLAY) {
+		if (p->cg1 < 1 || (uint32_t)p->cg1 >= LM1 || p->cg2 < 1 || (uint32_t)p->cg2 >= LM2)
+			return h->fail(QTIPSIM_ERANGE, "rnglib state out of range (set_seed, rnglib.cpp:1714-1728)");
+	}
+
+	int rc = upload_templates(h);
+	if (rc) return rc;
+
+	cudaEvent_t ev[4];
+	for (auto &e : ev) CK(cudaEventCreate(&e));
+	CK(cudaEventRecord(ev[0], h->st));
+
+	// ---- window table + N counts ----
+	std::vector<Window> win = h->hg.windows(p->chunksz, olap);
+	const uint32_t nwin = (uint32_t)win.size();
+	pp.win_lo = (uint64_t)p->shard_rank * nwin / p->shard_count;
+	pp.win_hi = (uint64_t)(p->shard_rank + 1) * nwin / p->shard_count;
+	std::vector<uint32_t> ncount(nwin, 0);
+	DevGenome dg;
+	dg.bases = h->d_bases.as<uint32_t>();
+	dg.nmask = h->d_nmask.as<uint32_t>();
+	dg.recs = h->d_recs.as<RecDev>();
+	dg.names = h->d_names.as<char>();
+	dg.nrecs = (uint32_t)h->hg.recs.size();
+	if (nwin) {
+		CK(h->d_win.ensure(nwin * sizeof(Window)));
+		CK(h->d_ncount.ensure(nwin * 4));
+		CK(cudaMemcpyAsync(h->d_win.p, win.data(), nwin * sizeof(Window), cudaMemcpyHostToDevice, h->st));
+		launch_window_ncount(dg, h->d_win.as<Window>(), nwin, h->d_ncount.as<uint32_t>(), h->st);
+		CK(cudaMemcpyAsync(ncount.data(), h->d_ncount.p, nwin * 4, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+	}
+
+	// ---- plan ----
+	const double t_plan0 = now_ms();
+	uint64_t nreads[NCAT] = {0, 0, 0, 0};
+	uint64_t read_base[NCAT] = {0, 0, 0, 0};
+	uint64_t draws = 0;
+	if (p->rng_mode == QTIPSIM_RNG_REPLAY) {
+		if (!h->host_packed) return h->fail(QTIPSIM_ESTATE, "host copy of the packed genome missing");
+		Plan plan;
+		rc = plan_replay_host(h->hg, h->ts, win, ncount, pp, LState{(uint32_t)p->cg1, (uint32_t)p->cg2}, plan, h->err);
+		if (rc) return rc;
+		for (int c = 0; c < NCAT; c++) {
+			nreads[c] = plan.recs[c].size();
+			if (!nreads[c]) continue;
+			CK(h->d_plan[c].ensure(nreads[c] * sizeof(PlanRec)));
+			CK(cudaMemcpyAsync(h->d_plan[c].p, plan.recs[c].data(), nreads[c] * sizeof(PlanRec), cudaMemcpyHostToDevice, h->st));
+		}
+		CK(cudaStreamSynchronize(h->st));  // plan vectors die at scope end
+		if (p->shard_count == 1) {
+			p->cg1 = (int32_t)plan.rng_out.s1;
+			p->cg2 = (int32_t)plan.rng_out.s2;
+		}
+		draws = plan.draws;
+	} else {
+		std::map<std::pair<int32_t, uint32_t>, BinomSetup> setups;
+		std::vector<uint64_t> cum((size_t)nwin + 1);
+		for (int c = 0; c < NCAT; c++) {
+			uint64_t acc = 0;
+			for (uint32_t w = 0; w < nwin; w++) {
+				cum[w] = acc;
+				if (!pp.target[c] || !window_live(win[w].retsz, olap, ncount[w])) continue;
+				const float bp = window_binom_p(win[w].retsz, olap, pp.tot_fasta_len);
+				uint32_t pb;
+				memcpy(&pb, &bp, 4);
+				auto key = std::make_pair((int32_t)pp.target[c], pb);
+				auto it = setups.find(key);
+				if (it == setups.end()) it = setups.emplace(key, binom_setup((int32_t)pp.target[c], bp)).first;
+				acc += philox_window_count(it->second, p->philox_seed, w, c);
+			}
+			cum[nwin] = acc;
+			const uint64_t lo = cum[pp.win_lo], hi = cum[pp.win_hi];
+			nreads[c] = hi - lo;
+			read_base[c] = lo;
+			if (!nreads[c]) continue;
+			// shard-local cumulative counts
+			std::vector<uint64_t> loc(pp.win_hi - pp.win_lo + 1);
+			for (uint64_t w = pp.win_lo; w <= pp.win_hi; w++) loc[w - pp.win_lo] = cum[w] - lo;
+			CK(h->d_cum.ensure(loc.size() * 8));
+			CK(cudaMemcpyAsync(h->d_cum.p, loc.data(), loc.size() * 8, cudaMemcpyHostToDevice, h->st));
+			CK(h->d_plan[c].ensure(nreads[c] * sizeof(PlanRec)));
+			launch_plan_philox(h->d_win.as<Window>() + pp.win_lo, h->d_cum.as<uint64_t>(), (uint32_t)(pp.win_hi - pp.win_lo),
+			                   olap, (uint32_t)h->ts.cat[c].t.size(), c, p->philox_seed, h->d_plan[c].as<PlanRec>(),
+			                   nreads[c], lo, h->st);
+			CK(cudaStreamSynchronize(h->st));  // loc dies at scope end; d_cum reused next category
+		}
+	}
+	const double t_plan_host = now_ms() - t_plan0;
+	CK(cudaEventRecord(ev[1], h->st));
+
+	// ---- lengths, offsets ----
+	uint64_t maxn = 0;
+	for (int c = 0; c < NCAT; c++) maxn = nreads[c] > maxn ? nreads[c] : maxn;
+	CK(h->d_len0.ensure(maxn * 4 + 16));
+	CK(h->d_len1.ensure(maxn * 4 + 16));
+	CK(h->d_scan_tmp.ensure((maxn / 1024 + 4) * 8));
+	CK(h->d_small.ensure(16 * 8));
+	CK(cudaMemsetAsync(h->d_small.p, 0, 16 * 8, h->st));
+	uint64_t *d_tot = h->d_small.as<uint64_t>();           // [0..6] stream totals
+	unsigned long long *d_gb = h->d_small.as<unsigned long long>() + 8;  // genome bytes
+	SimArgs sa[NCAT];
+	for (int c = 0; c < NCAT; c++) {
+		SimArgs &a = sa[c];
+		a.g = dg;
+		a.c.t = h->d_t[c].as<TmplDesc>();
+		a.c.qual = h->d_qual[c].as<char>();
+		a.c.xs = h->d_xs[c].as<char>();
+		a.c.n = (uint32_t)h->ts.cat[c].t.size();
+		a.plan = h->d_plan[c].as<PlanRec>();
+		a.nreads = nreads[c];
+		a.read_index_base = read_base[c];
+		a.cat = c;
+		a.rng_mode = p->rng_mode;
+		a.philox_seed = p->philox_seed;
+		a.jt1 = h->d_jt1.as<uint32_t>();
+		a.jt2 = h->d_jt2.as<uint32_t>();
+		if (!nreads[c]) continue;
+		const int s0 = cat_stream0(c);
+		CK(h->d_off0[c].ensure(nreads[c] * 8));
+		if (c != CAT_U) CK(h->d_off1[c].ensure(nreads[c] * 8));
+		launch_read_lengths(a, h->d_len0.as<uint32_t>(), c != CAT_U ? h->d_len1.as<uint32_t>() : nullptr, d_gb, h->st);
+		launch_scan(h->d_len0.as<uint32_t>(), h->d_off0[c].as<uint64_t>(), nreads[c], h->d_scan_tmp.as<uint64_t>(), d_tot + s0, h->st);
+		if (c != CAT_U)
+			launch_scan(h->d_len1.as<uint32_t>(), h->d_off1[c].as<uint64_t>(), nreads[c], h->d_scan_tmp.as<uint64_t>(), d_tot + s0 + 1, h->st);
+		a.off0 = h->d_off0[c].as<uint64_t>();
+		a.off1 = c != CAT_U ? h->d_off1[c].as<uint64_t>() : nullptr;
+	}
+	uint64_t small[16];
+	CK(cudaMemcpyAsync(small, h->d_small.p, sizeof(small), cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	for (int s = 0; s < NOUT; s++) {
+		h->out_bytes[s] = small[s];
+		CK(h->d_out[s].ensure(small[s] + 64));
+	}
+	CK(cudaEventRecord(ev[2], h->st));
+
+	// ---- simulate + emit ----
+	for (int c = 0; c < NCAT; c++) {
+		if (!nreads[c]) continue;
+		const int s0 = cat_stream0(c);
+		sa[c].out0 = h->d_out[s0].as<char>();
+		sa[c].out1 = c != CAT_U ? h->d_out[s0 + 1].as<char>() : nullptr;
+		launch_simulate(sa[c], h->st);
+	}
+	CK(cudaEventRecord(ev[3], h->st));
+	CK(cudaStreamSynchronize(h->st));
+	CK(cudaGetLastError());
+	h->have_result = true;
+
+	if (stats) {
+		memset(stats, 0, sizeof(*stats));
+		uint64_t fq = 0;
+		for (int c = 0; c < NCAT; c++) {
+			stats->wrote[c] = nreads[c];
+			stats->target[c] = pp.target[c];
+		}
+		for (int s = 0; s < NOUT; s++) {
+			stats->bytes[s] = h->out_bytes[s];
+			fq += h->out_bytes[s];
+		}
+		stats->draws = draws;
+		stats->algorithmic_bytes = fq + small[8];
+		stats->kernel_launches = (uint32_t)(kernels_launch_count() - launches0);
+		float ms = 0;
+		stats->ms_pack = 0;
+		cudaEventElapsedTime(&ms, ev[0], ev[2]);
+		stats->ms_plan = ms;  // includes the host chain walk in REPLAY mode
+		(void)t_plan_host;
+		cudaEventElapsedTime(&ms, ev[2], ev[3]);
+		stats->ms_simulate = ms;
+		cudaEventElapsedTime(&ms, ev[0], ev[3]);
+		stats->ms_total = ms;
+	}
+	for (auto &e : ev) cudaEventDestroy(e);
+	return QTIPSIM_OK;
+}
+
+int qtipsim_result_copy(qtipsim_t *h, int stream, void *dst, uint64_t cap) {
+	if (!h || stream < 0 || stream >= NOUT) return QTIPSIM_EINVAL;
+	if (!h->have_result) return h->fail(QTIPSIM_ESTATE, "no result: call qtipsim_run first");
+	if (cap < h->out_bytes[stream]) return h->fail(QTIPSIM_ERANGE, "destination buffer too small");
+	if (!h->out_bytes[stream]) return QTIPSIM_OK;
+	if (!dst) return QTIPSIM_EINVAL;
+	CK(cudaSetDevice(h->device));
+	CK(cudaMemcpyAsync(dst, h->d_out[stream].p, h->out_bytes[stream], cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	return QTIPSIM_OK;
+}
+
+int qtipsim_result_device_ptr(qtipsim_t *h, int stream, const void **ptr, uint64_t *nbytes) {
+	if (!h || stream < 0 || stream >= NOUT || !ptr || !nbytes) return QTIPSIM_EINVAL;
+	if (!h->have_result) return h->fail(QTIPSIM_ESTATE, "no result: call qtipsim_run first");
+	*ptr = h->d_out[stream].p;
+	*nbytes = h->out_bytes[stream];
+	return QTIPSIM_OK;
+}
+
+int qtipsim_result_write_fds(qtipsim_t *h, const int fds[QTIPSIM_NOUT]) {
+	if (!h || !fds) return QTIPSIM_EINVAL;
+	if (!h->have_result) return h->fail(QTIPSIM_ESTATE, "no result: call qtipsim_run first");
+	CK(cudaSetDevice(h->device));
+	const size_t STAGE = 32u << 20;
+	if (!h->h_stage) {
+		CK(cudaHostAlloc(&h->h_stage, 2 * STAGE, cudaHostAllocDefault));
+		h->h_stage_cap = 2 * STAGE;
+	}
+	cudaEvent_t done[2];
+	CK(cudaEventCreate(&done[0]));
+	CK(cudaEventCreate(&done[1]));
+	int rc = QTIPSIM_OK;
+	for (int s = 0; s < NOUT && rc == QTIPSIM_OK; s++) {
+		const uint64_t n = h->out_bytes[s];
+		if (!n || fds[s] < 0) continue;
+		const char *src = h->d_out[s].as<char>();
+		// double-buffered: copy slice k+1 while slice k is written to the file
+		uint64_t issued = 0, written = 0;
+		int slot = 0;
+		uint64_t len_in_slot[2] = {0, 0};
+		auto issue = [&](int sl) {
+			const uint64_t len = n - issued < STAGE ? n - issued : STAGE;
+			len_in_slot[sl] = len;
+			cudaMemcpyAsync((char *)h->h_stage + sl * STAGE, src + issued, len, cudaMemcpyDeviceToHost, h->st);
+			cudaEventRecord(done[sl], h->st);
+			issued += len;
+		};
+		issue(0);
+		while (written < n) {
+			if (issued < n) issue(slot ^ 1);
+			cudaError_t e = cudaEventSynchronize(done[slot]);
+			if (e != cudaSuccess) {
+				rc = h->cuda_fail(e, "cudaEventSynchronize");
+				break;
+			}
+			const char *hp = (const char *)h->h_stage + slot * STAGE;
+			uint64_t left = len_in_slot[slot];
+			while (left) {
+				ssize_t w = write(fds[s], hp, left);
+				if (w < 0) {
+					if (errno == EINTR) continue;
+					rc = h->fail(QTIPSIM_EIO, std::string("write: ") + strerror(errno));
+					break;
+				}
+				hp += w;
+				left -= (uint64_t)w;
+			}
+			if (rc) break;
+			written += len_in_slot[slot];
+			slot ^= 1;
+		}
+		cudaStreamSynchronize(h->st);
+	}
+	cudaEventDestroy(done[0]);
+	cudaEventDestroy(done[1]);
+	return rc;
+}
+
+int qtipsim_run_to_host(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats, void *const dst[QTIPSIM_NOUT],
+                        const uint64_t cap[QTIPSIM_NOUT]) {
+	if (!h || !dst || !cap) return QTIPSIM_EINVAL;
+	int rc = qtipsim_run(h, p, stats);
+	if (rc) return rc;
+	for (int s = 0; s < NOUT; s++) {
+		if (cap[s] < h->out_bytes[s]) return h->fail(QTIPSIM_ERANGE, "destination buffer too small");
+	}
+	for (int s = 0; s < NOUT; s++) {
+		if (h->out_bytes[s])
+			CK(cudaMemcpyAsync(dst[s], h->d_out[s].p, h->out_bytes[s], cudaMemcpyDeviceToHost, h->st));
+	}
+	CK(cudaStreamSynchronize(h->st));
+	return QTIPSIM_OK;
+}
+
+}  // extern "C"

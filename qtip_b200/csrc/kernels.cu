@@ -1,0 +1,507 @@
+// kernels.cu -- sm_100a kernels of libqtipsim (generic path, one warp per read).
+//
+//   k_window_ncount : N count per FASTA window            (simplesim.cpp:228-234)
+//   k_read_lengths  : FASTQ record length per read        (simplesim.cpp:102-171 byte counts)
+//   k_scan_*        : exclusive scan of lengths -> byte offsets in the output streams
+//   k_plan_philox   : native-RNG plan (template, window, offset per read)
+//   k_simulate      : SimulatedRead::init/mutate/init_random + write/write_pair
+//                     (simplesim.h:68-117, simplesim.cpp:31-71, :102-171)
+#include "kernels.cuh"
+#include "lecuyer.h"
+#include "philox.h"
+
+namespace qt {
+
+static int g_launches = 0;
+int kernels_launch_count() { return g_launches; }
+
+// ------------------------------------------------------------------ helpers --
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+__device__ __forceinline__ uint32_t fetch_code(const DevGenome &g, uint64_t gp, uint64_t gend) {
+	if (gp >= gend) return 4u;  // past the record: treated as N (reference reads stale buffer)
+	const uint32_t nm = __ldg(&g.nmask[gp >> 5]);
+	if ((nm >> (gp & 31)) & 1u) return 4u;
+	return (__ldg(&g.bases[gp >> 4]) >> (2 * (gp & 15))) & 3u;
+}
+
+__device__ __forceinline__ uint32_t ndigits_u64(uint64_t v) {
+	uint32_t d = 1;
+	while (v >= 10) {
+		v /= 10;
+		d++;
+	}
+	return d;
+}
+
+// name length incl. '@' and '\n' (simplesim.cpp:104-110, :140-150)
+__device__ __forceinline__ uint32_t name_len_unp(uint32_t refid_len, uint64_t refoff, const MateDesc &m,
+                                                 uint32_t typ_len) {
+	return 13u + refid_len + ndigits_u64(refoff) + m.score_len + typ_len;
+}
+__device__ __forceinline__ uint32_t name_len_pair(uint32_t refid_len, uint64_t off1, uint32_t sl1,
+                                                  uint64_t off2, uint32_t sl2, uint32_t typ_len) {
+	return 19u + 2u * refid_len + ndigits_u64(off1) + ndigits_u64(off2) + sl1 + sl2 + typ_len;
+}
+
+__device__ __forceinline__ char *put_u64(char *p, uint64_t v) {
+	char tmp[20];
+	int n = 0;
+	do {
+		tmp[n++] = (char)('0' + (int)(v % 10));
+		v /= 10;
+	} while (v);
+	while (n) *p++ = tmp[--n];
+	return p;
+}
+__device__ __forceinline__ char *put_bytes(char *p, const char *s, uint32_t n) {
+	for (uint32_t i = 0; i < n; i++) p[i] = s[i];
+	return p + n;
+}
+
+// "@qtip!:<refid>:<+|->:<refoff>:<score>" ... serial; one lane.
+__device__ char *put_origin(char *p, const char *refid, uint32_t refid_len, bool fw, uint64_t refoff,
+                            const char *score, uint32_t score_len) {
+	p = put_bytes(p, refid, refid_len);
+	*p++ = ':';
+	*p++ = fw ? '+' : '-';
+	*p++ = ':';
+	p = put_u64(p, refoff);
+	*p++ = ':';
+	p = put_bytes(p, score, score_len);
+	return p;
+}
+
+// ------------------------------------------------------------- window ncount --
+
+__global__ void __launch_bounds__(256) k_window_ncount(DevGenome g, const Window *win, uint32_t nwin,
+                                                        uint32_t *ncount) {
+	const uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	if (w >= nwin) return;
+	const Window wn = win[w];
+	const uint64_t b0 = g.recs[wn.record].gstart + wn.refoff;
+	const uint64_t b1 = b0 + wn.retsz;  // exclusive
+	const uint64_t w0 = b0 >> 5, w1 = (b1 + 31) >> 5;
+	uint32_t cnt = 0;
+	for (uint64_t i = w0 + lane_id(); i < w1; i += 32) {
+		uint32_t v = __ldg(&g.nmask[i]);
+		if (i == w0) v &= 0xffffffffu << (b0 & 31);
+		if (i == w1 - 1 && (b1 & 31)) v &= 0xffffffffu >> (32 - (b1 & 31));
+		cnt += __popc(v);
+	}
+	for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+	if (lane_id() == 0) ncount[w] = cnt;
+}
+
+void launch_window_ncount(const DevGenome &g, const Window *win, uint32_t nwin, uint32_t *ncount,
+                          cudaStream_t st) {
+	if (!nwin) return;
+	k_window_ncount<<<(nwin + 7) / 8, 256, 0, st>>>(g, win, nwin, ncount);
+	g_launches++;
+}
+
+// -------------------------------------------------------------- read lengths --
+
+// Geometry of one planned read: where each output record goes and how long it is.
+struct ReadGeom {
+	uint32_t name_len;
+	uint32_t body0, body1;  // read lengths written to stream 0 / 1
+	uint64_t refoff[2];     // leftmost ref base of mate 0 / 1 (record coordinates)
+};
+
+__device__ __forceinline__ ReadGeom read_geom(const SimArgs &a, const PlanRec &pr, const TmplDesc &t) {
+	ReadGeom gm;
+	const uint32_t rl = a.g.recs[pr.record].name_len;
+	gm.refoff[0] = pr.refoff + t.delta[0];
+	gm.refoff[1] = pr.refoff + t.delta[1];
+	if (a.cat == CAT_U) {
+		gm.name_len = name_len_unp(rl, gm.refoff[0], t.m[0], t.typ_len);
+		gm.body0 = t.m[0].len;
+		gm.body1 = 0;
+	} else if (a.cat == CAT_B) {
+		// both name halves describe the aligned mate (simplesim.cpp:299-330)
+		gm.name_len = name_len_pair(rl, gm.refoff[0], t.m[0].score_len, gm.refoff[0], t.m[0].score_len, t.typ_len);
+		gm.body0 = t.aligned_is_mate1 ? t.m[0].len : t.opp_len;
+		gm.body1 = t.aligned_is_mate1 ? t.opp_len : t.m[0].len;
+	} else {
+		gm.name_len = name_len_pair(rl, gm.refoff[0], t.m[0].score_len, gm.refoff[1], t.m[1].score_len, t.typ_len);
+		gm.body0 = t.m[0].len;
+		gm.body1 = t.m[1].len;
+	}
+	return gm;
+}
+
+__global__ void __launch_bounds__(256) k_read_lengths(SimArgs a, uint32_t *len0, uint32_t *len1,
+                                                       unsigned long long *gbytes) {
+	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t gb = 0;
+	if (r < a.nreads) {
+		const PlanRec pr = a.plan[r];
+		const TmplDesc &t = a.c.t[pr.tmpl];
+		const ReadGeom gm = read_geom(a, pr, t);
+		len0[r] = gm.name_len + 2u * gm.body0 + 4u;
+		if (len1) len1[r] = gm.name_len + 2u * gm.body1 + 4u;
+		gb = (t.m[0].rflen + 3u) / 4u;
+		if (t.nmates == 2) gb += (t.m[1].rflen + 3u) / 4u;
+	}
+	for (int o = 16; o; o >>= 1) gb += __shfl_xor_sync(0xffffffffu, gb, o);
+	__shared__ uint32_t ws[8];
+	if (lane_id() == 0) ws[threadIdx.x >> 5] = gb;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned long long s = 0;
+		for (int i = 0; i < 8; i++) s += ws[i];
+		if (s) atomicAdd(gbytes, s);
+	}
+}
+
+void launch_read_lengths(const SimArgs &a, uint32_t *len0, uint32_t *len1, unsigned long long *gbytes,
+                         cudaStream_t st) {
+	if (!a.nreads) return;
+	k_read_lengths<<<(unsigned)((a.nreads + 255) / 256), 256, 0, st>>>(a, len0, len1, gbytes);
+	g_launches++;
+}
+
+// ---------------------------------------------------------------------- scan --
+
+static constexpr int SCAN_T = 256;
+static constexpr int SCAN_ITEMS = 4;
+static constexpr int SCAN_TILE = SCAN_T * SCAN_ITEMS;
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t *total) {
+	__shared__ uint64_t wsum[SCAN_T / 32];
+	const uint32_t lane = lane_id(), wid = threadIdx.x >> 5;
+	uint64_t x = v;
+	for (int o = 1; o < 32; o <<= 1) {
+		uint64_t y = __shfl_up_sync(0xffffffffu, x, o);
+		if (lane >= (uint32_t)o) x += y;
+	}
+	if (lane == 31) wsum[wid] = x;
+	__syncthreads();
+	if (wid == 0) {
+		uint64_t s = lane < SCAN_T / 32 ? wsum[lane] : 0;
+		for (int o = 1; o < SCAN_T / 32; o <<= 1) {
+			uint64_t y = __shfl_up_sync(0xffffffffu, s, o);
+			if (lane >= (uint32_t)o) s += y;
+		}
+		if (lane < SCAN_T / 32) wsum[lane] = s;
+	}
+	__syncthreads();
+	const uint64_t base = wid ? wsum[wid - 1] : 0;
+	*total = wsum[SCAN_T / 32 - 1];
+	__syncthreads();
+	return base + x - v;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_tile_sums(const uint32_t *len, uint64_t n, uint64_t *tsum) {
+	const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+	uint64_t s = 0;
+	for (int i = 0; i < SCAN_ITEMS; i++)
+		if (base + i < n) s += len[base + i];
+	uint64_t tot;
+	block_exclusive_scan(s, &tot);
+	if (threadIdx.x == 0) tsum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_tile_prefix(uint64_t *tsum, uint64_t ntiles, uint64_t *total) {
+	// single block: exclusive scan of tile sums in place
+	uint64_t carry = 0;
+	for (uint64_t b = 0; b < ntiles; b += SCAN_T) {
+		const uint64_t i = b + threadIdx.x;
+		const uint64_t v = i < ntiles ? tsum[i] : 0;
+		uint64_t tot;
+		const uint64_t ex = block_exclusive_scan(v, &tot);
+		if (i < ntiles) tsum[i] = carry + ex;
+		carry += tot;
+	}
+	if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_final(const uint32_t *len, uint64_t *off, uint64_t n,
+                                                        const uint64_t *tsum) {
+	const uint64_t base = (uint64_t)blockIdx.x * SCAN_TILE + (uint64_t)threadIdx.x * SCAN_ITEMS;
+	uint32_t v[SCAN_ITEMS];
+	uint64_t s = 0;
+	for (int i = 0; i < SCAN_ITEMS; i++) {
+		v[i] = base + i < n ? len[base + i] : 0;
+		s += v[i];
+	}
+	uint64_t tot;
+	uint64_t ex = block_exclusive_scan(s, &tot) + tsum[blockIdx.x];
+	for (int i = 0; i < SCAN_ITEMS; i++) {
+		if (base + i < n) off[base + i] = ex;
+		ex += v[i];
+	}
+}
+
+void launch_scan(const uint32_t *len, uint64_t *off, uint64_t n, uint64_t *tmp, uint64_t *total,
+                 cudaStream_t st) {
+	if (!n) {
+		cudaMemsetAsync(total, 0, sizeof(uint64_t), st);
+		return;
+	}
+	const uint64_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+	k_scan_tile_sums<<<(unsigned)ntiles, SCAN_T, 0, st>>>(len, n, tmp);
+	k_scan_tile_prefix<<<1, SCAN_T, 0, st>>>(tmp, ntiles, total);
+	k_scan_final<<<(unsigned)ntiles, SCAN_T, 0, st>>>(len, off, n, tmp);
+	g_launches += 3;
+}
+
+// -------------------------------------------------------------- philox plan --
+
+__global__ void __launch_bounds__(256) k_plan_philox(const Window *win, const uint64_t *cum, uint32_t nwin,
+                                                      uint64_t olap, uint32_t ntmpl, int cat, uint64_t seed,
+                                                      PlanRec *plan, uint64_t n, uint64_t read_index_base) {
+	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n) return;
+	// window of read r: last w with cum[w] <= r  (length-weighted choice was made when the
+	// per-window counts were drawn; this is the binary search over their prefix sums)
+	uint32_t lo = 0, hi = nwin;  // invariant: cum[lo] <= r < cum[hi]
+	while (hi - lo > 1) {
+		const uint32_t mid = (lo + hi) >> 1;
+		if (cum[mid] <= r) lo = mid;
+		else hi = mid;
+	}
+	const Window w = win[lo];
+	const uint64_t gi = read_index_base + r;
+	const Philox4 x = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), 0u, PHILOX_DOM_PLAN | (uint32_t)cat,
+	                             (uint32_t)seed, (uint32_t)(seed >> 32));
+	const uint64_t nslots = (uint64_t)w.retsz - olap;
+	PlanRec pr;
+	pr.tmpl = __umulhi(x.v[0], ntmpl);
+	pr.record = w.record;
+	pr.refoff = w.refoff + (nslots ? (uint64_t)__umulhi(x.v[1], (uint32_t)nslots) : 0);
+	pr.s1 = 0;
+	pr.s2 = 0;
+	plan[r] = pr;
+}
+
+void launch_plan_philox(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap, uint32_t ntmpl,
+                        int cat, uint64_t seed, PlanRec *plan, uint64_t n, uint64_t read_index_base,
+                        cudaStream_t st) {
+	if (!n) return;
+	k_plan_philox<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(win, cum, nwin, olap, ntmpl, cat, seed, plan, n,
+	                                                          read_index_base);
+	g_launches++;
+}
+
+// ------------------------------------------------------------------ simulate --
+
+static constexpr int SIM_WARPS = 8;
+static constexpr int NAME_SMEM = 320;  // per-warp name staging; longer names go straight to global
+
+__device__ __forceinline__ char code_char(uint32_t c) { return "ACGTN"[c]; }
+__device__ __forceinline__ char code_char_comp(uint32_t c) { return "TGCAN"[c]; }  // asc2dnacomp, simplesim.cpp:76-97
+
+// Where this read's base draws come from.
+struct DrawSrc {
+	// REPLAY: draw k (0-based, counted from the read's first base draw) is the generator's
+	// output k+1 steps after `s` (the state left by the offset draw).
+	LState s;
+	const uint32_t *jt1, *jt2;
+	// PHILOX
+	uint64_t gi;
+	uint32_t k0, k1, dom;
+};
+
+__device__ __forceinline__ uint32_t replay_code(const DrawSrc &d, uint32_t k) {
+	const uint32_t j = k + 1;
+	LState s;
+	if (j < (uint32_t)JUMP_TBL) {
+		s.s1 = mulmod1(d.s.s1, __ldg(&d.jt1[j]));
+		s.s2 = mulmod2(d.s.s2, __ldg(&d.jt2[j]));
+	} else {
+		s = ljump(d.s, j);
+	}
+	return lbase_code(lfloat(lout(s)));
+}
+
+// 16 uniform bits for nominal draw k of the read
+__device__ __forceinline__ uint32_t philox_bits16(const DrawSrc &d, uint32_t k) {
+	const Philox4 x = philox4x32((uint32_t)d.gi, (uint32_t)(d.gi >> 32), k >> 3, d.dom, d.k0, d.k1);
+	const uint32_t w = x.v[(k >> 1) & 3];
+	return (k & 1) ? (w >> 16) : (w & 0xffffu);
+}
+
+// Applies one mate's edit transcript to the reference and writes sequence and qualities
+// in output orientation (simplesim.cpp:31-71 and the body of write, :111-126).
+// All 32 lanes of the warp call this together.  dcount = draws the read has consumed so far.
+template <int MODE>
+__device__ void emit_aligned_mate(const SimArgs &a, const MateDesc &m, uint64_t gpos, uint64_t gend,
+                                  const DrawSrc &ds, uint32_t &dcount, char *seq, char *qual) {
+	const uint32_t lane = lane_id();
+	const uint32_t lt = (1u << lane) - 1u;
+	const char *xs = a.c.xs + m.xs_off;
+	const uint32_t L = m.len;
+	const bool fw = m.fw != 0;
+	uint32_t rf_base = 0, rd_base = 0;
+	for (uint32_t i0 = 0; i0 < m.xs_len; i0 += 32) {
+		const uint32_t i = i0 + lane;
+		const char op = i < m.xs_len ? xs[i] : 0;
+		const bool cons = (op == '=') | (op == 'X') | (op == 'D') | (op == 'S');
+		const bool prod = (op == '=') | (op == 'X') | (op == 'I') | (op == 'S');
+		const bool drw = (op == 'X') | (op == 'I') | (op == 'S');
+		const uint32_t cm = __ballot_sync(0xffffffffu, cons);
+		const uint32_t pm = __ballot_sync(0xffffffffu, prod);
+		const uint32_t dm = __ballot_sync(0xffffffffu, drw);
+		const uint32_t rf = rf_base + __popc(cm & lt);
+		const uint32_t rd = rd_base + __popc(pm & lt);
+		uint32_t ref = 4u;
+		if (op == '=' || op == 'X') ref = fetch_code(a.g, gpos + rf, gend);
+		uint32_t code = ref;
+		uint32_t used = __popc(dm);  // draws this group of 32 ops consumes
+		if (MODE == QTIPSIM_RNG_REPLAY) {
+			// Draw positions: the e-th draw op of the group starts at dcount+e; every rejected
+			// X draw (equal to the reference base, simplesim.cpp:47-49) pushes itself and all
+			// later draw ops one draw further.  Resolve in order: lanes below the frontier
+			// are final, the lowest rejecting lane at or above it moves the frontier.
+			uint32_t pos = dcount + __popc(dm & lt);
+			uint32_t frontier = 0;
+			if (dm) {
+				for (;;) {
+					if (drw && lane >= frontier) code = replay_code(ds, pos);
+					const bool rej = (op == 'X') && lane >= frontier && code == ref;
+					const uint32_t rm = __ballot_sync(0xffffffffu, rej);
+					if (!rm) break;
+					frontier = __ffs(rm) - 1;
+					if (drw && lane >= frontier) pos++;
+					used++;
+				}
+			}
+		} else {
+			if (drw) {
+				const uint32_t k = dcount + __popc(dm & lt);
+				const uint32_t b = philox_bits16(ds, k);
+				if (op == 'X' && ref < 4u) code = (ref + 1u + ((b * 3u) >> 16)) & 3u;
+				else code = b >> 14;
+			}
+		}
+		if (prod) {
+			if (fw) seq[rd] = code_char(code);
+			else seq[L - 1 - rd] = code_char_comp(code);
+		}
+		rf_base += __popc(cm);
+		rd_base += __popc(pm);
+		dcount += used;
+	}
+	const char *q = a.c.qual + m.qual_off;
+	for (uint32_t j = lane; j < L; j += 32) qual[j] = fw ? q[j] : q[L - 1 - j];
+}
+
+// The unaligned mate of a bad-end pair: opp_len random bases, quality 'I'
+// (simplesim.h:89-117), written with the aligned mate's strand (simplesim.cpp:154-159).
+template <int MODE>
+__device__ void emit_random_mate(uint32_t L, bool fw, const DrawSrc &ds, uint32_t &dcount, char *seq,
+                                 char *qual) {
+	const uint32_t lane = lane_id();
+	for (uint32_t j = lane; j < L; j += 32) {
+		uint32_t code;
+		if (MODE == QTIPSIM_RNG_REPLAY) code = replay_code(ds, dcount + j);
+		else code = philox_bits16(ds, dcount + j) >> 14;
+		if (fw) seq[j] = code_char(code);
+		else seq[L - 1 - j] = code_char_comp(code);
+		qual[j] = 'I';
+	}
+	dcount += L;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SIM_WARPS * 32) k_simulate(SimArgs a) {
+	__shared__ char s_name[SIM_WARPS][NAME_SMEM];
+	const uint32_t lane = lane_id();
+	const uint32_t wib = threadIdx.x >> 5;
+	const uint64_t r = (uint64_t)blockIdx.x * SIM_WARPS + wib;
+	if (r >= a.nreads) return;
+	const PlanRec pr = a.plan[r];
+	const TmplDesc &t = a.c.t[pr.tmpl];
+	const RecDev rec = a.g.recs[pr.record];
+	const ReadGeom gm = read_geom(a, pr, t);
+	const uint64_t gend = rec.gstart + rec.len;
+	const bool paired_out = a.cat != CAT_U;
+	char *o0 = a.out0 + a.off0[r];
+	char *o1 = paired_out ? a.out1 + a.off1[r] : nullptr;
+
+	// ---- name: composed once by lane 0, copied by the warp to one or both files ----
+	const bool name_in_smem = gm.name_len <= (uint32_t)NAME_SMEM;
+	char *nb = name_in_smem ? s_name[wib] : o0;
+	if (lane == 0) {
+		const char *refid = a.g.names + rec.name_off;
+		char *p = nb;
+		p = put_bytes(p, "@qtip!:", 7);
+		if (a.cat == CAT_U) {
+			p = put_origin(p, refid, rec.name_len, t.m[0].fw, gm.refoff[0], t.m[0].score, t.m[0].score_len);
+		} else if (a.cat == CAT_B) {
+			p = put_origin(p, refid, rec.name_len, t.m[0].fw, gm.refoff[0], t.m[0].score, t.m[0].score_len);
+			*p++ = ':';
+			p = put_origin(p, refid, rec.name_len, t.m[0].fw, gm.refoff[0], t.m[0].score, t.m[0].score_len);
+		} else {
+			p = put_origin(p, refid, rec.name_len, t.m[0].fw, gm.refoff[0], t.m[0].score, t.m[0].score_len);
+			*p++ = ':';
+			p = put_origin(p, refid, rec.name_len, t.m[1].fw, gm.refoff[1], t.m[1].score, t.m[1].score_len);
+		}
+		*p++ = ':';
+		p = put_bytes(p, t.typ, t.typ_len);
+		*p++ = '\n';
+	}
+	__syncwarp();
+	if (name_in_smem) {
+		for (uint32_t j = lane; j < gm.name_len; j += 32) {
+			const char ch = nb[j];
+			o0[j] = ch;
+			if (paired_out) o1[j] = ch;
+		}
+	} else if (paired_out) {
+		__threadfence_block();
+		for (uint32_t j = lane; j < gm.name_len; j += 32) o1[j] = o0[j];
+	}
+
+	// ---- bodies ----
+	DrawSrc ds;
+	ds.s = LState{pr.s1, pr.s2};
+	ds.jt1 = a.jt1;
+	ds.jt2 = a.jt2;
+	ds.gi = a.read_index_base + r;
+	ds.k0 = (uint32_t)a.philox_seed;
+	ds.k1 = (uint32_t)(a.philox_seed >> 32);
+	ds.dom = PHILOX_DOM_BASE | (uint32_t)a.cat;
+	uint32_t dcount = 0;
+
+	char *seq0 = o0 + gm.name_len;
+	char *qual0 = seq0 + gm.body0 + 3;
+	char *seq1 = paired_out ? o1 + gm.name_len : nullptr;
+	char *qual1 = paired_out ? seq1 + gm.body1 + 3 : nullptr;
+
+	if (a.cat == CAT_U) {
+		emit_aligned_mate<MODE>(a, t.m[0], rec.gstart + gm.refoff[0], gend, ds, dcount, seq0, qual0);
+	} else if (a.cat == CAT_B) {
+		// aligned mate's draws first, then the random mate's (simplesim.cpp:299-331)
+		char *aseq = t.aligned_is_mate1 ? seq0 : seq1, *aqual = t.aligned_is_mate1 ? qual0 : qual1;
+		char *rseq = t.aligned_is_mate1 ? seq1 : seq0, *rqual = t.aligned_is_mate1 ? qual1 : qual0;
+		emit_aligned_mate<MODE>(a, t.m[0], rec.gstart + gm.refoff[0], gend, ds, dcount, aseq, aqual);
+		emit_random_mate<MODE>(t.opp_len, t.m[0].fw != 0, ds, dcount, rseq, rqual);
+	} else {
+		emit_aligned_mate<MODE>(a, t.m[0], rec.gstart + gm.refoff[0], gend, ds, dcount, seq0, qual0);
+		emit_aligned_mate<MODE>(a, t.m[1], rec.gstart + gm.refoff[1], gend, ds, dcount, seq1, qual1);
+	}
+	// separators: "\n+\n" after the sequence, "\n" after the qualities
+	if (lane < 4) {
+		const char sep[4] = {'\n', '+', '\n', '\n'};
+		const uint32_t p0 = lane < 3 ? gm.body0 + lane : 2u * gm.body0 + 3u;
+		seq0[p0] = sep[lane];
+		if (paired_out) {
+			const uint32_t p1 = lane < 3 ? gm.body1 + lane : 2u * gm.body1 + 3u;
+			seq1[p1] = sep[lane];
+		}
+	}
+}
+
+void launch_simulate(const SimArgs &a, cudaStream_t st) {
+	if (!a.nreads) return;
+	const unsigned grid = (unsigned)((a.nreads + SIM_WARPS - 1) / SIM_WARPS);
+	if (a.rng_mode == QTIPSIM_RNG_REPLAY) k_simulate<QTIPSIM_RNG_REPLAY><<<grid, SIM_WARPS * 32, 0, st>>>(a);
+	else k_simulate<QTIPSIM_RNG_PHILOX><<<grid, SIM_WARPS * 32, 0, st>>>(a);
+	g_launches++;
+}
+
+}  // namespace qt

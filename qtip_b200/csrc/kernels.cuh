@@ -1,0 +1,68 @@
+// kernels.cuh -- launch wrappers for the sm_100a kernels of libqtipsim.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/qtipsim.h"
+#include "common.h"
+
+namespace qt {
+
+static constexpr int JUMP_TBL = 4096;  // a^j mod m for j < JUMP_TBL, both components
+
+struct DevGenome {
+	const uint32_t *bases = nullptr;
+	const uint32_t *nmask = nullptr;
+	const RecDev *recs = nullptr;
+	const char *names = nullptr;
+	uint32_t nrecs = 0;
+};
+
+struct DevCategory {
+	const TmplDesc *t = nullptr;
+	const char *qual = nullptr;
+	const char *xs = nullptr;
+	uint32_t n = 0;
+};
+
+struct SimArgs {
+	DevGenome g;
+	DevCategory c;
+	const PlanRec *plan = nullptr;
+	uint64_t nreads = 0;
+	uint64_t read_index_base = 0;  // global index of plan[0] within its category (PHILOX counter)
+	const uint64_t *off0 = nullptr;  // byte offset of each read's record in stream 0 / 1
+	const uint64_t *off1 = nullptr;
+	char *out0 = nullptr;
+	char *out1 = nullptr;
+	int cat = 0;
+	int rng_mode = 0;
+	uint64_t philox_seed = 0;
+	const uint32_t *jt1 = nullptr;  // jump tables (REPLAY)
+	const uint32_t *jt2 = nullptr;
+};
+
+// number of N per window (simplesim.cpp:228-231 histogram, N bin only)
+void launch_window_ncount(const DevGenome &g, const Window *win, uint32_t nwin, uint32_t *ncount,
+                          cudaStream_t st);
+
+// FASTQ record lengths per read for the category's stream(s); also accumulates the
+// algorithmic genome bytes (sum of ceil(rflen/4)) into *gbytes.
+void launch_read_lengths(const SimArgs &a, uint32_t *len0, uint32_t *len1, unsigned long long *gbytes,
+                         cudaStream_t st);
+
+// exclusive scan u32 -> u64 offsets; total written to *total (device).  tmp: >= (n/1024+2) u64.
+void launch_scan(const uint32_t *len, uint64_t *off, uint64_t n, uint64_t *tmp, uint64_t *total,
+                 cudaStream_t st);
+
+// simulate + emit (SimulatedRead::init/mutate/init_random/write/write_pair)
+void launch_simulate(const SimArgs &a, cudaStream_t st);
+
+// PHILOX planning: fills plan[] for reads [0, n) of one category from per-window
+// cumulative counts (cum[w] = reads before window w, cum[nwin] = n).
+void launch_plan_philox(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap,
+                        uint32_t ntmpl, int cat, uint64_t seed, PlanRec *plan, uint64_t n,
+                        uint64_t read_index_base, cudaStream_t st);
+
+int kernels_launch_count();  // kernels launched through the wrappers above since process start
+
+}  // namespace qt

@@ -1,0 +1,162 @@
+// templates.cpp -- see templates.h.
+#include "templates.h"
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+
+namespace qt {
+
+namespace {
+
+// Flattens one (qual, transcript) into a MateDesc and its host draw program.
+// Returns false (with why) when the reference would throw / assert on this template:
+// unknown op (simplesim.cpp:58-60) or produced length != strlen(qual) (:63).
+bool add_mate(Category &c, MateDesc &m, HostMateProg &hp, const char *qual, const char *xs,
+              bool fw, int32_t score, std::string &why) {
+	memset(&m, 0, sizeof(m));
+	if (qual == NULL || xs == NULL) {
+		why = "NULL qual or transcript";
+		return false;
+	}
+	m.qual_off = (uint32_t)c.qual.size();
+	m.xs_off = (uint32_t)c.xs.size();
+	m.len = (uint32_t)strlen(qual);
+	m.xs_len = (uint32_t)strlen(xs);
+	m.fw = fw ? 1 : 0;
+	m.score_len = (uint8_t)snprintf(m.score, sizeof(m.score), "%d", score);
+	c.qual.append(qual, m.len);
+	c.xs.append(xs, m.xs_len);
+	hp.xs_begin = (uint32_t)c.xsteps.size();
+	uint32_t rf = 0, rd = 0, skip = 0, ndraw = 0;
+	bool ok = true;
+	for (uint32_t i = 0; i < m.xs_len; i++) {
+		switch (xs[i]) {
+		case '=': rf++; rd++; break;
+		case 'X': c.xsteps.push_back(XStep{skip, rf}); skip = 0; rf++; rd++; ndraw++; break;
+		case 'I': rd++; skip++; ndraw++; break;
+		case 'D': rf++; break;
+		case 'S': rf++; rd++; skip++; ndraw++; break;
+		default:
+			if (ok) {
+				char b[96];
+				snprintf(b, sizeof(b), "Unknown operation in edit transcript: '%c'", xs[i]);
+				why = b;
+			}
+			ok = false;
+		}
+	}
+	hp.xs_end = (uint32_t)c.xsteps.size();
+	hp.tail_skip = skip;
+	m.rflen = rf;
+	m.ndraw = ndraw;
+	if (ok && rd != m.len) {
+		why = "edit transcript produces a read of different length than the quality string";
+		ok = false;
+	}
+	return ok;
+}
+
+}  // namespace
+
+int TemplateStore::set_unpaired(int ci, const qtipsim_tmpl_unp *v, size_t kept, uint64_t added, std::string &err) {
+	if (ci != CAT_U && ci != CAT_B) {
+		err = "set_templates_unpaired: category must be U or B";
+		return QTIPSIM_EINVAL;
+	}
+	Category &c = cat[ci];
+	c.clear();
+	c.added = added;
+	c.t.resize(kept);
+	c.prog.resize(2 * kept);
+	double bytes = 0, draws = 0;
+	for (size_t i = 0; i < kept; i++) {
+		TmplDesc &t = c.t[i];
+		memset(&t, 0, sizeof(t));
+		std::string why;
+		if (!add_mate(c, t.m[0], c.prog[2 * i], v[i].qual, v[i].xscript, v[i].fw_flag == 'T',
+		              v[i].best_score, why) && c.valid) {
+			c.valid = false;
+			c.why = why;
+		}
+		t.nmates = 1;
+		if (ci == CAT_B) {
+			t.aligned_is_mate1 = (v[i].mate_flag == '1');
+			t.opp_len = v[i].opp_len > 0 ? (uint32_t)v[i].opp_len : 0;
+			if (v[i].opp_len <= 0 && c.valid) {  // assert(len > 0), simplesim.h:96
+				c.valid = false;
+				c.why = "bad-end template with opp_len <= 0";
+			}
+			t.typ[0] = 'b';
+			t.typ[1] = t.aligned_is_mate1 ? '1' : '2';
+			t.typ_len = 2;
+			// name (both scores) on both files + two bodies
+			bytes += 2.0 * (7 + 2 * (5 + t.m[0].score_len) + 2 + 1) + 2.0 * t.m[0].len + 2.0 * t.opp_len + 8;
+			draws += 2 + t.m[0].ndraw + t.opp_len;
+		} else {
+			t.typ[0] = 'u';
+			t.typ_len = 1;
+			bytes += 7 + 5 + t.m[0].score_len + 1 + 1 + 2.0 * t.m[0].len + 4;
+			draws += 2 + t.m[0].ndraw;
+		}
+		c.max_len = std::max<uint64_t>(c.max_len, t.m[0].rflen);  // input_model.h:38-41
+	}
+	if (kept) {
+		c.mean_bytes = bytes / kept;
+		c.mean_draws = draws / kept;
+	}
+	return QTIPSIM_OK;
+}
+
+int TemplateStore::set_paired(int ci, const qtipsim_tmpl_pair *v, size_t kept, uint64_t added, std::string &err) {
+	if (ci != CAT_C && ci != CAT_D) {
+		err = "set_templates_paired: category must be C or D";
+		return QTIPSIM_EINVAL;
+	}
+	Category &c = cat[ci];
+	c.clear();
+	c.added = added;
+	c.t.resize(kept);
+	c.prog.resize(2 * kept);
+	double bytes = 0, draws = 0;
+	for (size_t i = 0; i < kept; i++) {
+		TmplDesc &t = c.t[i];
+		memset(&t, 0, sizeof(t));
+		std::string why;
+		bool ok = add_mate(c, t.m[0], c.prog[2 * i], v[i].qual_1, v[i].xscript_1, v[i].fw_flag_1 == 'T',
+		                   v[i].score_1, why);
+		ok = ok && add_mate(c, t.m[1], c.prog[2 * i + 1], v[i].qual_2, v[i].xscript_2,
+		                    v[i].fw_flag_2 == 'T', v[i].score_2, why);
+		if (!ok && c.valid) {
+			c.valid = false;
+			c.why = why;
+		}
+		t.nmates = 2;
+		t.typ[0] = ci == CAT_C ? 'c' : 'd';
+		t.typ_len = 1;
+		// simplesim.cpp:354-363
+		const uint64_t fl = v[i].fraglen;
+		if (v[i].upstream1) {
+			t.delta[0] = 0;
+			t.delta[1] = (uint32_t)(std::max<uint64_t>(fl, t.m[1].rflen) - t.m[1].rflen);
+		} else {
+			t.delta[1] = 0;
+			t.delta[0] = (uint32_t)(std::max<uint64_t>(fl, t.m[0].rflen) - t.m[0].rflen);
+		}
+		c.max_len = std::max<uint64_t>(c.max_len, fl);  // input_model.h:112-115
+		bytes += 2.0 * (7 + 10 + t.m[0].score_len + t.m[1].score_len + 2) + 2.0 * t.m[0].len + 2.0 * t.m[1].len + 8;
+		draws += 2 + t.m[0].ndraw + t.m[1].ndraw;
+	}
+	if (kept) {
+		c.mean_bytes = bytes / kept;
+		c.mean_draws = draws / kept;
+	}
+	return QTIPSIM_OK;
+}
+
+uint64_t TemplateStore::olap() const {
+	uint64_t o = 0;
+	for (int i = 0; i < NCAT; i++) o = std::max(o, cat[i].max_len);
+	return o;
+}
+
+}  // namespace qt

@@ -1,0 +1,50 @@
+// templates.h -- the input model on the host: validated, flattened templates.
+//
+// Replaces InputModelUnpaired / InputModelPaired (input_model.h:22-167) and the per-read
+// rescans of the transcript the reference does (template.h:92-95, simplesim.cpp:32,37,
+// 355-356): lengths, reference spans and draw counts are computed once here.
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/qtipsim.h"
+#include "common.h"
+
+namespace qt {
+
+// Where one mate's draws fall: between consecutive X ops there are `skip` draws that are
+// always consumed exactly once (I, S); an X at reference offset `rf` consumes one draw
+// plus one more for every draw equal to the reference base (simplesim.cpp:45-50).
+struct XStep {
+	uint32_t skip;  // I/S draws before this X
+	uint32_t rf;    // reference offset of the X, relative to the mate's leftmost base
+};
+
+struct HostMateProg {
+	uint32_t xs_begin = 0, xs_end = 0;  // range in Category::xsteps
+	uint32_t tail_skip = 0;             // I/S draws after the last X
+};
+
+struct Category {
+	std::vector<TmplDesc> t;
+	std::string qual;                 // arena
+	std::string xs;                   // arena
+	std::vector<XStep> xsteps;        // host-side draw programs (replay planner)
+	std::vector<HostMateProg> prog;   // 2 per template
+	uint64_t added = 0;               // num_added(), input_model.h:68-70
+	uint64_t max_len = 0;             // max_len(), input_model.h:82-84 / :155-157
+	bool valid = true;                // all transcripts well-formed
+	std::string why;                  // first problem found
+	double mean_bytes = 0;            // expected FASTQ bytes per read, excluding refid/offset digits
+	double mean_draws = 0;            // expected draws per read
+	void clear() { *this = Category(); }
+};
+
+struct TemplateStore {
+	Category cat[NCAT];
+	int set_unpaired(int c, const qtipsim_tmpl_unp *v, size_t kept, uint64_t added, std::string &err);
+	int set_paired(int c, const qtipsim_tmpl_pair *v, size_t kept, uint64_t added, std::string &err);
+	uint64_t olap() const;  // simplesim.h:228-230
+};
+
+}  // namespace qt

@@ -1,0 +1,221 @@
+"""Host-side mirror of the reference's simulator interface, forwarding to libqtipsim.
+
+Same names, argument order and error behaviour as the reference classes:
+
+* ``InputModelUnpaired`` / ``InputModelPaired``  -- src/input_model.h:22-167
+* ``StreamingSimulator``                         -- src/simplesim.h:203-299,
+  ``simulate_batch``                               src/simplesim.cpp:195-407
+
+The work happens on the GPU behind the C ABI (include/qtipsim.h); nothing here computes
+reads on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import sys
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _abi, rnglib
+from ._abi import CAT_B, CAT_C, CAT_D, CAT_U, FUNC_CONST, FUNC_LINEAR, FUNC_SQRT, NOUT, RNG_PHILOX, RNG_REPLAY
+from .templates import TemplatePaired, TemplateUnpaired, marshal_paired, marshal_unpaired
+
+
+class QtipSimError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libqtipsim error {code}: {msg}")
+        self.code = code
+
+
+class InputModelUnpaired:
+    """input_model.h:22-94"""
+
+    def __init__(self, ts: Sequence[TemplateUnpaired], n: int, fraction_even: float = 1.0, low_score_bias: float = 1.0):
+        self.ts = list(ts)
+        self.n = int(n)
+        self.fraction_even = fraction_even  # unused, as in the reference
+        self.low_score_bias = low_score_bias  # unused
+        self._max = max((t.reflen() for t in self.ts), default=0)
+        self._avg = float(np.float32(sum(np.float32(t.reflen()) / np.float32(len(self.ts)) for t in self.ts))) if self.ts else 0.0
+
+    def empty(self) -> bool:
+        return not self.ts
+
+    def num_added(self) -> int:
+        return self.n
+
+    def avg_len(self) -> float:
+        return self._avg
+
+    def max_len(self) -> int:
+        return self._max
+
+
+class InputModelPaired:
+    """input_model.h:96-167"""
+
+    def __init__(self, ts: Sequence[TemplatePaired], n: int, fraction_even: float = 1.0, low_score_bias: float = 1.0):
+        self.ts = list(ts)
+        self.n = int(n)
+        self.fraction_even = fraction_even
+        self.low_score_bias = low_score_bias
+        self._max = max((t.fraglen for t in self.ts), default=0)
+        self._avg = float(sum(t.fraglen for t in self.ts) / len(self.ts)) if self.ts else 0.0
+
+    def empty(self) -> bool:
+        return not self.ts
+
+    def num_added(self) -> int:
+        return self.n
+
+    def avg_len(self) -> float:
+        return self._avg
+
+    def max_len(self) -> int:
+        return self._max
+
+
+class Engine:
+    """Thin RAII wrapper over one ``qtipsim_t`` handle."""
+
+    def __init__(self, device: int = -1):
+        self.lib = _abi.load()
+        h = C.c_void_p()
+        rc = self.lib.qtipsim_create(C.byref(h), device)
+        if rc != 0:
+            raise QtipSimError(rc, self.lib.qtipsim_last_error(None).decode())
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.qtipsim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise QtipSimError(rc, self.lib.qtipsim_last_error(self.h).decode())
+
+    def load_fasta(self, path: str):
+        arr = (C.c_char_p * 1)(path.encode())
+        self.check(self.lib.qtipsim_load_fasta(self.h, arr, 1))
+
+    def load_fasta_paths(self, paths: Sequence[str]):
+        arr = (C.c_char_p * len(paths))(*[p.encode() for p in paths])
+        self.check(self.lib.qtipsim_load_fasta(self.h, arr, len(paths)))
+
+    def load_fasta_bytes(self, data) -> None:
+        """data: bytes, or a numpy uint8 array (e.g. pinned host memory)"""
+        if isinstance(data, (bytes, bytearray)):
+            buf = (C.c_char * len(data)).from_buffer_copy(data) if isinstance(data, bytes) else (C.c_char * len(data)).from_buffer(data)
+            self.check(self.lib.qtipsim_load_fasta_bytes(self.h, C.cast(buf, C.c_void_p), len(data)))
+        else:
+            a = np.ascontiguousarray(data, dtype=np.uint8)
+            self.check(self.lib.qtipsim_load_fasta_bytes(self.h, C.c_void_p(a.ctypes.data), a.size))
+
+    def set_unpaired(self, cat: int, ts: Sequence[TemplateUnpaired], added: Optional[int] = None):
+        arr, keep = marshal_unpaired(ts)
+        self.check(self.lib.qtipsim_set_templates_unpaired(self.h, cat, arr, len(ts), len(ts) if added is None else added))
+
+    def set_paired(self, cat: int, ts: Sequence[TemplatePaired], added: Optional[int] = None):
+        arr, keep = marshal_paired(ts)
+        self.check(self.lib.qtipsim_set_templates_paired(self.h, cat, arr, len(ts), len(ts) if added is None else added))
+
+    def olap(self) -> int:
+        return int(self.lib.qtipsim_olap(self.h))
+
+    def num_estimated_bases(self) -> int:
+        return int(self.lib.qtipsim_num_estimated_bases(self.h))
+
+    def run(self, params: _abi.RunParams) -> _abi.Stats:
+        st = _abi.Stats()
+        self.check(self.lib.qtipsim_run(self.h, C.byref(params), C.byref(st)))
+        return st
+
+    def result(self, stream: int, nbytes: int) -> np.ndarray:
+        out = np.empty(nbytes, dtype=np.uint8)
+        if nbytes:
+            self.check(self.lib.qtipsim_result_copy(self.h, stream, C.c_void_p(out.ctypes.data), nbytes))
+        return out
+
+    def results(self, st: _abi.Stats) -> List[bytes]:
+        return [self.result(s, int(st.bytes[s])).tobytes() for s in range(NOUT)]
+
+    def result_device_ptr(self, stream: int):
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self.check(self.lib.qtipsim_result_device_ptr(self.h, stream, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    def write_fds(self, fds: Sequence[int]):
+        arr = (C.c_int * NOUT)(*fds)
+        self.check(self.lib.qtipsim_result_write_fds(self.h, arr))
+
+
+def make_params(chunksz=128 * 1024, fraction=30.0, function=FUNC_SQRT, min_u=30000, min_c=30000, min_d=10000,
+                min_b=10000, rng_mode=RNG_REPLAY, cg=None, philox_seed=0, shard_rank=0, shard_count=1) -> _abi.RunParams:
+    """Defaults are qtip_parse.cpp:797-807 (C++ side) and :1840 (chunksz)."""
+    p = _abi.RunParams()
+    p.chunksz = chunksz
+    p.fraction = fraction
+    p.function = function
+    p.min_u, p.min_c, p.min_d, p.min_b = min_u, min_c, min_d, min_b
+    p.rng_mode = rng_mode
+    cg1, cg2 = cg if cg is not None else rnglib.get_state()
+    p.cg1, p.cg2 = cg1, cg2
+    p.philox_seed = philox_seed
+    p.shard_rank, p.shard_count = shard_rank, shard_count
+    return p
+
+
+class StreamingSimulator:
+    """simplesim.h:203-299.  File arguments are binary file objects (the caller opens,
+    buffers and closes them, as qtip_parse.cpp:1831-1866 does with its FILE*s)."""
+
+    def __init__(self, fns: Sequence[str], chunksz: int, model_u: InputModelUnpaired, model_b: InputModelUnpaired,
+                 model_c: InputModelPaired, model_d: InputModelPaired, fh_u, fh_b_1, fh_b_2, fh_c_1, fh_c_2, fh_d_1,
+                 fh_d_2, device: int = -1, rng_mode: int = RNG_REPLAY, philox_seed: int = 0):
+        self.chunksz = int(chunksz)
+        self.models = (model_u, model_b, model_c, model_d)
+        self.fhs = (fh_u, fh_b_1, fh_b_2, fh_c_1, fh_c_2, fh_d_1, fh_d_2)
+        self.rng_mode = rng_mode
+        self.philox_seed = philox_seed
+        self.eng = Engine(device)
+        # olap_ = max over models (simplesim.h:228-230); assert(chunksz > olap), fasta.h:41
+        self.olap_ = max(m.max_len() for m in self.models)
+        if not self.chunksz > self.olap_:
+            raise AssertionError("chunksz > olap")
+        self.eng.load_fasta_paths(list(fns))
+        self.eng.set_unpaired(CAT_U, model_u.ts, model_u.num_added())
+        self.eng.set_unpaired(CAT_B, model_b.ts, model_b.num_added())
+        self.eng.set_paired(CAT_C, model_c.ts, model_c.num_added())
+        self.eng.set_paired(CAT_D, model_d.ts, model_d.num_added())
+        self.last_stats = None
+
+    def num_estimated_bases(self) -> int:
+        """simplesim.h:263-265"""
+        return self.eng.num_estimated_bases()
+
+    def simulate_batch(self, fraction: float, function: int, min_u: int, min_c: int, min_d: int, min_b: int):
+        """simplesim.cpp:195-407 (argument order u, c, d, b as in the reference)."""
+        p = make_params(self.chunksz, fraction, function, min_u, min_c, min_d, min_b, self.rng_mode,
+                        philox_seed=self.philox_seed)
+        st = self.eng.run(p)
+        if self.rng_mode == RNG_REPLAY:
+            rnglib.set_seed(p.cg1, p.cg2)  # the reference's global generator has advanced
+        for s, fh in enumerate(self.fhs):
+            if fh is not None and st.bytes[s]:
+                fh.write(self.eng.result(s, int(st.bytes[s])).data)
+        # simplesim.cpp:399-406
+        names = ("unpaired tandem reads", "bad-end tandem reads", "concordant tandem pairs", "discordant tandem pairs")
+        for i, nm in enumerate(names):
+            print(f"    Wrote {st.wrote[i]} {nm} (target={st.target[i]})", file=sys.stderr)
+        self.last_stats = st
+        return st
