@@ -68,6 +68,9 @@ struct PlanRec {
 enum { CAT_U = 0, CAT_B = 1, CAT_C = 2, CAT_D = 3, NCAT = 4, NOUT = 7 };
 
 // First output stream of each category (qtip_parse.cpp:1831-1837 order).
-__host__ __device__ inline int cat_stream0(int cat) { return cat == 0 ? 0 : 2 * cat - 1; }
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int cat_stream0(int cat) { return cat == 0 ? 0 : 2 * cat - 1; }
 
 }  // namespace qt

@@ -1,0 +1,147 @@
+"""Named parity cases: small seeded inputs the oracle finishes in well under a second.
+
+Each case is (fasta text as uint8 array, templates per category, simulate_batch kwargs).
+The same builders feed the oracle, the unmodified reference (tests/golden/make_golden.py)
+and the CUDA path, so all three see identical inputs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from qtip_b200 import synth
+from qtip_b200.templates import TemplatePaired, TemplateUnpaired
+
+
+def cli_seed(seed: int):
+    """qtip_parse.cpp:1669-1674"""
+    return (seed, (seed * 77) % 2147483562 + 1)
+
+
+def case_c1_lambda():
+    """BASELINE config 1: 48.5 kbp single record, 10k unpaired 100 bp templates with 0-3 X,
+    default sqrt/45/min 30000, seed 99099."""
+    fa = synth.make_fasta([("lambda_like", 48502)], seed=99099)
+    tu = synth.templates_unpaired(10000, 100, seed=99099, max_x=3)
+    return dict(fasta=fa, tu=tu, tb=[], tc=[], td=[],
+                kw=dict(fraction=45.0, function=2, min_u=30000, min_c=30000, min_d=10000, min_b=10000,
+                        cg=cli_seed(99099)))
+
+
+def case_mixed_small():
+    """All four categories, indel templates, leading N runs, lower-case bases, a record
+    shorter than olap, a record just over one window."""
+    fa = synth.make_fasta([("chrA desc", 300000), ("chrB", 150001), ("tiny", 120), ("chrC", 131072 + 77)], seed=5,
+                          lead_n=2000, lowercase_frac=0.1)
+    tu = synth.templates_unpaired(500, 100, 1, max_x=3) + synth.templates_unpaired(100, 200, 2, indel=True)
+    tb = synth.templates_badend(200, 100, 3, opp_len=50)
+    tc = synth.templates_paired(300, 100, 4, frag_mean=300, frag_sd=30)
+    td = synth.templates_paired(200, 100, 5, discordant=True, max_fraglen=5000)
+    return dict(fasta=fa, tu=tu, tb=tb, tc=tc, td=td,
+                kw=dict(fraction=3000.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=(34, 2619)))
+
+
+def case_c2_pairs():
+    """BASELINE config 2 shape, scaled: concordant 2x150 pairs, fraglen N(400,40), 0-4 X."""
+    fa = synth.make_fasta([("ecoli_like", 460000)], seed=21)
+    tc = synth.templates_paired(3000, 150, 22, frag_mean=400, frag_sd=40, max_x=4)
+    return dict(fasta=fa, tu=[], tb=[], tc=tc, td=[],
+                kw=dict(fraction=10000.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(2222)))
+
+
+def case_c5_indel():
+    """BASELINE config 5 shape, scaled: 1 kbp reads with ~10% edited columns, indel runs 1-6."""
+    fa = synth.make_fasta([("ecoli_like", 460000)], seed=51)
+    tu = synth.templates_unpaired(1000, 1000, 52, indel=True)
+    return dict(fasta=fa, tu=tu, tb=[], tc=[], td=[],
+                kw=dict(fraction=2000.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(555)))
+
+
+def case_c3_shape_small():
+    """BASELINE config 3 shape, scaled 1/2000: 24 GRCh38-proportioned records with leading
+    N runs, unpaired 250 bp templates with 0-5 X."""
+    fa = synth.make_fasta(synth.grch38_like_records(1.0 / 2000), seed=31, lead_n=500)
+    tu = synth.templates_unpaired(2000, 250, 32, max_x=5)
+    return dict(fasta=fa, tu=tu, tb=[], tc=[], td=[],
+                kw=dict(fraction=5000.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(333)))
+
+
+def case_c4_mix_small():
+    """BASELINE config 4 shape, scaled: c/d/b templates 2x150, 70/15/15 mix."""
+    fa = synth.make_fasta(synth.grch38_like_records(1.0 / 4000), seed=41, lead_n=300)
+    tc = synth.templates_paired(1500, 150, 42, frag_mean=400, frag_sd=40, max_x=4)
+    td = synth.templates_paired(1500, 150, 43, discordant=True, max_fraglen=20000)
+    tb = synth.templates_badend(1500, 150, 44, opp_len=150)
+    return dict(fasta=fa, tu=[], tb=tb, tc=tc, td=td, added=(0, 1500, 7000, 1500),
+                kw=dict(fraction=1.0, function=1, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(444)))
+
+
+def case_edges():
+    """Window edge cases with a small chunk size: records of exactly chunksz, chunksz+1,
+    olap-1, olap and olap+1 bases; a >90%-N window; IUPAC codes; CRLF; blank lines; a
+    header with a tab; bases before the first header."""
+    rng = np.random.default_rng(77)
+    chunksz, L = 4096, 100
+
+    def rec(name, n, width=60, nl=b"\n"):
+        s = synth.random_bases(n, rng).tobytes()
+        lines = [s[i:i + width] for i in range(0, len(s), width)]
+        return b">" + name + nl + nl.join(lines) + nl
+
+    parts = [b"ACGTACGTNNACGTTTGA" * 20 + b"\n"]  # headerless leading bases -> record ""
+    parts.append(rec(b"exact", chunksz))
+    parts.append(rec(b"plus1 some description", chunksz + 1))
+    parts.append(rec(b"olapm1", L - 1))
+    parts.append(rec(b"olap", L))
+    parts.append(rec(b"olapp1", L + 1))
+    parts.append(rec(b"crlf\tx y", 3 * chunksz + 17, width=70, nl=b"\r\n"))
+    parts.append(b">mostlyN\n" + b"N" * 3900 + synth.random_bases(196, rng).tobytes() + b"\n" +
+                 synth.random_bases(5000, rng).tobytes() + b"\n")
+    parts.append(b">iupac\n" + b"ACGTRYKMSWBDHVNacgtn-ACGT" * 400 + b"\n\n\n")
+    parts.append(rec(b"last_no_newline", 9000)[:-1])
+    fa = np.frombuffer(b"".join(parts), dtype=np.uint8).copy()
+    tu = synth.templates_unpaired(300, L, 78, max_x=6) + synth.templates_unpaired(50, L, 79, indel=True, len_jitter=30)
+    # trim indel templates whose reference span exceeds L so olap stays L
+    tu = [t for t in tu if t.reflen() <= L]
+    return dict(fasta=fa, tu=tu, tb=[], tc=[], td=[], chunksz=chunksz,
+                kw=dict(fraction=4000.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(7)))
+
+
+def case_inversion():
+    """Small targets: every ignbin call takes the inversion branch (n*p < 30,
+    ranlib.cpp:1198-1231), including categories with n = 0."""
+    fa = synth.make_fasta([("a", 700000), ("b", 90000)], seed=61)
+    tu = synth.templates_unpaired(40, 75, 62, max_x=2)
+    tc = synth.templates_paired(30, 75, 63, frag_mean=250, frag_sd=20)
+    return dict(fasta=fa, tu=tu, tb=[], tc=tc, td=[],
+                kw=dict(fraction=60.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(66)))
+
+
+def case_long_refid():
+    """A refid longer than the kernel's shared-memory name staging, all pair types."""
+    name = "contig_" + "x" * 400
+    fa = synth.make_fasta([(name + " description", 200000)], seed=71)
+    tb = synth.templates_badend(100, 80, 72, opp_len=40)
+    tc = synth.templates_paired(100, 80, 73, frag_mean=300, frag_sd=30)
+    tu = synth.templates_unpaired(100, 80, 74)
+    return dict(fasta=fa, tu=tu, tb=tb, tc=tc, td=[],
+                kw=dict(fraction=300.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(71)))
+
+
+CASES = {
+    "c1_lambda": case_c1_lambda,
+    "mixed_small": case_mixed_small,
+    "c2_pairs": case_c2_pairs,
+    "c3_shape_small": case_c3_shape_small,
+    "c4_mix_small": case_c4_mix_small,
+    "c5_indel": case_c5_indel,
+    "edges": case_edges,
+    "inversion": case_inversion,
+    "long_refid": case_long_refid,
+}
+
+
+def sim_kwargs(case: dict) -> dict:
+    kw = dict(case["kw"])
+    kw["chunksz"] = case.get("chunksz", 128 * 1024)
+    kw["added"] = case.get("added")
+    return kw

@@ -1,0 +1,273 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (include/qtipsim.h), against the
+CPU oracle and the golden fixtures generated from the unmodified reference.
+
+Replay mode must be BIT-EXACT (all seven FASTQ streams, counts, and the generator state handed
+back).  Native (Philox) mode is checked through size-independent properties and chi-square
+tests on position, strand, template/fragment length and edit spectrum.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(case, workdir, name):
+    from oracle import pyoracle as po
+    return po.oracle_simulate(util.write_fasta(case, workdir, name), tu=case["tu"], tb=case["tb"], tc=case["tc"],
+                              td=case["td"], **cases.sim_kwargs(case))
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_replay_bit_exact_vs_oracle_and_golden(name, workdir):
+    case = cases.CASES[name]()
+    streams, st, p = util.run_cuda(case, workdir, name)
+    o = _oracle(case, workdir, name)
+    g = util.golden()[name]
+    assert list(st.wrote) == o.wrote
+    assert list(st.target) == o.target
+    for i in range(7):
+        assert len(streams[i]) == len(o.streams[i]), (name, i)
+        if streams[i] != o.streams[i]:
+            a, b = np.frombuffer(streams[i], np.uint8), np.frombuffer(o.streams[i], np.uint8)
+            k = int(np.nonzero(a != b)[0][0])
+            lo = max(0, k - 200)
+            raise AssertionError(f"{name} stream {i} differs at byte {k}:\nGPU: {streams[i][lo:k + 60]!r}\nORC: {o.streams[i][lo:k + 60]!r}")
+        assert util.sha(streams[i]) == g["streams"][i]["sha256"], (name, i)
+    assert (p.cg1, p.cg2) == tuple(o.cg) == tuple(g["cg_exit"])
+    assert st.draws == o.draws
+    assert st.kernel_launches > 0
+
+
+def test_replay_from_host_bytes_equals_from_path(workdir):
+    case = cases.CASES["mixed_small"]()
+    a, _, _ = util.run_cuda(case, workdir, "mixed_small", via="path")
+    b, _, _ = util.run_cuda(case, workdir, "mixed_small", via="bytes")
+    assert a == b
+
+
+def test_replay_sharded_concatenation_is_identical(workdir):
+    """shards emit contiguous slices; rank-order concatenation == single run."""
+    case = cases.CASES["c4_mix_small"]()
+    full, st, _ = util.run_cuda(case, workdir, "c4_mix_small")
+    for nshard in (2, 3):
+        parts = [util.run_cuda(case, workdir, "c4_mix_small", shard=(r, nshard))[0] for r in range(nshard)]
+        for i in range(7):
+            assert b"".join(p[i] for p in parts) == full[i], (nshard, i)
+
+
+def test_python_mirror_of_reference_interface(workdir):
+    """StreamingSimulator/InputModel* mirror (qtip_b200/sim.py): same call sequence as
+    qtip_parse.cpp:1825-1867, files written, global generator advanced."""
+    from qtip_b200 import rnglib, sim
+    case = cases.CASES["mixed_small"]()
+    o = _oracle(case, workdir, "mixed_small")
+    fa = util.write_fasta(case, workdir, "mixed_small")
+    mu = sim.InputModelUnpaired(case["tu"], len(case["tu"]))
+    mb = sim.InputModelUnpaired(case["tb"], len(case["tb"]))
+    mc = sim.InputModelPaired(case["tc"], len(case["tc"]))
+    md = sim.InputModelPaired(case["td"], len(case["td"]))
+    paths = [os.path.join(workdir, f"mirror_reads_{n}.fastq") for n in sim._abi.OUT_NAMES]
+    fhs = [open(p, "wb") for p in paths]
+    rnglib.initialize()
+    rnglib.set_seed(*case["kw"]["cg"])
+    ss = sim.StreamingSimulator([fa], 128 * 1024, mu, mb, mc, md, *fhs)
+    assert ss.num_estimated_bases() == case["fasta"].size
+    kw = case["kw"]
+    ss.simulate_batch(kw["fraction"], kw["function"], kw["min_u"], kw["min_c"], kw["min_d"], kw["min_b"])
+    for fh in fhs:
+        fh.close()
+    for p, want in zip(paths, o.streams):
+        with open(p, "rb") as fh:
+            assert fh.read() == want
+    assert rnglib.get_state() == tuple(o.cg)
+
+
+def test_error_behaviour(workdir):
+    """Where the reference throws / asserts, the C ABI returns an error code."""
+    from qtip_b200 import sim
+    from qtip_b200.templates import TemplateUnpaired
+    eng = sim.Engine()
+    with pytest.raises(sim.QtipSimError) as ei:
+        eng.load_fasta(os.path.join(workdir, "does_not_exist.fa"))
+    assert ei.value.code == -4  # fasta.cpp:54-58
+    case = cases.CASES["inversion"]()
+    eng.load_fasta(util.write_fasta(case, workdir, "inversion"))
+    with pytest.raises(sim.QtipSimError) as ei:  # nothing to simulate: simplesim.cpp:209
+        eng.run(sim.make_params(cg=(1, 1)))
+    assert ei.value.code == -6
+    eng.set_unpaired(0, [TemplateUnpaired(0, 4, "T", "0", 0, b"IIII", b"==N=")], 1)
+    with pytest.raises(sim.QtipSimError) as ei:  # unknown op: simplesim.cpp:58-60
+        eng.run(sim.make_params(cg=(1, 1)))
+    assert ei.value.code == -5
+    eng.set_unpaired(0, case["tu"], len(case["tu"]))
+    with pytest.raises(sim.QtipSimError) as ei:  # chunksz <= olap: fasta.h:41
+        eng.run(sim.make_params(chunksz=60, cg=(1, 1)))
+    assert ei.value.code == -6
+    with pytest.raises(sim.QtipSimError) as ei:  # set_seed range: rnglib.cpp:1714-1728
+        eng.run(sim.make_params(cg=(0, 1)))
+    assert ei.value.code == -6
+    eng.close()
+
+
+# ------------------------------------------------------------------ native (Philox) mode --
+
+def _parse_fastq(b: bytes):
+    lines = b.split(b"\n")
+    assert lines[-1] == b""
+    n = (len(lines) - 1) // 4
+    return [(lines[4 * i], lines[4 * i + 1], lines[4 * i + 3]) for i in range(n)]
+
+
+def _revcomp(s: bytes) -> bytes:
+    return s.translate(bytes.maketrans(b"ACGTN", b"TGCAN"))[::-1]
+
+
+def _check_records_against_genome(case, recs, genome, typ):
+    """Every read is its template applied to the reference at the position its name claims:
+    '=' columns equal the reference, X columns differ from it (simplesim.cpp:38-62)."""
+    tmpl_by_key = {}
+    for t in case["tu"]:
+        key = (t.fw_flag == "T", t.best_score, t.qual if t.fw_flag == "T" else t.qual[::-1])
+        tmpl_by_key.setdefault(key, []).append(t)
+    nchecked = 0
+    for name, seq, qual in recs:
+        f = name.split(b":")
+        assert f[0] == b"@qtip!" and f[-1] == typ
+        refid, strand, off, score = f[1], f[2], int(f[3]), int(f[4])
+        fw = strand == b"+"
+        cands = tmpl_by_key.get((fw, score, qual))
+        assert cands, name
+        read = seq if fw else _revcomp(seq)
+        ref = genome[refid]
+        ok = False
+        for t in cands:
+            rd = rf = 0
+            good = True
+            for op in t.edit_xscript:
+                c = chr(op)
+                if c == "=":
+                    good &= read[rd] == ref[off + rf]
+                    rd += 1; rf += 1
+                elif c == "X":
+                    good &= read[rd] != ref[off + rf] and read[rd] in b"ACGT"
+                    rd += 1; rf += 1
+                elif c == "I":
+                    rd += 1
+                elif c == "D":
+                    rf += 1
+                elif c == "S":
+                    rd += 1; rf += 1
+                if not good:
+                    break
+            if good and rd == len(read):
+                ok = True
+                break
+        assert ok, name
+        nchecked += 1
+    return nchecked
+
+
+def _genome_dict(case, workdir, name):
+    import ctypes as C
+    from oracle import pyoracle as po
+    lib = po.orc()
+    fa = lib.orc_fasta_load(util.write_fasta(case, workdir, name).encode())
+    out = {}
+    for i in range(lib.orc_fasta_nrecords(fa)):
+        L = C.c_uint64()
+        p = lib.orc_fasta_seq(fa, i, C.byref(L))
+        out[lib.orc_fasta_name(fa, i)] = C.string_at(p, L.value)
+    lib.orc_fasta_free(fa)
+    return out
+
+
+@pytest.mark.parametrize("name", ["c3_shape_small", "c5_indel", "edges"])
+def test_native_reads_are_consistent_with_genome(name, workdir):
+    case = cases.CASES[name]()
+    streams, st, _ = util.run_cuda(case, workdir, name, rng_mode=1, philox_seed=12345)
+    recs = _parse_fastq(streams[0])
+    assert len(recs) == st.wrote[0] > 0
+    n = _check_records_against_genome(case, recs, _genome_dict(case, workdir, name), b"u")
+    assert n == len(recs)
+
+
+def test_native_is_deterministic_and_seed_sensitive(workdir):
+    case = cases.CASES["mixed_small"]()
+    a, _, _ = util.run_cuda(case, workdir, "mixed_small", rng_mode=1, philox_seed=7)
+    b, _, _ = util.run_cuda(case, workdir, "mixed_small", rng_mode=1, philox_seed=7)
+    c, _, _ = util.run_cuda(case, workdir, "mixed_small", rng_mode=1, philox_seed=8)
+    assert a == b
+    assert a != c
+
+
+def test_native_sharding_is_invariant(workdir):
+    """Counter-based draws are keyed by the global read index: any shard count gives the same bytes."""
+    case = cases.CASES["c4_mix_small"]()
+    full, _, _ = util.run_cuda(case, workdir, "c4_mix_small", rng_mode=1, philox_seed=99)
+    parts = [util.run_cuda(case, workdir, "c4_mix_small", rng_mode=1, philox_seed=99, shard=(r, 4))[0] for r in range(4)]
+    for i in range(7):
+        assert b"".join(p[i] for p in parts) == full[i]
+
+
+def _chi2_ok(obs_a, obs_b, alpha=1e-4):
+    """Two-sample chi-square homogeneity test on two histograms over the same bins."""
+    from scipy import stats
+    a, b = np.asarray(obs_a, float), np.asarray(obs_b, float)
+    keep = (a + b) >= 10
+    a, b = a[keep], b[keep]
+    if a.size < 2:
+        return True
+    _, p, _, _ = stats.chi2_contingency(np.vstack([a, b]))
+    return p > alpha
+
+
+def test_native_distributionally_equivalent_to_replay(workdir):
+    """north_star: native-RNG mode is distributionally equivalent to the reference's stream by
+    chi-square on position, strand, template (=> fragment length, quality) and edit spectrum."""
+    case = cases.CASES["c3_shape_small"]()
+    case["kw"] = dict(case["kw"], fraction=60000.0)
+    rep, st_r, _ = util.run_cuda(case, workdir, "c3_shape_small")
+    nat, st_n, _ = util.run_cuda(case, workdir, "c3_shape_small", rng_mode=1, philox_seed=2024)
+    ra, rb = _parse_fastq(rep[0]), _parse_fastq(nat[0])
+    # read count: both ~ sum of Binomial(n, p_w); compare within 5 sigma of each other
+    assert abs(len(ra) - len(rb)) < 5 * np.sqrt(len(ra) + len(rb))
+    genome = _genome_dict(case, workdir, "c3_shape_small")
+    names = sorted(genome)
+
+    def feats(recs):
+        rec_idx, pos_bin, strand, xcount, subst = [], [], [], [], np.zeros((4, 4))
+        for name, seq, qual in recs:
+            f = name.split(b":")
+            refid, fw, off = f[1], f[2] == b"+", int(f[3])
+            rec_idx.append(names.index(refid))
+            pos_bin.append(min(9, off * 10 // max(1, len(genome[refid]))))
+            strand.append(int(fw))
+            read = seq if fw else _revcomp(seq)
+            ref = genome[refid][off:off + len(read)]  # these templates have no indels
+            a = np.frombuffer(read, np.uint8)
+            b = np.frombuffer(ref, np.uint8)
+            mm = np.nonzero(a != b)[0]
+            xcount.append(len(mm))
+            for k in mm:
+                if ref[k:k + 1] in b"ACGT":
+                    subst[b"ACGT".index(ref[k:k + 1]), b"ACGT".index(read[k:k + 1])] += 1
+        return (np.bincount(rec_idx, minlength=len(names)), np.bincount(pos_bin, minlength=10),
+                np.bincount(strand, minlength=2), np.bincount(xcount, minlength=8), subst)
+
+    fa, fb = feats(ra), feats(rb)
+    assert _chi2_ok(fa[0], fb[0]), "record (position) distribution"
+    assert _chi2_ok(fa[1], fb[1]), "within-record position distribution"
+    assert _chi2_ok(fa[2], fb[2]), "strand"
+    assert _chi2_ok(fa[3], fb[3]), "mismatches per read (edit spectrum)"
+    assert _chi2_ok(fa[4].reshape(-1), fb[4].reshape(-1)), "substitution matrix"
+    # substituted base is uniform over the three alternatives in both modes
+    for f in (fa, fb):
+        for r in range(4):
+            alt = np.delete(f[4][r], r)
+            from scipy import stats
+            assert stats.chisquare(alt).pvalue > 1e-4

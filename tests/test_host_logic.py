@@ -1,0 +1,143 @@
+"""Host logic of libqtipsim (no GPU): FASTA parse + 2-bit pack, window table, template
+flattening, the addressable L'Ecuyer stream, ignbin set-up/sampler, glibc-exact logf and
+the replay chain walk -- each against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import util
+from oracle import pyoracle as po
+
+
+@pytest.mark.parametrize("name", ["edges", "mixed_small", "c3_shape_small"])
+def test_parse_and_pack_match_oracle(name, workdir):
+    case = cases.CASES[name]()
+    hs = util.HostSide(case)
+    lib = po.orc()
+    fa = lib.orc_fasta_load(util.write_fasta(case, workdir, name).encode())
+    recs = hs.records()
+    assert len(recs) == lib.orc_fasta_nrecords(fa)
+    for i, (nm, ln, gs) in enumerate(recs):
+        assert nm == lib.orc_fasta_name(fa, i)
+        L = C.c_uint64()
+        p = lib.orc_fasta_seq(fa, i, C.byref(L))
+        assert ln == L.value
+        assert gs % 64 == 0
+        assert hs.unpack(gs, ln) == C.string_at(p, ln)
+        # padding after every record is N
+        assert hs.unpack(gs + ln, 1) == b"N"
+    # windows
+    olap = int(hs.L.qthost_olap(hs.h))
+    chunksz = case.get("chunksz", 128 * 1024)
+    n = C.c_size_t()
+    ch = lib.orc_fasta_chunks(fa, chunksz, olap, C.byref(n))
+    want = [(ch[i].record, ch[i].refoff, ch[i].retsz, ch[i].n_count) for i in range(n.value)]
+    assert hs.windows(chunksz, olap) == want
+    lib.orc_fasta_free(fa)
+    hs.close()
+
+
+def test_stream_is_addressable():
+    """state_k = state_0 * a^k: jumping equals stepping (rnglib.cpp:645-659)."""
+    L = util.hosttest()
+    lib = po.orc()
+    r = po.OrcRng()
+    lib.orc_rng_set_seed(C.byref(r), 34, 2619)
+    s1, s2 = C.c_uint32(34), C.c_uint32(2619)
+    i4, r4 = C.c_int32(), C.c_float()
+    for k in range(1, 3000):
+        L.qthost_rng_step(C.byref(s1), C.byref(s2), C.byref(i4), C.byref(r4))
+        want = lib.orc_i4_uni(C.byref(r))
+        assert i4.value == want
+        if k in (1, 2, 31, 32, 33, 1000, 2999):
+            j1, j2 = C.c_uint32(34), C.c_uint32(2619)
+            L.qthost_rng_jump(C.byref(j1), C.byref(j2), k)
+            assert (j1.value, j2.value) == (s1.value, s2.value) == (r.cg1, r.cg2)
+    j1, j2 = C.c_uint32(34), C.c_uint32(2619)
+    L.qthost_rng_jump(C.byref(j1), C.byref(j2), 10**12 + 7)
+    k1, k2 = C.c_uint32(34), C.c_uint32(2619)
+    L.qthost_rng_jump(C.byref(k1), C.byref(k2), 10**12)
+    L.qthost_rng_jump(C.byref(k1), C.byref(k2), 7)
+    assert (j1.value, j2.value) == (k1.value, k2.value)
+
+
+def test_ignbin_split_matches_oracle():
+    """binom_setup + binom_sample (lecuyer.h) == orc_ignbin, value and state."""
+    L = util.hosttest()
+    o = po.orc()
+    rng = np.random.default_rng(11)
+    for _ in range(600):
+        n = int(rng.choice([0, 1, 7, 100, 3000, 30000, 1000000, 10000000, 100000000]))
+        p = float(np.float32(rng.choice([1e-6, 4.6e-5, 1e-3, 0.03, 0.3, 0.5, 0.7, 0.97, 0.999])))
+        s = (int(rng.integers(1, 2147483562)), int(rng.integers(1, 2147483398)))
+        st = po.OrcRng()
+        o.orc_rng_set_seed(C.byref(st), *s)
+        s1, s2 = C.c_uint32(s[0]), C.c_uint32(s[1])
+        for _k in range(4):
+            assert L.qthost_ignbin(C.byref(s1), C.byref(s2), n, p) == o.orc_ignbin(C.byref(st), n, p), (n, p, s)
+        assert (s1.value, s2.value) == (st.cg1, st.cg2)
+
+
+def test_logf_matches_libm_sampled():
+    """logf_glibc == host logf on a stride over all positive normal floats, and densely over
+    (0, 1] where ignbin's arguments live.  (Exhaustive: tests/test_logf_exhaustive.py, -m slow.)"""
+    L = util.hosttest()
+    assert L.qthost_logf_sweep(0x00800000, 0x7f800000, 4099) == 0
+    assert L.qthost_logf_sweep(0x30000000, 0x3f800001, 53) == 0
+
+
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_replay_plan_matches_oracle_trace(name, workdir):
+    """The chain walk reproduces, per read, the template and position the reference drew,
+    and hands the generator back in the same state after the same number of draws."""
+    case = cases.CASES[name]()
+    kw = cases.sim_kwargs(case)
+    r = po.oracle_simulate(util.write_fasta(case, workdir, name), tu=case["tu"], tb=case["tb"], tc=case["tc"],
+                           td=case["td"], want_trace=True, **kw)
+    assert r.rc == 0
+    hs = util.HostSide(case)
+    rc, cg, draws, nreads = hs.plan(kw)
+    assert rc == 0
+    assert cg == tuple(r.cg)
+    assert draws == r.draws
+    assert nreads == r.wrote
+    wins = hs.windows(kw["chunksz"], int(hs.L.qthost_olap(hs.h)))
+    for cat in range(4):
+        want = [(t[1], wins[t[2]][0], wins[t[2]][1] + t[3]) for t in r.trace if t[0] == cat]
+        got = [(p[0], p[1], p[2]) for p in hs.plan_recs(cat, nreads[cat])]
+        assert got == want, (name, cat)
+    hs.close()
+
+
+def test_sharded_plans_concatenate(workdir):
+    """Shards walk the same chain and emit disjoint, ordered slices of the plan."""
+    case = cases.CASES["c3_shape_small"]()
+    kw = cases.sim_kwargs(case)
+    hs = util.HostSide(case)
+    _, _, _, full_n = hs.plan(kw)
+    full = hs.plan_recs(0, full_n[0])
+    nwin = len(hs.windows(kw["chunksz"], int(hs.L.qthost_olap(hs.h))))
+    parts = []
+    for r in range(3):
+        lo, hi = r * nwin // 3, (r + 1) * nwin // 3
+        _, _, _, n = hs.plan(kw, lo, hi)
+        parts += hs.plan_recs(0, n[0])
+    assert parts == full
+    hs.close()
+
+
+def test_bad_transcripts_flagged():
+    """Unknown op (simplesim.cpp:58-60) and length mismatch (:63) are detected up front."""
+    from qtip_b200.templates import TemplateUnpaired
+    bad_op = dict(fasta=np.frombuffer(b">r\nACGT\n", dtype=np.uint8), tu=[TemplateUnpaired(0, 4, "T", "0", 0, b"IIII", b"==N=")],
+                  tb=[], tc=[], td=[])
+    hs = util.HostSide(bad_op)
+    assert hs.L.qthost_cat_valid(hs.h, 0) == 0
+    hs.close()
+    bad_len = dict(fasta=np.frombuffer(b">r\nACGT\n", dtype=np.uint8), tu=[TemplateUnpaired(0, 4, "T", "0", 0, b"IIII", b"===")],
+                   tb=[], tc=[], td=[])
+    hs = util.HostSide(bad_len)
+    assert hs.L.qthost_cat_valid(hs.h, 0) == 0
+    hs.close()
