@@ -42,7 +42,7 @@ __device__ __forceinline__ uint32_t name_len_unp(uint32_t refid_len, uint64_t re
 }
 __device__ __forceinline__ uint32_t name_len_pair(uint32_t refid_len, uint64_t off1, uint32_t sl1,
                                                   uint64_t off2, uint32_t sl2, uint32_t typ_len) {
-	return 19u + 2u * refid_len + ndigits_u64(off1) + ndigits_u64(off2) + sl1 + sl2 + typ_len;
+	return 18u + 2u * refid_len + ndigits_u64(off1) + ndigits_u64(off2) + sl1 + sl2 + typ_len;
 }
 
 __device__ __forceinline__ char *put_u64(char *p, uint64_t v) {

@@ -143,7 +143,7 @@ int TemplateStore::set_paired(int ci, const qtipsim_tmpl_pair *v, size_t kept, u
 			t.delta[0] = (uint32_t)(std::max<uint64_t>(fl, t.m[0].rflen) - t.m[0].rflen);
 		}
 		c.max_len = std::max<uint64_t>(c.max_len, fl);  // input_model.h:112-115
-		bytes += 2.0 * (7 + 10 + t.m[0].score_len + t.m[1].score_len + 2) + 2.0 * t.m[0].len + 2.0 * t.m[1].len + 8;
+		bytes += 2.0 * (7 + 9 + t.m[0].score_len + t.m[1].score_len + 2) + 2.0 * t.m[0].len + 2.0 * t.m[1].len + 8;
 		draws += 2 + t.m[0].ndraw + t.m[1].ndraw;
 	}
 	if (kept) {
