@@ -1,0 +1,430 @@
+#!/usr/bin/env python
+"""bench.py -- tandem-read simulator throughput on B200 (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale S]
+
+One "step" = one pass of the hot path over the workload: (pack the FASTA), resolve the
+reference's draw chain, simulate + emit FASTQ for every read.  Workload at N=1 is
+BASELINE.json configs[2] (the one quoted for 1 B200): GRCh38-sized synthetic 3.1 Gbp
+reference, 10 M unpaired 250 bp reads; at N>1 it is configs[3] (3.1 Gbp, mixed c/d/b pairs,
+12.5 M pairs per GPU, sharded by FASTA window range; weak scaling).
+
+Prints ONE JSON line on rank 0.  `value` = reads (or pairs) per second with the inputs
+resident in HBM; `e2e` = the same through the C ABI with host buffers (FASTA text and
+templates in host memory -> FASTQ bytes in pinned host memory).  `--impl reference` times the
+UNMODIFIED reference (oracle/_ref/libref.so = the reference's own simplesim.cpp, fasta.cpp,
+rnglib.cpp, ranlib.cpp) on the host CPU on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from qtip_b200 import synth  # noqa: E402
+
+CHUNKSZ = 128 * 1024
+METRIC = "tandem reads/sec"
+UNIT = "reads/s"
+
+
+# ------------------------------------------------------------------ workload --
+
+def workload(n_gpus: int, scale: float):
+    """Returns dict(name, records, templates, targets) for the bench configuration."""
+    recs = synth.grch38_like_records(scale)
+    if n_gpus == 1:
+        tu = synth.templates_unpaired(30000, 250, seed=3003, max_x=5)
+        return dict(name=f"C3: GRCh38-sized synthetic {sum(l for _, l in recs) / 1e9:.2f} Gbp ref (24 records, 10 kbp "
+                         f"leading N each), {10 * scale:.3g}M unpaired 250 bp reads from 30k templates (0-5 X)",
+                    records=recs, lead_n=10000, tu=tu, tb=[], tc=[], td=[],
+                    kw=dict(fraction=float(int(10_000_000 * scale)), function=3, min_u=1, min_c=1, min_d=1, min_b=1),
+                    unit="reads/s", genome_seed=3001)
+    tc = synth.templates_paired(30000, 150, seed=4002, frag_mean=400, frag_sd=40, max_x=4)
+    td = synth.templates_paired(30000, 150, seed=4003, discordant=True, max_fraglen=50000)
+    tb = synth.templates_badend(30000, 150, seed=4004, opp_len=150)
+    total = int(12_500_000 * n_gpus * scale)
+    # 70 / 15 / 15 mix through `added` and the linear function: target = added
+    added = (0, int(total * 0.15), int(total * 0.70), int(total * 0.15))
+    return dict(name=f"C4: GRCh38-sized synthetic {sum(l for _, l in recs) / 1e9:.2f} Gbp ref, {total / 1e6:.3g}M pairs "
+                     f"70/15/15 concordant/discordant/bad-end 2x150, sharded across {n_gpus} GPU(s)",
+                records=recs, lead_n=10000, tu=[], tb=tb, tc=tc, td=td, added=added,
+                kw=dict(fraction=1.0, function=1, min_u=1, min_c=1, min_d=1, min_b=1), unit="pairs/s", genome_seed=3001)
+
+
+def cli_seed(seed: int):
+    return (seed, (seed * 77) % 2147483562 + 1)
+
+
+# -------------------------------------------------------------------- clocks --
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------- reference --
+
+def reference_sample(wl, scale_note=""):
+    """A bounded sample of the workload for the CPU arm: the last records of the same genome
+    (about 3% of the bases) with the read targets scaled by the same fraction, so reads per base --
+    and therefore per-read and per-base costs -- are those of the full workload."""
+    recs = wl["records"]
+    tot = sum(l for _, l in recs)
+    pick, acc = [], 0
+    for nm, l in reversed(recs):
+        pick.append((nm, l))
+        acc += l
+        if acc >= 0.03 * tot:
+            break
+    pick.reverse()
+    frac = acc / tot
+    return pick, frac
+
+
+def run_reference_steps(wl, steps, warmup, threads_note="1 (the reference is single-threaded, qtip_parse.cpp:73)"):
+    from oracle import pyoracle as po
+    if not po.have_ref():
+        return None, "oracle/_ref not built"
+    pick, frac = reference_sample(wl)
+    fa = synth.make_fasta(pick, seed=wl["genome_seed"], lead_n=wl["lead_n"])
+    d = tempfile.mkdtemp(prefix="qtipref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    fa_path = os.path.join(d, "sample.fa")
+    fa.tofile(fa_path)
+    kw = dict(wl["kw"])
+    added = wl.get("added")
+    if kw["function"] == 3:
+        kw["fraction"] = float(max(1, int(kw["fraction"] * frac)))
+    else:
+        added = tuple(int(a * frac) for a in added)
+    times, nreads, nbytes = [], 0, 0
+    for i in range(warmup + steps):
+        r = po.ref_simulate(fa_path, tu=wl["tu"], tb=wl["tb"], tc=wl["tc"], td=wl["td"], added=added, chunksz=CHUNKSZ,
+                            cg=cli_seed(1000 + i), outdir=d, read_back=False, **kw)
+        dt = r.seconds
+        assert r.rc == 0
+        if i >= warmup:
+            times.append(dt)
+            nbytes = sum(r.streams)
+    # count reads from the first stream(s): 4 lines per record
+    def count(path):
+        n = 0
+        with open(path, "rb") as fh:
+            while True:
+                b = fh.read(1 << 24)
+                if not b:
+                    break
+                n += b.count(b"\n")
+        return n // 4
+    names = ("u", "b_1", "c_1", "d_1")
+    nreads = sum(count(os.path.join(d, f"ref_reads_{n}.fastq")) for n in names)
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
+    sec = float(np.mean(times))
+    return dict(reads_per_s=nreads / sec, gb_per_s=nbytes / sec / 1e9, sec_per_step=sec, reads=nreads, bytes=nbytes,
+                sample=f"{len(pick)} of {len(wl['records'])} records ({frac * 100:.1f}% of the bases, same read density), "
+                       f"{nreads} reads/pairs, outputs on tmpfs, FASTA scan included",
+                cores=1), None
+
+
+# ---------------------------------------------------------------------- main --
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("QTIP_BENCH_SCALE", "1.0")),
+                    help="shrink genome and read counts together (1.0 = the BASELINE.json configuration)")
+    ap.add_argument("--mode", default="replay", choices=["replay", "native"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_gpus = args.gpus
+    wl = workload(n_gpus, args.scale)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        res, why = run_reference_steps(wl, args.steps, max(1, min(args.warmup, 1)))
+        if res is None:
+            print(json.dumps({"impl": "reference", "unavailable": why}))
+            return 0
+        line = {
+            "impl": "reference", "metric": METRIC, "value": res["reads_per_s"], "unit": wl["unit"], "n_gpus": n_gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["sec_per_step"] * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": wl["name"], "sample": res["sample"]},
+            "output_gb_per_s": res["gb_per_s"],
+            "cpu_baseline": {"value": res["reads_per_s"], "unit": wl["unit"], "cores": res["cores"], "kind": "reference",
+                             "sample": res["sample"]},
+            "e2e": {"value": res["reads_per_s"], "unit": wl["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from qtip_b200 import _abi, sim
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    rng_mode = _abi.RNG_REPLAY if args.mode == "replay" else _abi.RNG_PHILOX
+
+    # ---- inputs: FASTA text in pinned host memory (rank 0 builds it) ----
+    eng = sim.Engine(local_rank)
+    fa_pinned = None
+    t_setup = time.perf_counter()
+    if rank == 0:
+        fa = synth.make_fasta(wl["records"], seed=wl["genome_seed"], lead_n=wl["lead_n"])
+        fa_pinned = torch.empty(fa.size, dtype=torch.uint8).pin_memory()
+        fa_pinned.numpy()[:] = fa
+        del fa
+        eng.load_fasta_bytes(fa_pinned.numpy())
+    if world > 1:
+        # replicate the packed genome: rank 0 packed it, NCCL broadcast over NVLink, others adopt
+        meta = [None]
+        if rank == 0:
+            bl = eng.lib.qtipsim_genome_export
+            import ctypes as C
+            ptrs = []
+            for which in (0, 1, 2):
+                p, n, isd = C.c_void_p(), C.c_uint64(), C.c_int()
+                eng.check(bl(eng.h, which, C.byref(p), C.byref(n), C.byref(isd)))
+                ptrs.append((p.value, n.value))
+            blob = (C.c_char * ptrs[2][1]).from_address(ptrs[2][0]).raw
+            meta = [(ptrs[0][1], ptrs[1][1], blob)]
+        dist.broadcast_object_list(meta, src=0)
+        nb_bytes, nm_bytes, blob = meta[0]
+
+        class _Raw:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+        if rank == 0:
+            tb_ = torch.as_tensor(_Raw(ptrs[0][0], nb_bytes), device="cuda")
+            tn_ = torch.as_tensor(_Raw(ptrs[1][0], nm_bytes), device="cuda")
+        else:
+            tb_ = torch.empty(nb_bytes, dtype=torch.uint8, device="cuda")
+            tn_ = torch.empty(nm_bytes, dtype=torch.uint8, device="cuda")
+        dist.broadcast(tb_, src=0)
+        dist.broadcast(tn_, src=0)
+        torch.cuda.synchronize()
+        if rank != 0:
+            import ctypes as C
+            eng.check(eng.lib.qtipsim_genome_adopt(eng.h, blob, len(blob), C.c_void_p(tb_.data_ptr()), nb_bytes,
+                                                   C.c_void_p(tn_.data_ptr()), nm_bytes))
+            del tb_, tn_
+    added = wl.get("added") or (len(wl["tu"]), len(wl["tb"]), len(wl["tc"]), len(wl["td"]))
+
+    def set_templates():
+        eng.set_unpaired(0, wl["tu"], added[0])
+        eng.set_unpaired(1, wl["tb"], added[1])
+        eng.set_paired(2, wl["tc"], added[2])
+        eng.set_paired(3, wl["td"], added[3])
+
+    set_templates()
+    setup_s = time.perf_counter() - t_setup
+
+    kw = wl["kw"]
+    state_buf = torch.zeros(2, dtype=torch.int64, device="cuda")
+
+    def one_step(seed, e2e=False, host_out=None):
+        """Runs one step on this rank's shard; returns (stats, h2d_bytes)."""
+        h2d = 0
+        if e2e:
+            if rank == 0 and world == 1:
+                eng.load_fasta_bytes(fa_pinned.numpy())  # parse + pack + upload of the FASTA text
+                h2d += int(eng.lib.qtipsim_num_estimated_bases(eng.h))  # counted below from the packed size
+            set_templates()
+        cg = cli_seed(seed)
+        if world > 1 and rng_mode == _abi.RNG_REPLAY and rank > 0:
+            dist.recv(state_buf, src=rank - 1)  # the chain is sequential across shards
+            cg = (int(state_buf[0].item()), int(state_buf[1].item()))
+        p = sim.make_params(CHUNKSZ, kw["fraction"], kw["function"], kw["min_u"], kw["min_c"], kw["min_d"], kw["min_b"],
+                            rng_mode, cg=cg, philox_seed=seed, shard_rank=rank, shard_count=world)
+        st = eng.run(p)
+        if world > 1 and rng_mode == _abi.RNG_REPLAY and rank < world - 1:
+            state_buf[0], state_buf[1] = p.cg1, p.cg2
+            dist.send(state_buf, dst=rank + 1)
+        if e2e:
+            import ctypes as C
+            for s in range(_abi.NOUT):
+                n = int(st.bytes[s])
+                if n:
+                    if host_out[s] is None or host_out[s].numel() < n:
+                        host_out[s] = torch.empty(int(n * 1.05) + 4096, dtype=torch.uint8).pin_memory()
+                    eng.check(eng.lib.qtipsim_result_copy(eng.h, s, C.c_void_p(host_out[s].data_ptr()), host_out[s].numel()))
+        return st
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ----
+    for i in range(args.warmup):
+        one_step(100 + i)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    t0 = time.perf_counter()
+    agg = dict(reads=0, bytes=0, alg=0, launches=0, ms_plan=0.0, ms_sim=0.0, ms_total=0.0)
+    for i in range(args.steps):
+        st = one_step(200 + i)
+        agg["reads"] += sum(st.wrote)
+        agg["bytes"] += sum(st.bytes)
+        agg["alg"] += int(st.algorithmic_bytes)
+        agg["launches"] += int(st.kernel_launches)
+        agg["ms_plan"] += st.ms_plan
+        agg["ms_sim"] += st.ms_simulate
+        agg["ms_total"] += st.ms_total
+    ev1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    barrier()
+
+    # ---- end-to-end arm (host buffers, H2D/D2H inside) ----
+    host_out = [None] * _abi.NOUT
+    one_step(300, e2e=True, host_out=host_out)  # warm (allocates pinned buffers)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    e2e_reads, e2e_d2h = 0, 0
+    e2e_steps = max(1, min(args.steps, 2))
+    for i in range(e2e_steps):
+        st = one_step(400 + i, e2e=True, host_out=host_out)
+        e2e_reads += sum(st.wrote)
+        e2e_d2h += sum(st.bytes)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1)
+    barrier()
+
+    # ---- reduce over ranks: time = max, work = sum ----
+    t = torch.tensor([ev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
+    w = torch.tensor([agg["reads"], agg["bytes"], agg["alg"], agg["launches"], e2e_reads, e2e_d2h], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+    ev_ms, e2e_ms, wall_ms = [float(x) for x in t.tolist()]
+    reads, obytes, alg, launches, e2e_reads, e2e_d2h = [float(x) for x in w.tolist()]
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        ms_step = ev_ms / args.steps
+        # dominant kernel: k_simulate; its launches per step = categories with reads; achieved =
+        # algorithmic bytes of the step / device time of those launches (CUDA events on the library's stream)
+        sim_ms_step = agg["ms_sim"] / args.steps
+        alg_step_rank0 = agg["alg"] / args.steps
+        achieved = alg_step_rank0 / (sim_ms_step * 1e-3) / 1e9 if sim_ms_step > 0 else 0.0
+        # H2D per e2e step: packed genome (2 bit + 1 bit per base) + templates + plan records
+        h2d = 0
+        if world == 1:
+            tot_bases = sum(l for _, l in wl["records"])
+            h2d = tot_bases // 4 + tot_bases // 8 + int(e2e_reads / e2e_steps) * 24
+        line = {
+            "metric": METRIC, "value": reads / (ev_ms * 1e-3), "unit": wl["unit"], "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": wl["name"], "rng_mode": args.mode, "chunksz": CHUNKSZ, "scale": args.scale,
+                       "l2": "per-step working set (packed genome + FASTQ output) is GBs, far larger than the 126 MB L2",
+                       "parallelism": f"windows sharded across {world} rank(s); packed genome broadcast over NCCL"},
+            "output_gb_per_s": obytes / (ev_ms * 1e-3) / 1e9,
+            "reads_per_step": reads / args.steps,
+            "wall_ms_per_step": wall_ms / args.steps,
+            "phase_ms_per_step_rank0": {"plan": agg["ms_plan"] / args.steps, "simulate": sim_ms_step,
+                                        "total": agg["ms_total"] / args.steps},
+            "roofline": {"bound": "hbm", "kernel": "k_simulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": alg_step_rank0},
+            "e2e": {"value": e2e_reads / (e2e_ms * 1e-3), "unit": wl["unit"], "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(e2e_d2h / e2e_steps), "ms_per_step": e2e_ms / e2e_steps,
+                    "output_gb_per_s": e2e_d2h / (e2e_ms * 1e-3) / 1e9},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "setup_s": setup_s,
+        }
+        if n_gpus == 1 and not args.no_cpu_baseline:
+            res, why = run_reference_steps(wl, 1, 0)
+            if res is not None:
+                line["cpu_baseline"] = {"value": res["reads_per_s"], "unit": wl["unit"], "cores": res["cores"],
+                                        "kind": "reference", "sample": res["sample"], "gb_per_s": res["gb_per_s"]}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": wl["unit"], "cores": 0, "kind": "reference", "sample": why}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -99,7 +99,9 @@ typedef struct {
 	uint64_t min_u, min_c, min_d, min_b;
 	int32_t rng_mode;  /* QTIPSIM_RNG_* */
 	int32_t cg1, cg2;  /* REPLAY: rnglib state at entry (get_state, rnglib.cpp:516); the
-	                      state at exit is written back here */
+	                      state at exit is written back here.  With shards the chain is
+	                      sequential across them: shard r's entry state is shard r-1's exit
+	                      state (the caller passes the two integers along, rank to rank) */
 	uint64_t philox_seed; /* PHILOX */
 	/* sharding across GPUs: this handle simulates the windows whose index i satisfies
 	 * shard_rank*nwin/shard_count <= i < (shard_rank+1)*nwin/shard_count.  {0,1} = all. */

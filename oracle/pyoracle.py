@@ -189,8 +189,11 @@ def ref_simulate(fasta_path: str, tu=(), tb=(), tc=(), td=(), added=None, chunks
     paths = [os.path.join(outdir, f"ref_reads_{n}.fastq").encode() for n in OUT_NAMES]
     arr = (C.c_char_p * 7)(*paths)
     lib.ref_set_seed(cg[0], cg[1])
+    import time as _time
+    _t0 = _time.perf_counter()
     rc = lib.ref_simulate(fasta_path.encode(), chunksz, au, len(tu), added[0], ab, len(tb), added[1], ac, len(tc),
                           added[2], ad, len(td), added[3], fraction, function, min_u, min_c, min_d, min_b, arr)
+    _dt = _time.perf_counter() - _t0
     a, b = C.c_int(), C.c_int()
     lib.ref_get_state(C.byref(a), C.byref(b))
     streams = []
@@ -203,7 +206,9 @@ def ref_simulate(fasta_path: str, tu=(), tb=(), tc=(), td=(), added=None, chunks
     if tmp is not None:
         tmp.cleanup()
     wrote = [0, 0, 0, 0]
-    return SimResult(streams, wrote, [0, 0, 0, 0], (a.value, b.value), None, rc)
+    res = SimResult(streams, wrote, [0, 0, 0, 0], (a.value, b.value), None, rc)
+    res.seconds = _dt  # time inside the reference's StreamingSimulator ctor + simulate_batch (+ template EList build)
+    return res
 
 
 def ref_qtip_parse(sam: str, fasta: str, outdir: str, seed: int, opts: Optional[dict] = None, exe: str = REF_PARSE,

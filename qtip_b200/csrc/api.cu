@@ -415,10 +415,8 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 			CK(cudaMemcpyAsync(h->d_plan[c].p, plan.recs[c].data(), nreads[c] * sizeof(PlanRec), cudaMemcpyHostToDevice, h->st));
 		}
 		CK(cudaStreamSynchronize(h->st));  // plan vectors die at scope end
-		if (p->shard_count == 1) {
-			p->cg1 = (int32_t)plan.rng_out.s1;
-			p->cg2 = (int32_t)plan.rng_out.s2;
-		}
+		p->cg1 = (int32_t)plan.rng_out.s1;
+		p->cg2 = (int32_t)plan.rng_out.s2;
 		draws = plan.draws;
 	} else {
 		std::map<std::pair<int32_t, uint32_t>, BinomSetup> setups;

@@ -71,10 +71,10 @@ int plan_replay_host(const HostGenome &g, const TemplateStore &ts, const std::ve
 	};
 	for (int c = 0; c < NCAT; c++) out.recs[c].clear();
 
-	for (size_t wi = 0; wi < win.size() && wi < pp.win_hi; wi++) {
+	for (size_t wi = pp.win_lo; wi < win.size() && wi < pp.win_hi; wi++) {
 		const Window &w = win[wi];
 		if (!window_live(w.retsz, pp.olap, ncount[wi])) continue;
-		const bool emit = wi >= pp.win_lo;
+		const bool emit = true;
 		const float p = window_binom_p(w.retsz, pp.olap, pp.tot_fasta_len);
 		const uint64_t nslots = w.retsz - pp.olap;
 		const RecDev &rec = g.recs[w.record];

@@ -21,7 +21,8 @@ struct PlanParams {
 	uint64_t chunksz = 0, olap = 0;
 	uint64_t target[NCAT] = {0, 0, 0, 0};  // nu, nb, nc, nd after apply_function
 	uint64_t tot_fasta_len = 0;
-	uint64_t win_lo = 0, win_hi = 0;       // windows this shard emits (chain is walked from 0)
+	uint64_t win_lo = 0, win_hi = 0;       // windows of this shard; the generator state passed in is
+	                                       // the state at window win_lo (rank r-1 hands it to rank r)
 };
 
 struct Plan {

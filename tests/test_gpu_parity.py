@@ -53,11 +53,16 @@ def test_replay_from_host_bytes_equals_from_path(workdir):
 def test_replay_sharded_concatenation_is_identical(workdir):
     """shards emit contiguous slices; rank-order concatenation == single run."""
     case = cases.CASES["c4_mix_small"]()
-    full, st, _ = util.run_cuda(case, workdir, "c4_mix_small")
+    full, st, pf = util.run_cuda(case, workdir, "c4_mix_small")
     for nshard in (2, 3):
-        parts = [util.run_cuda(case, workdir, "c4_mix_small", shard=(r, nshard))[0] for r in range(nshard)]
+        parts, cg = [], None
+        for r in range(nshard):  # the chain is sequential: rank r starts from rank r-1's exit state
+            s, _, p = util.run_cuda(case, workdir, "c4_mix_small", shard=(r, nshard), cg=cg)
+            cg = (p.cg1, p.cg2)
+            parts.append(s)
         for i in range(7):
             assert b"".join(p[i] for p in parts) == full[i], (nshard, i)
+        assert cg == (pf.cg1, pf.cg2)
 
 
 def test_python_mirror_of_reference_interface(workdir):

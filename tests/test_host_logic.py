@@ -119,12 +119,15 @@ def test_sharded_plans_concatenate(workdir):
     _, _, _, full_n = hs.plan(kw)
     full = hs.plan_recs(0, full_n[0])
     nwin = len(hs.windows(kw["chunksz"], int(hs.L.qthost_olap(hs.h))))
-    parts = []
+    _, full_cg, full_draws, _ = hs.plan(kw)
+    parts, cg, draws = [], None, 0
     for r in range(3):
         lo, hi = r * nwin // 3, (r + 1) * nwin // 3
-        _, _, _, n = hs.plan(kw, lo, hi)
+        _, cg, d, n = hs.plan(kw, lo, hi, cg=cg)  # rank r starts from rank r-1's exit state
+        draws += d
         parts += hs.plan_recs(0, n[0])
     assert parts == full
+    assert cg == full_cg and draws == full_draws
     hs.close()
 
 

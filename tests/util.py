@@ -123,8 +123,9 @@ class HostSide:
             out.append((r.value, ro.value, rs.value, nc.value))
         return out
 
-    def plan(self, kw, win_lo=0, win_hi=1 << 60):
-        cg1, cg2 = C.c_int32(kw["cg"][0]), C.c_int32(kw["cg"][1])
+    def plan(self, kw, win_lo=0, win_hi=1 << 60, cg=None):
+        cg = cg or kw["cg"]
+        cg1, cg2 = C.c_int32(cg[0]), C.c_int32(cg[1])
         draws = C.c_uint64()
         nr = (C.c_uint64 * 4)()
         rc = self.L.qthost_plan(self.h, kw["chunksz"], kw["fraction"], kw["function"], kw["min_u"], kw["min_c"],
@@ -142,7 +143,7 @@ class HostSide:
         return out
 
 
-def run_cuda(case, workdir, name, rng_mode=0, philox_seed=0, shard=(0, 1), via="path"):
+def run_cuda(case, workdir, name, rng_mode=0, philox_seed=0, shard=(0, 1), via="path", cg=None):
     """Runs the case through libqtipsim's C ABI on the GPU; returns (streams, stats, params)."""
     from qtip_b200 import sim
     eng = sim.Engine()
@@ -158,7 +159,7 @@ def run_cuda(case, workdir, name, rng_mode=0, philox_seed=0, shard=(0, 1), via="
         eng.set_paired(3, case["td"], added[3])
         kw = case["kw"]
         p = sim.make_params(case.get("chunksz", 128 * 1024), kw["fraction"], kw["function"], kw["min_u"], kw["min_c"],
-                            kw["min_d"], kw["min_b"], rng_mode, cg=kw["cg"], philox_seed=philox_seed,
+                            kw["min_d"], kw["min_b"], rng_mode, cg=cg or kw["cg"], philox_seed=philox_seed,
                             shard_rank=shard[0], shard_count=shard[1])
         st = eng.run(p)
         streams = eng.results(st)
