@@ -73,7 +73,7 @@ struct qtipsim {
 
 	TemplateStore ts;
 	bool tmpl_dirty[NCAT] = {true, true, true, true};
-	DevBuf d_t[NCAT], d_qual[NCAT], d_xs[NCAT];
+	DevBuf d_t[NCAT], d_qual[NCAT], d_xs[NCAT], d_qual_out[NCAT], d_ops[NCAT], d_segs[NCAT];
 
 	DevBuf d_jt1, d_jt2;
 	bool have_jt = false;
@@ -155,6 +155,9 @@ void qtipsim_destroy(qtipsim_t *h) {
 		h->d_t[c].release();
 		h->d_qual[c].release();
 		h->d_xs[c].release();
+		h->d_qual_out[c].release();
+		h->d_ops[c].release();
+		h->d_segs[c].release();
 		h->d_plan[c].release();
 		h->d_off0[c].release();
 		h->d_off1[c].release();
@@ -295,6 +298,16 @@ static int upload_templates(qtipsim *h) {
 			CK(cudaMemcpyAsync(h->d_t[c].p, cg.t.data(), cg.t.size() * sizeof(TmplDesc), cudaMemcpyHostToDevice, h->st));
 			CK(cudaMemcpyAsync(h->d_qual[c].p, cg.qual.data(), cg.qual.size(), cudaMemcpyHostToDevice, h->st));
 			CK(cudaMemcpyAsync(h->d_xs[c].p, cg.xs.data(), cg.xs.size(), cudaMemcpyHostToDevice, h->st));
+			// compiled form; the quality arena is read with aligned 4-byte loads up to 16 bytes past an entry
+			CK(h->d_qual_out[c].ensure(cg.qual_out.size() + 64));
+			CK(h->d_ops[c].ensure(cg.ops.size() * 4 + 16));
+			CK(h->d_segs[c].ensure(cg.segs.size() * sizeof(SegDev) + 16));
+			CK(cudaMemsetAsync(h->d_qual_out[c].p, 0, cg.qual_out.size() + 64, h->st));
+			CK(cudaMemcpyAsync(h->d_qual_out[c].p, cg.qual_out.data(), cg.qual_out.size(), cudaMemcpyHostToDevice, h->st));
+			if (!cg.ops.empty())
+				CK(cudaMemcpyAsync(h->d_ops[c].p, cg.ops.data(), cg.ops.size() * 4, cudaMemcpyHostToDevice, h->st));
+			if (!cg.segs.empty())
+				CK(cudaMemcpyAsync(h->d_segs[c].p, cg.segs.data(), cg.segs.size() * sizeof(SegDev), cudaMemcpyHostToDevice, h->st));
 		}
 		h->tmpl_dirty[c] = false;
 	}
@@ -472,6 +485,10 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 		a.c.qual = h->d_qual[c].as<char>();
 		a.c.xs = h->d_xs[c].as<char>();
 		a.c.n = (uint32_t)h->ts.cat[c].t.size();
+		a.c.qual_out = h->d_qual_out[c].as<char>();
+		a.c.ops = h->d_ops[c].as<uint32_t>();
+		a.c.segs = h->d_segs[c].as<SegDev>();
+		a.genome_words = (h->hg.total_bases + 15) / 16 + 4;
 		a.plan = h->d_plan[c].as<PlanRec>();
 		a.nreads = nreads[c];
 		a.read_index_base = read_base[c];
@@ -506,7 +523,25 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 		const int s0 = cat_stream0(c);
 		sa[c].out0 = h->d_out[s0].as<char>();
 		sa[c].out1 = c != CAT_U ? h->d_out[s0 + 1].as<char>() : nullptr;
-		launch_simulate(sa[c], h->st);
+		sa[c].tot0 = d_tot + s0;
+		sa[c].tot1 = d_tot + s0 + 1;
+		// upper bound on one FASTQ record of this category (name + 2 * body + 4)
+		uint32_t max_refid = 0;
+		uint64_t max_reclen = 0;
+		for (const RecDev &r : h->hg.recs) {
+			max_refid = r.name_len > max_refid ? r.name_len : max_refid;
+			max_reclen = r.len > max_reclen ? r.len : max_reclen;
+		}
+		uint32_t dig = 1;
+		for (uint64_t v = max_reclen + p->chunksz; v >= 10; v /= 10) dig++;
+		const Category &cg = h->ts.cat[c];
+		const uint32_t max_rec = (c == CAT_U ? 13u + max_refid + dig + cg.max_score_len + 2u
+		                                     : 18u + 2u * (max_refid + dig + cg.max_score_len) + 2u) +
+		                         2u * cg.max_body + 4u;
+		const char *force = getenv("QTIPSIM_KERNEL");
+		bool done = false;
+		if (cg.compiled_ok && !(force && strcmp(force, "generic") == 0)) done = launch_simulate_tiled(sa[c], max_rec, h->st);
+		if (!done) launch_simulate(sa[c], h->st);
 	}
 	CK(cudaEventRecord(ev[3], h->st));
 	CK(cudaStreamSynchronize(h->st));

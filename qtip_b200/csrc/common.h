@@ -42,7 +42,27 @@ struct MateDesc {
 	uint8_t score_len;
 	char score[12];      // "%d" of the score
 	uint16_t pad;
+	// compiled, output-oriented form (tiled kernel): see templates.cpp
+	uint32_t qual_out_off;  // qual arena in OUTPUT orientation (reversed for '-'), 16-byte aligned
+	uint32_t ops_off;       // draw-op list (X/I/S in transcript order), u32 entries
+	uint32_t seg_off;       // reference-copy segments, ascending output position
+	uint16_t nops;
+	uint16_t nseg;
 };
+
+// A maximal run of transcript ops that copy reference to read (=, X, S), in output
+// orientation: output positions [out_start, out_end) come from reference offsets
+// ref0 + (k - out_start) for '+' mates and ref0 - (k - out_start) for '-' mates
+// (relative to the mate's leftmost reference base).
+struct SegDev {
+	uint16_t out_start, out_end;
+	int32_t ref0;
+};
+
+// draw-op entry: bits 0-1 kind (0 = X: redraw while equal to the reference base,
+// 1 = I or S: one draw), bits 2-16 output position, bits 17-31 reference offset (X)
+static constexpr uint32_t OP_X = 0u, OP_IS = 1u;
+static constexpr uint32_t COMPILED_MAX_LEN = 32767u;
 
 struct TmplDesc {
 	MateDesc m[2];       // [0] = rd1's source (aligned mate for U/B), [1] = mate 2 (C/D)

@@ -36,11 +36,13 @@ void HostGenome::parse(const uint8_t *text, uint64_t n) {
 		nhdr++;
 		p = q + 1;
 	}
-	const uint64_t cap_bases = n + 64 * (nhdr + 2);
+	const uint64_t cap_bases = n + 64 * (nhdr + 4);
 	bases.assign((size_t)(cap_bases / 16 + 4), 0u);
 	nmask.assign((size_t)(cap_bases / 32 + 4), 0u);
 
-	uint64_t g = 0;       // next base slot
+	// 64 bases of N padding in front: kernels may read up to 15 bases before a record
+	uint64_t g = 64;      // next base slot
+	nmask[0] = nmask[1] = 0xffffffffu;
 	bool have = false;    // inside a record?
 	uint64_t i = 0;
 	auto close_record = [&]() {

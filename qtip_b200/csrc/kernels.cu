@@ -14,6 +14,7 @@ namespace qt {
 
 static int g_launches = 0;
 int kernels_launch_count() { return g_launches; }
+void kernels_count_launch() { g_launches++; }
 
 // ------------------------------------------------------------------ helpers --
 

@@ -22,6 +22,10 @@ struct DevCategory {
 	const char *qual = nullptr;
 	const char *xs = nullptr;
 	uint32_t n = 0;
+	// compiled form (tiled kernel)
+	const char *qual_out = nullptr;
+	const uint32_t *ops = nullptr;
+	const SegDev *segs = nullptr;
 };
 
 struct SimArgs {
@@ -39,6 +43,9 @@ struct SimArgs {
 	uint64_t philox_seed = 0;
 	const uint32_t *jt1 = nullptr;  // jump tables (REPLAY)
 	const uint32_t *jt2 = nullptr;
+	const uint64_t *tot0 = nullptr;  // total bytes of stream 0 / 1 (device)
+	const uint64_t *tot1 = nullptr;
+	uint64_t genome_words = 0;       // u32 words in g.bases (for clamping speculative loads)
 };
 
 // number of N per window (simplesim.cpp:228-231 histogram, N bin only)
@@ -55,7 +62,14 @@ void launch_scan(const uint32_t *len, uint64_t *off, uint64_t n, uint64_t *tmp, 
                  cudaStream_t st);
 
 // simulate + emit (SimulatedRead::init/mutate/init_random/write/write_pair)
+// generic path: one warp per read, byte-granular
 void launch_simulate(const SimArgs &a, cudaStream_t st);
+// tiled path: a CTA stages a tile of consecutive records in shared memory, 16 output bytes
+// per lane per step, then streams the tile to HBM with aligned 16-byte stores.
+// max_rec_bytes = upper bound on one FASTQ record of this category.  Returns false when the
+// category cannot use it (record too large for the staging buffer) -- caller falls back.
+bool launch_simulate_tiled(const SimArgs &a, uint32_t max_rec_bytes, cudaStream_t st);
+void kernels_count_launch();
 
 // PHILOX planning: fills plan[] for reads [0, n) of one category from per-window
 // cumulative counts (cum[w] = reads before window w, cum[nwin] = n).

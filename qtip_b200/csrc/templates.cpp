@@ -49,6 +49,71 @@ bool add_mate(Category &c, MateDesc &m, HostMateProg &hp, const char *qual, cons
 	hp.tail_skip = skip;
 	m.rflen = rf;
 	m.ndraw = ndraw;
+	c.max_body = std::max(c.max_body, m.len);
+	c.max_score_len = std::max<uint32_t>(c.max_score_len, m.score_len);
+
+	// ---- compiled, output-oriented form for the tiled kernel ----
+	// qualities as they are printed (simplesim.cpp:119-125): reversed for '-' mates
+	if (c.qual_out.empty()) c.qual_out.assign(16, '\0');
+	m.qual_out_off = (uint32_t)c.qual_out.size();
+	if (fw) c.qual_out.append(qual, m.len);
+	else
+		for (uint32_t i = 0; i < m.len; i++) c.qual_out.push_back(qual[m.len - 1 - i]);
+	while (c.qual_out.size() % 16) c.qual_out.push_back('\0');
+	m.ops_off = (uint32_t)c.ops.size();
+	m.seg_off = (uint32_t)c.segs.size();
+	if (ok && rd == m.len && m.len <= COMPILED_MAX_LEN && rf <= COMPILED_MAX_LEN) {
+		const uint32_t L = m.len;
+		uint32_t r_d = 0, r_f = 0;
+		bool in_run = false;
+		uint32_t run_rd = 0, run_rf = 0;
+		std::vector<SegDev> segs;
+		auto close_run = [&]() {
+			if (!in_run) return;
+			in_run = false;
+			SegDev sg;
+			if (fw) {
+				sg.out_start = (uint16_t)run_rd;
+				sg.out_end = (uint16_t)r_d;
+				sg.ref0 = (int32_t)run_rf;
+			} else {
+				sg.out_start = (uint16_t)(L - r_d);
+				sg.out_end = (uint16_t)(L - run_rd);
+				sg.ref0 = (int32_t)(r_f - 1);
+			}
+			segs.push_back(sg);
+		};
+		for (uint32_t i = 0; i < m.xs_len; i++) {
+			const char op = xs[i];
+			const uint32_t outp = fw ? r_d : L - 1 - r_d;
+			if (op == '=' || op == 'X' || op == 'S') {
+				if (!in_run) {
+					in_run = true;
+					run_rd = r_d;
+					run_rf = r_f;
+				}
+				if (op == 'X') c.ops.push_back(OP_X | (outp << 2) | (r_f << 17));
+				if (op == 'S') c.ops.push_back(OP_IS | (outp << 2));
+				r_d++;
+				r_f++;
+			} else if (op == 'I') {
+				close_run();
+				c.ops.push_back(OP_IS | (outp << 2));
+				r_d++;
+			} else {  // D
+				close_run();
+				r_f++;
+			}
+		}
+		close_run();
+		if (!fw) std::reverse(segs.begin(), segs.end());
+		c.segs.insert(c.segs.end(), segs.begin(), segs.end());
+		if (c.segs.size() - m.seg_off > 65535 || c.ops.size() - m.ops_off > 65535) c.compiled_ok = false;
+		m.nseg = (uint16_t)(c.segs.size() - m.seg_off);
+		m.nops = (uint16_t)(c.ops.size() - m.ops_off);
+	} else {
+		c.compiled_ok = false;
+	}
 	if (ok && rd != m.len) {
 		why = "edit transcript produces a read of different length than the quality string";
 		ok = false;
@@ -82,6 +147,8 @@ int TemplateStore::set_unpaired(int ci, const qtipsim_tmpl_unp *v, size_t kept, 
 		if (ci == CAT_B) {
 			t.aligned_is_mate1 = (v[i].mate_flag == '1');
 			t.opp_len = v[i].opp_len > 0 ? (uint32_t)v[i].opp_len : 0;
+			c.max_body = std::max(c.max_body, t.opp_len);
+			if (t.opp_len > COMPILED_MAX_LEN) c.compiled_ok = false;
 			if (v[i].opp_len <= 0 && c.valid) {  // assert(len > 0), simplesim.h:96
 				c.valid = false;
 				c.why = "bad-end template with opp_len <= 0";

@@ -29,6 +29,12 @@ struct Category {
 	std::vector<TmplDesc> t;
 	std::string qual;                 // arena
 	std::string xs;                   // arena
+	std::string qual_out;             // arena, output orientation, 16-byte aligned entries
+	std::vector<uint32_t> ops;        // compiled draw-op lists
+	std::vector<SegDev> segs;         // compiled reference-copy segments
+	bool compiled_ok = true;          // false: some mate exceeds the compiled format's limits
+	uint32_t max_body = 0;            // longest read body (either mate / random mate)
+	uint32_t max_score_len = 0;
 	std::vector<XStep> xsteps;        // host-side draw programs (replay planner)
 	std::vector<HostMateProg> prog;   // 2 per template
 	uint64_t added = 0;               // num_added(), input_model.h:68-70

@@ -276,3 +276,17 @@ def test_native_distributionally_equivalent_to_replay(workdir):
             alt = np.delete(f[4][r], r)
             from scipy import stats
             assert stats.chisquare(alt).pvalue > 1e-4
+
+
+@pytest.mark.parametrize("name", ["mixed_small", "c5_indel", "long_refid"])
+def test_generic_kernel_path_still_bit_exact(name, workdir, monkeypatch):
+    """The warp-per-read generic kernel (fallback for records too large to stage) stays covered."""
+    monkeypatch.setenv("QTIPSIM_KERNEL", "generic")
+    case = cases.CASES[name]()
+    streams, st, p = util.run_cuda(case, workdir, name)
+    o = _oracle(case, workdir, name)
+    assert streams == o.streams
+    nat_g, _, _ = util.run_cuda(case, workdir, name, rng_mode=1, philox_seed=5)
+    monkeypatch.delenv("QTIPSIM_KERNEL")
+    nat_t, _, _ = util.run_cuda(case, workdir, name, rng_mode=1, philox_seed=5)
+    assert nat_g == nat_t  # both kernels consume the Philox stream identically
