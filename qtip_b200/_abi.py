@@ -12,7 +12,7 @@ import os
 from .templates import CTmplPair, CTmplUnp
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqtipsim.so")
+LIB_PATH = os.environ.get("QTIPSIM_LIB") or os.path.join(_HERE, "libqtipsim.so")
 
 NOUT = 7
 OUT_NAMES = ("u", "b_1", "b_2", "c_1", "c_2", "d_1", "d_2")

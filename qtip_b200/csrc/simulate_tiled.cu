@@ -5,10 +5,12 @@
 // once.  The reference produces a read one byte at a time (a branch per transcript op, an
 // fputc per base on the '-' strand); here the unit of work is 16 OUTPUT bytes:
 //
-//   phase A  one thread per read: plan record + template -> geometry in shared memory
-//            (record offset inside the tile, name length, genome position of each mate)
-//   phase B  one thread per 16-byte chunk of the tile's FASTQ bytes: locate the read
-//            (binary search over the tile's record offsets), then
+//   phase A  one thread per read: plan record + template -> per-read geometry in shared
+//            memory (where the record sits in the tile, body length, strand, genome
+//            position, segment / quality table offsets)
+//   phase B  one thread per 16-byte chunk of a read's body (sequence .. qualities).  Work
+//            items are ordered chunk-major (chunk j of reads 0..nr-1, then chunk j+1, ...)
+//            so the lanes of a warp handle the same kind of chunk for 32 different reads:
 //              sequence chunk = 32 bits of 2-bit genome (funnel-shifted from two packed
 //                               words, reversed+complemented for '-' mates) expanded to 16
 //                               ASCII bases with PRMT, N mask applied, indel segments merged
@@ -19,31 +21,40 @@
 //            draws -- X / I / S bases patched over the staged sequence (REPLAY: the
 //            reference's L'Ecuyer stream stepped from the plan's state, with X redraws;
 //            PHILOX: counter-based)
-//   phase D  the staged tile goes to HBM as aligned 16-byte vectors (byte stores only for
-//            the ragged first/last chunk of the tile)
+//   phase D  the staged tile goes to HBM: one bulk asynchronous copy (cp.async.bulk,
+//            shared -> global) for the 16-byte aligned interior, byte stores for the ragged
+//            first/last chunk of the tile
 //
 // Shared-memory staging address == global address (mod 16), so phase D needs no shifting.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include "kernels.cuh"
 #include "lecuyer.h"
 #include "philox.h"
-#include <stdlib.h>
 
 namespace qt {
 
+// Debug build (-DQT_BOUNDS, `make dbg`): every shared/global access of the tiled kernel is
+// range-checked; the first violation is recorded in a device word and the access skipped.
+#ifdef QT_BOUNDS
+__device__ unsigned long long g_qt_violation[4];
+#define QT_CHK(cond, id, v0, v1)                                                          \
+	do {                                                                                   \
+		if (!(cond)) {                                                                     \
+			if (atomicCAS(&g_qt_violation[0], 0ull, (unsigned long long)(id)) == 0ull) {   \
+				g_qt_violation[1] = (unsigned long long)(v0);                              \
+				g_qt_violation[2] = (unsigned long long)(v1);                              \
+				g_qt_violation[3] = ((unsigned long long)blockIdx.x << 32) | threadIdx.x;  \
+			}                                                                              \
+		}                                                                                  \
+	} while (0)
+#else
+#define QT_CHK(cond, id, v0, v1) do { } while (0)
+#endif
+
 static constexpr int TL_THREADS = 256;
 static constexpr uint32_t TL_STAGE_DEFAULT = 44 * 1024;  // staging per CTA, all streams (4 CTAs per SM)
-
-__device__ __forceinline__ uint32_t bytemask32(int l, int h) {
-	// bytes [l, h) of a 32-bit word set to 0xff; l, h clamped to [0, 4]
-	l = l < 0 ? 0 : (l > 4 ? 4 : l);
-	h = h < 0 ? 0 : (h > 4 ? 4 : h);
-	const uint64_t hi = (1ull << (8 * h)) - 1ull, lo = (1ull << (8 * l)) - 1ull;
-	return (uint32_t)(hi & ~lo);
-}
-
-__device__ __forceinline__ uint4 bytemask128(int l, int h) {
-	return make_uint4(bytemask32(l, h), bytemask32(l - 4, h - 4), bytemask32(l - 8, h - 8), bytemask32(l - 12, h - 12));
-}
 
 // bit i of m (i < 4) -> byte i = 0xff
 __device__ __forceinline__ uint32_t spread4(uint32_t m) {
@@ -58,6 +69,7 @@ struct GenomeView {
 // 16 consecutive bases starting at g (2-bit codes, base j in bits 2j) and their N bits
 __device__ __forceinline__ void load16(const GenomeView &gv, uint64_t g, uint32_t &w, uint32_t &nm) {
 	uint64_t wi = g >> 4;
+	QT_CHK(g < (gv.max_word + 2) * 16 + (1ull << 20), 1, g, gv.max_word);
 	wi = wi < gv.max_word ? wi : gv.max_word;
 	const uint32_t lo = __ldg(&gv.bases[wi]), hi = __ldg(&gv.bases[wi + 1]);
 	w = __funnelshift_r(lo, hi, 2u * (uint32_t)(g & 15));
@@ -72,13 +84,72 @@ __device__ __forceinline__ uint32_t fetch_code_v(const GenomeView &gv, uint64_t 
 	return (__ldg(&gv.bases[gp >> 4]) >> (2 * (gp & 15))) & 3u;
 }
 
-// Sequence bytes for output positions [k0, k0+16) of one aligned mate; bytes outside the
+// bytes [l, h) of a 16-byte chunk, l and h clamped to [0, 16]; lowmask[n] = bytes [0, n)
+__device__ __forceinline__ uint4 range_mask(const uint4 *lowmask, int l, int h) {
+	l = l < 0 ? 0 : (l > 16 ? 16 : l);
+	h = h < 0 ? 0 : (h > 16 ? 16 : h);
+	const uint4 a = lowmask[h], b = lowmask[l];
+	return make_uint4(a.x & ~b.x, a.y & ~b.y, a.z & ~b.z, a.w & ~b.w);
+}
+
+// 16 two-bit codes -> 16 ASCII bases.  A nibble of w holds codes 2k (bits 0-1) and 2k+1
+// (bits 2-3); masked to 2 bits, every nibble is directly a PRMT selector into the table
+// "ACGT".  Look up even and odd codes separately (4 per PRMT), then interleave the bytes.
+__device__ __forceinline__ uint4 expand16(uint32_t w) {
+	const uint32_t T = 0x54474341u;  // "ACGT"
+	const uint32_t ev = w & 0x33333333u, od = (w >> 2) & 0x33333333u;
+	const uint32_t E0 = __byte_perm(T, 0u, ev), O0 = __byte_perm(T, 0u, od);
+	const uint32_t E1 = __byte_perm(T, 0u, ev >> 16), O1 = __byte_perm(T, 0u, od >> 16);
+	return make_uint4(__byte_perm(E0, O0, 0x5140u), __byte_perm(E0, O0, 0x7362u), __byte_perm(E1, O1, 0x5140u),
+	                  __byte_perm(E1, O1, 0x7362u));
+}
+
+// Sequence bytes for output positions [k0, k0+16) of one aligned mate under ONE segment's
+// mapping (positions outside the segment are garbage; the caller masks).
+__device__ __forceinline__ uint4 seq16(const GenomeView &gv, bool fw, uint64_t gpos, uint64_t gend, int32_t ref0,
+                                       int d /* k0 - out_start */) {
+	uint32_t w, nm;
+	if (fw) {
+		const uint64_t g0 = (uint64_t)((int64_t)gpos + ref0 + d);
+		load16(gv, g0, w, nm);
+		if (g0 + 16 > gend) nm |= g0 >= gend ? 0xffffu : (0xffffu << (uint32_t)(gend - g0)) & 0xffffu;  // past the record: N
+	} else {
+		const uint64_t ghi = (uint64_t)((int64_t)gpos + ref0 - d);
+		load16(gv, ghi - 15, w, nm);
+		// reverse the order of the 16 bases, then complement (asc2dnacomp, simplesim.cpp:76-97)
+		w = __brev(w);
+		w = ((w >> 1) & 0x55555555u) | ((w & 0x55555555u) << 1);
+		w = ~w;
+		nm = __brev(nm) >> 16;
+		if (ghi >= gend) nm |= (ghi - gend) >= 15 ? 0xffffu : (1u << ((uint32_t)(ghi - gend) + 1u)) - 1u;
+	}
+	uint4 v = expand16(w);
+	if (nm) {
+		const uint32_t N4 = 0x4e4e4e4eu;
+		uint32_t m;
+		m = spread4(nm);       v.x = (v.x & ~m) | (N4 & m);
+		m = spread4(nm >> 4);  v.y = (v.y & ~m) | (N4 & m);
+		m = spread4(nm >> 8);  v.z = (v.z & ~m) | (N4 & m);
+		m = spread4(nm >> 12); v.w = (v.w & ~m) | (N4 & m);
+	}
+	return v;
+}
+
+// Sequence bytes for output positions [k0, k0+16); bytes outside [0, L) and outside the
 // mate's reference-copy segments are zero.
-__device__ __forceinline__ uint4 gen_seq(const GenomeView &gv, const SegDev *__restrict__ segs, int nseg, bool fw,
-                                         int L, uint64_t gpos, uint64_t gend, int k0) {
-	uint4 out = make_uint4(0u, 0u, 0u, 0u);
+__device__ __forceinline__ uint4 gen_seq(const GenomeView &gv, const uint4 *lowmask, const SegDev *__restrict__ segs,
+                                         int nseg, bool fw, int L, uint64_t gpos, uint64_t gend, int k0) {
 	const int lo_k = k0 > 0 ? k0 : 0;
 	const int hi_k = k0 + 16 < L ? k0 + 16 : L;
+	if (nseg == 1) {  // no indels: the whole read is one segment starting at output position 0
+		const SegDev sg = segs[0];
+		const uint4 v = seq16(gv, fw, gpos, gend, sg.ref0, k0 - (int)sg.out_start);
+		if (k0 >= (int)sg.out_start && k0 + 16 <= (int)sg.out_end) return v;
+		const uint4 m = range_mask(lowmask, ((int)sg.out_start > lo_k ? (int)sg.out_start : lo_k) - k0,
+		                           ((int)sg.out_end < hi_k ? (int)sg.out_end : hi_k) - k0);
+		return make_uint4(v.x & m.x, v.y & m.y, v.z & m.z, v.w & m.w);
+	}
+	uint4 out = make_uint4(0u, 0u, 0u, 0u);
 	// first segment whose end lies beyond lo_k
 	int a = 0, b = nseg;
 	while (a < b) {
@@ -89,52 +160,9 @@ __device__ __forceinline__ uint4 gen_seq(const GenomeView &gv, const SegDev *__r
 	for (int si = a; si < nseg; si++) {
 		const SegDev sg = segs[si];
 		if ((int)sg.out_start >= hi_k) break;
-		const int d = k0 - (int)sg.out_start;  // > -16
-		uint32_t w, nm;
-		int nbeyond_lo = 16, nbeyond_hi = 16;  // chunk positions [nbeyond_lo, nbeyond_hi) lie past the record
-		if (fw) {
-			const uint64_t g0 = (uint64_t)((int64_t)gpos + sg.ref0 + d);
-			load16(gv, g0, w, nm);
-			if (g0 + 16 > gend) {
-				nbeyond_lo = g0 >= gend ? 0 : (int)(gend - g0);
-				nbeyond_hi = 16;
-			}
-		} else {
-			const uint64_t ghi = (uint64_t)((int64_t)gpos + sg.ref0 - d);
-			const uint64_t g0 = ghi - 15;
-			load16(gv, g0, w, nm);
-			// reverse the order of the 16 bases, then complement (asc2dnacomp, simplesim.cpp:76-97)
-			w = __brev(w);
-			w = ((w >> 1) & 0x55555555u) | ((w & 0x55555555u) << 1);
-			w = ~w;
-			nm = __brev(nm) >> 16;
-			if (ghi >= gend) {
-				nbeyond_lo = 0;
-				nbeyond_hi = (ghi - gend) >= 15 ? 16 : (int)(ghi - gend) + 1;
-			}
-		}
-		if (nbeyond_lo < nbeyond_hi) nm |= ((1u << nbeyond_hi) - 1u) & ~((1u << nbeyond_lo) - 1u) & 0xffffu;
-		// 16 codes -> 16 ASCII bases.  A nibble of w holds codes 2k (bits 0-1) and 2k+1 (bits 2-3);
-		// masked to 2 bits, every nibble is directly a PRMT selector into the table "ACGT".
-		// Look up even and odd codes separately (4 per PRMT), then interleave the bytes.
-		const uint32_t T = 0x54474341u;  // "ACGT"
-		const uint32_t ev = w & 0x33333333u, od = (w >> 2) & 0x33333333u;
-		const uint32_t E0 = __byte_perm(T, 0u, ev), O0 = __byte_perm(T, 0u, od);
-		const uint32_t E1 = __byte_perm(T, 0u, ev >> 16), O1 = __byte_perm(T, 0u, od >> 16);
-		uint4 v = make_uint4(__byte_perm(E0, O0, 0x5140u), __byte_perm(E0, O0, 0x7362u), __byte_perm(E1, O1, 0x5140u),
-		                     __byte_perm(E1, O1, 0x7362u));
-		if (nm) {
-			const uint32_t N4 = 0x4e4e4e4eu;
-			uint32_t m;
-			m = spread4(nm);       v.x = (v.x & ~m) | (N4 & m);
-			m = spread4(nm >> 4);  v.y = (v.y & ~m) | (N4 & m);
-			m = spread4(nm >> 8);  v.z = (v.z & ~m) | (N4 & m);
-			m = spread4(nm >> 12); v.w = (v.w & ~m) | (N4 & m);
-		}
-		const int sa = ((int)sg.out_start > lo_k ? (int)sg.out_start : lo_k) - k0;
-		const int sb = ((int)sg.out_end < hi_k ? (int)sg.out_end : hi_k) - k0;
-		if (sa == 0 && sb == 16) return v;
-		const uint4 m = bytemask128(sa, sb);
+		const uint4 v = seq16(gv, fw, gpos, gend, sg.ref0, k0 - (int)sg.out_start);
+		const uint4 m = range_mask(lowmask, ((int)sg.out_start > lo_k ? (int)sg.out_start : lo_k) - k0,
+		                           ((int)sg.out_end < hi_k ? (int)sg.out_end : hi_k) - k0);
 		out.x |= v.x & m.x;
 		out.y |= v.y & m.y;
 		out.z |= v.z & m.z;
@@ -144,15 +172,17 @@ __device__ __forceinline__ uint4 gen_seq(const GenomeView &gv, const SegDev *__r
 }
 
 // Quality bytes for output positions [k0q, k0q+16), from the pre-oriented quality arena.
-__device__ __forceinline__ uint4 gen_qual(const char *__restrict__ qual_out, uint32_t qoff, int L, int k0q) {
-	const int64_t A = (int64_t)qoff + k0q;  // >= 1 (the arena has 16 bytes of front padding)
+__device__ __forceinline__ uint4 gen_qual(const uint4 *lowmask, const char *__restrict__ qual_out, uint32_t qoff, int L,
+                                          int k0q) {
+	const int A = (int)qoff + k0q;  // >= 1 (the arena has 16 bytes of front padding)
+	QT_CHK(A >= 0 && A < (1 << 28), 2, A, qoff);
 	const uint32_t *wp = (const uint32_t *)qual_out + (A >> 2);
 	const uint32_t sh = 8u * (uint32_t)(A & 3);
 	const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
-	uint4 v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
-	                     __funnelshift_r(w3, w4, sh));
+	const uint4 v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+	                           __funnelshift_r(w3, w4, sh));
 	if (k0q >= 0 && k0q + 16 <= L) return v;
-	const uint4 m = bytemask128(-k0q, L - k0q);
+	const uint4 m = range_mask(lowmask, -k0q, L - k0q);
 	return make_uint4(v.x & m.x, v.y & m.y, v.z & m.z, v.w & m.w);
 }
 
@@ -191,17 +221,29 @@ __device__ __forceinline__ char *s_origin(char *p, const char *refid, uint32_t r
 	return p;
 }
 
+// per-read, per-stream body geometry kept in shared memory between the phases
+struct BodyInfo {
+	uint64_t gpos;    // genome position of the body's leftmost reference base (aligned mates)
+	uint32_t P;       // staging byte position of the first sequence byte
+	uint32_t segoff;  // into DevCategory::segs
+	uint32_t qoff;    // into DevCategory::qual_out
+	uint16_t L;       // body length
+	uint16_t nseg;
+	uint8_t fw;
+	uint8_t random;   // bad-end random mate: no reference copy, qualities 'I'
+	uint16_t nl;      // name length
+};
+
 template <int MODE, int CAT>
-__global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R, uint32_t stage_stride) {
+__global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R, uint32_t stage_stride, int K) {
 	constexpr int NS = CAT == CAT_U ? 1 : 2;
 	extern __shared__ __align__(16) unsigned char smem[];
-	unsigned char *stage = smem;  // NS * stage_stride
-	uint32_t *s_recoff = (uint32_t *)(smem + (size_t)NS * stage_stride);  // [NS][R+1]
-	uint64_t *s_gpos = (uint64_t *)(s_recoff + (size_t)NS * (R + 1) + ((NS * (R + 1)) & 1));  // [2][R]
-	uint64_t *s_gend = s_gpos + 2 * (size_t)R;                                                 // [R]
-	uint32_t *s_tmpl = (uint32_t *)(s_gend + R);                                                // [R]
-	uint16_t *s_nl = (uint16_t *)(s_tmpl + R);                                                  // [R]
+	unsigned char *stage = smem;                                                   // NS * stage_stride
+	BodyInfo *s_body = (BodyInfo *)(smem + (size_t)NS * stage_stride);             // [NS][R]
+	uint64_t *s_gend = (uint64_t *)(s_body + (size_t)NS * R);                      // [R]
+	uint32_t *s_tmpl = (uint32_t *)(s_gend + R);                                   // [R]
 	__shared__ uint64_t s_G0[2], s_G1[2];
+	__shared__ uint4 s_lowmask[17];
 
 	const int tid = threadIdx.x;
 	const uint64_t r0 = (uint64_t)blockIdx.x * (uint64_t)R;
@@ -215,6 +257,16 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 		s_G0[tid] = offs[tid][r0];
 		s_G1[tid] = (r0 + nr < a.nreads) ? offs[tid][r0 + nr] : *tots[tid];
 	}
+	if (tid >= 32 && tid < 32 + 17) {
+		const int n = tid - 32;
+		uint32_t w[4];
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const int k = n - 4 * j;
+			w[j] = k >= 4 ? 0xffffffffu : (k <= 0 ? 0u : (1u << (8 * k)) - 1u);
+		}
+		s_lowmask[n] = make_uint4(w[0], w[1], w[2], w[3]);
+	}
 	__syncthreads();
 
 	// ---------------- phase A: geometry ----------------
@@ -227,66 +279,68 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 		if (CAT == CAT_U) nl = 13u + rec.name_len + ndig(ro0) + t.m[0].score_len + t.typ_len;
 		else if (CAT == CAT_B) nl = 18u + 2u * rec.name_len + 2u * ndig(ro0) + 2u * t.m[0].score_len + t.typ_len;
 		else nl = 18u + 2u * rec.name_len + ndig(ro0) + ndig(ro1) + t.m[0].score_len + t.m[1].score_len + t.typ_len;
-		s_nl[i] = (uint16_t)nl;
 		s_tmpl[i] = pr.tmpl;
-		s_gpos[i] = rec.gstart + ro0;
-		s_gpos[R + i] = rec.gstart + ro1;
 		s_gend[i] = rec.gstart + rec.len;
 #pragma unroll
-		for (int s = 0; s < NS; s++) s_recoff[s * (R + 1) + i] = (uint32_t)(offs[s][r0 + i] - s_G0[s]);
-	}
-	if (tid < NS) s_recoff[tid * (R + 1) + nr] = (uint32_t)(s_G1[tid] - s_G0[tid]);
-	__syncthreads();
-
-	// ---------------- phase B: 16-byte chunks ----------------
-#pragma unroll
-	for (int s = 0; s < NS; s++) {
-		const int ph = (int)(s_G0[s] & 15);
-		const int total = (int)(s_G1[s] - s_G0[s]);
-		const int nchunks = (ph + total + 15) >> 4;
-		const uint32_t *ro = s_recoff + s * (R + 1);
-		unsigned char *stg = stage + (size_t)s * stage_stride;
-		for (int c = tid; c < nchunks; c += TL_THREADS) {
-			const int b0 = 16 * c - ph;
-			const int bs = b0 > 0 ? b0 : 0;
-			int lo = 0, hi = nr;
-			while (hi - lo > 1) {
-				const int mid = (lo + hi) >> 1;
-				if ((int)ro[mid] <= bs) lo = mid;
-				else hi = mid;
-			}
-			const int i = lo;
-			const int rel = b0 - (int)ro[i];
-			const TmplDesc &t = a.c.t[s_tmpl[i]];
-			// which body does this stream carry for this read?
+		for (int s = 0; s < NS; s++) {
 			int mate = s;
-			bool random_body = false;
+			bool random = false;
 			if (CAT == CAT_B) {
 				mate = 0;
-				random_body = (s == 0) != (t.aligned_is_mate1 != 0);
+				random = (s == 0) != (t.aligned_is_mate1 != 0);
 			}
 			const MateDesc &md = t.m[mate];
-			const int L = random_body ? (int)t.opp_len : (int)md.len;
-			const int k0 = rel - (int)s_nl[i];
-			const int k0q = k0 - (L + 3);
-			if (k0 + 16 <= 0 || k0q >= L) continue;  // name / trailing newline only: phase C
-			uint4 v = make_uint4(0u, 0u, 0u, 0u);
-			if (k0 < L && !random_body)
-				v = gen_seq(gv, a.c.segs + md.seg_off, md.nseg, md.fw != 0, L, s_gpos[mate * R + i], s_gend[i], k0);
-			if (k0q + 16 > 0) {
-				uint4 q;
-				if (random_body) {
-					const uint4 m = bytemask128(-k0q, L - k0q);
-					q = make_uint4(0x49494949u & m.x, 0x49494949u & m.y, 0x49494949u & m.z, 0x49494949u & m.w);
-				} else {
-					q = gen_qual(a.c.qual_out, md.qual_out_off, L, k0q);
+			BodyInfo bi;
+			bi.gpos = rec.gstart + (mate == 0 ? ro0 : ro1);
+			bi.P = (uint32_t)(s_G0[s] & 15) + (uint32_t)(offs[s][r0 + i] - s_G0[s]) + nl;
+			bi.segoff = md.seg_off;
+			bi.qoff = md.qual_out_off;
+			bi.L = (uint16_t)(random ? t.opp_len : md.len);
+			bi.nseg = md.nseg;
+			bi.fw = md.fw;
+			bi.random = random ? 1 : 0;
+			bi.nl = (uint16_t)nl;
+			s_body[s * R + i] = bi;
+		}
+	}
+	__syncthreads();
+
+	// ---------------- phase B: 16-byte chunks, chunk-major over the tile's reads ----------------
+	{
+		const uint64_t magic = 0x100000000ull / (uint32_t)nr + 1ull;  // (q * magic) >> 32 == q / nr for q < 2^16
+		const int nitems = K * nr;
+#pragma unroll
+		for (int s = 0; s < NS; s++) {
+			unsigned char *stg = stage + (size_t)s * stage_stride;
+			for (int q = tid; q < nitems; q += TL_THREADS) {
+				const int j = (int)(((uint64_t)(uint32_t)q * magic) >> 32);
+				const int i = q - j * nr;
+				const BodyInfo bi = s_body[s * R + i];
+				const int L = bi.L;
+				const int c = (int)(bi.P >> 4) + j;
+				const int k0 = 16 * c - (int)bi.P;  // output position of the chunk's first byte, >= -15
+				const int k0q = k0 - (L + 3);
+				if (k0q >= L) continue;  // beyond this read's qualities
+				uint4 v = make_uint4(0u, 0u, 0u, 0u);
+				if (k0 < L && !bi.random)
+					v = gen_seq(gv, s_lowmask, a.c.segs + bi.segoff, bi.nseg, bi.fw != 0, L, bi.gpos, s_gend[i], k0);
+				if (k0q + 16 > 0) {
+					uint4 qv;
+					if (bi.random) {
+						const uint4 m = range_mask(s_lowmask, -k0q, L - k0q);
+						qv = make_uint4(0x49494949u & m.x, 0x49494949u & m.y, 0x49494949u & m.z, 0x49494949u & m.w);
+					} else {
+						qv = gen_qual(s_lowmask, a.c.qual_out, bi.qoff, L, k0q);
+					}
+					v.x |= qv.x;
+					v.y |= qv.y;
+					v.z |= qv.z;
+					v.w |= qv.w;
 				}
-				v.x |= q.x;
-				v.y |= q.y;
-				v.z |= q.z;
-				v.w |= q.w;
+				QT_CHK(c >= 0 && 16u * (uint32_t)c + 16u <= stage_stride, 3, c, bi.P);
+				QT_CHK(i >= 0 && i < nr, 4, i, q);
+				*(uint4 *)(stg + 16 * (size_t)c) = v;
 			}
-			*(uint4 *)(stg + 16 * (size_t)c) = v;
 		}
 	}
 	__syncthreads();
@@ -297,9 +351,12 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 		const PlanRec pr = a.plan[r0 + i];
 		const RecDev rec = a.g.recs[pr.record];
 		const char *refid = a.g.names + rec.name_off;
-		const uint32_t nl = s_nl[i];
-		char *rec0 = (char *)stage + (s_G0[0] & 15) + s_recoff[i];
-		char *rec1 = NS == 2 ? (char *)stage + stage_stride + (s_G0[NS - 1] & 15) + s_recoff[(NS - 1) * (R + 1) + i] : nullptr;
+		const BodyInfo b0 = s_body[i];
+		const BodyInfo b1 = NS == 2 ? s_body[R + i] : b0;
+		const uint32_t nl = b0.nl;
+		char *seq0 = (char *)stage + b0.P;
+		char *seq1 = NS == 2 ? (char *)stage + stage_stride + b1.P : nullptr;
+		char *rec0 = seq0 - nl;
 		{
 			char *p = s_put(rec0, "@qtip!:", 7);
 			const uint64_t ro0 = pr.refoff + t.delta[0], ro1 = pr.refoff + t.delta[1];
@@ -314,24 +371,14 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 			*p++ = ':';
 			p = s_put(p, t.typ, t.typ_len);
 			*p++ = '\n';
-			if (NS == 2)
+			if (NS == 2) {
+				char *rec1 = seq1 - nl;
 				for (uint32_t j = 0; j < nl; j++) rec1[j] = rec0[j];
+			}
 		}
-		// body lengths per stream
-		uint32_t bl0, bl1 = 0;
-		bool s0_random = false, s1_random = false;
-		if (CAT == CAT_U) {
-			bl0 = t.m[0].len;
-		} else if (CAT == CAT_B) {
-			s0_random = !t.aligned_is_mate1;
-			s1_random = !s0_random;
-			bl0 = s0_random ? t.opp_len : t.m[0].len;
-			bl1 = s1_random ? t.opp_len : t.m[0].len;
-		} else {
-			bl0 = t.m[0].len;
-			bl1 = t.m[1].len;
-		}
-		char *seq0 = rec0 + nl, *seq1 = NS == 2 ? rec1 + nl : nullptr;
+		const uint32_t bl0 = b0.L, bl1 = b1.L;
+		QT_CHK(b0.P >= nl && b0.P + 2 * bl0 + 4 <= stage_stride, 5, b0.P, bl0);
+		QT_CHK(NS == 1 || (b1.P >= nl && b1.P + 2 * bl1 + 4 <= stage_stride), 6, b1.P, bl1);
 		seq0[bl0] = '\n';
 		seq0[bl0 + 1] = '+';
 		seq0[bl0 + 2] = '\n';
@@ -358,11 +405,13 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 			return b;
 		};
 		const int nm = CAT == CAT_C || CAT == CAT_D ? 2 : 1;
+		const bool s0_random = b0.random != 0;
 		for (int m = 0; m < nm; m++) {
 			const MateDesc &md = t.m[m];
 			char *seq = (CAT == CAT_B) ? (s0_random ? seq1 : seq0) : (m == 0 ? seq0 : seq1);
 			const uint32_t *ops = a.c.ops + md.ops_off;
-			const uint64_t gpos = s_gpos[m * R + i], gend = s_gend[i];
+			const uint64_t gpos = (CAT == CAT_B) ? (s0_random ? b1.gpos : b0.gpos) : (m == 0 ? b0.gpos : b1.gpos);
+			const uint64_t gend = s_gend[i];
 			const uint32_t T = md.fw ? 0x54474341u : 0x41434754u;  // "ACGT" / "TGCA"
 			for (uint32_t j = 0; j < md.nops; j++) {
 				const uint32_t e = __ldg(&ops[j]);
@@ -387,6 +436,7 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 						code = draw16() >> 14;
 					}
 				}
+				QT_CHK(outp < md.len, 7, outp, md.len);
 				seq[outp] = (char)((T >> (8u * code)) & 0xffu);
 			}
 		}
@@ -408,6 +458,8 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 			}
 		}
 	}
+	// make the generic-proxy shared-memory writes visible to the async (bulk copy) proxy
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	__syncthreads();
 
 	// ---------------- phase D: staged tile -> HBM ----------------
@@ -416,26 +468,36 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 		const uint64_t G0 = s_G0[s], G1 = s_G1[s];
 		const int ph = (int)(G0 & 15);
 		const int total = (int)(G1 - G0);
-		const int nchunks = (ph + total + 15) >> 4;
 		const unsigned char *stg = stage + (size_t)s * stage_stride;
-		char *gbase = outs[s] + (G0 - ph);
-		for (int c = tid; c < nchunks; c += TL_THREADS) {
-			const int b0 = 16 * c - ph;
-			if (b0 >= 0 && b0 + 16 <= total) {
-				const uint4 v = *(const uint4 *)(stg + 16 * (size_t)c);
-				__stcs((uint4 *)(gbase + 16 * (size_t)c), v);  // streaming store: written once, never re-read
-			} else {
-				for (int j = 0; j < 16; j++) {
-					const int b = b0 + j;
-					if (b >= 0 && b < total) gbase[16 * (size_t)c + j] = (char)stg[16 * (size_t)c + j];
-				}
-			}
+		char *gbase = outs[s] + (G0 - ph);  // 16-byte aligned
+		// interior: whole 16-byte chunks [c_lo, c_hi)
+		const int c_lo = ph ? 1 : 0;
+		const int c_hi = (ph + total) >> 4;
+		if (tid == s * 32 && c_hi > c_lo) {
+			const uint32_t nbytes = (uint32_t)(c_hi - c_lo) * 16u;
+			QT_CHK(16u * c_hi <= stage_stride && total >= 0, 8, c_hi, total);
+			const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stg + 16 * c_lo);
+			asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gbase + 16 * (size_t)c_lo),
+			             "r"(saddr), "r"(nbytes)
+			             : "memory");
+			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+		}
+		// ragged head (bytes [0, 16-ph) of the tile when ph != 0) and tail
+		if (tid >= 64 && tid < 64 + 32) {
+			// staging positions [ph, ph+total) are this tile's; chunk 0 (if ph != 0) and chunk c_hi are partial
+			const int j = tid - 64;
+			const int end = ph + total;
+			const int p = j < 16 ? j : 16 * c_hi + (j - 16);
+			const int hi = j < 16 ? (16 * c_lo < end ? 16 * c_lo : end) : end;
+			if (p >= ph && p < hi) gbase[p] = (char)stg[p];
 		}
 	}
+	// the staging buffer must stay allocated until the bulk copies have read it
+	if (tid == 0 || tid == 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 template <int MODE, int CAT>
-static bool launch_cat(const SimArgs &a, uint32_t max_rec_bytes, cudaStream_t st) {
+static bool launch_cat(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, cudaStream_t st) {
 	constexpr int NS = CAT == CAT_U ? 1 : 2;
 	static uint32_t stage_bytes = 0;
 	if (!stage_bytes) {
@@ -447,10 +509,13 @@ static bool launch_cat(const SimArgs &a, uint32_t max_rec_bytes, cudaStream_t st
 	int R = (int)((per_stream - 64) / max_rec_bytes);
 	if (R > TL_THREADS) R = TL_THREADS;
 	if (R < 4) return false;
-	// a tile's bytes are at most R * max_rec_bytes; +32 for the alignment phase and the ragged tail
-	const uint32_t stage_stride = ((uint32_t)R * max_rec_bytes + 32 + 15) & ~15u;
-	const size_t meta = (size_t)NS * (R + 1) * 4 + 8 + 2 * (size_t)R * 8 + (size_t)R * 8 + (size_t)R * 4 + (size_t)R * 2 + 16;
+	// a tile's bytes are at most R * max_rec_bytes; +48 for the alignment phase and the ragged tail
+	const uint32_t stage_stride = ((uint32_t)R * max_rec_bytes + 48 + 15) & ~15u;
+	const size_t meta = (size_t)NS * R * sizeof(BodyInfo) + (size_t)R * 8 + (size_t)R * 4 + 16;
 	const size_t smem = (size_t)NS * stage_stride + meta;
+	// chunks a body (sequence, "\n+\n", qualities) can touch: ceil((2*maxL+3)/16) + 1 for misalignment
+	const int K = (int)((2u * max_body + 3u + 15u) / 16u) + 1;
+	if ((uint64_t)K * (uint64_t)R >= 65536ull) return false;
 	auto kern = k_simulate_tiled<MODE, CAT>;
 	static bool attr_set = false;
 	if (!attr_set) {
@@ -458,25 +523,40 @@ static bool launch_cat(const SimArgs &a, uint32_t max_rec_bytes, cudaStream_t st
 		attr_set = true;
 	}
 	const uint64_t ntiles = (a.nreads + R - 1) / R;
-	kern<<<(unsigned)ntiles, TL_THREADS, smem, st>>>(a, R, stage_stride);
+	kern<<<(unsigned)ntiles, TL_THREADS, smem, st>>>(a, R, stage_stride, K);
 	kernels_count_launch();
 	return true;
 }
 
 template <int MODE>
-static bool launch_mode(const SimArgs &a, uint32_t max_rec_bytes, cudaStream_t st) {
+static bool launch_mode(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, cudaStream_t st) {
 	switch (a.cat) {
-	case CAT_U: return launch_cat<MODE, CAT_U>(a, max_rec_bytes, st);
-	case CAT_B: return launch_cat<MODE, CAT_B>(a, max_rec_bytes, st);
-	case CAT_C: return launch_cat<MODE, CAT_C>(a, max_rec_bytes, st);
-	default: return launch_cat<MODE, CAT_D>(a, max_rec_bytes, st);
+	case CAT_U: return launch_cat<MODE, CAT_U>(a, max_rec_bytes, max_body, st);
+	case CAT_B: return launch_cat<MODE, CAT_B>(a, max_rec_bytes, max_body, st);
+	case CAT_C: return launch_cat<MODE, CAT_C>(a, max_rec_bytes, max_body, st);
+	default: return launch_cat<MODE, CAT_D>(a, max_rec_bytes, max_body, st);
 	}
 }
 
-bool launch_simulate_tiled(const SimArgs &a, uint32_t max_rec_bytes, cudaStream_t st) {
+#ifdef QT_BOUNDS
+void tiled_debug_report() {
+	unsigned long long v[4] = {0, 0, 0, 0};
+	cudaMemcpyFromSymbol(v, g_qt_violation, sizeof(v));
+	if (v[0]) fprintf(stderr, "QT_BOUNDS violation id=%llu v0=%lld v1=%lld block=%llu thread=%llu\n", v[0], (long long)v[1], (long long)v[2], v[3] >> 32, v[3] & 0xffffffffu);
+	else fprintf(stderr, "QT_BOUNDS: no violation\n");
+	memset(v, 0, sizeof(v));
+	cudaMemcpyToSymbol(g_qt_violation, v, sizeof(v));
+}
+#endif
+
+bool launch_simulate_tiled(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, cudaStream_t st) {
 	if (!a.nreads) return true;
-	if (a.rng_mode == QTIPSIM_RNG_REPLAY) return launch_mode<QTIPSIM_RNG_REPLAY>(a, max_rec_bytes, st);
-	return launch_mode<QTIPSIM_RNG_PHILOX>(a, max_rec_bytes, st);
+	if (a.rng_mode == QTIPSIM_RNG_REPLAY) return launch_mode<QTIPSIM_RNG_REPLAY>(a, max_rec_bytes, max_body, st);
+	return launch_mode<QTIPSIM_RNG_PHILOX>(a, max_rec_bytes, max_body, st);
 }
 
 }  // namespace qt
+
+#ifdef QT_BOUNDS
+extern "C" void qt_tiled_debug_report() { qt::tiled_debug_report(); }
+#endif
