@@ -486,6 +486,7 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 		a.c.xs = h->d_xs[c].as<char>();
 		a.c.n = (uint32_t)h->ts.cat[c].t.size();
 		a.c.qual_out = h->d_qual_out[c].as<char>();
+		a.c.qual_out_bytes = (uint32_t)h->ts.cat[c].qual_out.size();
 		a.c.ops = h->d_ops[c].as<uint32_t>();
 		a.c.segs = h->d_segs[c].as<SegDev>();
 		a.genome_words = (h->hg.total_bases + 15) / 16 + 4;

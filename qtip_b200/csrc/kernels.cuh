@@ -24,6 +24,7 @@ struct DevCategory {
 	uint32_t n = 0;
 	// compiled form (tiled kernel)
 	const char *qual_out = nullptr;
+	uint32_t qual_out_bytes = 0;
 	const uint32_t *ops = nullptr;
 	const SegDev *segs = nullptr;
 };

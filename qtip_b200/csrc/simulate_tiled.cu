@@ -3,29 +3,32 @@
 // Replaces SimulatedRead::init/mutate/init_random (simplesim.h:68-117, simplesim.cpp:31-71)
 // and SimulatedRead::write/write_pair (simplesim.cpp:102-171) for a whole tile of reads at
 // once.  The reference produces a read one byte at a time (a branch per transcript op, an
-// fputc per base on the '-' strand); here the unit of work is 16 OUTPUT bytes:
+// fputc per base on the '-' strand); here the unit of work is 16 OUTPUT bytes.
+//
+// A CTA stages a tile of consecutive FASTQ records in shared memory at the same 16-byte
+// phase they have in the output file, then ships the tile with one bulk asynchronous copy.
 //
 //   phase A  one thread per read: plan record + template -> per-read geometry in shared
 //            memory (where the record sits in the tile, body length, strand, genome
-//            position, segment / quality table offsets)
-//   phase B  one thread per 16-byte chunk of a read's body (sequence .. qualities).  Work
-//            items are ordered chunk-major (chunk j of reads 0..nr-1, then chunk j+1, ...)
-//            so the lanes of a warp handle the same kind of chunk for 32 different reads:
-//              sequence chunk = 32 bits of 2-bit genome (funnel-shifted from two packed
-//                               words, reversed+complemented for '-' mates) expanded to 16
-//                               ASCII bases with PRMT, N mask applied, indel segments merged
-//              quality chunk  = 16 bytes of the template's (pre-oriented) quality string,
-//                               re-aligned with funnel shifts
-//            one 16-byte shared-memory store per chunk
-//   phase C  one thread per read: read name (itoa), separators, and the read's random
-//            draws -- X / I / S bases patched over the staged sequence (REPLAY: the
-//            reference's L'Ecuyer stream stepped from the plan's state, with X redraws;
-//            PHILOX: counter-based)
-//   phase D  the staged tile goes to HBM: one bulk asynchronous copy (cp.async.bulk,
-//            shared -> global) for the 16-byte aligned interior, byte stores for the ragged
-//            first/last chunk of the tile
-//
-// Shared-memory staging address == global address (mod 16), so phase D needs no shifting.
+//            position, single-segment shortcut, "any N / past the record end" flag)
+//   phase B  three independent loops, no barrier between them (every store writes exactly
+//            the bytes it owns, so they cannot clobber one another):
+//              names      one thread per read: "@qtip!:refid:+:off:score:typ\n" and the
+//                         "\n+\n" / "\n" separators
+//              sequence   one thread per 16-byte chunk, READ-major (consecutive lanes =
+//                         consecutive chunks of one read => coalesced genome loads,
+//                         conflict-free shared stores): 32 bits of 2-bit genome, funnel-
+//                         shifted from two packed words (reversed + complemented for '-'
+//                         mates), expanded to 16 ASCII bases with PRMT; N mask and indel
+//                         segments only on the slow path
+//              qualities  one thread per 16-byte chunk, read-major: two aligned 16-byte
+//                         loads of the template's pre-oriented quality string, re-aligned
+//                         to the output phase with funnel shifts
+//   phase C  one thread per read: the read's random draws -- X / I / S bases patched over
+//            the staged sequence (REPLAY: the reference's L'Ecuyer stream stepped from the
+//            plan's state, with X redraws; PHILOX: counter-based)
+//   phase D  the staged tile goes to HBM: cp.async.bulk (shared -> global) for the 16-byte
+//            aligned interior, byte stores for the ragged first/last chunk of the tile
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -35,8 +38,8 @@
 
 namespace qt {
 
-// Debug build (-DQT_BOUNDS, `make dbg`): every shared/global access of the tiled kernel is
-// range-checked; the first violation is recorded in a device word and the access skipped.
+// Debug build (-DQT_BOUNDS, `make dbg`): accesses of the tiled kernel are range-checked;
+// the first violation is recorded in a device word.
 #ifdef QT_BOUNDS
 __device__ unsigned long long g_qt_violation[4];
 #define QT_CHK(cond, id, v0, v1)                                                          \
@@ -56,6 +59,22 @@ __device__ unsigned long long g_qt_violation[4];
 static constexpr int TL_THREADS = 256;
 static constexpr uint32_t TL_STAGE_DEFAULT = 44 * 1024;  // staging per CTA, all streams (4 CTAs per SM)
 
+enum : uint8_t { BF_FW = 1, BF_RANDOM = 2, BF_SLOW = 4, BF_SINGLE = 8 };
+
+// per-read, per-stream body geometry kept in shared memory between the phases (32 bytes)
+struct BodyInfo {
+	uint64_t gpos;    // genome position of the body's leftmost reference base (aligned mates)
+	uint32_t P;       // staging byte position of the first sequence byte
+	uint32_t segoff;  // into DevCategory::segs
+	uint32_t qoff;    // into DevCategory::qual_out
+	int32_t ref0;     // BF_SINGLE: reference offset of output position 0
+	uint16_t L;       // body length
+	uint16_t nseg;
+	uint16_t nl;      // name length
+	uint8_t flags;    // BF_*
+	uint8_t pad;
+};
+
 // bit i of m (i < 4) -> byte i = 0xff
 __device__ __forceinline__ uint32_t spread4(uint32_t m) {
 	return (((m & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;
@@ -65,18 +84,6 @@ struct GenomeView {
 	const uint32_t *bases, *nmask;
 	uint64_t max_word;  // last valid index of bases[] minus 1
 };
-
-// 16 consecutive bases starting at g (2-bit codes, base j in bits 2j) and their N bits
-__device__ __forceinline__ void load16(const GenomeView &gv, uint64_t g, uint32_t &w, uint32_t &nm) {
-	uint64_t wi = g >> 4;
-	QT_CHK(g < (gv.max_word + 2) * 16 + (1ull << 20), 1, g, gv.max_word);
-	wi = wi < gv.max_word ? wi : gv.max_word;
-	const uint32_t lo = __ldg(&gv.bases[wi]), hi = __ldg(&gv.bases[wi + 1]);
-	w = __funnelshift_r(lo, hi, 2u * (uint32_t)(g & 15));
-	const uint64_t mi = wi >> 1;
-	const uint32_t mlo = __ldg(&gv.nmask[mi]), mhi = __ldg(&gv.nmask[mi + 1]);
-	nm = __funnelshift_r(mlo, mhi, (uint32_t)(g & 31)) & 0xffffu;
-}
 
 __device__ __forceinline__ uint32_t fetch_code_v(const GenomeView &gv, uint64_t gp, uint64_t gend) {
 	if (gp >= gend) return 4u;
@@ -104,23 +111,49 @@ __device__ __forceinline__ uint4 expand16(uint32_t w) {
 	                  __byte_perm(E1, O1, 0x7362u));
 }
 
-// Sequence bytes for output positions [k0, k0+16) of one aligned mate under ONE segment's
-// mapping (positions outside the segment are garbage; the caller masks).
-__device__ __forceinline__ uint4 seq16(const GenomeView &gv, bool fw, uint64_t gpos, uint64_t gend, int32_t ref0,
-                                       int d /* k0 - out_start */) {
+// reverse the order of 16 two-bit codes and complement them (asc2dnacomp, simplesim.cpp:76-97)
+__device__ __forceinline__ uint32_t revcomp16(uint32_t w) {
+	w = __brev(w);
+	w = ((w >> 1) & 0x55555555u) | ((w & 0x55555555u) << 1);
+	return ~w;
+}
+
+// 16 consecutive bases starting at g (2-bit codes, base j in bits 2j)
+__device__ __forceinline__ uint32_t load16_bases(const GenomeView &gv, uint64_t g) {
+	uint64_t wi = g >> 4;
+	QT_CHK(g < (gv.max_word + 2) * 16 + (1ull << 20), 1, g, gv.max_word);
+	wi = wi < gv.max_word ? wi : gv.max_word;
+	const uint32_t lo = __ldg(&gv.bases[wi]), hi = __ldg(&gv.bases[wi + 1]);
+	return __funnelshift_r(lo, hi, 2u * (uint32_t)(g & 15));
+}
+__device__ __forceinline__ uint32_t load16_nmask(const GenomeView &gv, uint64_t g) {
+	uint64_t mi = g >> 5;
+	const uint64_t mmax = gv.max_word >> 1;
+	mi = mi < mmax ? mi : mmax;
+	const uint32_t mlo = __ldg(&gv.nmask[mi]), mhi = __ldg(&gv.nmask[mi + 1]);
+	return __funnelshift_r(mlo, mhi, (uint32_t)(g & 31)) & 0xffffu;
+}
+
+// Fast path: sequence bytes for output positions [k0, k0+16) of a mate whose bases are all
+// ACGT and inside the record.  d = k0 - (output position whose reference offset is ref0).
+__device__ __forceinline__ uint4 seq16_fast(const GenomeView &gv, bool fw, uint64_t gpos, int32_t ref0, int d) {
+	if (fw) return expand16(load16_bases(gv, (uint64_t)((int64_t)gpos + ref0 + d)));
+	return expand16(revcomp16(load16_bases(gv, (uint64_t)((int64_t)gpos + ref0 - d) - 15)));
+}
+
+// Slow path: also applies the N mask and treats positions past the record end as N.
+__device__ __forceinline__ uint4 seq16_slow(const GenomeView &gv, bool fw, uint64_t gpos, uint64_t gend, int32_t ref0,
+                                            int d) {
 	uint32_t w, nm;
 	if (fw) {
 		const uint64_t g0 = (uint64_t)((int64_t)gpos + ref0 + d);
-		load16(gv, g0, w, nm);
-		if (g0 + 16 > gend) nm |= g0 >= gend ? 0xffffu : (0xffffu << (uint32_t)(gend - g0)) & 0xffffu;  // past the record: N
+		w = load16_bases(gv, g0);
+		nm = load16_nmask(gv, g0);
+		if (g0 + 16 > gend) nm |= g0 >= gend ? 0xffffu : (0xffffu << (uint32_t)(gend - g0)) & 0xffffu;
 	} else {
 		const uint64_t ghi = (uint64_t)((int64_t)gpos + ref0 - d);
-		load16(gv, ghi - 15, w, nm);
-		// reverse the order of the 16 bases, then complement (asc2dnacomp, simplesim.cpp:76-97)
-		w = __brev(w);
-		w = ((w >> 1) & 0x55555555u) | ((w & 0x55555555u) << 1);
-		w = ~w;
-		nm = __brev(nm) >> 16;
+		w = revcomp16(load16_bases(gv, ghi - 15));
+		nm = __brev(load16_nmask(gv, ghi - 15)) >> 16;
 		if (ghi >= gend) nm |= (ghi - gend) >= 15 ? 0xffffu : (1u << ((uint32_t)(ghi - gend) + 1u)) - 1u;
 	}
 	uint4 v = expand16(w);
@@ -135,23 +168,15 @@ __device__ __forceinline__ uint4 seq16(const GenomeView &gv, bool fw, uint64_t g
 	return v;
 }
 
-// Sequence bytes for output positions [k0, k0+16); bytes outside [0, L) and outside the
-// mate's reference-copy segments are zero.
-__device__ __forceinline__ uint4 gen_seq(const GenomeView &gv, const uint4 *lowmask, const SegDev *__restrict__ segs,
-                                         int nseg, bool fw, int L, uint64_t gpos, uint64_t gend, int k0) {
+// General path: merges the contributions of every reference-copy segment that overlaps
+// output positions [k0, k0+16); other bytes are zero.
+__device__ __noinline__ uint4 gen_seq_segments(const GenomeView &gv, const uint4 *lowmask,
+                                               const SegDev *__restrict__ segs, int nseg, bool fw, int L,
+                                               uint64_t gpos, uint64_t gend, int k0) {
 	const int lo_k = k0 > 0 ? k0 : 0;
 	const int hi_k = k0 + 16 < L ? k0 + 16 : L;
-	if (nseg == 1) {  // no indels: the whole read is one segment starting at output position 0
-		const SegDev sg = segs[0];
-		const uint4 v = seq16(gv, fw, gpos, gend, sg.ref0, k0 - (int)sg.out_start);
-		if (k0 >= (int)sg.out_start && k0 + 16 <= (int)sg.out_end) return v;
-		const uint4 m = range_mask(lowmask, ((int)sg.out_start > lo_k ? (int)sg.out_start : lo_k) - k0,
-		                           ((int)sg.out_end < hi_k ? (int)sg.out_end : hi_k) - k0);
-		return make_uint4(v.x & m.x, v.y & m.y, v.z & m.z, v.w & m.w);
-	}
 	uint4 out = make_uint4(0u, 0u, 0u, 0u);
-	// first segment whose end lies beyond lo_k
-	int a = 0, b = nseg;
+	int a = 0, b = nseg;  // first segment whose end lies beyond lo_k
 	while (a < b) {
 		const int mid = (a + b) >> 1;
 		if ((int)segs[mid].out_end <= lo_k) a = mid + 1;
@@ -160,7 +185,7 @@ __device__ __forceinline__ uint4 gen_seq(const GenomeView &gv, const uint4 *lowm
 	for (int si = a; si < nseg; si++) {
 		const SegDev sg = segs[si];
 		if ((int)sg.out_start >= hi_k) break;
-		const uint4 v = seq16(gv, fw, gpos, gend, sg.ref0, k0 - (int)sg.out_start);
+		const uint4 v = seq16_slow(gv, fw, gpos, gend, sg.ref0, k0 - (int)sg.out_start);
 		const uint4 m = range_mask(lowmask, ((int)sg.out_start > lo_k ? (int)sg.out_start : lo_k) - k0,
 		                           ((int)sg.out_end < hi_k ? (int)sg.out_end : hi_k) - k0);
 		out.x |= v.x & m.x;
@@ -171,19 +196,47 @@ __device__ __forceinline__ uint4 gen_seq(const GenomeView &gv, const uint4 *lowm
 	return out;
 }
 
-// Quality bytes for output positions [k0q, k0q+16), from the pre-oriented quality arena.
-__device__ __forceinline__ uint4 gen_qual(const uint4 *lowmask, const char *__restrict__ qual_out, uint32_t qoff, int L,
-                                          int k0q) {
+// Quality bytes for output positions [k0q, k0q+16): two aligned 16-byte loads from the
+// pre-oriented quality arena, shifted to the output phase.
+__device__ __forceinline__ uint4 gen_qual(const char *__restrict__ qual_out, uint32_t qbytes, uint32_t qoff, int k0q) {
 	const int A = (int)qoff + k0q;  // >= 1 (the arena has 16 bytes of front padding)
-	QT_CHK(A >= 0 && A < (1 << 28), 2, A, qoff);
-	const uint32_t *wp = (const uint32_t *)qual_out + (A >> 2);
+	QT_CHK(A >= 0 && (uint32_t)A < qbytes, 2, A, qoff);
+#ifdef QT_BOUNDS
+	if (!(A >= 0 && (uint32_t)A < qbytes)) return make_uint4(0, 0, 0, 0);
+#endif
+	const uint4 *bp = (const uint4 *)qual_out + (A >> 4);
+	const uint4 x = __ldg(bp), y = __ldg(bp + 1);
 	const uint32_t sh = 8u * (uint32_t)(A & 3);
-	const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
-	const uint4 v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
-	                           __funnelshift_r(w3, w4, sh));
-	if (k0q >= 0 && k0q + 16 <= L) return v;
-	const uint4 m = range_mask(lowmask, -k0q, L - k0q);
-	return make_uint4(v.x & m.x, v.y & m.y, v.z & m.z, v.w & m.w);
+	switch ((A >> 2) & 3) {
+	case 0:
+		return make_uint4(__funnelshift_r(x.x, x.y, sh), __funnelshift_r(x.y, x.z, sh), __funnelshift_r(x.z, x.w, sh),
+		                  __funnelshift_r(x.w, y.x, sh));
+	case 1:
+		return make_uint4(__funnelshift_r(x.y, x.z, sh), __funnelshift_r(x.z, x.w, sh), __funnelshift_r(x.w, y.x, sh),
+		                  __funnelshift_r(y.x, y.y, sh));
+	case 2:
+		return make_uint4(__funnelshift_r(x.z, x.w, sh), __funnelshift_r(x.w, y.x, sh), __funnelshift_r(y.x, y.y, sh),
+		                  __funnelshift_r(y.y, y.z, sh));
+	default:
+		return make_uint4(__funnelshift_r(x.w, y.x, sh), __funnelshift_r(y.x, y.y, sh), __funnelshift_r(y.y, y.z, sh),
+		                  __funnelshift_r(y.z, y.w, sh));
+	}
+}
+
+// Stores bytes [lo, hi) of v at p (16-byte aligned shared memory); never touches other bytes.
+__device__ __forceinline__ void store_partial(unsigned char *p, const uint4 &v, int lo, int hi) {
+	const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+	for (int k = 0; k < 4; k++) {
+		const int a = lo - 4 * k, b = hi - 4 * k;
+		if (a <= 0 && b >= 4) {
+			*(uint32_t *)(p + 4 * k) = w[k];
+		} else {
+#pragma unroll
+			for (int t = 0; t < 4; t++)
+				if (t >= a && t < b) p[4 * k + t] = (unsigned char)(w[k] >> (8 * t));
+		}
+	}
 }
 
 __device__ __forceinline__ uint32_t ndig(uint64_t v) {
@@ -221,27 +274,14 @@ __device__ __forceinline__ char *s_origin(char *p, const char *refid, uint32_t r
 	return p;
 }
 
-// per-read, per-stream body geometry kept in shared memory between the phases
-struct BodyInfo {
-	uint64_t gpos;    // genome position of the body's leftmost reference base (aligned mates)
-	uint32_t P;       // staging byte position of the first sequence byte
-	uint32_t segoff;  // into DevCategory::segs
-	uint32_t qoff;    // into DevCategory::qual_out
-	uint16_t L;       // body length
-	uint16_t nseg;
-	uint8_t fw;
-	uint8_t random;   // bad-end random mate: no reference copy, qualities 'I'
-	uint16_t nl;      // name length
-};
-
 template <int MODE, int CAT>
-__global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R, uint32_t stage_stride, int K) {
+__global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R, uint32_t stage_stride, int K, int skip) {
 	constexpr int NS = CAT == CAT_U ? 1 : 2;
 	extern __shared__ __align__(16) unsigned char smem[];
-	unsigned char *stage = smem;                                                   // NS * stage_stride
-	BodyInfo *s_body = (BodyInfo *)(smem + (size_t)NS * stage_stride);             // [NS][R]
-	uint64_t *s_gend = (uint64_t *)(s_body + (size_t)NS * R);                      // [R]
-	uint32_t *s_tmpl = (uint32_t *)(s_gend + R);                                   // [R]
+	unsigned char *stage = smem;                                        // NS * stage_stride
+	BodyInfo *s_body = (BodyInfo *)(smem + (size_t)NS * stage_stride);  // [NS][R]
+	uint64_t *s_gend = (uint64_t *)(s_body + (size_t)NS * R);           // [R]
+	uint32_t *s_tmpl = (uint32_t *)(s_gend + R);                        // [R]
 	__shared__ uint64_t s_G0[2], s_G1[2];
 	__shared__ uint4 s_lowmask[17];
 
@@ -275,12 +315,13 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 		const TmplDesc &t = a.c.t[pr.tmpl];
 		const RecDev rec = a.g.recs[pr.record];
 		const uint64_t ro0 = pr.refoff + t.delta[0], ro1 = pr.refoff + t.delta[1];
+		const uint64_t gend = rec.gstart + rec.len;
 		uint32_t nl;
 		if (CAT == CAT_U) nl = 13u + rec.name_len + ndig(ro0) + t.m[0].score_len + t.typ_len;
 		else if (CAT == CAT_B) nl = 18u + 2u * rec.name_len + 2u * ndig(ro0) + 2u * t.m[0].score_len + t.typ_len;
 		else nl = 18u + 2u * rec.name_len + ndig(ro0) + ndig(ro1) + t.m[0].score_len + t.m[1].score_len + t.typ_len;
 		s_tmpl[i] = pr.tmpl;
-		s_gend[i] = rec.gstart + rec.len;
+		s_gend[i] = gend;
 #pragma unroll
 		for (int s = 0; s < NS; s++) {
 			int mate = s;
@@ -297,99 +338,131 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 			bi.qoff = md.qual_out_off;
 			bi.L = (uint16_t)(random ? t.opp_len : md.len);
 			bi.nseg = md.nseg;
-			bi.fw = md.fw;
-			bi.random = random ? 1 : 0;
 			bi.nl = (uint16_t)nl;
+			bi.pad = 0;
+			bi.ref0 = 0;
+			uint8_t fl = (md.fw ? BF_FW : 0) | (random ? BF_RANDOM : 0);
+			if (!random) {
+				// one segment covering the whole read: no indels (=, X, S only)
+				if (md.nseg == 1) {
+					const SegDev sg = a.c.segs[md.seg_off];
+					if (sg.out_start == 0 && sg.out_end == md.len) {
+						fl |= BF_SINGLE;
+						bi.ref0 = sg.ref0;
+					}
+				}
+				// any N within reach of the sequence chunks, or reach past the record end -> slow path
+				const uint64_t glo = bi.gpos - 16, ghi = bi.gpos + md.rflen + 16;
+				bool slow = ghi > gend;
+				for (uint64_t w = glo >> 5; w <= ((ghi < gend ? ghi : gend) >> 5) && !slow; w++)
+					slow = __ldg(&gv.nmask[w]) != 0u;
+				if (slow) fl |= BF_SLOW;
+			}
+			bi.flags = fl;
 			s_body[s * R + i] = bi;
 		}
 	}
 	__syncthreads();
 
-	// ---------------- phase B: 16-byte chunks, chunk-major over the tile's reads ----------------
-	{
-		const uint64_t magic = 0x100000000ull / (uint32_t)nr + 1ull;  // (q * magic) >> 32 == q / nr for q < 2^16
-		const int nitems = K * nr;
-#pragma unroll
-		for (int s = 0; s < NS; s++) {
-			unsigned char *stg = stage + (size_t)s * stage_stride;
-			for (int q = tid; q < nitems; q += TL_THREADS) {
-				const int j = (int)(((uint64_t)(uint32_t)q * magic) >> 32);
-				const int i = q - j * nr;
-				const BodyInfo bi = s_body[s * R + i];
-				const int L = bi.L;
-				const int c = (int)(bi.P >> 4) + j;
-				const int k0 = 16 * c - (int)bi.P;  // output position of the chunk's first byte, >= -15
-				const int k0q = k0 - (L + 3);
-				if (k0q >= L) continue;  // beyond this read's qualities
-				uint4 v = make_uint4(0u, 0u, 0u, 0u);
-				if (k0 < L && !bi.random)
-					v = gen_seq(gv, s_lowmask, a.c.segs + bi.segoff, bi.nseg, bi.fw != 0, L, bi.gpos, s_gend[i], k0);
-				if (k0q + 16 > 0) {
-					uint4 qv;
-					if (bi.random) {
-						const uint4 m = range_mask(s_lowmask, -k0q, L - k0q);
-						qv = make_uint4(0x49494949u & m.x, 0x49494949u & m.y, 0x49494949u & m.z, 0x49494949u & m.w);
-					} else {
-						qv = gen_qual(s_lowmask, a.c.qual_out, bi.qoff, L, k0q);
-					}
-					v.x |= qv.x;
-					v.y |= qv.y;
-					v.z |= qv.z;
-					v.w |= qv.w;
-				}
-				QT_CHK(c >= 0 && 16u * (uint32_t)c + 16u <= stage_stride, 3, c, bi.P);
-				QT_CHK(i >= 0 && i < nr, 4, i, q);
-				*(uint4 *)(stg + 16 * (size_t)c) = v;
-			}
-		}
-	}
-	__syncthreads();
-
-	// ---------------- phase C: names, separators, random draws ----------------
-	for (int i = tid; i < nr; i += TL_THREADS) {
+	// ---------------- phase B.1: names and separators (one thread per read) ----------------
+	for (int i = tid; i < nr && !(skip & 1); i += TL_THREADS) {
 		const TmplDesc &t = a.c.t[s_tmpl[i]];
 		const PlanRec pr = a.plan[r0 + i];
 		const RecDev rec = a.g.recs[pr.record];
 		const char *refid = a.g.names + rec.name_off;
 		const BodyInfo b0 = s_body[i];
-		const BodyInfo b1 = NS == 2 ? s_body[R + i] : b0;
 		const uint32_t nl = b0.nl;
 		char *seq0 = (char *)stage + b0.P;
-		char *seq1 = NS == 2 ? (char *)stage + stage_stride + b1.P : nullptr;
 		char *rec0 = seq0 - nl;
-		{
-			char *p = s_put(rec0, "@qtip!:", 7);
-			const uint64_t ro0 = pr.refoff + t.delta[0], ro1 = pr.refoff + t.delta[1];
-			p = s_origin(p, refid, rec.name_len, t.m[0].fw != 0, ro0, t.m[0]);
-			if (CAT == CAT_B) {
-				*p++ = ':';
-				p = s_origin(p, refid, rec.name_len, t.m[0].fw != 0, ro0, t.m[0]);
-			} else if (CAT != CAT_U) {
-				*p++ = ':';
-				p = s_origin(p, refid, rec.name_len, t.m[1].fw != 0, ro1, t.m[1]);
-			}
+		QT_CHK(b0.P >= nl && b0.P + 2u * b0.L + 4u <= stage_stride, 5, b0.P, b0.L);
+		char *p = s_put(rec0, "@qtip!:", 7);
+		const uint64_t ro0 = pr.refoff + t.delta[0], ro1 = pr.refoff + t.delta[1];
+		p = s_origin(p, refid, rec.name_len, t.m[0].fw != 0, ro0, t.m[0]);
+		if (CAT == CAT_B) {
 			*p++ = ':';
-			p = s_put(p, t.typ, t.typ_len);
-			*p++ = '\n';
-			if (NS == 2) {
-				char *rec1 = seq1 - nl;
-				for (uint32_t j = 0; j < nl; j++) rec1[j] = rec0[j];
+			p = s_origin(p, refid, rec.name_len, t.m[0].fw != 0, ro0, t.m[0]);
+		} else if (CAT != CAT_U) {
+			*p++ = ':';
+			p = s_origin(p, refid, rec.name_len, t.m[1].fw != 0, ro1, t.m[1]);
+		}
+		*p++ = ':';
+		p = s_put(p, t.typ, t.typ_len);
+		*p++ = '\n';
+		seq0[b0.L] = '\n';
+		seq0[b0.L + 1] = '+';
+		seq0[b0.L + 2] = '\n';
+		seq0[2 * b0.L + 3] = '\n';
+		if (NS == 2) {
+			const BodyInfo b1 = s_body[R + i];
+			QT_CHK(b1.P >= nl && b1.P + 2u * b1.L + 4u <= stage_stride, 6, b1.P, b1.L);
+			char *seq1 = (char *)stage + stage_stride + b1.P;
+			char *rec1 = seq1 - nl;
+			for (uint32_t j = 0; j < nl; j++) rec1[j] = rec0[j];
+			seq1[b1.L] = '\n';
+			seq1[b1.L + 1] = '+';
+			seq1[b1.L + 2] = '\n';
+			seq1[2 * b1.L + 3] = '\n';
+		}
+	}
+
+	// ---------------- phase B.2 / B.3: sequence and quality chunks, read-major ----------------
+	{
+		const int nitems = K * nr;
+#pragma unroll
+		for (int s = 0; s < NS; s++) {
+			unsigned char *stg = stage + (size_t)s * stage_stride;
+			const BodyInfo *body = s_body + s * R;
+			// sequence
+			for (int q = tid; q < nitems && !(skip & 2); q += TL_THREADS) {
+				const int i = q / K;
+				const int j = q - i * K;
+				const BodyInfo bi = body[i];
+				if (bi.flags & BF_RANDOM) continue;  // every base of a random mate is a draw (phase C)
+				const int L = bi.L;
+				const int c = (int)(bi.P >> 4) + j;
+				const int k0 = 16 * c - (int)bi.P;  // output position of the chunk's first byte, >= -15
+				if (k0 >= L) continue;
+				QT_CHK(c >= 0 && 16u * (uint32_t)c + 16u <= stage_stride, 3, c, bi.P);
+				uint4 v;
+				const bool fw = (bi.flags & BF_FW) != 0;
+				if ((bi.flags & (BF_SINGLE | BF_SLOW)) == BF_SINGLE) v = seq16_fast(gv, fw, bi.gpos, bi.ref0, k0);
+				else if (bi.flags & BF_SINGLE) v = seq16_slow(gv, fw, bi.gpos, s_gend[i], bi.ref0, k0);
+				else v = gen_seq_segments(gv, s_lowmask, a.c.segs + bi.segoff, bi.nseg, fw, L, bi.gpos, s_gend[i], k0);
+				if (k0 >= 0 && k0 + 16 <= L) *(uint4 *)(stg + 16 * (size_t)c) = v;
+				else store_partial(stg + 16 * (size_t)c, v, -k0, L - k0);
+			}
+			// qualities
+			for (int q = tid; q < nitems && !(skip & 4); q += TL_THREADS) {
+				const int i = q / K;
+				const int j = q - i * K;
+				const BodyInfo bi = body[i];
+				const int L = bi.L;
+				const uint32_t Pq = bi.P + (uint32_t)L + 3u;
+				const int c = (int)(Pq >> 4) + j;
+				const int k0q = 16 * c - (int)Pq;
+				if (k0q >= L) continue;
+				QT_CHK(c >= 0 && 16u * (uint32_t)c + 16u <= stage_stride, 4, c, Pq);
+#ifdef QT_BOUNDS
+				if (!(c >= 0 && 16u * (uint32_t)c + 16u <= stage_stride)) continue;
+#endif
+				uint4 v;
+				if (bi.flags & BF_RANDOM) v = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);  // 'I'
+				else v = gen_qual(a.c.qual_out, a.c.qual_out_bytes, bi.qoff, k0q);
+				if (k0q >= 0 && k0q + 16 <= L) *(uint4 *)(stg + 16 * (size_t)c) = v;
+				else store_partial(stg + 16 * (size_t)c, v, -k0q, L - k0q);
 			}
 		}
-		const uint32_t bl0 = b0.L, bl1 = b1.L;
-		QT_CHK(b0.P >= nl && b0.P + 2 * bl0 + 4 <= stage_stride, 5, b0.P, bl0);
-		QT_CHK(NS == 1 || (b1.P >= nl && b1.P + 2 * bl1 + 4 <= stage_stride), 6, b1.P, bl1);
-		seq0[bl0] = '\n';
-		seq0[bl0 + 1] = '+';
-		seq0[bl0 + 2] = '\n';
-		seq0[2 * bl0 + 3] = '\n';
-		if (NS == 2) {
-			seq1[bl1] = '\n';
-			seq1[bl1 + 1] = '+';
-			seq1[bl1 + 2] = '\n';
-			seq1[2 * bl1 + 3] = '\n';
-		}
+	}
+	__syncthreads();
 
+	// ---------------- phase C: random draws ----------------
+	for (int i = tid; i < nr && !(skip & 8); i += TL_THREADS) {
+		const TmplDesc &t = a.c.t[s_tmpl[i]];
+		const PlanRec pr = a.plan[r0 + i];
+		const BodyInfo b0 = s_body[i];
+		const BodyInfo b1 = NS == 2 ? s_body[R + i] : b0;
+		char *seq0 = (char *)stage + b0.P;
+		char *seq1 = NS == 2 ? (char *)stage + stage_stride + b1.P : nullptr;
 		// draws, in the reference's order: mate 1's transcript, mate 2's, then the random mate
 		LState st{pr.s1, pr.s2};
 		const uint64_t gi = a.read_index_base + r0 + i;
@@ -405,7 +478,7 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 			return b;
 		};
 		const int nm = CAT == CAT_C || CAT == CAT_D ? 2 : 1;
-		const bool s0_random = b0.random != 0;
+		const bool s0_random = (b0.flags & BF_RANDOM) != 0;
 		for (int m = 0; m < nm; m++) {
 			const MateDesc &md = t.m[m];
 			char *seq = (CAT == CAT_B) ? (s0_random ? seq1 : seq0) : (m == 0 ? seq0 : seq1);
@@ -473,7 +546,7 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 		// interior: whole 16-byte chunks [c_lo, c_hi)
 		const int c_lo = ph ? 1 : 0;
 		const int c_hi = (ph + total) >> 4;
-		if (tid == s * 32 && c_hi > c_lo) {
+		if (tid == s * 32 && c_hi > c_lo && !(skip & 16)) {
 			const uint32_t nbytes = (uint32_t)(c_hi - c_lo) * 16u;
 			QT_CHK(16u * c_hi <= stage_stride && total >= 0, 8, c_hi, total);
 			const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(stg + 16 * c_lo);
@@ -482,7 +555,6 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 			             : "memory");
 			asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 		}
-		// ragged head (bytes [0, 16-ph) of the tile when ph != 0) and tail
 		if (tid >= 64 && tid < 64 + 32) {
 			// staging positions [ph, ph+total) are this tile's; chunk 0 (if ph != 0) and chunk c_hi are partial
 			const int j = tid - 64;
@@ -513,8 +585,8 @@ static bool launch_cat(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_bo
 	const uint32_t stage_stride = ((uint32_t)R * max_rec_bytes + 48 + 15) & ~15u;
 	const size_t meta = (size_t)NS * R * sizeof(BodyInfo) + (size_t)R * 8 + (size_t)R * 4 + 16;
 	const size_t smem = (size_t)NS * stage_stride + meta;
-	// chunks a body (sequence, "\n+\n", qualities) can touch: ceil((2*maxL+3)/16) + 1 for misalignment
-	const int K = (int)((2u * max_body + 3u + 15u) / 16u) + 1;
+	// chunks a sequence / quality string of maxL bytes can touch at any alignment
+	const int K = (int)((max_body + 15u) / 16u) + 1;
 	if ((uint64_t)K * (uint64_t)R >= 65536ull) return false;
 	auto kern = k_simulate_tiled<MODE, CAT>;
 	static bool attr_set = false;
@@ -523,7 +595,13 @@ static bool launch_cat(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_bo
 		attr_set = true;
 	}
 	const uint64_t ntiles = (a.nreads + R - 1) / R;
-	kern<<<(unsigned)ntiles, TL_THREADS, smem, st>>>(a, R, stage_stride, K);
+	// QTIPSIM_SKIP (debug / attribution only): bit mask of phases to leave out -- output is then incomplete
+	static int skip = -1;
+	if (skip < 0) {
+		const char *e = getenv("QTIPSIM_SKIP");
+		skip = e ? atoi(e) : 0;
+	}
+	kern<<<(unsigned)ntiles, TL_THREADS, smem, st>>>(a, R, stage_stride, K, skip);
 	kernels_count_launch();
 	return true;
 }
@@ -542,7 +620,9 @@ static bool launch_mode(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_b
 void tiled_debug_report() {
 	unsigned long long v[4] = {0, 0, 0, 0};
 	cudaMemcpyFromSymbol(v, g_qt_violation, sizeof(v));
-	if (v[0]) fprintf(stderr, "QT_BOUNDS violation id=%llu v0=%lld v1=%lld block=%llu thread=%llu\n", v[0], (long long)v[1], (long long)v[2], v[3] >> 32, v[3] & 0xffffffffu);
+	if (v[0])
+		fprintf(stderr, "QT_BOUNDS violation id=%llu v0=%lld v1=%lld block=%llu thread=%llu\n", v[0], (long long)v[1],
+		        (long long)v[2], v[3] >> 32, v[3] & 0xffffffffu);
 	else fprintf(stderr, "QT_BOUNDS: no violation\n");
 	memset(v, 0, sizeof(v));
 	cudaMemcpyToSymbol(g_qt_violation, v, sizeof(v));
