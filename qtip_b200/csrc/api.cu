@@ -541,7 +541,7 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 		                         2u * cg.max_body + 4u;
 		const char *force = getenv("QTIPSIM_KERNEL");
 		bool done = false;
-		if (cg.compiled_ok && !(force && strcmp(force, "generic") == 0)) done = launch_simulate_tiled(sa[c], max_rec, cg.max_body, h->st);
+		if (cg.compiled_ok && !(force && strcmp(force, "generic") == 0)) done = launch_simulate_tiled(sa[c], max_rec, cg.max_body, cg.max_rflen, h->st);
 		if (!done) launch_simulate(sa[c], h->st);
 	}
 	CK(cudaEventRecord(ev[3], h->st));

@@ -48,6 +48,9 @@ struct MateDesc {
 	uint32_t seg_off;       // reference-copy segments, ascending output position
 	uint16_t nops;
 	uint16_t nseg;
+	int32_t ref0;           // single != 0: reference offset of output position 0
+	uint8_t single;         // one segment covering the whole read (no indels: =, X, S only)
+	uint8_t pad2[3];
 };
 
 // A maximal run of transcript ops that copy reference to read (=, X, S), in output

@@ -69,7 +69,8 @@ void launch_simulate(const SimArgs &a, cudaStream_t st);
 // per lane per step, then streams the tile to HBM with aligned 16-byte stores.
 // max_rec_bytes = upper bound on one FASTQ record of this category.  Returns false when the
 // category cannot use it (record too large for the staging buffer) -- caller falls back.
-bool launch_simulate_tiled(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, cudaStream_t st);
+bool launch_simulate_tiled(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, uint32_t max_rflen,
+                           cudaStream_t st);
 void kernels_count_launch();
 
 // PHILOX planning: fills plan[] for reads [0, n) of one category from per-window

@@ -57,7 +57,7 @@ __device__ unsigned long long g_qt_violation[4];
 #endif
 
 static constexpr int TL_THREADS = 256;
-static constexpr uint32_t TL_STAGE_DEFAULT = 44 * 1024;  // staging per CTA, all streams (4 CTAs per SM)
+static constexpr uint32_t TL_STAGE_DEFAULT = 52 * 1024;  // dynamic shared memory per CTA (4 CTAs per SM)
 
 enum : uint8_t { BF_FW = 1, BF_RANDOM = 2, BF_SLOW = 4, BF_SINGLE = 8 };
 
@@ -274,14 +274,127 @@ __device__ __forceinline__ char *s_origin(char *p, const char *refid, uint32_t r
 	return p;
 }
 
+// ---- shared-memory genome cache -------------------------------------------------------
+// Phase A copies, per aligned mate, the packed bases of [gpos-16, gpos+rflen+48) into shared
+// memory with cp.async (16-byte pieces, 64-base aligned), so the sequence chunks and the X
+// look-ups of phase C never wait on HBM.
+__device__ __forceinline__ uint64_t gcache_origin(uint64_t gpos) { return (gpos - 16) & ~(uint64_t)63; }
+
+__device__ __forceinline__ uint32_t cache16_bases(const uint32_t *cache, uint64_t gc0, uint64_t g) {
+	const uint32_t off = (uint32_t)(g - gc0);
+	const uint32_t lo = cache[off >> 4], hi = cache[(off >> 4) + 1];
+	return __funnelshift_r(lo, hi, 2u * (off & 15u));
+}
+
+__device__ __forceinline__ uint4 cseq16_fast(const uint32_t *cache, uint64_t gc0, bool fw, uint64_t gpos, int32_t ref0,
+                                             int d) {
+	if (fw) return expand16(cache16_bases(cache, gc0, (uint64_t)((int64_t)gpos + ref0 + d)));
+	return expand16(revcomp16(cache16_bases(cache, gc0, (uint64_t)((int64_t)gpos + ref0 - d) - 15)));
+}
+
+__device__ __forceinline__ uint4 cseq16_slow(const GenomeView &gv, const uint32_t *cache, uint64_t gc0, bool fw,
+                                             uint64_t gpos, uint64_t gend, int32_t ref0, int d) {
+	uint32_t w, nm;
+	if (fw) {
+		const uint64_t g0 = (uint64_t)((int64_t)gpos + ref0 + d);
+		w = cache16_bases(cache, gc0, g0);
+		nm = load16_nmask(gv, g0);
+		if (g0 + 16 > gend) nm |= g0 >= gend ? 0xffffu : (0xffffu << (uint32_t)(gend - g0)) & 0xffffu;
+	} else {
+		const uint64_t ghi = (uint64_t)((int64_t)gpos + ref0 - d);
+		w = revcomp16(cache16_bases(cache, gc0, ghi - 15));
+		nm = __brev(load16_nmask(gv, ghi - 15)) >> 16;
+		if (ghi >= gend) nm |= (ghi - gend) >= 15 ? 0xffffu : (1u << ((uint32_t)(ghi - gend) + 1u)) - 1u;
+	}
+	uint4 v = expand16(w);
+	if (nm) {
+		const uint32_t N4 = 0x4e4e4e4eu;
+		uint32_t m;
+		m = spread4(nm);       v.x = (v.x & ~m) | (N4 & m);
+		m = spread4(nm >> 4);  v.y = (v.y & ~m) | (N4 & m);
+		m = spread4(nm >> 8);  v.z = (v.z & ~m) | (N4 & m);
+		m = spread4(nm >> 12); v.w = (v.w & ~m) | (N4 & m);
+	}
+	return v;
+}
+
+// General path: merges the contributions of every reference-copy segment that overlaps
+// output positions [k0, k0+16); other bytes are zero.
+__device__ __noinline__ uint4 cgen_seq_segments(const GenomeView &gv, const uint32_t *cache, uint64_t gc0,
+                                                const uint4 *lowmask, const SegDev *__restrict__ segs, int nseg, bool fw,
+                                                int L, uint64_t gpos, uint64_t gend, int k0) {
+	const int lo_k = k0 > 0 ? k0 : 0;
+	const int hi_k = k0 + 16 < L ? k0 + 16 : L;
+	uint4 out = make_uint4(0u, 0u, 0u, 0u);
+	int a = 0, b = nseg;  // first segment whose end lies beyond lo_k
+	while (a < b) {
+		const int mid = (a + b) >> 1;
+		if ((int)segs[mid].out_end <= lo_k) a = mid + 1;
+		else b = mid;
+	}
+	for (int si = a; si < nseg; si++) {
+		const SegDev sg = segs[si];
+		if ((int)sg.out_start >= hi_k) break;
+		const uint4 v = cseq16_slow(gv, cache, gc0, fw, gpos, gend, sg.ref0, k0 - (int)sg.out_start);
+		const uint4 m = range_mask(lowmask, ((int)sg.out_start > lo_k ? (int)sg.out_start : lo_k) - k0,
+		                           ((int)sg.out_end < hi_k ? (int)sg.out_end : hi_k) - k0);
+		out.x |= v.x & m.x;
+		out.y |= v.y & m.y;
+		out.z |= v.z & m.z;
+		out.w |= v.w & m.w;
+	}
+	return out;
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+	const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// quality chunk: issue the two aligned loads first (so several chunks can be in flight) ...
+struct QualLoad {
+	uint4 x, y;
+	int A;
+};
+__device__ __forceinline__ QualLoad qual_issue(const char *__restrict__ qual_out, uint32_t qoff, int k0q) {
+	QualLoad ql;
+	ql.A = (int)qoff + k0q;  // >= 1 (the arena has 16 bytes of front padding)
+	const uint4 *bp = (const uint4 *)qual_out + (ql.A >> 4);
+	ql.x = __ldg(bp);
+	ql.y = __ldg(bp + 1);
+	return ql;
+}
+// ... then shift them to the output phase
+__device__ __forceinline__ uint4 qual_finish(const QualLoad &ql) {
+	const uint4 &x = ql.x, &y = ql.y;
+	const uint32_t sh = 8u * (uint32_t)(ql.A & 3);
+	switch ((ql.A >> 2) & 3) {
+	case 0:
+		return make_uint4(__funnelshift_r(x.x, x.y, sh), __funnelshift_r(x.y, x.z, sh), __funnelshift_r(x.z, x.w, sh),
+		                  __funnelshift_r(x.w, y.x, sh));
+	case 1:
+		return make_uint4(__funnelshift_r(x.y, x.z, sh), __funnelshift_r(x.z, x.w, sh), __funnelshift_r(x.w, y.x, sh),
+		                  __funnelshift_r(y.x, y.y, sh));
+	case 2:
+		return make_uint4(__funnelshift_r(x.z, x.w, sh), __funnelshift_r(x.w, y.x, sh), __funnelshift_r(y.x, y.y, sh),
+		                  __funnelshift_r(y.y, y.z, sh));
+	default:
+		return make_uint4(__funnelshift_r(x.w, y.x, sh), __funnelshift_r(y.x, y.y, sh), __funnelshift_r(y.y, y.z, sh),
+		                  __funnelshift_r(y.z, y.w, sh));
+	}
+}
+
 template <int MODE, int CAT>
-__global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R, uint32_t stage_stride, int K, int skip) {
-	constexpr int NS = CAT == CAT_U ? 1 : 2;
+__global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R, uint32_t stage_stride, int K,
+                                                                uint32_t gc_stride, int skip) {
+	constexpr int NS = CAT == CAT_U ? 1 : 2;                     // output streams
+	constexpr int NM = (CAT == CAT_C || CAT == CAT_D) ? 2 : 1;   // aligned mates per read
 	extern __shared__ __align__(16) unsigned char smem[];
-	unsigned char *stage = smem;                                        // NS * stage_stride
-	BodyInfo *s_body = (BodyInfo *)(smem + (size_t)NS * stage_stride);  // [NS][R]
-	uint64_t *s_gend = (uint64_t *)(s_body + (size_t)NS * R);           // [R]
-	uint32_t *s_tmpl = (uint32_t *)(s_gend + R);                        // [R]
+	unsigned char *stage = smem;                                                      // NS * stage_stride
+	unsigned char *gcache = smem + (size_t)NS * stage_stride;                         // NM * R * gc_stride
+	BodyInfo *s_body = (BodyInfo *)(gcache + (size_t)NM * R * gc_stride);             // [NS][R]
+	uint64_t *s_gend = (uint64_t *)(s_body + (size_t)NS * R);                         // [R]
+	uint32_t *s_tmpl = (uint32_t *)(s_gend + R);                                      // [R]
 	__shared__ uint64_t s_G0[2], s_G1[2];
 	__shared__ uint4 s_lowmask[17];
 
@@ -309,7 +422,7 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 	}
 	__syncthreads();
 
-	// ---------------- phase A: geometry ----------------
+	// ---------------- phase A (one thread per read): geometry, genome prefetch, name ----------------
 	for (int i = tid; i < nr; i += TL_THREADS) {
 		const PlanRec pr = a.plan[r0 + i];
 		const TmplDesc &t = a.c.t[pr.tmpl];
@@ -322,6 +435,30 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 		else nl = 18u + 2u * rec.name_len + ndig(ro0) + ndig(ro1) + t.m[0].score_len + t.m[1].score_len + t.typ_len;
 		s_tmpl[i] = pr.tmpl;
 		s_gend[i] = gend;
+		// genome prefetch + N scan, per aligned mate
+		uint8_t slowf[2] = {0, 0};
+#pragma unroll
+		for (int m = 0; m < NM; m++) {
+			const MateDesc &md = t.m[m];
+			const uint64_t gpos = rec.gstart + (m == 0 ? ro0 : ro1);
+			const uint64_t gc0 = gcache_origin(gpos);
+			const uint32_t nch = (uint32_t)((gpos + md.rflen + 48 - gc0 + 63) >> 6);
+			unsigned char *dst = gcache + ((size_t)m * R + i) * gc_stride;
+			const unsigned char *src = (const unsigned char *)a.g.bases + (gc0 >> 2);
+			const uint64_t src_limit = a.genome_words * 4;
+			QT_CHK(nch * 16u <= gc_stride, 9, nch, gc_stride);
+			for (uint32_t c = 0; c < nch; c++)
+				if ((gc0 >> 2) + 16ull * c + 16ull <= src_limit) cp_async16(dst + 16 * c, src + 16 * c);
+			// any N within reach of the sequence chunks, or reach past the record end -> slow path
+			const uint64_t glo = gpos - 16, ghi = gpos + md.rflen + 16;
+			uint32_t acc = ghi > gend ? 1u : 0u;
+			const uint64_t w1 = (ghi < gend ? ghi : gend) >> 5;
+			for (uint64_t w = glo >> 5; w <= w1; w++) acc |= __ldg(&gv.nmask[w]);  // independent loads
+			slowf[m] = acc ? BF_SLOW : 0;
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		char *rec_ptr[2] = {nullptr, nullptr};
+		uint32_t blen[2] = {0, 0};
 #pragma unroll
 		for (int s = 0; s < NS; s++) {
 			int mate = s;
@@ -340,72 +477,44 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 			bi.nseg = md.nseg;
 			bi.nl = (uint16_t)nl;
 			bi.pad = 0;
-			bi.ref0 = 0;
-			uint8_t fl = (md.fw ? BF_FW : 0) | (random ? BF_RANDOM : 0);
-			if (!random) {
-				// one segment covering the whole read: no indels (=, X, S only)
-				if (md.nseg == 1) {
-					const SegDev sg = a.c.segs[md.seg_off];
-					if (sg.out_start == 0 && sg.out_end == md.len) {
-						fl |= BF_SINGLE;
-						bi.ref0 = sg.ref0;
-					}
-				}
-				// any N within reach of the sequence chunks, or reach past the record end -> slow path
-				const uint64_t glo = bi.gpos - 16, ghi = bi.gpos + md.rflen + 16;
-				bool slow = ghi > gend;
-				for (uint64_t w = glo >> 5; w <= ((ghi < gend ? ghi : gend) >> 5) && !slow; w++)
-					slow = __ldg(&gv.nmask[w]) != 0u;
-				if (slow) fl |= BF_SLOW;
-			}
-			bi.flags = fl;
+			bi.ref0 = md.ref0;
+			bi.flags = (md.fw ? BF_FW : 0) | (random ? BF_RANDOM : 0) | (md.single ? BF_SINGLE : 0) | slowf[mate];
 			s_body[s * R + i] = bi;
+			rec_ptr[s] = (char *)stage + (size_t)s * stage_stride + bi.P - nl;
+			blen[s] = bi.L;
+			QT_CHK(bi.P >= nl && bi.P + 2u * bi.L + 4u <= stage_stride, 5, bi.P, bi.L);
+		}
+		if (!(skip & 1)) {
+			// name (simplesim.cpp:104-110, :140-150) and separators
+			const char *refid = a.g.names + rec.name_off;
+			char *p = s_put(rec_ptr[0], "@qtip!:", 7);
+			p = s_origin(p, refid, rec.name_len, t.m[0].fw != 0, ro0, t.m[0]);
+			if (CAT == CAT_B) {
+				*p++ = ':';
+				p = s_origin(p, refid, rec.name_len, t.m[0].fw != 0, ro0, t.m[0]);
+			} else if (CAT != CAT_U) {
+				*p++ = ':';
+				p = s_origin(p, refid, rec.name_len, t.m[1].fw != 0, ro1, t.m[1]);
+			}
+			*p++ = ':';
+			p = s_put(p, t.typ, t.typ_len);
+			*p++ = '\n';
+#pragma unroll
+			for (int s = 0; s < NS; s++) {
+				char *sq = rec_ptr[s] + nl;
+				if (s == 1)
+					for (uint32_t j = 0; j < nl; j++) rec_ptr[1][j] = rec_ptr[0][j];
+				sq[blen[s]] = '\n';
+				sq[blen[s] + 1] = '+';
+				sq[blen[s] + 2] = '\n';
+				sq[2 * blen[s] + 3] = '\n';
+			}
 		}
 	}
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
 	__syncthreads();
 
-	// ---------------- phase B.1: names and separators (one thread per read) ----------------
-	for (int i = tid; i < nr && !(skip & 1); i += TL_THREADS) {
-		const TmplDesc &t = a.c.t[s_tmpl[i]];
-		const PlanRec pr = a.plan[r0 + i];
-		const RecDev rec = a.g.recs[pr.record];
-		const char *refid = a.g.names + rec.name_off;
-		const BodyInfo b0 = s_body[i];
-		const uint32_t nl = b0.nl;
-		char *seq0 = (char *)stage + b0.P;
-		char *rec0 = seq0 - nl;
-		QT_CHK(b0.P >= nl && b0.P + 2u * b0.L + 4u <= stage_stride, 5, b0.P, b0.L);
-		char *p = s_put(rec0, "@qtip!:", 7);
-		const uint64_t ro0 = pr.refoff + t.delta[0], ro1 = pr.refoff + t.delta[1];
-		p = s_origin(p, refid, rec.name_len, t.m[0].fw != 0, ro0, t.m[0]);
-		if (CAT == CAT_B) {
-			*p++ = ':';
-			p = s_origin(p, refid, rec.name_len, t.m[0].fw != 0, ro0, t.m[0]);
-		} else if (CAT != CAT_U) {
-			*p++ = ':';
-			p = s_origin(p, refid, rec.name_len, t.m[1].fw != 0, ro1, t.m[1]);
-		}
-		*p++ = ':';
-		p = s_put(p, t.typ, t.typ_len);
-		*p++ = '\n';
-		seq0[b0.L] = '\n';
-		seq0[b0.L + 1] = '+';
-		seq0[b0.L + 2] = '\n';
-		seq0[2 * b0.L + 3] = '\n';
-		if (NS == 2) {
-			const BodyInfo b1 = s_body[R + i];
-			QT_CHK(b1.P >= nl && b1.P + 2u * b1.L + 4u <= stage_stride, 6, b1.P, b1.L);
-			char *seq1 = (char *)stage + stage_stride + b1.P;
-			char *rec1 = seq1 - nl;
-			for (uint32_t j = 0; j < nl; j++) rec1[j] = rec0[j];
-			seq1[b1.L] = '\n';
-			seq1[b1.L + 1] = '+';
-			seq1[b1.L + 2] = '\n';
-			seq1[2 * b1.L + 3] = '\n';
-		}
-	}
-
-	// ---------------- phase B.2 / B.3: sequence and quality chunks, read-major ----------------
+	// ---------------- phase B: sequence and quality chunks, read-major, exact-byte stores ----------------
 	{
 		const int nitems = K * nr;
 #pragma unroll
@@ -423,33 +532,49 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 				const int k0 = 16 * c - (int)bi.P;  // output position of the chunk's first byte, >= -15
 				if (k0 >= L) continue;
 				QT_CHK(c >= 0 && 16u * (uint32_t)c + 16u <= stage_stride, 3, c, bi.P);
+				const int cm = (CAT == CAT_C || CAT == CAT_D) ? s : 0;
+				const uint32_t *cache = (const uint32_t *)(gcache + ((size_t)cm * R + i) * gc_stride);
+				const uint64_t gc0 = gcache_origin(bi.gpos);
 				uint4 v;
 				const bool fw = (bi.flags & BF_FW) != 0;
-				if ((bi.flags & (BF_SINGLE | BF_SLOW)) == BF_SINGLE) v = seq16_fast(gv, fw, bi.gpos, bi.ref0, k0);
-				else if (bi.flags & BF_SINGLE) v = seq16_slow(gv, fw, bi.gpos, s_gend[i], bi.ref0, k0);
-				else v = gen_seq_segments(gv, s_lowmask, a.c.segs + bi.segoff, bi.nseg, fw, L, bi.gpos, s_gend[i], k0);
+				if ((bi.flags & (BF_SINGLE | BF_SLOW)) == BF_SINGLE) v = cseq16_fast(cache, gc0, fw, bi.gpos, bi.ref0, k0);
+				else if (bi.flags & BF_SINGLE) v = cseq16_slow(gv, cache, gc0, fw, bi.gpos, s_gend[i], bi.ref0, k0);
+				else v = cgen_seq_segments(gv, cache, gc0, s_lowmask, a.c.segs + bi.segoff, bi.nseg, fw, L, bi.gpos, s_gend[i], k0);
 				if (k0 >= 0 && k0 + 16 <= L) *(uint4 *)(stg + 16 * (size_t)c) = v;
 				else store_partial(stg + 16 * (size_t)c, v, -k0, L - k0);
 			}
-			// qualities
-			for (int q = tid; q < nitems && !(skip & 4); q += TL_THREADS) {
-				const int i = q / K;
-				const int j = q - i * K;
-				const BodyInfo bi = body[i];
-				const int L = bi.L;
-				const uint32_t Pq = bi.P + (uint32_t)L + 3u;
-				const int c = (int)(Pq >> 4) + j;
-				const int k0q = 16 * c - (int)Pq;
-				if (k0q >= L) continue;
-				QT_CHK(c >= 0 && 16u * (uint32_t)c + 16u <= stage_stride, 4, c, Pq);
-#ifdef QT_BOUNDS
-				if (!(c >= 0 && 16u * (uint32_t)c + 16u <= stage_stride)) continue;
-#endif
-				uint4 v;
-				if (bi.flags & BF_RANDOM) v = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);  // 'I'
-				else v = gen_qual(a.c.qual_out, a.c.qual_out_bytes, bi.qoff, k0q);
-				if (k0q >= 0 && k0q + 16 <= L) *(uint4 *)(stg + 16 * (size_t)c) = v;
-				else store_partial(stg + 16 * (size_t)c, v, -k0q, L - k0q);
+			// qualities: two chunks per iteration, loads issued before either is consumed
+			for (int q = tid; q < nitems && !(skip & 4); q += 2 * TL_THREADS) {
+				QualLoad ql[2];
+				int cc[2], kq[2], LL[2];
+				bool live[2], rnd[2];
+#pragma unroll
+				for (int u = 0; u < 2; u++) {
+					const int qq = q + u * TL_THREADS;
+					live[u] = false;
+					rnd[u] = false;
+					if (qq < nitems) {
+						const int i = qq / K;
+						const int j = qq - i * K;
+						const BodyInfo bi = body[i];
+						LL[u] = bi.L;
+						const uint32_t Pq = bi.P + (uint32_t)bi.L + 3u;
+						cc[u] = (int)(Pq >> 4) + j;
+						kq[u] = 16 * cc[u] - (int)Pq;
+						live[u] = kq[u] < LL[u];
+						rnd[u] = (bi.flags & BF_RANDOM) != 0;
+						if (live[u] && !rnd[u]) ql[u] = qual_issue(a.c.qual_out, bi.qoff, kq[u]);
+					}
+				}
+#pragma unroll
+				for (int u = 0; u < 2; u++) {
+					if (!live[u]) continue;
+					QT_CHK(cc[u] >= 0 && 16u * (uint32_t)cc[u] + 16u <= stage_stride, 4, cc[u], kq[u]);
+					const uint4 v = rnd[u] ? make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u)  // 'I'
+					                       : qual_finish(ql[u]);
+					if (kq[u] >= 0 && kq[u] + 16 <= LL[u]) *(uint4 *)(stg + 16 * (size_t)cc[u]) = v;
+					else store_partial(stg + 16 * (size_t)cc[u], v, -kq[u], LL[u] - kq[u]);
+				}
 			}
 		}
 	}
@@ -477,21 +602,30 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 			dk++;
 			return b;
 		};
-		const int nm = CAT == CAT_C || CAT == CAT_D ? 2 : 1;
 		const bool s0_random = (b0.flags & BF_RANDOM) != 0;
-		for (int m = 0; m < nm; m++) {
+		const uint64_t gend = s_gend[i];
+		for (int m = 0; m < NM; m++) {
 			const MateDesc &md = t.m[m];
+			const BodyInfo &bm = (CAT == CAT_B) ? (s0_random ? b1 : b0) : (m == 0 ? b0 : b1);
 			char *seq = (CAT == CAT_B) ? (s0_random ? seq1 : seq0) : (m == 0 ? seq0 : seq1);
 			const uint32_t *ops = a.c.ops + md.ops_off;
-			const uint64_t gpos = (CAT == CAT_B) ? (s0_random ? b1.gpos : b0.gpos) : (m == 0 ? b0.gpos : b1.gpos);
-			const uint64_t gend = s_gend[i];
+			const uint64_t gpos = bm.gpos;
+			const uint64_t gc0 = gcache_origin(gpos);
+			const uint32_t *cache = (const uint32_t *)(gcache + ((size_t)m * R + i) * gc_stride);
+			const bool slow = (bm.flags & BF_SLOW) != 0;
 			const uint32_t T = md.fw ? 0x54474341u : 0x41434754u;  // "ACGT" / "TGCA"
 			for (uint32_t j = 0; j < md.nops; j++) {
 				const uint32_t e = __ldg(&ops[j]);
 				const uint32_t outp = (e >> 2) & 0x7fffu;
 				uint32_t code;
 				if ((e & 3u) == OP_X) {
-					const uint32_t ref = fetch_code_v(gv, gpos + (e >> 17), gend);
+					const uint64_t gp = gpos + (e >> 17);
+					uint32_t ref;
+					if (slow && (gp >= gend || ((__ldg(&gv.nmask[gp >> 5]) >> (gp & 31)) & 1u))) ref = 4u;
+					else {
+						const uint32_t off = (uint32_t)(gp - gc0);
+						ref = (cache[off >> 4] >> (2u * (off & 15u))) & 3u;
+					}
 					if (MODE == QTIPSIM_RNG_REPLAY) {
 						do {  // simplesim.cpp:47-49
 							st = lstep(st);
@@ -569,29 +703,31 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 }
 
 template <int MODE, int CAT>
-static bool launch_cat(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, cudaStream_t st) {
+static bool launch_cat(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, uint32_t max_rflen, cudaStream_t st) {
 	constexpr int NS = CAT == CAT_U ? 1 : 2;
-	static uint32_t stage_bytes = 0;
-	if (!stage_bytes) {
+	constexpr int NM = (CAT == CAT_C || CAT == CAT_D) ? 2 : 1;
+	static uint32_t smem_budget = 0;
+	if (!smem_budget) {
 		const char *e = getenv("QTIPSIM_STAGE_KB");
-		stage_bytes = e ? (uint32_t)atoi(e) * 1024u : TL_STAGE_DEFAULT;
-		if (stage_bytes < 8 * 1024 || stage_bytes > 190 * 1024) stage_bytes = TL_STAGE_DEFAULT;
+		smem_budget = e ? (uint32_t)atoi(e) * 1024u : TL_STAGE_DEFAULT;
+		if (smem_budget < 8 * 1024 || smem_budget > 200 * 1024) smem_budget = TL_STAGE_DEFAULT;
 	}
-	const uint32_t per_stream = stage_bytes / NS;
-	int R = (int)((per_stream - 64) / max_rec_bytes);
+	// genome cache per aligned mate: [gpos-16 rounded down to 64, gpos+rflen+48), in 16-byte pieces
+	const uint32_t gc_stride = ((max_rflen + 16 + 48 + 63 + 63) / 64) * 16 + 16;
+	const uint32_t per_read = NS * max_rec_bytes + NM * gc_stride + NS * (uint32_t)sizeof(BodyInfo) + 12;
+	int R = (int)((smem_budget - NS * 64 - 64) / per_read);
 	if (R > TL_THREADS) R = TL_THREADS;
 	if (R < 4) return false;
 	// a tile's bytes are at most R * max_rec_bytes; +48 for the alignment phase and the ragged tail
 	const uint32_t stage_stride = ((uint32_t)R * max_rec_bytes + 48 + 15) & ~15u;
-	const size_t meta = (size_t)NS * R * sizeof(BodyInfo) + (size_t)R * 8 + (size_t)R * 4 + 16;
-	const size_t smem = (size_t)NS * stage_stride + meta;
+	const size_t smem = (size_t)NS * stage_stride + (size_t)NM * R * gc_stride + (size_t)NS * R * sizeof(BodyInfo) +
+	                    (size_t)R * 12 + 16;
 	// chunks a sequence / quality string of maxL bytes can touch at any alignment
 	const int K = (int)((max_body + 15u) / 16u) + 1;
-	if ((uint64_t)K * (uint64_t)R >= 65536ull) return false;
 	auto kern = k_simulate_tiled<MODE, CAT>;
 	static bool attr_set = false;
 	if (!attr_set) {
-		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
 		attr_set = true;
 	}
 	const uint64_t ntiles = (a.nreads + R - 1) / R;
@@ -601,18 +737,18 @@ static bool launch_cat(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_bo
 		const char *e = getenv("QTIPSIM_SKIP");
 		skip = e ? atoi(e) : 0;
 	}
-	kern<<<(unsigned)ntiles, TL_THREADS, smem, st>>>(a, R, stage_stride, K, skip);
+	kern<<<(unsigned)ntiles, TL_THREADS, smem, st>>>(a, R, stage_stride, K, gc_stride, skip);
 	kernels_count_launch();
 	return true;
 }
 
 template <int MODE>
-static bool launch_mode(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, cudaStream_t st) {
+static bool launch_mode(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, uint32_t max_rflen, cudaStream_t st) {
 	switch (a.cat) {
-	case CAT_U: return launch_cat<MODE, CAT_U>(a, max_rec_bytes, max_body, st);
-	case CAT_B: return launch_cat<MODE, CAT_B>(a, max_rec_bytes, max_body, st);
-	case CAT_C: return launch_cat<MODE, CAT_C>(a, max_rec_bytes, max_body, st);
-	default: return launch_cat<MODE, CAT_D>(a, max_rec_bytes, max_body, st);
+	case CAT_U: return launch_cat<MODE, CAT_U>(a, max_rec_bytes, max_body, max_rflen, st);
+	case CAT_B: return launch_cat<MODE, CAT_B>(a, max_rec_bytes, max_body, max_rflen, st);
+	case CAT_C: return launch_cat<MODE, CAT_C>(a, max_rec_bytes, max_body, max_rflen, st);
+	default: return launch_cat<MODE, CAT_D>(a, max_rec_bytes, max_body, max_rflen, st);
 	}
 }
 
@@ -629,10 +765,11 @@ void tiled_debug_report() {
 }
 #endif
 
-bool launch_simulate_tiled(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, cudaStream_t st) {
+bool launch_simulate_tiled(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, uint32_t max_rflen,
+                           cudaStream_t st) {
 	if (!a.nreads) return true;
-	if (a.rng_mode == QTIPSIM_RNG_REPLAY) return launch_mode<QTIPSIM_RNG_REPLAY>(a, max_rec_bytes, max_body, st);
-	return launch_mode<QTIPSIM_RNG_PHILOX>(a, max_rec_bytes, max_body, st);
+	if (a.rng_mode == QTIPSIM_RNG_REPLAY) return launch_mode<QTIPSIM_RNG_REPLAY>(a, max_rec_bytes, max_body, max_rflen, st);
+	return launch_mode<QTIPSIM_RNG_PHILOX>(a, max_rec_bytes, max_body, max_rflen, st);
 }
 
 }  // namespace qt

@@ -50,6 +50,7 @@ bool add_mate(Category &c, MateDesc &m, HostMateProg &hp, const char *qual, cons
 	m.rflen = rf;
 	m.ndraw = ndraw;
 	c.max_body = std::max(c.max_body, m.len);
+	c.max_rflen = std::max(c.max_rflen, rf);
 	c.max_score_len = std::max<uint32_t>(c.max_score_len, m.score_len);
 
 	// ---- compiled, output-oriented form for the tiled kernel ----
@@ -111,6 +112,10 @@ bool add_mate(Category &c, MateDesc &m, HostMateProg &hp, const char *qual, cons
 		if (c.segs.size() - m.seg_off > 65535 || c.ops.size() - m.ops_off > 65535) c.compiled_ok = false;
 		m.nseg = (uint16_t)(c.segs.size() - m.seg_off);
 		m.nops = (uint16_t)(c.ops.size() - m.ops_off);
+		if (segs.size() == 1 && segs[0].out_start == 0 && segs[0].out_end == L) {
+			m.single = 1;
+			m.ref0 = segs[0].ref0;
+		}
 	} else {
 		c.compiled_ok = false;
 	}

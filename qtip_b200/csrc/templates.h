@@ -35,6 +35,7 @@ struct Category {
 	bool compiled_ok = true;          // false: some mate exceeds the compiled format's limits
 	uint32_t max_body = 0;            // longest read body (either mate / random mate)
 	uint32_t max_score_len = 0;
+	uint32_t max_rflen = 0;           // longest reference span of a mate
 	std::vector<XStep> xsteps;        // host-side draw programs (replay planner)
 	std::vector<HostMateProg> prog;   // 2 per template
 	uint64_t added = 0;               // num_added(), input_model.h:68-70
