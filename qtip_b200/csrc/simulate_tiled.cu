@@ -223,18 +223,22 @@ __device__ __forceinline__ uint4 gen_qual(const char *__restrict__ qual_out, uin
 	}
 }
 
-// Stores bytes [lo, hi) of v at p (16-byte aligned shared memory); never touches other bytes.
-__device__ __forceinline__ void store_partial(unsigned char *p, const uint4 &v, int lo, int hi) {
-	const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+// Stores bytes [lo, hi) of v at p (16-byte aligned shared memory) and never disturbs the other
+// bytes, which belong to a neighbouring component another thread may be writing right now:
+// fully covered words are plain stores, partially covered words are cleared and set with
+// shared-memory atomics (AND / OR touch only this chunk's own bits).
+__device__ __forceinline__ void store_partial(unsigned char *p, const uint4 *lowmask, const uint4 &v, int lo, int hi) {
+	const uint4 m = range_mask(lowmask, lo, hi);
+	uint32_t *p32 = (uint32_t *)p;
+	const uint32_t mw[4] = {m.x, m.y, m.z, m.w};
+	const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
 	for (int k = 0; k < 4; k++) {
-		const int a = lo - 4 * k, b = hi - 4 * k;
-		if (a <= 0 && b >= 4) {
-			*(uint32_t *)(p + 4 * k) = w[k];
-		} else {
-#pragma unroll
-			for (int t = 0; t < 4; t++)
-				if (t >= a && t < b) p[4 * k + t] = (unsigned char)(w[k] >> (8 * t));
+		if (mw[k] == 0xffffffffu) {
+			p32[k] = vw[k];
+		} else if (mw[k]) {
+			atomicAnd(&p32[k], ~mw[k]);
+			atomicOr(&p32[k], vw[k] & mw[k]);
 		}
 	}
 }
@@ -541,7 +545,7 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 				else if (bi.flags & BF_SINGLE) v = cseq16_slow(gv, cache, gc0, fw, bi.gpos, s_gend[i], bi.ref0, k0);
 				else v = cgen_seq_segments(gv, cache, gc0, s_lowmask, a.c.segs + bi.segoff, bi.nseg, fw, L, bi.gpos, s_gend[i], k0);
 				if (k0 >= 0 && k0 + 16 <= L) *(uint4 *)(stg + 16 * (size_t)c) = v;
-				else store_partial(stg + 16 * (size_t)c, v, -k0, L - k0);
+				else store_partial(stg + 16 * (size_t)c, s_lowmask, v, -k0, L - k0);
 			}
 			// qualities: two chunks per iteration, loads issued before either is consumed
 			for (int q = tid; q < nitems && !(skip & 4); q += 2 * TL_THREADS) {
@@ -573,7 +577,7 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 					const uint4 v = rnd[u] ? make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u)  // 'I'
 					                       : qual_finish(ql[u]);
 					if (kq[u] >= 0 && kq[u] + 16 <= LL[u]) *(uint4 *)(stg + 16 * (size_t)cc[u]) = v;
-					else store_partial(stg + 16 * (size_t)cc[u], v, -kq[u], LL[u] - kq[u]);
+					else store_partial(stg + 16 * (size_t)cc[u], s_lowmask, v, -kq[u], LL[u] - kq[u]);
 				}
 			}
 		}
