@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
+#include <algorithm>
 #include <chrono>
 #include <map>
 #include <string>
@@ -69,6 +70,7 @@ struct qtipsim {
 	bool have_genome = false;
 	bool host_packed = false;  // hg.bases/nmask valid on the host (needed by the host planner)
 	DevBuf d_bases, d_nmask, d_recs, d_names;
+	DevBuf d_text, d_pk_a, d_pk_b, d_pk_c, d_pk_d, d_pk_e;  // K0 scratch
 	float ms_pack_pending = 0;
 
 	TemplateStore ts;
@@ -148,7 +150,7 @@ void qtipsim_destroy(qtipsim_t *h) {
 	if (!h) return;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->st);
-	DevBuf *all[] = {&h->d_bases, &h->d_nmask, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
+	DevBuf *all[] = {&h->d_text, &h->d_pk_a, &h->d_pk_b, &h->d_pk_c, &h->d_pk_d, &h->d_pk_e, &h->d_bases, &h->d_nmask, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
 	                 &h->d_ncount, &h->d_cum, &h->d_len0, &h->d_len1, &h->d_scan_tmp, &h->d_small};
 	for (DevBuf *b : all) b->release();
 	for (int c = 0; c < NCAT; c++) {
@@ -189,8 +191,175 @@ static int upload_genome(qtipsim *h) {
 	return QTIPSIM_OK;
 }
 
+// K0 on the device: `text` is the FASTA text in host memory.  The host only resolves header
+// lines; classification, counting and packing of the sequence bytes run on the GPU (pack.cu).
+static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
+	CK(cudaSetDevice(h->device));
+	cudaEvent_t e0, e1;
+	CK(cudaEventCreate(&e0));
+	CK(cudaEventCreate(&e1));
+	CK(cudaEventRecord(e0, h->st));
+	HostGenome &g = h->hg;
+	g.recs.clear();
+	g.names.clear();
+	g.bases.clear();
+	g.nmask.clear();
+	g.file_bytes = n;
+	CK(h->d_text.ensure(n + 64));
+	if (n) CK(cudaMemcpyAsync(h->d_text.p, text, n, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemsetAsync((char *)h->d_text.p + n, ' ', 64, h->st));
+	// ---- header lines: every '>' found by the GPU, resolved against the host text ----
+	const uint32_t cap = 1u << 22;
+	CK(h->d_pk_a.ensure((size_t)cap * 8 + 16));
+	CK(h->d_small.ensure(16 * 8));
+	CK(cudaMemsetAsync(h->d_small.p, 0, 16 * 8, h->st));
+	launch_find_gt(h->d_text.as<uint8_t>(), n, h->d_pk_a.as<uint64_t>(), cap, h->d_small.as<uint32_t>(), h->st);
+	uint32_t ngt = 0;
+	CK(cudaMemcpyAsync(&ngt, h->d_small.p, 4, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	std::vector<uint64_t> gts;
+	if (ngt > cap) {  // pathological: fall back to a host scan for '>'
+		for (const uint8_t *p = text, *e = text + n; p < e;) {
+			const uint8_t *q = (const uint8_t *)memchr(p, '>', (size_t)(e - p));
+			if (!q) break;
+			gts.push_back((uint64_t)(q - text));
+			p = q + 1;
+		}
+	} else {
+		gts.resize(ngt);
+		if (ngt) CK(cudaMemcpy(gts.data(), h->d_pk_a.p, (size_t)ngt * 8, cudaMemcpyDeviceToHost));
+		std::sort(gts.begin(), gts.end());
+	}
+	auto is_sp = [](uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); };
+	std::vector<uint64_t> seg_start, seg_end;
+	uint64_t hdr_end = 0;
+	// sequence bytes before the first header form a record with an empty name (fasta.cpp:72-124)
+	{
+		const uint64_t first = gts.empty() ? n : gts[0];
+		bool any = false;
+		for (uint64_t i = 0; i < first && !any; i++) any = !is_sp(text[i]);
+		if (any) {
+			RecDev r{0, 0, 0, 0};
+			g.recs.push_back(r);
+			seg_start.push_back(0);
+			seg_end.push_back(first);
+		}
+	}
+	for (size_t k = 0; k < gts.size(); k++) {
+		const uint64_t p = gts[k];
+		if (p < hdr_end) continue;  // a '>' inside a header line is part of the name
+		if (!seg_end.empty()) seg_end.back() = p;
+		uint64_t i = p + 1;
+		const uint64_t s0 = i;
+		while (i < n && !is_sp(text[i])) i++;
+		RecDev r{0, 0, (uint32_t)g.names.size(), (uint32_t)(i - s0)};
+		g.names.append((const char *)text + s0, (size_t)(i - s0));
+		while (i < n && text[i] != '\n' && text[i] != '\r') i++;
+		hdr_end = i;
+		g.recs.push_back(r);
+		seg_start.push_back(i);
+		seg_end.push_back(n);
+	}
+	const uint32_t nseg = (uint32_t)seg_start.size();
+	std::vector<uint64_t> unit_base((size_t)nseg + 1, 0);
+	for (uint32_t s = 0; s < nseg; s++) unit_base[s + 1] = unit_base[s] + (seg_end[s] - seg_start[s] + 4095) / 4096;
+	const uint64_t nunits = unit_base[nseg];
+	std::vector<uint64_t> unit_pref((size_t)nunits + 1, 0);
+	if (nunits) {
+		CK(h->d_pk_b.ensure((size_t)(3 * nseg + 1) * 8 + 16));
+		uint64_t *d_ss = h->d_pk_b.as<uint64_t>(), *d_se = d_ss + nseg, *d_ub = d_se + nseg;
+		CK(cudaMemcpyAsync(d_ss, seg_start.data(), nseg * 8, cudaMemcpyHostToDevice, h->st));
+		CK(cudaMemcpyAsync(d_se, seg_end.data(), nseg * 8, cudaMemcpyHostToDevice, h->st));
+		CK(cudaMemcpyAsync(d_ub, unit_base.data(), ((size_t)nseg + 1) * 8, cudaMemcpyHostToDevice, h->st));
+		CK(h->d_pk_c.ensure((size_t)nunits * 4 + 16));                   // counts
+		CK(h->d_pk_d.ensure(((size_t)nunits + 1) * 8 + 16));             // exclusive prefix
+		CK(h->d_pk_e.ensure(((size_t)nunits / 1024 + 4) * 8));           // scan scratch
+		launch_count_bases(h->d_text.as<uint8_t>(), d_ss, d_se, d_ub, nseg, nunits, h->d_pk_c.as<uint32_t>(), h->st);
+		launch_scan(h->d_pk_c.as<uint32_t>(), h->d_pk_d.as<uint64_t>(), nunits, h->d_pk_e.as<uint64_t>(),
+		            h->d_pk_d.as<uint64_t>() + nunits, h->st);
+		CK(cudaMemcpyAsync(unit_pref.data(), h->d_pk_d.p, ((size_t)nunits + 1) * 8, cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+	}
+	// ---- genome coordinates: 64 N in front, every record 64-aligned with an N gap behind it ----
+	std::vector<int64_t> seg_gbase(nseg);
+	std::vector<uint64_t> pad_lo, pad_hi;
+	uint64_t gp = 64;
+	pad_lo.push_back(0);
+	pad_hi.push_back(64);
+	for (uint32_t s = 0; s < nseg; s++) {
+		const uint64_t len = unit_pref[unit_base[s + 1]] - unit_pref[unit_base[s]];
+		g.recs[s].gstart = gp;
+		g.recs[s].len = len;
+		seg_gbase[s] = (int64_t)gp - (int64_t)unit_pref[unit_base[s]];
+		gp += len;
+		uint64_t end = (gp + 63) & ~(uint64_t)63;
+		if (end == gp) end += 64;
+		pad_lo.push_back(gp);
+		pad_hi.push_back(end);
+		gp = end;
+	}
+	g.total_bases = gp;
+	const size_t bw = (size_t)((gp + 15) / 16 + 4), mw = (size_t)((gp + 31) / 32 + 4);
+	CK(h->d_bases.ensure(bw * 4));
+	CK(h->d_nmask.ensure(mw * 4));
+	CK(cudaMemsetAsync(h->d_bases.p, 0, bw * 4, h->st));
+	CK(cudaMemsetAsync(h->d_nmask.p, 0, mw * 4, h->st));
+	if (nunits) {
+		CK(h->d_pk_a.ensure((size_t)nseg * 8 + 16));
+		CK(cudaMemcpyAsync(h->d_pk_a.p, seg_gbase.data(), nseg * 8, cudaMemcpyHostToDevice, h->st));
+		uint64_t *d_ss = h->d_pk_b.as<uint64_t>(), *d_se = d_ss + nseg, *d_ub = d_se + nseg;
+		launch_pack_units(h->d_text.as<uint8_t>(), d_ss, d_se, d_ub, nseg, nunits, h->d_pk_d.as<uint64_t>(),
+		                  h->d_pk_a.as<int64_t>(), h->d_bases.as<uint32_t>(), h->d_nmask.as<uint32_t>(), h->st);
+	}
+	{
+		const uint32_t np = (uint32_t)pad_lo.size();
+		CK(h->d_pk_c.ensure((size_t)np * 16 + 16));
+		uint64_t *d_lo = h->d_pk_c.as<uint64_t>(), *d_hi = d_lo + np;
+		CK(cudaMemcpyAsync(d_lo, pad_lo.data(), np * 8, cudaMemcpyHostToDevice, h->st));
+		CK(cudaMemcpyAsync(d_hi, pad_hi.data(), np * 8, cudaMemcpyHostToDevice, h->st));
+		launch_fill_n(d_lo, d_hi, np, h->d_nmask.as<uint32_t>(), h->st);
+	}
+	CK(h->d_recs.ensure(g.recs.size() * sizeof(RecDev) + 16));
+	CK(h->d_names.ensure(g.names.size() + 16));
+	if (!g.recs.empty())
+		CK(cudaMemcpyAsync(h->d_recs.p, g.recs.data(), g.recs.size() * sizeof(RecDev), cudaMemcpyHostToDevice, h->st));
+	if (!g.names.empty())
+		CK(cudaMemcpyAsync(h->d_names.p, g.names.data(), g.names.size(), cudaMemcpyHostToDevice, h->st));
+	CK(cudaEventRecord(e1, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	CK(cudaGetLastError());
+	float ms = 0;
+	cudaEventElapsedTime(&ms, e0, e1);
+	h->ms_pack_pending = ms;
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	h->have_genome = true;
+	h->host_packed = false;
+	h->have_result = false;
+	return QTIPSIM_OK;
+}
+
+// The host replay planner reads reference bases at X positions: fetch the packed genome back once.
+static int ensure_host_packed(qtipsim *h) {
+	if (h->host_packed) return QTIPSIM_OK;
+	const size_t bw = (size_t)((h->hg.total_bases + 15) / 16 + 4), mw = (size_t)((h->hg.total_bases + 31) / 32 + 4);
+	h->hg.bases.resize(bw);
+	h->hg.nmask.resize(mw);
+	CK(cudaMemcpyAsync(h->hg.bases.data(), h->d_bases.p, bw * 4, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(h->hg.nmask.data(), h->d_nmask.p, mw * 4, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	h->host_packed = true;
+	return QTIPSIM_OK;
+}
+
+static bool use_host_pack() {
+	const char *e = getenv("QTIPSIM_HOST_PACK");
+	return e && e[0] == '1';
+}
+
 int qtipsim_load_fasta_bytes(qtipsim_t *h, const void *bytes, size_t nbytes) {
 	if (!h || (!bytes && nbytes)) return QTIPSIM_EINVAL;
+	if (!use_host_pack()) return device_pack(h, (const uint8_t *)bytes, nbytes);
 	h->hg.parse((const uint8_t *)bytes, nbytes);
 	return upload_genome(h);
 }
@@ -211,6 +380,7 @@ int qtipsim_load_fasta(qtipsim_t *h, const char *const *paths, size_t npaths) {
 	const bool bad = ferror(fh) || got != buf.size();
 	fclose(fh);
 	if (bad) return h->fail(QTIPSIM_EIO, std::string("read error on FASTA file \"") + paths[0] + "\"");
+	if (!use_host_pack()) return device_pack(h, buf.data(), buf.size());
 	h->hg.parse(buf.data(), buf.size());
 	return upload_genome(h);
 }
@@ -417,7 +587,8 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 	uint64_t read_base[NCAT] = {0, 0, 0, 0};
 	uint64_t draws = 0;
 	if (p->rng_mode == QTIPSIM_RNG_REPLAY) {
-		if (!h->host_packed) return h->fail(QTIPSIM_ESTATE, "host copy of the packed genome missing");
+		rc = ensure_host_packed(h);
+		if (rc) return rc;
 		Plan plan;
 		rc = plan_replay_host(h->hg, h->ts, win, ncount, pp, LState{(uint32_t)p->cg1, (uint32_t)p->cg2}, plan, h->err);
 		if (rc) return rc;
@@ -571,7 +742,8 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 		stats->algorithmic_bytes = fq + small[8];
 		stats->kernel_launches = (uint32_t)(kernels_launch_count() - launches0);
 		float ms = 0;
-		stats->ms_pack = 0;
+		stats->ms_pack = h->ms_pack_pending;
+		h->ms_pack_pending = 0;
 		cudaEventElapsedTime(&ms, ev[0], ev[2]);
 		stats->ms_plan = ms;  // includes the host chain walk in REPLAY mode
 		(void)t_plan_host;

@@ -79,6 +79,15 @@ void launch_plan_philox(const Window *win, const uint64_t *cum, uint32_t nwin, u
                         uint32_t ntmpl, int cat, uint64_t seed, PlanRec *plan, uint64_t n,
                         uint64_t read_index_base, cudaStream_t st);
 
+// K0: FASTA text -> packed genome (pack.cu)
+void launch_find_gt(const uint8_t *text, uint64_t n, uint64_t *list, uint32_t cap, uint32_t *count, cudaStream_t st);
+void launch_count_bases(const uint8_t *text, const uint64_t *seg_start, const uint64_t *seg_end,
+                        const uint64_t *unit_base, uint32_t nseg, uint64_t nunits, uint32_t *counts, cudaStream_t st);
+void launch_pack_units(const uint8_t *text, const uint64_t *seg_start, const uint64_t *seg_end,
+                       const uint64_t *unit_base, uint32_t nseg, uint64_t nunits, const uint64_t *base_of_unit,
+                       const int64_t *seg_gbase, uint32_t *bases, uint32_t *nmask, cudaStream_t st);
+void launch_fill_n(const uint64_t *lo, const uint64_t *hi, uint32_t n, uint32_t *nmask, cudaStream_t st);
+
 int kernels_launch_count();  // kernels launched through the wrappers above since process start
 
 }  // namespace qt

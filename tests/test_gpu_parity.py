@@ -290,3 +290,12 @@ def test_generic_kernel_path_still_bit_exact(name, workdir, monkeypatch):
     monkeypatch.delenv("QTIPSIM_KERNEL")
     nat_t, _, _ = util.run_cuda(case, workdir, name, rng_mode=1, philox_seed=5)
     assert nat_g == nat_t  # both kernels consume the Philox stream identically
+
+
+def test_host_pack_path_equals_device_pack(workdir, monkeypatch):
+    """K0 on the device (default) and the host FASTA packer produce the same reads."""
+    case = cases.CASES["edges"]()
+    dev, _, _ = util.run_cuda(case, workdir, "edges")
+    monkeypatch.setenv("QTIPSIM_HOST_PACK", "1")
+    host, _, _ = util.run_cuda(case, workdir, "edges")
+    assert dev == host
