@@ -19,6 +19,7 @@
 #include "lecuyer.h"
 #include "philox.h"
 #include "planner.h"
+#include "resolve.h"
 #include "templates.h"
 
 using namespace qt;
@@ -75,7 +76,8 @@ struct qtipsim {
 
 	TemplateStore ts;
 	bool tmpl_dirty[NCAT] = {true, true, true, true};
-	DevBuf d_t[NCAT], d_qual[NCAT], d_xs[NCAT], d_qual_out[NCAT], d_ops[NCAT], d_segs[NCAT];
+	DevBuf d_t[NCAT], d_qual[NCAT], d_xs[NCAT], d_qual_out[NCAT], d_ops[NCAT], d_segs[NCAT], d_xsteps[NCAT], d_prog[NCAT];
+	DevBuf d_setups, d_pclass, d_rsresult;
 
 	DevBuf d_jt1, d_jt2;
 	bool have_jt = false;
@@ -150,7 +152,7 @@ void qtipsim_destroy(qtipsim_t *h) {
 	if (!h) return;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->st);
-	DevBuf *all[] = {&h->d_text, &h->d_pk_a, &h->d_pk_b, &h->d_pk_c, &h->d_pk_d, &h->d_pk_e, &h->d_bases, &h->d_nmask, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
+	DevBuf *all[] = {&h->d_setups, &h->d_pclass, &h->d_rsresult, &h->d_text, &h->d_pk_a, &h->d_pk_b, &h->d_pk_c, &h->d_pk_d, &h->d_pk_e, &h->d_bases, &h->d_nmask, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
 	                 &h->d_ncount, &h->d_cum, &h->d_len0, &h->d_len1, &h->d_scan_tmp, &h->d_small};
 	for (DevBuf *b : all) b->release();
 	for (int c = 0; c < NCAT; c++) {
@@ -160,6 +162,8 @@ void qtipsim_destroy(qtipsim_t *h) {
 		h->d_qual_out[c].release();
 		h->d_ops[c].release();
 		h->d_segs[c].release();
+		h->d_xsteps[c].release();
+		h->d_prog[c].release();
 		h->d_plan[c].release();
 		h->d_off0[c].release();
 		h->d_off1[c].release();
@@ -478,6 +482,13 @@ static int upload_templates(qtipsim *h) {
 				CK(cudaMemcpyAsync(h->d_ops[c].p, cg.ops.data(), cg.ops.size() * 4, cudaMemcpyHostToDevice, h->st));
 			if (!cg.segs.empty())
 				CK(cudaMemcpyAsync(h->d_segs[c].p, cg.segs.data(), cg.segs.size() * sizeof(SegDev), cudaMemcpyHostToDevice, h->st));
+			// draw programs for the device-side replay resolver
+			CK(h->d_xsteps[c].ensure(cg.xsteps.size() * sizeof(XStep) + 16));
+			CK(h->d_prog[c].ensure(cg.prog.size() * sizeof(HostMateProg) + 16));
+			if (!cg.xsteps.empty())
+				CK(cudaMemcpyAsync(h->d_xsteps[c].p, cg.xsteps.data(), cg.xsteps.size() * sizeof(XStep), cudaMemcpyHostToDevice, h->st));
+			if (!cg.prog.empty())
+				CK(cudaMemcpyAsync(h->d_prog[c].p, cg.prog.data(), cg.prog.size() * sizeof(HostMateProg), cudaMemcpyHostToDevice, h->st));
 		}
 		h->tmpl_dirty[c] = false;
 	}
@@ -586,7 +597,77 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 	uint64_t nreads[NCAT] = {0, 0, 0, 0};
 	uint64_t read_base[NCAT] = {0, 0, 0, 0};
 	uint64_t draws = 0;
-	if (p->rng_mode == QTIPSIM_RNG_REPLAY) {
+	const char *planner_env = getenv("QTIPSIM_PLANNER");
+	const bool host_planner = planner_env && strcmp(planner_env, "host") == 0;
+	if (p->rng_mode == QTIPSIM_RNG_REPLAY && !host_planner) {
+		// ---- K2 on the device: speculative resolution of the draw chain (resolve.cu) ----
+		// binomial set-ups per distinct window probability, computed with the host's libm
+		std::map<uint32_t, uint32_t> pclass_of;  // float bits of p -> class
+		std::vector<BinomSetup> setups;
+		std::vector<uint32_t> pclass(nwin, 0);
+		for (uint32_t w = (uint32_t)pp.win_lo; w < (uint32_t)pp.win_hi; w++) {
+			if (win[w].retsz < olap) continue;
+			const float bp = window_binom_p(win[w].retsz, olap, pp.tot_fasta_len);
+			uint32_t pb;
+			memcpy(&pb, &bp, 4);
+			auto it = pclass_of.find(pb);
+			if (it == pclass_of.end()) {
+				it = pclass_of.emplace(pb, (uint32_t)pclass_of.size()).first;
+				for (int c = 0; c < NCAT; c++) setups.push_back(binom_setup((int32_t)pp.target[c], bp));
+			}
+			pclass[w] = it->second;
+		}
+		if (setups.empty()) setups.resize(NCAT);
+		CK(h->d_setups.ensure(setups.size() * sizeof(BinomSetup)));
+		CK(h->d_pclass.ensure((size_t)nwin * 4 + 16));
+		CK(h->d_rsresult.ensure(8 * 8));
+		CK(cudaMemcpyAsync(h->d_setups.p, setups.data(), setups.size() * sizeof(BinomSetup), cudaMemcpyHostToDevice, h->st));
+		if (nwin) CK(cudaMemcpyAsync(h->d_pclass.p, pclass.data(), (size_t)nwin * 4, cudaMemcpyHostToDevice, h->st));
+		double grow = 1.0;
+		for (int attempt = 0;; attempt++) {
+			ResolveArgs ra;
+			ra.g = dg;
+			ra.win = h->d_win.as<Window>();
+			ra.ncount = h->d_ncount.as<uint32_t>();
+			ra.pclass = h->d_pclass.as<uint32_t>();
+			ra.setups = h->d_setups.as<BinomSetup>();
+			ra.win_lo = (uint32_t)pp.win_lo;
+			ra.win_hi = (uint32_t)pp.win_hi;
+			ra.olap = olap;
+			const double share = nwin ? (double)(pp.win_hi - pp.win_lo) / (double)nwin : 1.0;
+			for (int c = 0; c < NCAT; c++) {
+				ra.t[c] = h->d_t[c].as<TmplDesc>();
+				ra.xsteps[c] = h->d_xsteps[c].as<XStep>();
+				ra.prog[c] = h->d_prog[c].as<HostMateProg>();
+				ra.ntmpl[c] = (uint32_t)h->ts.cat[c].t.size();
+				ra.target[c] = pp.target[c];
+				// expected reads <= 1.1 * target * (this shard's share of the windows); generous margin
+				ra.cap[c] = pp.target[c] ? (uint64_t)((1.25 * share * (double)pp.target[c] + 65536.0) * grow) : 0;
+				if (ra.cap[c]) CK(h->d_plan[c].ensure(ra.cap[c] * sizeof(PlanRec)));
+				ra.plan[c] = h->d_plan[c].as<PlanRec>();
+			}
+			ra.jt1 = h->d_jt1.as<uint32_t>();
+			ra.jt2 = h->d_jt2.as<uint32_t>();
+			ra.s1 = (uint32_t)p->cg1;
+			ra.s2 = (uint32_t)p->cg2;
+			ra.result = h->d_rsresult.as<unsigned long long>();
+			launch_resolve_replay(ra, h->st);
+			unsigned long long res[8];
+			CK(cudaMemcpyAsync(res, h->d_rsresult.p, sizeof(res), cudaMemcpyDeviceToHost, h->st));
+			CK(cudaStreamSynchronize(h->st));
+			if (res[7] == 3 && attempt < 6) {  // plan buffer too small: retry larger
+				grow *= 2.0;
+				continue;
+			}
+			if (res[7] == 1) return h->fail(QTIPSIM_ERANGE, "window with zero slots (assert(nslots > 0), simplesim.cpp:252)");
+			if (res[7]) return h->fail(QTIPSIM_ERANGE, "replay resolver failed");
+			for (int c = 0; c < NCAT; c++) nreads[c] = res[c];
+			p->cg1 = (int32_t)res[4];
+			p->cg2 = (int32_t)res[5];
+			draws = res[6];
+			break;
+		}
+	} else if (p->rng_mode == QTIPSIM_RNG_REPLAY) {
 		rc = ensure_host_packed(h);
 		if (rc) return rc;
 		Plan plan;

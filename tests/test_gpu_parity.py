@@ -299,3 +299,15 @@ def test_host_pack_path_equals_device_pack(workdir, monkeypatch):
     monkeypatch.setenv("QTIPSIM_HOST_PACK", "1")
     host, _, _ = util.run_cuda(case, workdir, "edges")
     assert dev == host
+
+
+@pytest.mark.parametrize("name", ["mixed_small", "c4_mix_small", "edges"])
+def test_host_planner_path_still_bit_exact(name, workdir, monkeypatch):
+    """The host chain walk (QTIPSIM_PLANNER=host) and the device resolver (default) agree."""
+    case = cases.CASES[name]()
+    dev, st_d, p_d = util.run_cuda(case, workdir, name)
+    monkeypatch.setenv("QTIPSIM_PLANNER", "host")
+    host, st_h, p_h = util.run_cuda(case, workdir, name)
+    assert dev == host
+    assert (p_d.cg1, p_d.cg2) == (p_h.cg1, p_h.cg2)
+    assert st_d.draws == st_h.draws
