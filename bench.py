@@ -187,7 +187,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=float(os.environ.get("QTIP_BENCH_SCALE", "1.0")),
                     help="shrink genome and read counts together (1.0 = the BASELINE.json configuration)")
-    ap.add_argument("--mode", default="replay", choices=["replay", "native"])
+    ap.add_argument("--mode", default="native", choices=["replay", "native"],
+                    help="RNG mode of the primary numbers; the other mode is measured too (1 step) and reported alongside")
+    ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -283,23 +285,23 @@ def main():
 
     kw = wl["kw"]
     state_buf = torch.zeros(2, dtype=torch.int64, device="cuda")
+    host_out = [None] * _abi.NOUT
 
-    def one_step(seed, e2e=False, host_out=None):
-        """Runs one step on this rank's shard; returns (stats, h2d_bytes)."""
-        h2d = 0
+    def one_step(seed, rng_mode, e2e=False):
+        """Runs one step on this rank's shard; returns stats."""
         if e2e:
             if rank == 0 and world == 1:
-                eng.load_fasta_bytes(fa_pinned.numpy())  # parse + pack + upload of the FASTA text
-                h2d += int(eng.lib.qtipsim_num_estimated_bases(eng.h))  # counted below from the packed size
+                eng.load_fasta_bytes(fa_pinned.numpy())  # H2D of the FASTA text + device pack
             set_templates()
         cg = cli_seed(seed)
-        if world > 1 and rng_mode == _abi.RNG_REPLAY and rank > 0:
-            dist.recv(state_buf, src=rank - 1)  # the chain is sequential across shards
+        chain = world > 1 and rng_mode == _abi.RNG_REPLAY
+        if chain and rank > 0:
+            dist.recv(state_buf, src=rank - 1)  # the replay chain is sequential across shards
             cg = (int(state_buf[0].item()), int(state_buf[1].item()))
         p = sim.make_params(CHUNKSZ, kw["fraction"], kw["function"], kw["min_u"], kw["min_c"], kw["min_d"], kw["min_b"],
                             rng_mode, cg=cg, philox_seed=seed, shard_rank=rank, shard_count=world)
         st = eng.run(p)
-        if world > 1 and rng_mode == _abi.RNG_REPLAY and rank < world - 1:
+        if chain and rank < world - 1:
             state_buf[0], state_buf[1] = p.cg1, p.cg2
             dist.send(state_buf, dst=rank + 1)
         if e2e:
@@ -318,57 +320,73 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm ----
-    for i in range(args.warmup):
-        one_step(100 + i)
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    t0 = time.perf_counter()
-    agg = dict(reads=0, bytes=0, alg=0, launches=0, ms_plan=0.0, ms_sim=0.0, ms_total=0.0)
-    for i in range(args.steps):
-        st = one_step(200 + i)
-        agg["reads"] += sum(st.wrote)
-        agg["bytes"] += sum(st.bytes)
-        agg["alg"] += int(st.algorithmic_bytes)
-        agg["launches"] += int(st.kernel_launches)
-        agg["ms_plan"] += st.ms_plan
-        agg["ms_sim"] += st.ms_simulate
-        agg["ms_total"] += st.ms_total
-    ev1.record()
-    torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    ev_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
-    barrier()
+    def measure(rng_mode, steps, warmup, with_clocks):
+        """Device-resident arm + end-to-end arm for one RNG mode; returns a dict (rank 0) of reduced numbers."""
+        for i in range(warmup):
+            one_step(100 + i, rng_mode)
+        sampler = ClockSampler(local_rank) if with_clocks else None
+        barrier()
+        if sampler:
+            sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        t0 = time.perf_counter()
+        agg = dict(reads=0, bytes=0, alg=0, launches=0, ms_plan=0.0, ms_sim=0.0, ms_total=0.0)
+        for i in range(steps):
+            st = one_step(200 + i, rng_mode)
+            agg["reads"] += sum(st.wrote)
+            agg["bytes"] += sum(st.bytes)
+            agg["alg"] += int(st.algorithmic_bytes)
+            agg["launches"] += int(st.kernel_launches)
+            agg["ms_plan"] += st.ms_plan
+            agg["ms_sim"] += st.ms_simulate
+            agg["ms_total"] += st.ms_total
+        ev1.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ev_ms = ev0.elapsed_time(ev1)
+        clocks = sampler.stop() if sampler else None
+        barrier()
+        # end-to-end arm (host buffers; H2D of the FASTA text and templates, D2H of the FASTQ bytes inside)
+        one_step(300, rng_mode, e2e=True)  # warm (allocates the pinned result buffers)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_reads, e2e_d2h, e2e_launch = 0, 0, 0
+        e2e_steps = max(1, min(steps, 2))
+        for i in range(e2e_steps):
+            st = one_step(400 + i, rng_mode, e2e=True)
+            e2e_reads += sum(st.wrote)
+            e2e_d2h += sum(st.bytes)
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_ms = e0.elapsed_time(e1)
+        barrier()
+        t = torch.tensor([ev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
+        w = torch.tensor([agg["reads"], agg["bytes"], agg["alg"], agg["launches"], e2e_reads, e2e_d2h], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        ev_ms, e2e_ms, wall_ms = [float(x) for x in t.tolist()]
+        reads, obytes, alg, launches, e2e_reads, e2e_d2h = [float(x) for x in w.tolist()]
+        sim_ms_step = agg["ms_sim"] / steps
+        alg_step_rank0 = agg["alg"] / steps
+        achieved = alg_step_rank0 / (sim_ms_step * 1e-3) / 1e9 if sim_ms_step > 0 else 0.0
+        h2d = 0
+        if world == 1:
+            h2d = sum(l for _, l in wl["records"]) * 71 // 70 + 64 * len(wl["records"])  # FASTA text bytes
+        return dict(value=reads / (ev_ms * 1e-3), ms_per_step=ev_ms / steps, wall_ms_per_step=wall_ms / steps,
+                    output_gb_per_s=obytes / (ev_ms * 1e-3) / 1e9, reads_per_step=reads / steps,
+                    phase={"plan": agg["ms_plan"] / steps, "simulate": sim_ms_step, "total": agg["ms_total"] / steps},
+                    achieved=achieved, alg_step=alg_step_rank0, launches=int(launches), clocks=clocks,
+                    e2e={"value": e2e_reads / (e2e_ms * 1e-3), "unit": wl["unit"], "h2d_bytes_per_step": int(h2d),
+                         "d2h_bytes_per_step": int(e2e_d2h / e2e_steps), "ms_per_step": e2e_ms / e2e_steps,
+                         "output_gb_per_s": e2e_d2h / (e2e_ms * 1e-3) / 1e9})
 
-    # ---- end-to-end arm (host buffers, H2D/D2H inside) ----
-    host_out = [None] * _abi.NOUT
-    one_step(300, e2e=True, host_out=host_out)  # warm (allocates pinned buffers)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    e2e_reads, e2e_d2h = 0, 0
-    e2e_steps = max(1, min(args.steps, 2))
-    for i in range(e2e_steps):
-        st = one_step(400 + i, e2e=True, host_out=host_out)
-        e2e_reads += sum(st.wrote)
-        e2e_d2h += sum(st.bytes)
-    e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1)
-    barrier()
-
-    # ---- reduce over ranks: time = max, work = sum ----
-    t = torch.tensor([ev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
-    w = torch.tensor([agg["reads"], agg["bytes"], agg["alg"], agg["launches"], e2e_reads, e2e_d2h], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-    ev_ms, e2e_ms, wall_ms = [float(x) for x in t.tolist()]
-    reads, obytes, alg, launches, e2e_reads, e2e_d2h = [float(x) for x in w.tolist()]
+    primary_mode = _abi.RNG_PHILOX if args.mode == "native" else _abi.RNG_REPLAY
+    other_mode = _abi.RNG_REPLAY if args.mode == "native" else _abi.RNG_PHILOX
+    m = measure(primary_mode, args.steps, args.warmup, True)
+    m2 = None if args.no_secondary else measure(other_mode, 1, 1, False)
 
     if rank == 0:
         peaks = {}
@@ -379,39 +397,34 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        ms_step = ev_ms / args.steps
-        # dominant kernel: k_simulate; its launches per step = categories with reads; achieved =
-        # algorithmic bytes of the step / device time of those launches (CUDA events on the library's stream)
-        sim_ms_step = agg["ms_sim"] / args.steps
-        alg_step_rank0 = agg["alg"] / args.steps
-        achieved = alg_step_rank0 / (sim_ms_step * 1e-3) / 1e9 if sim_ms_step > 0 else 0.0
-        # H2D per e2e step: packed genome (2 bit + 1 bit per base) + templates + plan records
-        h2d = 0
-        if world == 1:
-            tot_bases = sum(l for _, l in wl["records"])
-            h2d = tot_bases // 4 + tot_bases // 8 + int(e2e_reads / e2e_steps) * 24
+        names = {"native": "philox (native counter-based RNG: the product default)",
+                 "replay": "replay (consumes the reference's rnglib/ranlib stream: bit-exact with the reference)"}
+        other = "replay" if args.mode == "native" else "native"
         line = {
-            "metric": METRIC, "value": reads / (ev_ms * 1e-3), "unit": wl["unit"], "n_gpus": n_gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": m["value"], "unit": wl["unit"], "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": wl["name"], "rng_mode": args.mode, "chunksz": CHUNKSZ, "scale": args.scale,
+            "config": {"workload": wl["name"], "rng_mode": names[args.mode], "chunksz": CHUNKSZ, "scale": args.scale,
                        "l2": "per-step working set (packed genome + FASTQ output) is GBs, far larger than the 126 MB L2",
                        "parallelism": f"windows sharded across {world} rank(s); packed genome broadcast over NCCL"},
-            "output_gb_per_s": obytes / (ev_ms * 1e-3) / 1e9,
-            "reads_per_step": reads / args.steps,
-            "wall_ms_per_step": wall_ms / args.steps,
-            "phase_ms_per_step_rank0": {"plan": agg["ms_plan"] / args.steps, "simulate": sim_ms_step,
-                                        "total": agg["ms_total"] / args.steps},
-            "roofline": {"bound": "hbm", "kernel": "k_simulate", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_step": alg_step_rank0},
-            "e2e": {"value": e2e_reads / (e2e_ms * 1e-3), "unit": wl["unit"], "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(e2e_d2h / e2e_steps), "ms_per_step": e2e_ms / e2e_steps,
-                    "output_gb_per_s": e2e_d2h / (e2e_ms * 1e-3) / 1e9},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
+            "output_gb_per_s": m["output_gb_per_s"],
+            "reads_per_step": m["reads_per_step"],
+            "wall_ms_per_step": m["wall_ms_per_step"],
+            "phase_ms_per_step_rank0": m["phase"],
+            "roofline": {"bound": "hbm", "kernel": "k_simulate_tiled", "achieved": m["achieved"], "peak": peak, "unit": "GB/s",
+                         "frac": m["achieved"] / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": m["alg_step"]},
+            "e2e": m["e2e"],
+            "gpu_launches": m["launches"],
+            "clocks": m["clocks"],
             "setup_s": setup_s,
         }
+        if m2 is not None:
+            line[other] = {"rng_mode": names[other], "value": m2["value"], "unit": wl["unit"], "ms_per_step": m2["ms_per_step"],
+                           "phase_ms_per_step_rank0": m2["phase"], "steps": 1, "warmup": 1,
+                           "roofline": {"achieved": m2["achieved"], "frac": m2["achieved"] / peak if peak else None,
+                                        "kernel": "k_simulate_tiled"},
+                           "e2e": m2["e2e"], "output_gb_per_s": m2["output_gb_per_s"]}
         if n_gpus == 1 and not args.no_cpu_baseline:
             res, why = run_reference_steps(wl, 1, 0)
             if res is not None:

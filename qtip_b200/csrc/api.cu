@@ -509,23 +509,26 @@ static int upload_templates(qtipsim *h) {
 	return QTIPSIM_OK;
 }
 
-// PHILOX mode: per-window counts ~ Binomial(target, p_window), the same model as the
-// reference (simplesim.cpp:224-226,242,279,340-341), drawn from a Philox stream keyed
-// by (seed, window, category).
-static uint64_t philox_window_count(const BinomSetup &bs, uint64_t seed, uint32_t win, int cat) {
-	uint32_t ctr = 0;
-	uint32_t have = 0;
-	Philox4 blk{};
-	auto nx = [&]() -> float {
-		if (!have) {
-			blk = philox4x32(win, 0u, ctr++, PHILOX_DOM_WINDOW | (uint32_t)cat, (uint32_t)seed, (uint32_t)(seed >> 32));
-			have = 4;
+// Binomial set-ups (ignbin's (n, p)-dependent constants, computed with the host's libm) for every
+// distinct window probability in [lo, hi); pclass[w] = row of the table for window w.
+static void window_setups(const std::vector<Window> &win, uint64_t olap, const PlanParams &pp, uint32_t lo, uint32_t hi,
+                          std::vector<uint32_t> &pclass, std::vector<BinomSetup> &setups) {
+	std::map<uint32_t, uint32_t> pclass_of;  // float bits of p -> class
+	pclass.assign(win.size(), 0);
+	setups.clear();
+	for (uint32_t w = lo; w < hi; w++) {
+		if (win[w].retsz < olap) continue;
+		const float bp = window_binom_p(win[w].retsz, olap, pp.tot_fasta_len);
+		uint32_t pb;
+		memcpy(&pb, &bp, 4);
+		auto it = pclass_of.find(pb);
+		if (it == pclass_of.end()) {
+			it = pclass_of.emplace(pb, (uint32_t)pclass_of.size()).first;
+			for (int c = 0; c < NCAT; c++) setups.push_back(binom_setup((int32_t)pp.target[c], bp));
 		}
-		const uint32_t x = blk.v[4 - have];
-		have--;
-		return (float)((x >> 8) + 1u) * (1.0f / 16777216.0f);  // (0, 1]
-	};
-	return (uint64_t)binom_sample(bs, nx);
+		pclass[w] = it->second;
+	}
+	if (setups.empty()) setups.resize(NCAT);
 }
 
 int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
@@ -602,22 +605,9 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 	if (p->rng_mode == QTIPSIM_RNG_REPLAY && !host_planner) {
 		// ---- K2 on the device: speculative resolution of the draw chain (resolve.cu) ----
 		// binomial set-ups per distinct window probability, computed with the host's libm
-		std::map<uint32_t, uint32_t> pclass_of;  // float bits of p -> class
 		std::vector<BinomSetup> setups;
-		std::vector<uint32_t> pclass(nwin, 0);
-		for (uint32_t w = (uint32_t)pp.win_lo; w < (uint32_t)pp.win_hi; w++) {
-			if (win[w].retsz < olap) continue;
-			const float bp = window_binom_p(win[w].retsz, olap, pp.tot_fasta_len);
-			uint32_t pb;
-			memcpy(&pb, &bp, 4);
-			auto it = pclass_of.find(pb);
-			if (it == pclass_of.end()) {
-				it = pclass_of.emplace(pb, (uint32_t)pclass_of.size()).first;
-				for (int c = 0; c < NCAT; c++) setups.push_back(binom_setup((int32_t)pp.target[c], bp));
-			}
-			pclass[w] = it->second;
-		}
-		if (setups.empty()) setups.resize(NCAT);
+		std::vector<uint32_t> pclass;
+		window_setups(win, olap, pp, (uint32_t)pp.win_lo, (uint32_t)pp.win_hi, pclass, setups);
 		CK(h->d_setups.ensure(setups.size() * sizeof(BinomSetup)));
 		CK(h->d_pclass.ensure((size_t)nwin * 4 + 16));
 		CK(h->d_rsresult.ensure(8 * 8));
@@ -684,36 +674,38 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 		p->cg2 = (int32_t)plan.rng_out.s2;
 		draws = plan.draws;
 	} else {
-		std::map<std::pair<int32_t, uint32_t>, BinomSetup> setups;
-		std::vector<uint64_t> cum((size_t)nwin + 1);
+		// ---- PHILOX: per-window counts ~ Binomial(target, p_window) drawn on the device from a Philox
+		// stream keyed by (seed, window, category); prefix sums give each read's window ----
+		std::vector<BinomSetup> setups;
+		std::vector<uint32_t> pclass;
+		window_setups(win, olap, pp, 0, nwin, pclass, setups);
+		CK(h->d_setups.ensure(setups.size() * sizeof(BinomSetup)));
+		CK(h->d_pclass.ensure((size_t)nwin * 4 + 16));
+		CK(cudaMemcpyAsync(h->d_setups.p, setups.data(), setups.size() * sizeof(BinomSetup), cudaMemcpyHostToDevice, h->st));
+		if (nwin) CK(cudaMemcpyAsync(h->d_pclass.p, pclass.data(), (size_t)nwin * 4, cudaMemcpyHostToDevice, h->st));
+		CK(h->d_len0.ensure((size_t)nwin * 4 + 16));
+		CK(h->d_scan_tmp.ensure(((size_t)nwin / 1024 + 4) * 8));
+		CK(h->d_cum.ensure(((size_t)nwin + 1) * 8 * NCAT));
+		uint64_t edge[NCAT][2];
 		for (int c = 0; c < NCAT; c++) {
-			uint64_t acc = 0;
-			for (uint32_t w = 0; w < nwin; w++) {
-				cum[w] = acc;
-				if (!pp.target[c] || !window_live(win[w].retsz, olap, ncount[w])) continue;
-				const float bp = window_binom_p(win[w].retsz, olap, pp.tot_fasta_len);
-				uint32_t pb;
-				memcpy(&pb, &bp, 4);
-				auto key = std::make_pair((int32_t)pp.target[c], pb);
-				auto it = setups.find(key);
-				if (it == setups.end()) it = setups.emplace(key, binom_setup((int32_t)pp.target[c], bp)).first;
-				acc += philox_window_count(it->second, p->philox_seed, w, c);
-			}
-			cum[nwin] = acc;
-			const uint64_t lo = cum[pp.win_lo], hi = cum[pp.win_hi];
-			nreads[c] = hi - lo;
-			read_base[c] = lo;
+			uint64_t *cum = h->d_cum.as<uint64_t>() + (size_t)c * (nwin + 1);
+			launch_philox_counts(h->d_win.as<Window>(), h->d_ncount.as<uint32_t>(), h->d_pclass.as<uint32_t>(),
+			                     h->d_setups.as<BinomSetup>(), nwin, olap, pp.target[c], p->philox_seed, c,
+			                     h->d_len0.as<uint32_t>(), h->st);
+			launch_scan(h->d_len0.as<uint32_t>(), cum, nwin, h->d_scan_tmp.as<uint64_t>(), cum + nwin, h->st);
+			CK(cudaMemcpyAsync(&edge[c][0], cum + pp.win_lo, 8, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaMemcpyAsync(&edge[c][1], cum + pp.win_hi, 8, cudaMemcpyDeviceToHost, h->st));
+		}
+		CK(cudaStreamSynchronize(h->st));
+		for (int c = 0; c < NCAT; c++) {
+			nreads[c] = edge[c][1] - edge[c][0];
+			read_base[c] = edge[c][0];
 			if (!nreads[c]) continue;
-			// shard-local cumulative counts
-			std::vector<uint64_t> loc(pp.win_hi - pp.win_lo + 1);
-			for (uint64_t w = pp.win_lo; w <= pp.win_hi; w++) loc[w - pp.win_lo] = cum[w] - lo;
-			CK(h->d_cum.ensure(loc.size() * 8));
-			CK(cudaMemcpyAsync(h->d_cum.p, loc.data(), loc.size() * 8, cudaMemcpyHostToDevice, h->st));
+			const uint64_t *cum = h->d_cum.as<uint64_t>() + (size_t)c * (nwin + 1);
 			CK(h->d_plan[c].ensure(nreads[c] * sizeof(PlanRec)));
-			launch_plan_philox(h->d_win.as<Window>() + pp.win_lo, h->d_cum.as<uint64_t>(), (uint32_t)(pp.win_hi - pp.win_lo),
-			                   olap, (uint32_t)h->ts.cat[c].t.size(), c, p->philox_seed, h->d_plan[c].as<PlanRec>(),
-			                   nreads[c], lo, h->st);
-			CK(cudaStreamSynchronize(h->st));  // loc dies at scope end; d_cum reused next category
+			launch_plan_philox(h->d_win.as<Window>() + pp.win_lo, cum + pp.win_lo, (uint32_t)(pp.win_hi - pp.win_lo), olap,
+			                   (uint32_t)h->ts.cat[c].t.size(), c, p->philox_seed, h->d_plan[c].as<PlanRec>(), nreads[c],
+			                   read_base[c], h->st);
 		}
 	}
 	const double t_plan_host = now_ms() - t_plan0;

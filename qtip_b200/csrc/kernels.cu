@@ -251,21 +251,58 @@ void launch_scan(const uint32_t *len, uint64_t *off, uint64_t n, uint64_t *tmp, 
 
 // -------------------------------------------------------------- philox plan --
 
+// Per-window read counts in native mode: Binomial(target, p_window) -- the reference's own model
+// (simplesim.cpp:224-226, 242, 279, 340-341) -- sampled with binom_sample from a Philox stream keyed
+// by (seed, window, category).  One thread per window.
+__global__ void __launch_bounds__(128) k_philox_counts(const Window *win, const uint32_t *ncount, const uint32_t *pclass,
+                                                        const BinomSetup *setups, uint32_t nwin, uint64_t olap,
+                                                        uint64_t target, uint64_t seed, int cat, uint32_t *counts) {
+	const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+	if (w >= nwin) return;
+	const Window wn = win[w];
+	uint32_t n = 0;
+	if (target && wn.retsz >= olap && !((int)ncount[w] > (int)(0.9 * (double)wn.retsz))) {
+		const BinomSetup bs = setups[(size_t)pclass[w] * NCAT + cat];
+		uint32_t ctr = 0, have = 0;
+		Philox4 blk{};
+		auto nx = [&]() -> float {
+			if (!have) {
+				blk = philox4x32(w, 0u, ctr++, PHILOX_DOM_WINDOW | (uint32_t)cat, (uint32_t)seed, (uint32_t)(seed >> 32));
+				have = 4;
+			}
+			const uint32_t x = blk.v[4 - have];
+			have--;
+			return __fmul_rn((float)((x >> 8) + 1u), 1.0f / 16777216.0f);  // (0, 1]
+		};
+		n = (uint32_t)binom_sample(bs, nx);
+	}
+	counts[w] = n;
+}
+
+void launch_philox_counts(const Window *win, const uint32_t *ncount, const uint32_t *pclass, const BinomSetup *setups,
+                          uint32_t nwin, uint64_t olap, uint64_t target, uint64_t seed, int cat, uint32_t *counts,
+                          cudaStream_t st) {
+	if (!nwin) return;
+	k_philox_counts<<<(nwin + 127) / 128, 128, 0, st>>>(win, ncount, pclass, setups, nwin, olap, target, seed, cat, counts);
+	g_launches++;
+}
+
 __global__ void __launch_bounds__(256) k_plan_philox(const Window *win, const uint64_t *cum, uint32_t nwin,
                                                       uint64_t olap, uint32_t ntmpl, int cat, uint64_t seed,
                                                       PlanRec *plan, uint64_t n, uint64_t read_index_base) {
 	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n) return;
-	// window of read r: last w with cum[w] <= r  (length-weighted choice was made when the
-	// per-window counts were drawn; this is the binary search over their prefix sums)
-	uint32_t lo = 0, hi = nwin;  // invariant: cum[lo] <= r < cum[hi]
+	// window of read r: last w with cum[w] <= global index (the length-weighted choice was made when the
+	// per-window counts were drawn; this is the binary search over their prefix sums).
+	// cum[] holds GLOBAL cumulative counts for this shard's windows; read_index_base = cum[0].
+	const uint64_t gi = read_index_base + r;
+	uint32_t lo = 0, hi = nwin;  // invariant: cum[lo] <= gi < cum[hi]
 	while (hi - lo > 1) {
 		const uint32_t mid = (lo + hi) >> 1;
-		if (cum[mid] <= r) lo = mid;
+		if (cum[mid] <= gi) lo = mid;
 		else hi = mid;
 	}
 	const Window w = win[lo];
-	const uint64_t gi = read_index_base + r;
 	const Philox4 x = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), 0u, PHILOX_DOM_PLAN | (uint32_t)cat,
 	                             (uint32_t)seed, (uint32_t)(seed >> 32));
 	const uint64_t nslots = (uint64_t)w.retsz - olap;

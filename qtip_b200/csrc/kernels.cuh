@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include "../../include/qtipsim.h"
 #include "common.h"
+#include "lecuyer.h"
 
 namespace qt {
 
@@ -73,6 +74,10 @@ bool launch_simulate_tiled(const SimArgs &a, uint32_t max_rec_bytes, uint32_t ma
                            cudaStream_t st);
 void kernels_count_launch();
 
+// PHILOX planning: per-window counts on the device
+void launch_philox_counts(const Window *win, const uint32_t *ncount, const uint32_t *pclass, const BinomSetup *setups,
+                          uint32_t nwin, uint64_t olap, uint64_t target, uint64_t seed, int cat, uint32_t *counts,
+                          cudaStream_t st);
 // PHILOX planning: fills plan[] for reads [0, n) of one category from per-window
 // cumulative counts (cum[w] = reads before window w, cum[nwin] = n).
 void launch_plan_philox(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap,

@@ -87,6 +87,7 @@ class Engine:
             raise QtipSimError(rc, self.lib.qtipsim_last_error(None).decode())
         self.h = h
         self._keep = []
+        self._marsh = {}
 
     def close(self):
         if getattr(self, "h", None):
@@ -120,12 +121,21 @@ class Engine:
             a = np.ascontiguousarray(data, dtype=np.uint8)
             self.check(self.lib.qtipsim_load_fasta_bytes(self.h, C.c_void_p(a.ctypes.data), a.size))
 
+    def _marshalled(self, cat: int, ts, fn):
+        # the ctypes array for a template list is built once and reused (the C call itself is cheap)
+        key = (cat, id(ts), len(ts))
+        hit = self._marsh.get(cat)
+        if hit is None or hit[0] != key:
+            arr, keep = fn(ts)
+            self._marsh[cat] = (key, arr, keep)
+        return self._marsh[cat][1]
+
     def set_unpaired(self, cat: int, ts: Sequence[TemplateUnpaired], added: Optional[int] = None):
-        arr, keep = marshal_unpaired(ts)
+        arr = self._marshalled(cat, ts, marshal_unpaired)
         self.check(self.lib.qtipsim_set_templates_unpaired(self.h, cat, arr, len(ts), len(ts) if added is None else added))
 
     def set_paired(self, cat: int, ts: Sequence[TemplatePaired], added: Optional[int] = None):
-        arr, keep = marshal_paired(ts)
+        arr = self._marshalled(cat, ts, marshal_paired)
         self.check(self.lib.qtipsim_set_templates_paired(self.h, cat, arr, len(ts), len(ts) if added is None else added))
 
     def olap(self) -> int:
