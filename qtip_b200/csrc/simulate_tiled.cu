@@ -56,7 +56,10 @@ __device__ unsigned long long g_qt_violation[4];
 #define QT_CHK(cond, id, v0, v1) do { } while (0)
 #endif
 
-static constexpr int TL_THREADS = 256;
+#ifndef QT_TL_THREADS
+#define QT_TL_THREADS 256
+#endif
+static constexpr int TL_THREADS = QT_TL_THREADS;
 static constexpr uint32_t TL_STAGE_DEFAULT = 52 * 1024;  // dynamic shared memory per CTA (4 CTAs per SM)
 
 enum : uint8_t { BF_FW = 1, BF_RANDOM = 2, BF_SLOW = 4, BF_SINGLE = 8 };
@@ -525,60 +528,103 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 		for (int s = 0; s < NS; s++) {
 			unsigned char *stg = stage + (size_t)s * stage_stride;
 			const BodyInfo *body = s_body + s * R;
-			// sequence
-			for (int q = tid; q < nitems && !(skip & 2); q += TL_THREADS) {
-				const int i = q / K;
-				const int j = q - i * K;
-				const BodyInfo bi = body[i];
-				if (bi.flags & BF_RANDOM) continue;  // every base of a random mate is a draw (phase C)
-				const int L = bi.L;
-				const int c = (int)(bi.P >> 4) + j;
-				const int k0 = 16 * c - (int)bi.P;  // output position of the chunk's first byte, >= -15
-				if (k0 >= L) continue;
-				QT_CHK(c >= 0 && 16u * (uint32_t)c + 16u <= stage_stride, 3, c, bi.P);
-				const int cm = (CAT == CAT_C || CAT == CAT_D) ? s : 0;
-				const uint32_t *cache = (const uint32_t *)(gcache + ((size_t)cm * R + i) * gc_stride);
-				const uint64_t gc0 = gcache_origin(bi.gpos);
-				uint4 v;
-				const bool fw = (bi.flags & BF_FW) != 0;
-				if ((bi.flags & (BF_SINGLE | BF_SLOW)) == BF_SINGLE) v = cseq16_fast(cache, gc0, fw, bi.gpos, bi.ref0, k0);
-				else if (bi.flags & BF_SINGLE) v = cseq16_slow(gv, cache, gc0, fw, bi.gpos, s_gend[i], bi.ref0, k0);
-				else v = cgen_seq_segments(gv, cache, gc0, s_lowmask, a.c.segs + bi.segoff, bi.nseg, fw, L, bi.gpos, s_gend[i], k0);
-				if (k0 >= 0 && k0 + 16 <= L) *(uint4 *)(stg + 16 * (size_t)c) = v;
-				else store_partial(stg + 16 * (size_t)c, s_lowmask, v, -k0, L - k0);
+			// (i, j) = (read, chunk) of item q = i*K + j, advanced without a division
+			const int di = TL_THREADS / K, dj = TL_THREADS - di * K;
+			// sequence: whole chunks only
+			{
+				int i = tid / K, j = tid - i * K;
+				for (int q = tid; q < nitems && !(skip & 2); q += TL_THREADS) {
+					const BodyInfo bi = body[i];
+					const int ii = i;
+					const int c = (int)(bi.P >> 4) + j;
+					i += di;
+					j += dj;
+					if (j >= K) {
+						j -= K;
+						i++;
+					}
+					if (bi.flags & BF_RANDOM) continue;  // every base of a random mate is a draw (phase C)
+					const int L = bi.L;
+					const int k0 = 16 * c - (int)bi.P;  // output position of the chunk's first byte, >= -15
+					if (k0 < 0 || k0 + 16 > L) continue;  // ragged first / last chunk: handled below
+					QT_CHK(c >= 0 && 16u * (uint32_t)c + 16u <= stage_stride, 3, c, bi.P);
+					const int cm = (CAT == CAT_C || CAT == CAT_D) ? s : 0;
+					const uint32_t *cache = (const uint32_t *)(gcache + ((size_t)cm * R + ii) * gc_stride);
+					const uint64_t gc0 = gcache_origin(bi.gpos);
+					uint4 v;
+					const bool fw = (bi.flags & BF_FW) != 0;
+					if ((bi.flags & (BF_SINGLE | BF_SLOW)) == BF_SINGLE) v = cseq16_fast(cache, gc0, fw, bi.gpos, bi.ref0, k0);
+					else if (bi.flags & BF_SINGLE) v = cseq16_slow(gv, cache, gc0, fw, bi.gpos, s_gend[ii], bi.ref0, k0);
+					else v = cgen_seq_segments(gv, cache, gc0, s_lowmask, a.c.segs + bi.segoff, bi.nseg, fw, L, bi.gpos, s_gend[ii], k0);
+					*(uint4 *)(stg + 16 * (size_t)c) = v;
+				}
 			}
-			// qualities: two chunks per iteration, loads issued before either is consumed
-			for (int q = tid; q < nitems && !(skip & 4); q += 2 * TL_THREADS) {
-				QualLoad ql[2];
-				int cc[2], kq[2], LL[2];
-				bool live[2], rnd[2];
+			// qualities: whole chunks only, two per iteration with the loads issued before either is consumed
+			{
+				int i0 = tid / K, j0 = tid - i0 * K;
+				for (int q = tid; q < nitems && !(skip & 4); q += 2 * TL_THREADS) {
+					QualLoad ql[2];
+					int cc[2];
+					bool live[2], rnd[2];
 #pragma unroll
-				for (int u = 0; u < 2; u++) {
-					const int qq = q + u * TL_THREADS;
-					live[u] = false;
-					rnd[u] = false;
-					if (qq < nitems) {
-						const int i = qq / K;
-						const int j = qq - i * K;
-						const BodyInfo bi = body[i];
-						LL[u] = bi.L;
-						const uint32_t Pq = bi.P + (uint32_t)bi.L + 3u;
-						cc[u] = (int)(Pq >> 4) + j;
-						kq[u] = 16 * cc[u] - (int)Pq;
-						live[u] = kq[u] < LL[u];
-						rnd[u] = (bi.flags & BF_RANDOM) != 0;
-						if (live[u] && !rnd[u]) ql[u] = qual_issue(a.c.qual_out, bi.qoff, kq[u]);
+					for (int u = 0; u < 2; u++) {
+						live[u] = false;
+						rnd[u] = false;
+						if (q + u * TL_THREADS < nitems) {
+							const BodyInfo bi = body[i0];
+							const int L = bi.L;
+							const uint32_t Pq = bi.P + (uint32_t)L + 3u;
+							cc[u] = (int)(Pq >> 4) + j0;
+							const int kq = 16 * cc[u] - (int)Pq;
+							live[u] = kq >= 0 && kq + 16 <= L;
+							rnd[u] = (bi.flags & BF_RANDOM) != 0;
+							if (live[u] && !rnd[u]) ql[u] = qual_issue(a.c.qual_out, bi.qoff, kq);
+						}
+						i0 += di;
+						j0 += dj;
+						if (j0 >= K) {
+							j0 -= K;
+							i0++;
+						}
+					}
+#pragma unroll
+					for (int u = 0; u < 2; u++) {
+						if (!live[u]) continue;
+						QT_CHK(cc[u] >= 0 && 16u * (uint32_t)cc[u] + 16u <= stage_stride, 4, cc[u], u);
+						const uint4 v = rnd[u] ? make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u)  // 'I'
+						                       : qual_finish(ql[u]);
+						*(uint4 *)(stg + 16 * (size_t)cc[u]) = v;
 					}
 				}
-#pragma unroll
-				for (int u = 0; u < 2; u++) {
-					if (!live[u]) continue;
-					QT_CHK(cc[u] >= 0 && 16u * (uint32_t)cc[u] + 16u <= stage_stride, 4, cc[u], kq[u]);
-					const uint4 v = rnd[u] ? make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u)  // 'I'
-					                       : qual_finish(ql[u]);
-					if (kq[u] >= 0 && kq[u] + 16 <= LL[u]) *(uint4 *)(stg + 16 * (size_t)cc[u]) = v;
-					else store_partial(stg + 16 * (size_t)cc[u], s_lowmask, v, -kq[u], LL[u] - kq[u]);
+			}
+			// ragged ends: the first and last chunk of each sequence and each quality string (4 per read),
+			// one uniform pass, exact-byte stores
+			for (int q = tid; q < 4 * nr && !(skip & 6); q += TL_THREADS) {
+				const int i = q >> 2, which = q & 3;  // 0 seq head, 1 seq tail, 2 qual head, 3 qual tail
+				const BodyInfo bi = body[i];
+				const int L = bi.L;
+				const bool isq = which >= 2;
+				const uint32_t P0 = isq ? bi.P + (uint32_t)L + 3u : bi.P;
+				const int c_first = (int)(P0 >> 4), c_last = (int)((P0 + (uint32_t)L - 1u) >> 4);
+				const int c = (which & 1) ? c_last : c_first;
+				if ((which & 1) && c_last == c_first) continue;  // single chunk: the head item handles it
+				const int k0 = 16 * c - (int)P0;
+				if (k0 >= 0 && k0 + 16 <= L) continue;  // whole chunk: done above
+				uint4 v;
+				if (isq) {
+					if (bi.flags & BF_RANDOM) v = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);
+					else v = qual_finish(qual_issue(a.c.qual_out, bi.qoff, k0));
+				} else {
+					if (bi.flags & BF_RANDOM) continue;
+					const int cm = (CAT == CAT_C || CAT == CAT_D) ? s : 0;
+					const uint32_t *cache = (const uint32_t *)(gcache + ((size_t)cm * R + i) * gc_stride);
+					const uint64_t gc0 = gcache_origin(bi.gpos);
+					const bool fw = (bi.flags & BF_FW) != 0;
+					if ((bi.flags & (BF_SINGLE | BF_SLOW)) == BF_SINGLE) v = cseq16_fast(cache, gc0, fw, bi.gpos, bi.ref0, k0);
+					else if (bi.flags & BF_SINGLE) v = cseq16_slow(gv, cache, gc0, fw, bi.gpos, s_gend[i], bi.ref0, k0);
+					else v = cgen_seq_segments(gv, cache, gc0, s_lowmask, a.c.segs + bi.segoff, bi.nseg, fw, L, bi.gpos, s_gend[i], k0);
 				}
+				store_partial(stg + 16 * (size_t)c, s_lowmask, v, -k0, L - k0);
 			}
 		}
 	}
