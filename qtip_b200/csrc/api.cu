@@ -789,6 +789,13 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 		if (!done) launch_simulate(sa[c], h->st);
 	}
 	CK(cudaEventRecord(ev[3], h->st));
+#ifdef QT_PHASE_CLOCKS
+	{
+		extern void qt_tiled_phase_report();
+		cudaStreamSynchronize(h->st);
+		qt_tiled_phase_report();
+	}
+#endif
 #ifdef QT_BOUNDS
 	{
 		extern void qt_tiled_debug_report();

@@ -60,6 +60,31 @@ __device__ unsigned long long g_qt_violation[4];
 #define QT_TL_THREADS 256
 #endif
 static constexpr int TL_THREADS = QT_TL_THREADS;
+#ifndef QT_SEQ_UNROLL
+#define QT_SEQ_UNROLL 2
+#endif
+#ifndef QT_RAG_UNROLL
+#define QT_RAG_UNROLL 2
+#endif
+#ifndef QT_MIN_BLOCKS
+#define QT_MIN_BLOCKS (768 / QT_TL_THREADS)
+#endif
+
+// Profiling build (-DQT_PHASE_CLOCKS): thread 0 of every CTA accumulates the cycles between phase
+// boundaries into g_qt_phase[] (A, B, C, D, whole CTA, CTA count).
+#ifdef QT_PHASE_CLOCKS
+__device__ unsigned long long g_qt_phase[8];
+#define QT_MARK(slot)                                                   \
+	do {                                                                \
+		if (threadIdx.x == 0) {                                         \
+			const long long now_ = clock64();                           \
+			atomicAdd(&g_qt_phase[slot], (unsigned long long)(now_ - t_mark_)); \
+			t_mark_ = now_;                                             \
+		}                                                               \
+	} while (0)
+#else
+#define QT_MARK(slot) do { } while (0)
+#endif
 static constexpr uint32_t TL_STAGE_DEFAULT = 52 * 1024;  // dynamic shared memory per CTA (4 CTAs per SM)
 
 enum : uint8_t { BF_FW = 1, BF_RANDOM = 2, BF_SLOW = 4, BF_SINGLE = 8 };
@@ -391,27 +416,144 @@ __device__ __forceinline__ uint4 qual_finish(const QualLoad &ql) {
 	}
 }
 
+// 32-bit decimal helpers: reference offsets fit 32 bits in every supported genome (< 4 Gbp per record);
+// 64-bit division is ~100 instructions on the GPU, so the wide path is only taken when needed.
+__device__ __forceinline__ uint32_t ndig32(uint32_t v) {
+	return v < 10u ? 1u : v < 100u ? 2u : v < 1000u ? 3u : v < 10000u ? 4u : v < 100000u ? 5u : v < 1000000u ? 6u
+	     : v < 10000000u ? 7u : v < 100000000u ? 8u : v < 1000000000u ? 9u : 10u;
+}
+__device__ __forceinline__ uint32_t ndig_fast(uint64_t v) { return v <= 0xffffffffull ? ndig32((uint32_t)v) : ndig(v); }
+__device__ __forceinline__ char *s_put_dec(char *p, uint64_t v) {
+	if (v > 0xffffffffull) return s_put_u64(p, v);
+	uint32_t x = (uint32_t)v;
+	const uint32_t n = ndig32(x);
+	for (int i = (int)n - 1; i >= 0; i--) {
+		const uint32_t q = x / 10u;
+		p[i] = (char)('0' + (int)(x - q * 10u));
+		x = q;
+	}
+	return p + n;
+}
+__device__ __forceinline__ char *s_origin_fast(char *p, const char *refid, uint32_t rl, bool fw, uint64_t off,
+                                               const MateDesc &m) {
+	p = s_put(p, refid, rl);
+	*p++ = ':';
+	*p++ = fw ? '+' : '-';
+	*p++ = ':';
+	p = s_put_dec(p, off);
+	*p++ = ':';
+	p = s_put(p, m.score, m.score_len);
+	return p;
+}
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+	const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+// N bits of 16 consecutive bases starting at g, from the shared-memory copy of the N mask
+__device__ __forceinline__ uint32_t cache16_nmask(const uint32_t *mcache, uint64_t gc0, uint64_t g) {
+	const uint32_t off = (uint32_t)(g - gc0);
+	const uint32_t lo = mcache[off >> 5], hi = mcache[(off >> 5) + 1];
+	return __funnelshift_r(lo, hi, off & 31u) & 0xffffu;
+}
+
+__device__ __forceinline__ uint4 apply_n(uint4 v, uint32_t nm) {
+	const uint32_t N4 = 0x4e4e4e4eu;
+	uint32_t m;
+	m = spread4(nm);       v.x = (v.x & ~m) | (N4 & m);
+	m = spread4(nm >> 4);  v.y = (v.y & ~m) | (N4 & m);
+	m = spread4(nm >> 8);  v.z = (v.z & ~m) | (N4 & m);
+	m = spread4(nm >> 12); v.w = (v.w & ~m) | (N4 & m);
+	return v;
+}
+
+// Sequence bytes for output positions [k0, k0+16) under one segment's mapping, everything from the
+// shared-memory genome cache.  `past` = the mate may reach past its record (those bases print as N).
+__device__ __forceinline__ uint4 cseq16(const uint32_t *cache, const uint32_t *mcache, uint64_t gc0, bool fw, bool past,
+                                        uint64_t gpos, uint64_t gend, int32_t ref0, int d) {
+	uint32_t w, nm;
+	if (fw) {
+		const uint64_t g0 = (uint64_t)((int64_t)gpos + ref0 + d);
+		w = cache16_bases(cache, gc0, g0);
+		nm = cache16_nmask(mcache, gc0, g0);
+		if (past && g0 + 16 > gend) nm |= g0 >= gend ? 0xffffu : (0xffffu << (uint32_t)(gend - g0)) & 0xffffu;
+	} else {
+		const uint64_t ghi = (uint64_t)((int64_t)gpos + ref0 - d);
+		w = revcomp16(cache16_bases(cache, gc0, ghi - 15));
+		nm = __brev(cache16_nmask(mcache, gc0, ghi - 15)) >> 16;
+		if (past && ghi >= gend) nm |= (ghi - gend) >= 15 ? 0xffffu : (1u << ((uint32_t)(ghi - gend) + 1u)) - 1u;
+	}
+	uint4 v = expand16(w);
+	if (nm) v = apply_n(v, nm);
+	return v;
+}
+
+// General path: merges the contributions of every reference-copy segment that overlaps
+// output positions [k0, k0+16); other bytes are zero.
+__device__ __noinline__ uint4 cseq16_segments(const uint32_t *cache, const uint32_t *mcache, uint64_t gc0,
+                                              const uint4 *lowmask, const SegDev *__restrict__ segs, int nseg, bool fw,
+                                              bool past, int L, uint64_t gpos, uint64_t gend, int k0) {
+	const int lo_k = k0 > 0 ? k0 : 0;
+	const int hi_k = k0 + 16 < L ? k0 + 16 : L;
+	uint4 out = make_uint4(0u, 0u, 0u, 0u);
+	int a = 0, b = nseg;  // first segment whose end lies beyond lo_k
+	while (a < b) {
+		const int mid = (a + b) >> 1;
+		if ((int)segs[mid].out_end <= lo_k) a = mid + 1;
+		else b = mid;
+	}
+	for (int si = a; si < nseg; si++) {
+		const SegDev sg = segs[si];
+		if ((int)sg.out_start >= hi_k) break;
+		const uint4 v = cseq16(cache, mcache, gc0, fw, past, gpos, gend, sg.ref0, k0 - (int)sg.out_start);
+		const uint4 m = range_mask(lowmask, ((int)sg.out_start > lo_k ? (int)sg.out_start : lo_k) - k0,
+		                           ((int)sg.out_end < hi_k ? (int)sg.out_end : hi_k) - k0);
+		out.x |= v.x & m.x;
+		out.y |= v.y & m.y;
+		out.z |= v.z & m.z;
+		out.w |= v.w & m.w;
+	}
+	return out;
+}
+
+static constexpr int OPS_PREFETCH = 6;  // draw ops per mate kept in shared memory by phase A
+
+// what phase C needs per read and mate, so it never goes back to the template in HBM
+struct DrawInfo {
+	uint32_t ops_off;
+	uint16_t nops;
+	uint8_t fw;
+	uint8_t pad;
+	uint32_t ops[OPS_PREFETCH];
+};
+
 template <int MODE, int CAT>
-__global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R, uint32_t stage_stride, int K,
-                                                                uint32_t gc_stride, int skip) {
+__global__ void __launch_bounds__(TL_THREADS, QT_MIN_BLOCKS) k_simulate_tiled(SimArgs a, int R, uint32_t stage_stride, int K,
+                                                                uint32_t gc_stride, uint32_t gc_mask_off, int skip) {
 	constexpr int NS = CAT == CAT_U ? 1 : 2;                     // output streams
 	constexpr int NM = (CAT == CAT_C || CAT == CAT_D) ? 2 : 1;   // aligned mates per read
 	extern __shared__ __align__(16) unsigned char smem[];
 	unsigned char *stage = smem;                                                      // NS * stage_stride
 	unsigned char *gcache = smem + (size_t)NS * stage_stride;                         // NM * R * gc_stride
 	BodyInfo *s_body = (BodyInfo *)(gcache + (size_t)NM * R * gc_stride);             // [NS][R]
-	uint64_t *s_gend = (uint64_t *)(s_body + (size_t)NS * R);                         // [R]
-	uint32_t *s_tmpl = (uint32_t *)(s_gend + R);                                      // [R]
+	DrawInfo *s_draw = (DrawInfo *)(s_body + (size_t)NS * R);                         // [NM][R]
+	uint64_t *s_gend = (uint64_t *)(s_draw + (size_t)NM * R);                         // [R]
+	LState *s_rng = (LState *)(s_gend + R);                                           // [R]
+	uint32_t *s_opp = (uint32_t *)(s_rng + R);                                        // [R] (B: opp_len)
 	__shared__ uint64_t s_G0[2], s_G1[2];
 	__shared__ uint4 s_lowmask[17];
 
+#ifdef QT_PHASE_CLOCKS
+	long long t_mark_ = clock64();
+	const long long t_start_ = t_mark_;
+#endif
 	const int tid = threadIdx.x;
 	const uint64_t r0 = (uint64_t)blockIdx.x * (uint64_t)R;
 	const int nr = (int)((a.nreads - r0) < (uint64_t)R ? (a.nreads - r0) : (uint64_t)R);
 	const uint64_t *offs[2] = {a.off0, a.off1};
 	const uint64_t *tots[2] = {a.tot0, a.tot1};
 	char *outs[2] = {a.out0, a.out1};
-	GenomeView gv{a.g.bases, a.g.nmask, a.genome_words - 2};
 
 	if (tid < NS) {
 		s_G0[tid] = offs[tid][r0];
@@ -432,18 +574,22 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 	// ---------------- phase A (one thread per read): geometry, genome prefetch, name ----------------
 	for (int i = tid; i < nr; i += TL_THREADS) {
 		const PlanRec pr = a.plan[r0 + i];
+		uint64_t myoff[2];
+#pragma unroll
+		for (int s = 0; s < NS; s++) myoff[s] = offs[s][r0 + i];
 		const TmplDesc &t = a.c.t[pr.tmpl];
 		const RecDev rec = a.g.recs[pr.record];
 		const uint64_t ro0 = pr.refoff + t.delta[0], ro1 = pr.refoff + t.delta[1];
 		const uint64_t gend = rec.gstart + rec.len;
 		uint32_t nl;
-		if (CAT == CAT_U) nl = 13u + rec.name_len + ndig(ro0) + t.m[0].score_len + t.typ_len;
-		else if (CAT == CAT_B) nl = 18u + 2u * rec.name_len + 2u * ndig(ro0) + 2u * t.m[0].score_len + t.typ_len;
-		else nl = 18u + 2u * rec.name_len + ndig(ro0) + ndig(ro1) + t.m[0].score_len + t.m[1].score_len + t.typ_len;
-		s_tmpl[i] = pr.tmpl;
+		if (CAT == CAT_U) nl = 13u + rec.name_len + ndig_fast(ro0) + t.m[0].score_len + t.typ_len;
+		else if (CAT == CAT_B) nl = 18u + 2u * rec.name_len + 2u * ndig_fast(ro0) + 2u * t.m[0].score_len + t.typ_len;
+		else nl = 18u + 2u * rec.name_len + ndig_fast(ro0) + ndig_fast(ro1) + t.m[0].score_len + t.m[1].score_len + t.typ_len;
 		s_gend[i] = gend;
-		// genome prefetch + N scan, per aligned mate
-		uint8_t slowf[2] = {0, 0};
+		s_rng[i] = LState{pr.s1, pr.s2};
+		if (CAT == CAT_B) s_opp[i] = t.opp_len;
+		// genome prefetch (bases + N mask), per aligned mate; draw ops for phase C
+		uint8_t pastf[2] = {0, 0};
 #pragma unroll
 		for (int m = 0; m < NM; m++) {
 			const MateDesc &md = t.m[m];
@@ -452,16 +598,24 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 			const uint32_t nch = (uint32_t)((gpos + md.rflen + 48 - gc0 + 63) >> 6);
 			unsigned char *dst = gcache + ((size_t)m * R + i) * gc_stride;
 			const unsigned char *src = (const unsigned char *)a.g.bases + (gc0 >> 2);
+			const unsigned char *msrc = (const unsigned char *)a.g.nmask + (gc0 >> 3);
 			const uint64_t src_limit = a.genome_words * 4;
-			QT_CHK(nch * 16u <= gc_stride, 9, nch, gc_stride);
-			for (uint32_t c = 0; c < nch; c++)
-				if ((gc0 >> 2) + 16ull * c + 16ull <= src_limit) cp_async16(dst + 16 * c, src + 16 * c);
-			// any N within reach of the sequence chunks, or reach past the record end -> slow path
-			const uint64_t glo = gpos - 16, ghi = gpos + md.rflen + 16;
-			uint32_t acc = ghi > gend ? 1u : 0u;
-			const uint64_t w1 = (ghi < gend ? ghi : gend) >> 5;
-			for (uint64_t w = glo >> 5; w <= w1; w++) acc |= __ldg(&gv.nmask[w]);  // independent loads
-			slowf[m] = acc ? BF_SLOW : 0;
+			QT_CHK(nch * 16u <= gc_mask_off && gc_mask_off + nch * 8u <= gc_stride, 9, nch, gc_stride);
+			for (uint32_t c = 0; c < nch; c++) {
+				if ((gc0 >> 2) + 16ull * c + 16ull <= src_limit) {
+					cp_async16(dst + 16 * c, src + 16 * c);
+					cp_async8(dst + gc_mask_off + 8 * c, msrc + 8 * c);
+				}
+			}
+			pastf[m] = (gpos + md.rflen + 16 > gend) ? BF_SLOW : 0;  // may reach past the record end
+			DrawInfo di;
+			di.ops_off = md.ops_off;
+			di.nops = md.nops;
+			di.fw = md.fw;
+			di.pad = 0;
+#pragma unroll
+			for (int j = 0; j < OPS_PREFETCH; j++) di.ops[j] = j < (int)md.nops ? __ldg(&a.c.ops[md.ops_off + j]) : 0u;
+			s_draw[m * R + i] = di;
 		}
 		asm volatile("cp.async.commit_group;" ::: "memory");
 		char *rec_ptr[2] = {nullptr, nullptr};
@@ -477,7 +631,7 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 			const MateDesc &md = t.m[mate];
 			BodyInfo bi;
 			bi.gpos = rec.gstart + (mate == 0 ? ro0 : ro1);
-			bi.P = (uint32_t)(s_G0[s] & 15) + (uint32_t)(offs[s][r0 + i] - s_G0[s]) + nl;
+			bi.P = (uint32_t)(s_G0[s] & 15) + (uint32_t)(myoff[s] - s_G0[s]) + nl;
 			bi.segoff = md.seg_off;
 			bi.qoff = md.qual_out_off;
 			bi.L = (uint16_t)(random ? t.opp_len : md.len);
@@ -485,7 +639,7 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 			bi.nl = (uint16_t)nl;
 			bi.pad = 0;
 			bi.ref0 = md.ref0;
-			bi.flags = (md.fw ? BF_FW : 0) | (random ? BF_RANDOM : 0) | (md.single ? BF_SINGLE : 0) | slowf[mate];
+			bi.flags = (md.fw ? BF_FW : 0) | (random ? BF_RANDOM : 0) | (md.single ? BF_SINGLE : 0) | pastf[mate];
 			s_body[s * R + i] = bi;
 			rec_ptr[s] = (char *)stage + (size_t)s * stage_stride + bi.P - nl;
 			blen[s] = bi.L;
@@ -495,13 +649,13 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 			// name (simplesim.cpp:104-110, :140-150) and separators
 			const char *refid = a.g.names + rec.name_off;
 			char *p = s_put(rec_ptr[0], "@qtip!:", 7);
-			p = s_origin(p, refid, rec.name_len, t.m[0].fw != 0, ro0, t.m[0]);
+			p = s_origin_fast(p, refid, rec.name_len, t.m[0].fw != 0, ro0, t.m[0]);
 			if (CAT == CAT_B) {
 				*p++ = ':';
-				p = s_origin(p, refid, rec.name_len, t.m[0].fw != 0, ro0, t.m[0]);
+				p = s_origin_fast(p, refid, rec.name_len, t.m[0].fw != 0, ro0, t.m[0]);
 			} else if (CAT != CAT_U) {
 				*p++ = ':';
-				p = s_origin(p, refid, rec.name_len, t.m[1].fw != 0, ro1, t.m[1]);
+				p = s_origin_fast(p, refid, rec.name_len, t.m[1].fw != 0, ro1, t.m[1]);
 			}
 			*p++ = ':';
 			p = s_put(p, t.typ, t.typ_len);
@@ -520,6 +674,7 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 	}
 	asm volatile("cp.async.wait_group 0;" ::: "memory");
 	__syncthreads();
+	QT_MARK(0);
 
 	// ---------------- phase B: sequence and quality chunks, read-major, exact-byte stores ----------------
 	{
@@ -528,35 +683,46 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 		for (int s = 0; s < NS; s++) {
 			unsigned char *stg = stage + (size_t)s * stage_stride;
 			const BodyInfo *body = s_body + s * R;
+			const int cm = (CAT == CAT_C || CAT == CAT_D) ? s : 0;
 			// (i, j) = (read, chunk) of item q = i*K + j, advanced without a division
 			const int di = TL_THREADS / K, dj = TL_THREADS - di * K;
-			// sequence: whole chunks only
+			// one sequence chunk (whole or ragged) of read i
+			auto seq_chunk = [&](const BodyInfo &bi, int i, int k0) -> uint4 {
+				const uint32_t *cache = (const uint32_t *)(gcache + ((size_t)cm * R + i) * gc_stride);
+				const uint32_t *mcache = (const uint32_t *)((const unsigned char *)cache + gc_mask_off);
+				const uint64_t gc0 = gcache_origin(bi.gpos);
+				const bool fw = (bi.flags & BF_FW) != 0, past = (bi.flags & BF_SLOW) != 0;
+				if (bi.flags & BF_SINGLE) return cseq16(cache, mcache, gc0, fw, past, bi.gpos, s_gend[i], bi.ref0, k0);
+				return cseq16_segments(cache, mcache, gc0, s_lowmask, a.c.segs + bi.segoff, bi.nseg, fw, past, bi.L, bi.gpos,
+				                       s_gend[i], k0);
+			};
+			// sequence: whole chunks only, two per iteration
 			{
 				int i = tid / K, j = tid - i * K;
-				for (int q = tid; q < nitems && !(skip & 2); q += TL_THREADS) {
-					const BodyInfo bi = body[i];
-					const int ii = i;
-					const int c = (int)(bi.P >> 4) + j;
-					i += di;
-					j += dj;
-					if (j >= K) {
-						j -= K;
-						i++;
+				for (int q = tid; q < nitems && !(skip & 2); q += QT_SEQ_UNROLL * TL_THREADS) {
+					uint4 v[QT_SEQ_UNROLL];
+					int cc[QT_SEQ_UNROLL];
+					bool live[QT_SEQ_UNROLL];
+#pragma unroll
+					for (int u = 0; u < QT_SEQ_UNROLL; u++) {
+						live[u] = false;
+						if (q + u * TL_THREADS < nitems) {
+							const BodyInfo bi = body[i];
+							cc[u] = (int)(bi.P >> 4) + j;
+							const int k0 = 16 * cc[u] - (int)bi.P;  // output position of the chunk's first byte
+							live[u] = !(bi.flags & BF_RANDOM) && k0 >= 0 && k0 + 16 <= (int)bi.L;
+							if (live[u]) v[u] = seq_chunk(bi, i, k0);
+						}
+						i += di;
+						j += dj;
+						if (j >= K) {
+							j -= K;
+							i++;
+						}
 					}
-					if (bi.flags & BF_RANDOM) continue;  // every base of a random mate is a draw (phase C)
-					const int L = bi.L;
-					const int k0 = 16 * c - (int)bi.P;  // output position of the chunk's first byte, >= -15
-					if (k0 < 0 || k0 + 16 > L) continue;  // ragged first / last chunk: handled below
-					QT_CHK(c >= 0 && 16u * (uint32_t)c + 16u <= stage_stride, 3, c, bi.P);
-					const int cm = (CAT == CAT_C || CAT == CAT_D) ? s : 0;
-					const uint32_t *cache = (const uint32_t *)(gcache + ((size_t)cm * R + ii) * gc_stride);
-					const uint64_t gc0 = gcache_origin(bi.gpos);
-					uint4 v;
-					const bool fw = (bi.flags & BF_FW) != 0;
-					if ((bi.flags & (BF_SINGLE | BF_SLOW)) == BF_SINGLE) v = cseq16_fast(cache, gc0, fw, bi.gpos, bi.ref0, k0);
-					else if (bi.flags & BF_SINGLE) v = cseq16_slow(gv, cache, gc0, fw, bi.gpos, s_gend[ii], bi.ref0, k0);
-					else v = cgen_seq_segments(gv, cache, gc0, s_lowmask, a.c.segs + bi.segoff, bi.nseg, fw, L, bi.gpos, s_gend[ii], k0);
-					*(uint4 *)(stg + 16 * (size_t)c) = v;
+#pragma unroll
+					for (int u = 0; u < QT_SEQ_UNROLL; u++)
+						if (live[u]) *(uint4 *)(stg + 16 * (size_t)cc[u]) = v[u];
 				}
 			}
 			// qualities: whole chunks only, two per iteration with the loads issued before either is consumed
@@ -598,48 +764,63 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 				}
 			}
 			// ragged ends: the first and last chunk of each sequence and each quality string (4 per read),
-			// one uniform pass, exact-byte stores
-			for (int q = tid; q < 4 * nr && !(skip & 6); q += TL_THREADS) {
-				const int i = q >> 2, which = q & 3;  // 0 seq head, 1 seq tail, 2 qual head, 3 qual tail
-				const BodyInfo bi = body[i];
-				const int L = bi.L;
-				const bool isq = which >= 2;
-				const uint32_t P0 = isq ? bi.P + (uint32_t)L + 3u : bi.P;
-				const int c_first = (int)(P0 >> 4), c_last = (int)((P0 + (uint32_t)L - 1u) >> 4);
-				const int c = (which & 1) ? c_last : c_first;
-				if ((which & 1) && c_last == c_first) continue;  // single chunk: the head item handles it
-				const int k0 = 16 * c - (int)P0;
-				if (k0 >= 0 && k0 + 16 <= L) continue;  // whole chunk: done above
-				uint4 v;
-				if (isq) {
-					if (bi.flags & BF_RANDOM) v = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);
-					else v = qual_finish(qual_issue(a.c.qual_out, bi.qoff, k0));
-				} else {
-					if (bi.flags & BF_RANDOM) continue;
-					const int cm = (CAT == CAT_C || CAT == CAT_D) ? s : 0;
-					const uint32_t *cache = (const uint32_t *)(gcache + ((size_t)cm * R + i) * gc_stride);
-					const uint64_t gc0 = gcache_origin(bi.gpos);
-					const bool fw = (bi.flags & BF_FW) != 0;
-					if ((bi.flags & (BF_SINGLE | BF_SLOW)) == BF_SINGLE) v = cseq16_fast(cache, gc0, fw, bi.gpos, bi.ref0, k0);
-					else if (bi.flags & BF_SINGLE) v = cseq16_slow(gv, cache, gc0, fw, bi.gpos, s_gend[i], bi.ref0, k0);
-					else v = cgen_seq_segments(gv, cache, gc0, s_lowmask, a.c.segs + bi.segoff, bi.nseg, fw, L, bi.gpos, s_gend[i], k0);
+			// one uniform pass, exact-byte stores; two items per iteration, loads first
+			for (int q = tid; q < 4 * nr && !(skip & 6); q += QT_RAG_UNROLL * TL_THREADS) {
+				QualLoad ql[QT_RAG_UNROLL];
+				uint4 v[QT_RAG_UNROLL];
+				int cc[QT_RAG_UNROLL], kk[QT_RAG_UNROLL], LL[QT_RAG_UNROLL];
+				bool live[QT_RAG_UNROLL], needq[QT_RAG_UNROLL];
+#pragma unroll
+				for (int u = 0; u < QT_RAG_UNROLL; u++) {
+					const int qq = q + u * TL_THREADS;
+					live[u] = false;
+					needq[u] = false;
+					if (qq >= 4 * nr) continue;
+					const int i = qq >> 2, which = qq & 3;  // 0 seq head, 1 seq tail, 2 qual head, 3 qual tail
+					const BodyInfo bi = body[i];
+					const int L = bi.L;
+					const bool isq = which >= 2;
+					const uint32_t P0 = isq ? bi.P + (uint32_t)L + 3u : bi.P;
+					const int c_first = (int)(P0 >> 4), c_last = (int)((P0 + (uint32_t)L - 1u) >> 4);
+					const int c = (which & 1) ? c_last : c_first;
+					if ((which & 1) && c_last == c_first) continue;  // single chunk: the head item handles it
+					const int k0 = 16 * c - (int)P0;
+					if (k0 >= 0 && k0 + 16 <= L) continue;  // whole chunk: done above
+					cc[u] = c;
+					kk[u] = k0;
+					LL[u] = L;
+					if (isq) {
+						live[u] = true;
+						if (bi.flags & BF_RANDOM) v[u] = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);
+						else {
+							needq[u] = true;
+							ql[u] = qual_issue(a.c.qual_out, bi.qoff, k0);
+						}
+					} else if (!(bi.flags & BF_RANDOM)) {
+						live[u] = true;
+						v[u] = seq_chunk(bi, i, k0);
+					}
 				}
-				store_partial(stg + 16 * (size_t)c, s_lowmask, v, -k0, L - k0);
+#pragma unroll
+				for (int u = 0; u < QT_RAG_UNROLL; u++) {
+					if (!live[u]) continue;
+					if (needq[u]) v[u] = qual_finish(ql[u]);
+					store_partial(stg + 16 * (size_t)cc[u], s_lowmask, v[u], -kk[u], LL[u] - kk[u]);
+				}
 			}
 		}
 	}
 	__syncthreads();
+	QT_MARK(1);
 
-	// ---------------- phase C: random draws ----------------
+	// ---------------- phase C: random draws (shared memory only, except long draw-op lists) ----------------
 	for (int i = tid; i < nr && !(skip & 8); i += TL_THREADS) {
-		const TmplDesc &t = a.c.t[s_tmpl[i]];
-		const PlanRec pr = a.plan[r0 + i];
 		const BodyInfo b0 = s_body[i];
 		const BodyInfo b1 = NS == 2 ? s_body[R + i] : b0;
 		char *seq0 = (char *)stage + b0.P;
 		char *seq1 = NS == 2 ? (char *)stage + stage_stride + b1.P : nullptr;
 		// draws, in the reference's order: mate 1's transcript, mate 2's, then the random mate
-		LState st{pr.s1, pr.s2};
+		LState st = s_rng[i];
 		const uint64_t gi = a.read_index_base + r0 + i;
 		uint32_t dk = 0;
 		Philox4 blk{};
@@ -655,27 +836,25 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 		const bool s0_random = (b0.flags & BF_RANDOM) != 0;
 		const uint64_t gend = s_gend[i];
 		for (int m = 0; m < NM; m++) {
-			const MateDesc &md = t.m[m];
+			const DrawInfo &dinfo = s_draw[m * R + i];
 			const BodyInfo &bm = (CAT == CAT_B) ? (s0_random ? b1 : b0) : (m == 0 ? b0 : b1);
 			char *seq = (CAT == CAT_B) ? (s0_random ? seq1 : seq0) : (m == 0 ? seq0 : seq1);
-			const uint32_t *ops = a.c.ops + md.ops_off;
+			const uint32_t *ops = a.c.ops + dinfo.ops_off;
 			const uint64_t gpos = bm.gpos;
 			const uint64_t gc0 = gcache_origin(gpos);
 			const uint32_t *cache = (const uint32_t *)(gcache + ((size_t)m * R + i) * gc_stride);
-			const bool slow = (bm.flags & BF_SLOW) != 0;
-			const uint32_t T = md.fw ? 0x54474341u : 0x41434754u;  // "ACGT" / "TGCA"
-			for (uint32_t j = 0; j < md.nops; j++) {
-				const uint32_t e = __ldg(&ops[j]);
+			const uint32_t *mcache = (const uint32_t *)((const unsigned char *)cache + gc_mask_off);
+			const uint32_t T = dinfo.fw ? 0x54474341u : 0x41434754u;  // "ACGT" / "TGCA"
+			const uint32_t nops = dinfo.nops;
+			for (uint32_t j = 0; j < nops; j++) {
+				const uint32_t e = j < (uint32_t)OPS_PREFETCH ? dinfo.ops[j] : __ldg(&ops[j]);
 				const uint32_t outp = (e >> 2) & 0x7fffu;
 				uint32_t code;
 				if ((e & 3u) == OP_X) {
 					const uint64_t gp = gpos + (e >> 17);
-					uint32_t ref;
-					if (slow && (gp >= gend || ((__ldg(&gv.nmask[gp >> 5]) >> (gp & 31)) & 1u))) ref = 4u;
-					else {
-						const uint32_t off = (uint32_t)(gp - gc0);
-						ref = (cache[off >> 4] >> (2u * (off & 15u))) & 3u;
-					}
+					const uint32_t off = (uint32_t)(gp - gc0);
+					uint32_t ref = (cache[off >> 4] >> (2u * (off & 15u))) & 3u;
+					if (gp >= gend || ((mcache[off >> 5] >> (off & 31u)) & 1u)) ref = 4u;
 					if (MODE == QTIPSIM_RNG_REPLAY) {
 						do {  // simplesim.cpp:47-49
 							st = lstep(st);
@@ -693,15 +872,15 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 						code = draw16() >> 14;
 					}
 				}
-				QT_CHK(outp < md.len, 7, outp, md.len);
+				QT_CHK(outp < bm.L, 7, outp, bm.L);
 				seq[outp] = (char)((T >> (8u * code)) & 0xffu);
 			}
 		}
 		if (CAT == CAT_B) {
 			// init_random (simplesim.h:89-117): opp_len draws, printed with the aligned mate's strand
 			char *seq = s0_random ? seq0 : seq1;
-			const uint32_t L = t.opp_len;
-			const bool fw = t.m[0].fw != 0;
+			const uint32_t L = s_opp[i];
+			const bool fw = s_draw[i].fw != 0;
 			const uint32_t T = fw ? 0x54474341u : 0x41434754u;
 			for (uint32_t j = 0; j < L; j++) {
 				uint32_t code;
@@ -718,6 +897,7 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 	// make the generic-proxy shared-memory writes visible to the async (bulk copy) proxy
 	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	__syncthreads();
+	QT_MARK(2);
 
 	// ---------------- phase D: staged tile -> HBM ----------------
 #pragma unroll
@@ -750,6 +930,13 @@ __global__ void __launch_bounds__(TL_THREADS) k_simulate_tiled(SimArgs a, int R,
 	}
 	// the staging buffer must stay allocated until the bulk copies have read it
 	if (tid == 0 || tid == 32) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+	QT_MARK(3);
+#ifdef QT_PHASE_CLOCKS
+	if (tid == 0) {
+		atomicAdd(&g_qt_phase[4], (unsigned long long)(clock64() - t_start_));
+		atomicAdd(&g_qt_phase[5], 1ull);
+	}
+#endif
 }
 
 template <int MODE, int CAT>
@@ -763,15 +950,20 @@ static bool launch_cat(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_bo
 		if (smem_budget < 8 * 1024 || smem_budget > 200 * 1024) smem_budget = TL_STAGE_DEFAULT;
 	}
 	// genome cache per aligned mate: [gpos-16 rounded down to 64, gpos+rflen+48), in 16-byte pieces
-	const uint32_t gc_stride = ((max_rflen + 16 + 48 + 63 + 63) / 64) * 16 + 16;
-	const uint32_t per_read = NS * max_rec_bytes + NM * gc_stride + NS * (uint32_t)sizeof(BodyInfo) + 12;
+	// (+1 piece so that the word after the last needed one exists), bases then N mask (8 bytes per piece)
+	uint32_t gc_pieces = (max_rflen + 16 + 48 + 63 + 63) / 64 + 1;
+	gc_pieces += gc_pieces & 1;  // even, so that gc_stride = 24 * pieces is a multiple of 16 (cp.async alignment)
+	const uint32_t gc_mask_off = gc_pieces * 16;
+	const uint32_t gc_stride = gc_pieces * 24;
+	const uint32_t per_read = NS * max_rec_bytes + NM * gc_stride + NS * (uint32_t)sizeof(BodyInfo) +
+	                          NM * (uint32_t)sizeof(DrawInfo) + 20;
 	int R = (int)((smem_budget - NS * 64 - 64) / per_read);
 	if (R > TL_THREADS) R = TL_THREADS;
 	if (R < 4) return false;
 	// a tile's bytes are at most R * max_rec_bytes; +48 for the alignment phase and the ragged tail
 	const uint32_t stage_stride = ((uint32_t)R * max_rec_bytes + 48 + 15) & ~15u;
 	const size_t smem = (size_t)NS * stage_stride + (size_t)NM * R * gc_stride + (size_t)NS * R * sizeof(BodyInfo) +
-	                    (size_t)R * 12 + 16;
+	                    (size_t)NM * R * sizeof(DrawInfo) + (size_t)R * 20 + 16;
 	// chunks a sequence / quality string of maxL bytes can touch at any alignment
 	const int K = (int)((max_body + 15u) / 16u) + 1;
 	auto kern = k_simulate_tiled<MODE, CAT>;
@@ -787,7 +979,7 @@ static bool launch_cat(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_bo
 		const char *e = getenv("QTIPSIM_SKIP");
 		skip = e ? atoi(e) : 0;
 	}
-	kern<<<(unsigned)ntiles, TL_THREADS, smem, st>>>(a, R, stage_stride, K, gc_stride, skip);
+	kern<<<(unsigned)ntiles, TL_THREADS, smem, st>>>(a, R, stage_stride, K, gc_stride, gc_mask_off, skip);
 	kernels_count_launch();
 	return true;
 }
@@ -801,6 +993,18 @@ static bool launch_mode(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_b
 	default: return launch_cat<MODE, CAT_D>(a, max_rec_bytes, max_body, max_rflen, st);
 	}
 }
+
+#ifdef QT_PHASE_CLOCKS
+void tiled_phase_report() {
+	unsigned long long v[8];
+	cudaMemcpyFromSymbol(v, g_qt_phase, sizeof(v));
+	if (v[5])
+		fprintf(stderr, "QT_PHASE_CLOCKS per CTA (cycles): A=%llu B=%llu C=%llu D=%llu total=%llu  (%llu CTAs)\n", v[0] / v[5],
+		        v[1] / v[5], v[2] / v[5], v[3] / v[5], v[4] / v[5], v[5]);
+	memset(v, 0, sizeof(v));
+	cudaMemcpyToSymbol(g_qt_phase, v, sizeof(v));
+}
+#endif
 
 #ifdef QT_BOUNDS
 void tiled_debug_report() {
@@ -826,4 +1030,7 @@ bool launch_simulate_tiled(const SimArgs &a, uint32_t max_rec_bytes, uint32_t ma
 
 #ifdef QT_BOUNDS
 extern "C" void qt_tiled_debug_report() { qt::tiled_debug_report(); }
+#endif
+#ifdef QT_PHASE_CLOCKS
+extern "C" void qt_tiled_phase_report() { qt::tiled_phase_report(); }
 #endif
