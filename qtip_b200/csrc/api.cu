@@ -70,7 +70,7 @@ struct qtipsim {
 	HostGenome hg;
 	bool have_genome = false;
 	bool host_packed = false;  // hg.bases/nmask valid on the host (needed by the host planner)
-	DevBuf d_bases, d_nmask, d_recs, d_names;
+	DevBuf d_bases, d_nmask, d_nblk, d_recs, d_names;
 	DevBuf d_text, d_pk_a, d_pk_b, d_pk_c, d_pk_d, d_pk_e;  // K0 scratch
 	float ms_pack_pending = 0;
 
@@ -152,7 +152,7 @@ void qtipsim_destroy(qtipsim_t *h) {
 	if (!h) return;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->st);
-	DevBuf *all[] = {&h->d_setups, &h->d_pclass, &h->d_rsresult, &h->d_text, &h->d_pk_a, &h->d_pk_b, &h->d_pk_c, &h->d_pk_d, &h->d_pk_e, &h->d_bases, &h->d_nmask, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
+	DevBuf *all[] = {&h->d_setups, &h->d_pclass, &h->d_rsresult, &h->d_text, &h->d_pk_a, &h->d_pk_b, &h->d_pk_c, &h->d_pk_d, &h->d_pk_e, &h->d_bases, &h->d_nmask, &h->d_nblk, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
 	                 &h->d_ncount, &h->d_cum, &h->d_len0, &h->d_len1, &h->d_scan_tmp, &h->d_small};
 	for (DevBuf *b : all) b->release();
 	for (int c = 0; c < NCAT; c++) {
@@ -176,6 +176,15 @@ void qtipsim_destroy(qtipsim_t *h) {
 
 const char *qtipsim_last_error(const qtipsim_t *h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 
+// 64-base block summary of the N mask (bit b = any N in bases [64 b, 64 b + 64)): lets the simulate kernel
+// decide per read, from one or two L2-resident words, whether the N-free fast path applies
+static int build_nblock(qtipsim *h, uint64_t mask_words) {
+	const uint64_t nblk_words = (h->hg.total_bases / 64) / 32 + 4;
+	CK(h->d_nblk.ensure(nblk_words * 4));
+	launch_nblock(h->d_nmask.as<uint32_t>(), mask_words, h->d_nblk.as<uint32_t>(), nblk_words, h->st);
+	return QTIPSIM_OK;
+}
+
 static int upload_genome(qtipsim *h) {
 	CK(cudaSetDevice(h->device));
 	const HostGenome &g = h->hg;
@@ -188,6 +197,10 @@ static int upload_genome(qtipsim *h) {
 	CK(cudaMemcpyAsync(h->d_recs.p, g.recs.data(), g.recs.size() * sizeof(RecDev), cudaMemcpyHostToDevice, h->st));
 	if (!g.names.empty())
 		CK(cudaMemcpyAsync(h->d_names.p, g.names.data(), g.names.size(), cudaMemcpyHostToDevice, h->st));
+	{
+		const int rc = build_nblock(h, g.nmask.size());
+		if (rc) return rc;
+	}
 	CK(cudaStreamSynchronize(h->st));
 	h->have_genome = true;
 	h->host_packed = true;
@@ -323,6 +336,10 @@ static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
 		CK(cudaMemcpyAsync(d_hi, pad_hi.data(), np * 8, cudaMemcpyHostToDevice, h->st));
 		launch_fill_n(d_lo, d_hi, np, h->d_nmask.as<uint32_t>(), h->st);
 	}
+	{
+		const int rc = build_nblock(h, mw);
+		if (rc) return rc;
+	}
 	CK(h->d_recs.ensure(g.recs.size() * sizeof(RecDev) + 16));
 	CK(h->d_names.ensure(g.names.size() + 16));
 	if (!g.recs.empty())
@@ -430,6 +447,10 @@ int qtipsim_genome_adopt(qtipsim_t *h, const void *blob, uint64_t blob_bytes, co
 	CK(h->d_names.ensure(h->hg.names.size() + 16));
 	CK(cudaMemcpyAsync(h->d_bases.p, d_bases, need_b, cudaMemcpyDeviceToDevice, h->st));
 	CK(cudaMemcpyAsync(h->d_nmask.p, d_nmask, need_n, cudaMemcpyDeviceToDevice, h->st));
+	{
+		const int rc = build_nblock(h, need_n / 4);
+		if (rc) return rc;
+	}
 	CK(cudaMemcpyAsync(h->d_recs.p, h->hg.recs.data(), h->hg.recs.size() * sizeof(RecDev), cudaMemcpyHostToDevice, h->st));
 	if (!h->hg.names.empty())
 		CK(cudaMemcpyAsync(h->d_names.p, h->hg.names.data(), h->hg.names.size(), cudaMemcpyHostToDevice, h->st));
@@ -583,6 +604,7 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 	DevGenome dg;
 	dg.bases = h->d_bases.as<uint32_t>();
 	dg.nmask = h->d_nmask.as<uint32_t>();
+	dg.nblk = h->d_nblk.as<uint32_t>();
 	dg.recs = h->d_recs.as<RecDev>();
 	dg.names = h->d_names.as<char>();
 	dg.nrecs = (uint32_t)h->hg.recs.size();
@@ -785,7 +807,8 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 		                         2u * cg.max_body + 4u;
 		const char *force = getenv("QTIPSIM_KERNEL");
 		bool done = false;
-		if (cg.compiled_ok && !(force && strcmp(force, "generic") == 0)) done = launch_simulate_tiled(sa[c], max_rec, cg.max_body, cg.max_rflen, h->st);
+		if (cg.compiled_ok && force && strcmp(force, "tiled") == 0) done = launch_simulate_tiled(sa[c], max_rec, cg.max_body, cg.max_rflen, h->st);
+		else if (cg.compiled_ok && !(force && strcmp(force, "generic") == 0)) done = launch_simulate_warp(sa[c], max_rec, cg.max_body, h->st);
 		if (!done) launch_simulate(sa[c], h->st);
 	}
 	CK(cudaEventRecord(ev[3], h->st));
@@ -799,8 +822,10 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 #ifdef QT_BOUNDS
 	{
 		extern void qt_tiled_debug_report();
+		extern void qt_warp_debug_report();
 		cudaStreamSynchronize(h->st);
 		qt_tiled_debug_report();
+		qt_warp_debug_report();
 	}
 #endif
 	CK(cudaStreamSynchronize(h->st));

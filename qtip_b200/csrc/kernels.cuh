@@ -13,6 +13,7 @@ static constexpr int JUMP_TBL = 4096;  // a^j mod m for j < JUMP_TBL, both compo
 struct DevGenome {
 	const uint32_t *bases = nullptr;
 	const uint32_t *nmask = nullptr;
+	const uint32_t *nblk = nullptr;  // 1 bit per 64 bases: any N in the block
 	const RecDev *recs = nullptr;
 	const char *names = nullptr;
 	uint32_t nrecs = 0;
@@ -72,6 +73,10 @@ void launch_simulate(const SimArgs &a, cudaStream_t st);
 // category cannot use it (record too large for the staging buffer) -- caller falls back.
 bool launch_simulate_tiled(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, uint32_t max_rflen,
                            cudaStream_t st);
+// warp-autonomous path (simulate_warp.cu): a warp stages a tile of consecutive records in its own slice of
+// shared memory and ships it with one bulk copy; no CTA barriers.  Same contract as the tiled path.
+bool launch_simulate_warp(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, cudaStream_t st);
+void launch_nblock(const uint32_t *nmask, uint64_t mask_words, uint32_t *nblk, uint64_t nblk_words, cudaStream_t st);
 void kernels_count_launch();
 
 // PHILOX planning: per-window counts on the device
