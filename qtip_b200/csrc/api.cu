@@ -807,24 +807,21 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 		                         2u * cg.max_body + 4u;
 		const char *force = getenv("QTIPSIM_KERNEL");
 		bool done = false;
-		if (cg.compiled_ok && force && strcmp(force, "tiled") == 0) done = launch_simulate_tiled(sa[c], max_rec, cg.max_body, cg.max_rflen, h->st);
-		else if (cg.compiled_ok && !(force && strcmp(force, "generic") == 0)) done = launch_simulate_warp(sa[c], max_rec, cg.max_body, h->st);
+		// production: the direct kernel; categories it cannot take (a body under 17 bytes) use the staged kernel,
+		// records too large for either the generic warp-per-read kernel.  QTIPSIM_KERNEL forces one (tests).
+		const bool want_direct = !force || strcmp(force, "direct") == 0;
+		const bool want_staged = !force || strcmp(force, "direct") == 0 || strcmp(force, "staged") == 0;
+		if (cg.compiled_ok && want_direct) done = launch_simulate_direct(sa[c], max_rec - 2u * cg.max_body - 4u, cg.min_body, cg.max_body, h->st);
+		if (!done && cg.compiled_ok && want_staged) done = launch_simulate_warp(sa[c], max_rec, cg.max_body, h->st);
 		if (!done) launch_simulate(sa[c], h->st);
 	}
 	CK(cudaEventRecord(ev[3], h->st));
-#ifdef QT_PHASE_CLOCKS
-	{
-		extern void qt_tiled_phase_report();
-		cudaStreamSynchronize(h->st);
-		qt_tiled_phase_report();
-	}
-#endif
 #ifdef QT_BOUNDS
 	{
-		extern void qt_tiled_debug_report();
+		extern void qt_direct_debug_report();
 		extern void qt_warp_debug_report();
 		cudaStreamSynchronize(h->st);
-		qt_tiled_debug_report();
+		qt_direct_debug_report();
 		qt_warp_debug_report();
 	}
 #endif

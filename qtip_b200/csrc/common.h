@@ -16,11 +16,12 @@
 
 namespace qt {
 
-struct RecDev {
+struct alignas(16) RecDev {
 	uint64_t gstart;    // first base in the concatenated space
 	uint64_t len;       // bases in the record
 	uint32_t name_off;  // into the names arena
 	uint32_t name_len;  // refid = header up to first whitespace (fasta.cpp:98-104)
+	uint32_t pad[2];    // 32 bytes: two 16-byte loads
 };
 
 // One FASTA window as the reference's chunk parser would return it (fasta.cpp:42-127).
@@ -31,26 +32,30 @@ struct Window {
 };
 
 // One SimulatedRead::init worth of template data (template.h:97-104 / :218-230).
-struct MateDesc {
-	uint32_t qual_off;   // qual arena, read orientation as given
-	uint32_t xs_off;     // transcript arena, ASCII ops
-	uint32_t len;        // read length = strlen(qual)
-	uint32_t xs_len;     // number of ops
-	uint32_t rflen;      // reference bases consumed (edit_xscript.h:15-25)
-	uint32_t ndraw;      // X+I+S ops (draws without rejections)
-	uint8_t fw;          // 1 = '+'
-	uint8_t score_len;
-	char score[12];      // "%d" of the score
-	uint16_t pad;
-	// compiled, output-oriented form (tiled kernel): see templates.cpp
+// 64 bytes in four 16-byte blocks; the simulate kernel reads blocks 0-2 with vector loads.
+struct alignas(16) MateDesc {
+	// block 0: compiled, output-oriented form (see templates.cpp)
 	uint32_t qual_out_off;  // qual arena in OUTPUT orientation (reversed for '-'), 16-byte aligned
 	uint32_t ops_off;       // draw-op list (X/I/S in transcript order), u32 entries
 	uint32_t seg_off;       // reference-copy segments, ascending output position
+	int32_t ref0;           // single != 0: reference offset of output position 0
+	// block 1
+	uint32_t len;        // read length = strlen(qual)
+	uint32_t rflen;      // reference bases consumed (edit_xscript.h:15-25)
 	uint16_t nops;
 	uint16_t nseg;
-	int32_t ref0;           // single != 0: reference offset of output position 0
-	uint8_t single;         // one segment covering the whole read (no indels: =, X, S only)
-	uint8_t pad2[3];
+	uint8_t fw;          // 1 = '+'
+	uint8_t single;      // one segment covering the whole read (no indels: =, X, S only)
+	uint8_t score_len;
+	uint8_t pad;
+	// block 2
+	char score[12];      // "%d" of the score
+	uint32_t ndraw;      // X+I+S ops (draws without rejections)
+	// block 3: as given (generic kernel, planners)
+	uint32_t qual_off;   // qual arena, read orientation as given
+	uint32_t xs_off;     // transcript arena, ASCII ops
+	uint32_t xs_len;     // number of ops
+	uint32_t pad2;
 };
 
 // A maximal run of transcript ops that copy reference to read (=, X, S), in output
@@ -67,17 +72,20 @@ struct SegDev {
 static constexpr uint32_t OP_X = 0u, OP_IS = 1u;
 static constexpr uint32_t COMPILED_MAX_LEN = 32767u;
 
-struct TmplDesc {
+struct alignas(16) TmplDesc {
 	MateDesc m[2];       // [0] = rd1's source (aligned mate for U/B), [1] = mate 2 (C/D)
+	// one 16-byte block
 	uint32_t delta[2];   // offset of each mate's leftmost ref base from the drawn `off`
 	                     // (simplesim.cpp:354-363; 0 for U/B)
 	uint32_t opp_len;    // B: length of the random opposite mate (simplesim.h:89-117)
-	uint8_t nmates;      // 1 (U, B) or 2 (C, D)
-	uint8_t aligned_is_mate1;  // B: mate_flag == '1' (simplesim.cpp:288)
-	uint8_t typ_len;
 	char typ[2];         // "u" "b1" "b2" "c" "d"
-	uint8_t pad[3];
+	uint8_t typ_len;
+	uint8_t aligned_is_mate1;  // B: mate_flag == '1' (simplesim.cpp:288)
+	// --
+	uint8_t nmates;      // 1 (U, B) or 2 (C, D)
+	uint8_t pad[15];
 };
+static_assert(sizeof(MateDesc) == 64 && sizeof(TmplDesc) == 160 && sizeof(RecDev) == 32, "descriptor layout");
 
 // One simulated read (U), bad-end pair (B) or pair (C/D).
 struct PlanRec {

@@ -56,7 +56,7 @@ void HostGenome::parse(const uint8_t *text, uint64_t n) {
 	};
 	auto open_record = [&](uint32_t name_off, uint32_t name_len) {
 		close_record();
-		RecDev r;
+		RecDev r{};
 		r.gstart = g;
 		r.len = 0;
 		r.name_off = name_off;

@@ -76,6 +76,9 @@ bool launch_simulate_tiled(const SimArgs &a, uint32_t max_rec_bytes, uint32_t ma
 // warp-autonomous path (simulate_warp.cu): a warp stages a tile of consecutive records in its own slice of
 // shared memory and ships it with one bulk copy; no CTA barriers.  Same contract as the tiled path.
 bool launch_simulate_warp(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, cudaStream_t st);
+// direct path (simulate_direct.cu): interior chunks go from registers to HBM, only a record's edge chunks are
+// staged.  max_name bounds the read name; returns false when the category cannot use it (caller falls back).
+bool launch_simulate_direct(const SimArgs &a, uint32_t max_name, uint32_t min_body, uint32_t max_body, cudaStream_t st);
 void launch_nblock(const uint32_t *nmask, uint64_t mask_words, uint32_t *nblk, uint64_t nblk_words, cudaStream_t st);
 void kernels_count_launch();
 

@@ -50,6 +50,7 @@ bool add_mate(Category &c, MateDesc &m, HostMateProg &hp, const char *qual, cons
 	m.rflen = rf;
 	m.ndraw = ndraw;
 	c.max_body = std::max(c.max_body, m.len);
+	c.min_body = std::min(c.min_body, m.len);
 	c.max_rflen = std::max(c.max_rflen, rf);
 	c.max_score_len = std::max<uint32_t>(c.max_score_len, m.score_len);
 
@@ -153,6 +154,7 @@ int TemplateStore::set_unpaired(int ci, const qtipsim_tmpl_unp *v, size_t kept, 
 			t.aligned_is_mate1 = (v[i].mate_flag == '1');
 			t.opp_len = v[i].opp_len > 0 ? (uint32_t)v[i].opp_len : 0;
 			c.max_body = std::max(c.max_body, t.opp_len);
+			c.min_body = std::min(c.min_body, t.opp_len);
 			if (t.opp_len > COMPILED_MAX_LEN) c.compiled_ok = false;
 			if (v[i].opp_len <= 0 && c.valid) {  // assert(len > 0), simplesim.h:96
 				c.valid = false;

@@ -34,6 +34,7 @@ struct Category {
 	std::vector<SegDev> segs;         // compiled reference-copy segments
 	bool compiled_ok = true;          // false: some mate exceeds the compiled format's limits
 	uint32_t max_body = 0;            // longest read body (either mate / random mate)
+	uint32_t min_body = 0xffffffffu;  // shortest
 	uint32_t max_score_len = 0;
 	uint32_t max_rflen = 0;           // longest reference span of a mate
 	std::vector<XStep> xsteps;        // host-side draw programs (replay planner)

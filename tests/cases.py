@@ -127,6 +127,20 @@ def case_long_refid():
                 kw=dict(fraction=300.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(71)))
 
 
+def case_short_reads():
+    """Bodies shorter than one 16-byte output chunk next to normal ones, all categories: the direct
+    kernel declines the category (first / last chunk of a string could coincide) and the staged kernel
+    takes it."""
+    fa = synth.make_fasta([("s1", 90000), ("s2 x", 40000)], seed=81, lead_n=100)
+    tu = (synth.templates_unpaired(60, 12, 82, max_x=2) + synth.templates_unpaired(60, 17, 83, max_x=2) +
+          synth.templates_unpaired(60, 40, 84, indel=True) + synth.templates_unpaired(40, 5, 85, max_x=1))
+    tb = synth.templates_badend(80, 30, 86, opp_len=8)
+    tc = synth.templates_paired(80, 14, 87, frag_mean=60, frag_sd=8, max_x=2)
+    td = synth.templates_paired(60, 33, 88, discordant=True, max_fraglen=3000)
+    return dict(fasta=fa, tu=tu, tb=tb, tc=tc, td=td,
+                kw=dict(fraction=400.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(81)))
+
+
 CASES = {
     "c1_lambda": case_c1_lambda,
     "mixed_small": case_mixed_small,
@@ -137,6 +151,7 @@ CASES = {
     "edges": case_edges,
     "inversion": case_inversion,
     "long_refid": case_long_refid,
+    "short_reads": case_short_reads,
 }
 
 

@@ -292,6 +292,21 @@ def test_generic_kernel_path_still_bit_exact(name, workdir, monkeypatch):
     assert nat_g == nat_t  # both kernels consume the Philox stream identically
 
 
+@pytest.mark.parametrize("name", ["mixed_small", "c5_indel", "c4_mix_small", "edges"])
+def test_staged_kernel_path_still_bit_exact(name, workdir, monkeypatch):
+    """The staged warp-tile kernel (taken by categories with bodies under 17 bytes) stays covered on the
+    ordinary cases too."""
+    monkeypatch.setenv("QTIPSIM_KERNEL", "staged")
+    case = cases.CASES[name]()
+    streams, st, p = util.run_cuda(case, workdir, name)
+    o = _oracle(case, workdir, name)
+    assert streams == o.streams
+    nat_s, _, _ = util.run_cuda(case, workdir, name, rng_mode=1, philox_seed=5)
+    monkeypatch.delenv("QTIPSIM_KERNEL")
+    nat_d, _, _ = util.run_cuda(case, workdir, name, rng_mode=1, philox_seed=5)
+    assert nat_s == nat_d  # both kernels consume the Philox stream identically
+
+
 def test_host_pack_path_equals_device_pack(workdir, monkeypatch):
     """K0 on the device (default) and the host FASTA packer produce the same reads."""
     case = cases.CASES["edges"]()
