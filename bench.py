@@ -411,7 +411,7 @@ def main():
             "reads_per_step": m["reads_per_step"],
             "wall_ms_per_step": m["wall_ms_per_step"],
             "phase_ms_per_step_rank0": m["phase"],
-            "roofline": {"bound": "hbm", "kernel": "k_simulate_tiled", "achieved": m["achieved"], "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_simulate_direct", "achieved": m["achieved"], "peak": peak, "unit": "GB/s",
                          "frac": m["achieved"] / peak if peak else None, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": m["alg_step"]},
             "e2e": m["e2e"],
@@ -423,7 +423,7 @@ def main():
             line[other] = {"rng_mode": names[other], "value": m2["value"], "unit": wl["unit"], "ms_per_step": m2["ms_per_step"],
                            "phase_ms_per_step_rank0": m2["phase"], "steps": 1, "warmup": 1,
                            "roofline": {"achieved": m2["achieved"], "frac": m2["achieved"] / peak if peak else None,
-                                        "kernel": "k_simulate_tiled"},
+                                        "kernel": "k_simulate_direct"},
                            "e2e": m2["e2e"], "output_gb_per_s": m2["output_gb_per_s"]}
         if n_gpus == 1 and not args.no_cpu_baseline:
             res, why = run_reference_steps(wl, 1, 0)

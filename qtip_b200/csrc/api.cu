@@ -187,6 +187,7 @@ static int build_nblock(qtipsim *h, uint64_t mask_words) {
 
 static int upload_genome(qtipsim *h) {
 	CK(cudaSetDevice(h->device));
+	h->hg.fill_name16();
 	const HostGenome &g = h->hg;
 	CK(h->d_bases.ensure(g.bases.size() * 4));
 	CK(h->d_nmask.ensure(g.nmask.size() * 4));
@@ -340,6 +341,7 @@ static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
 		const int rc = build_nblock(h, mw);
 		if (rc) return rc;
 	}
+	g.fill_name16();
 	CK(h->d_recs.ensure(g.recs.size() * sizeof(RecDev) + 16));
 	CK(h->d_names.ensure(g.names.size() + 16));
 	if (!g.recs.empty())
@@ -439,6 +441,7 @@ int qtipsim_genome_adopt(qtipsim_t *h, const void *blob, uint64_t blob_bytes, co
 	if (!h || !blob || !d_bases || !d_nmask) return QTIPSIM_EINVAL;
 	CK(cudaSetDevice(h->device));
 	if (!h->hg.from_blob(blob, blob_bytes)) return h->fail(QTIPSIM_EINVAL, "bad genome blob");
+	h->hg.fill_name16();
 	const uint64_t need_b = (h->hg.total_bases + 15) / 16 * 4 + 16, need_n = (h->hg.total_bases + 31) / 32 * 4 + 16;
 	if (bases_bytes < need_b || nmask_bytes < need_n) return h->fail(QTIPSIM_EINVAL, "packed genome buffers too small");
 	CK(h->d_bases.ensure(need_b));
@@ -495,7 +498,7 @@ static int upload_templates(qtipsim *h) {
 			CK(cudaMemcpyAsync(h->d_xs[c].p, cg.xs.data(), cg.xs.size(), cudaMemcpyHostToDevice, h->st));
 			// compiled form; the quality arena is read with aligned 4-byte loads up to 16 bytes past an entry
 			CK(h->d_qual_out[c].ensure(cg.qual_out.size() + 64));
-			CK(h->d_ops[c].ensure(cg.ops.size() * 4 + 16));
+			CK(h->d_ops[c].ensure(cg.ops.size() * 4 + 64));
 			CK(h->d_segs[c].ensure(cg.segs.size() * sizeof(SegDev) + 16));
 			CK(cudaMemsetAsync(h->d_qual_out[c].p, 0, cg.qual_out.size() + 64, h->st));
 			CK(cudaMemcpyAsync(h->d_qual_out[c].p, cg.qual_out.data(), cg.qual_out.size(), cudaMemcpyHostToDevice, h->st));

@@ -21,8 +21,9 @@ struct alignas(16) RecDev {
 	uint64_t len;       // bases in the record
 	uint32_t name_off;  // into the names arena
 	uint32_t name_len;  // refid = header up to first whitespace (fasta.cpp:98-104)
-	uint32_t pad[2];    // 32 bytes: two 16-byte loads
-};
+	uint32_t pad[2];
+	char name16[16];    // first 16 bytes of the refid (the kernels print short names from registers)
+};                      // 48 bytes: three 16-byte loads
 
 // One FASTA window as the reference's chunk parser would return it (fasta.cpp:42-127).
 struct Window {
@@ -85,7 +86,7 @@ struct alignas(16) TmplDesc {
 	uint8_t nmates;      // 1 (U, B) or 2 (C, D)
 	uint8_t pad[15];
 };
-static_assert(sizeof(MateDesc) == 64 && sizeof(TmplDesc) == 160 && sizeof(RecDev) == 32, "descriptor layout");
+static_assert(sizeof(MateDesc) == 64 && sizeof(TmplDesc) == 160 && sizeof(RecDev) == 48, "descriptor layout");
 
 // One simulated read (U), bad-end pair (B) or pair (C/D).
 struct PlanRec {

@@ -111,6 +111,14 @@ std::vector<Window> HostGenome::windows(uint64_t chunksz, uint64_t olap) const {
 	return out;
 }
 
+void HostGenome::fill_name16() {
+	for (RecDev &r : recs) {
+		memset(r.name16, 0, sizeof(r.name16));
+		const uint32_t n = r.name_len < 16u ? r.name_len : 16u;
+		if (n) memcpy(r.name16, names.data() + r.name_off, n);
+	}
+}
+
 std::string HostGenome::blob() const {
 	std::string b;
 	uint64_t hdr[4] = {(uint64_t)recs.size(), (uint64_t)names.size(), total_bases, file_bytes};

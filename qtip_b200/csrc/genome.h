@@ -36,6 +36,9 @@ struct HostGenome {
 		return (bases[g >> 4] >> (2 * (g & 15))) & 3u;
 	}
 
+	// copies the first 16 bytes of every refid into its record (RecDev::name16)
+	void fill_name16();
+
 	// serialise / restore the record table (multi-GPU replication)
 	std::string blob() const;
 	bool from_blob(const void *p, uint64_t n);

@@ -38,6 +38,20 @@ __device__ __forceinline__ uint4 expand16(uint32_t w, uint32_t T) {
 	return make_uint4(__byte_perm(E0, O0, 0x5140u), __byte_perm(E0, O0, 0x7362u), __byte_perm(E1, O1, 0x5140u),
 	                  __byte_perm(E1, O1, 0x7362u));
 }
+// The same for a mate on either strand: '-' mates print the complement of the bases in reverse order
+// (asc2dnacomp, simplesim.cpp:76-97).  Complement = the table "TGCA"; reversal costs one rotate: with the
+// two 16-bit halves of w swapped, the byte-interleaving PRMTs pick their bytes in descending order
+// (selectors 0x5140 / 0x7362 xor 0x7777 = 0x2637 / 0x0415).
+__device__ __forceinline__ uint4 expand16_strand(uint32_t w, bool fw) {
+	const uint32_t T = fw ? 0x54474341u : 0x41434754u;
+	const uint32_t x7 = fw ? 0u : 0x7777u;
+	w = __funnelshift_l(w, w, fw ? 0u : 16u);
+	const uint32_t ev = w & 0x33333333u, od = (w >> 2) & 0x33333333u;
+	const uint32_t E0 = __byte_perm(T, 0u, ev), O0 = __byte_perm(T, 0u, od);
+	const uint32_t E1 = __byte_perm(T, 0u, ev >> 16), O1 = __byte_perm(T, 0u, od >> 16);
+	const uint32_t sa = 0x5140u ^ x7, sb = 0x7362u ^ x7;
+	return make_uint4(__byte_perm(E0, O0, sa), __byte_perm(E0, O0, sb), __byte_perm(E1, O1, sa), __byte_perm(E1, O1, sb));
+}
 static constexpr uint32_t TBL_FW = 0x54474341u;  // "ACGT"
 static constexpr uint32_t TBL_RC = 0x41434754u;  // "TGCA": complement (asc2dnacomp, simplesim.cpp:76-97)
 
@@ -133,9 +147,7 @@ __device__ __forceinline__ SeqLoad seq_issue(const uint32_t *__restrict__ bases,
 }
 __device__ __forceinline__ uint4 seq_finish(const SeqLoad &sl, uint32_t meta) {
 	const bool fw = (meta & RF_FW) != 0;
-	uint32_t w = __funnelshift_r(sl.lo, sl.hi, (meta >> 7) & 30u);
-	if (!fw) w = rev16(w);
-	return expand16(w, fw ? TBL_FW : TBL_RC);
+	return expand16_strand(__funnelshift_r(sl.lo, sl.hi, (meta >> 7) & 30u), fw);
 }
 
 // quality chunk: two aligned 16-byte loads of the pre-oriented string ...
@@ -156,6 +168,29 @@ __device__ __forceinline__ uint4 qual_finish(const QualLoad &ql, uint32_t a) {
 	const uint32_t t0 = s2 ? x.z : x.x, t1 = s2 ? x.w : x.y, t2 = s2 ? y.x : x.z, t3 = s2 ? y.y : x.w, t4 = s2 ? y.z : y.x,
 	               t5 = s2 ? y.w : y.y;
 	const uint32_t u0 = s1 ? t1 : t0, u1 = s1 ? t2 : t1, u2 = s1 ? t3 : t2, u3 = s1 ? t4 : t3, u4 = s1 ? t5 : t4;
+	const uint32_t sh = 8u * (a & 3u);
+	return make_uint4(__funnelshift_r(u0, u1, sh), __funnelshift_r(u1, u2, sh), __funnelshift_r(u2, u3, sh),
+	                  __funnelshift_r(u3, u4, sh));
+}
+
+// The same with three 8-byte loads: the bytes wanted start a (0..15) bytes into 16-byte unit `unit`; loading
+// from the 8-byte boundary below them leaves one word-select stage instead of two (ALU-pipe instructions
+// are what bounds the chunk loops).
+struct QualLoad8 {
+	uint2 p, q, r;
+};
+__device__ __forceinline__ QualLoad8 qual_issue8(const char *__restrict__ qual_out, uint32_t unit, uint32_t a) {
+	const uint2 *bp = (const uint2 *)(qual_out + 16ull * unit + (a & 8u));
+	QualLoad8 ql;
+	ql.p = __ldg(bp);
+	ql.q = __ldg(bp + 1);
+	ql.r = __ldg(bp + 2);
+	return ql;
+}
+__device__ __forceinline__ uint4 qual_finish8(const QualLoad8 &ql, uint32_t a) {
+	const bool s1 = (a & 4u) != 0;
+	const uint32_t u0 = s1 ? ql.p.y : ql.p.x, u1 = s1 ? ql.q.x : ql.p.y, u2 = s1 ? ql.q.y : ql.q.x, u3 = s1 ? ql.r.x : ql.q.y,
+	               u4 = s1 ? ql.r.y : ql.r.x;
 	const uint32_t sh = 8u * (a & 3u);
 	return make_uint4(__funnelshift_r(u0, u1, sh), __funnelshift_r(u1, u2, sh), __funnelshift_r(u2, u3, sh),
 	                  __funnelshift_r(u3, u4, sh));
@@ -237,10 +272,18 @@ __device__ __forceinline__ char *s_put_dec(char *p, uint64_t v, uint32_t n) {
 	}
 	return p + n;
 }
-// "<refid>:<+|->:<off>:<score>" (simplesim.cpp:104-110); the score comes from registers
-__device__ __forceinline__ char *s_origin(char *p, const char *__restrict__ refid, uint32_t rl, uint64_t off, uint32_t nd,
-                                          const MateHot &m) {
-	for (uint32_t i = 0; i < rl; i++) p[i] = refid[i];
+// "<refid>:<+|->:<off>:<score>" (simplesim.cpp:104-110); the score and refids of up to 16 bytes come
+// from registers (n16 = RecDev::name16)
+__device__ __forceinline__ char *s_origin(char *p, const char *__restrict__ refid, const uint4 &n16, uint32_t rl, uint64_t off,
+                                          uint32_t nd, const MateHot &m) {
+	if (rl <= 16u) {
+		const uint32_t nw[4] = {n16.x, n16.y, n16.z, n16.w};
+#pragma unroll
+		for (int k = 0; k < 16; k++)
+			if (k < (int)rl) p[k] = (char)(nw[k >> 2] >> (8 * (k & 3)));
+	} else {
+		for (uint32_t i = 0; i < rl; i++) p[i] = refid[i];
+	}
 	p += rl;
 	p[0] = ':';
 	p[1] = m.fw ? '+' : '-';

@@ -62,7 +62,7 @@ __device__ unsigned long long g_qd_violation[4];
 #define QT_DT_MAX_WARPS 4
 #endif
 #ifndef QT_DT_MIN_BLOCKS
-#define QT_DT_MIN_BLOCKS 6
+#define QT_DT_MIN_BLOCKS 8
 #endif
 #ifndef QT_DT_UNROLL
 #define QT_DT_UNROLL 2
@@ -72,15 +72,22 @@ static constexpr int DT_OPS = 6;                 // draw ops per mate kept in sh
 static constexpr int DT_UNROLL = QT_DT_UNROLL;   // step B: chunk iterations with their loads in flight together
 static constexpr uint32_t T_BYTES = 32;          // staging for the chunks of the sequence's last byte .. the qualities' first
 
-// per-read, per-stream interior-chunk geometry (positions are relative to the tile base, which is
-// the output offset of the tile's first byte rounded down to 16)
-struct __align__(16) DHot {
-	uint32_t sdst;    // byte position of interior sequence slot 0
-	uint32_t w0;      // fast path: packed-genome word of that slot, step +1 ('+') / -1 ('-')
-	uint32_t qdst;    // byte position of interior quality slot 0
-	uint32_t qsrc;    // quality arena, 16-byte unit of that slot
-	uint32_t nsq;     // interior sequence slots | interior quality slots << 16
-	uint32_t meta;    // RF_* | genome phase << 8 | quality phase << 12
+// per-read, per-stream chunk geometry (positions are relative to the tile base, which is the output
+// offset of the tile's first byte rounded down to 16); slot j of a string = its j-th 16-byte chunk
+struct __align__(16) DHot {   // what a sequence-chunk lane reads
+	uint32_t grow;    // fast path: shared-memory address of slot 0's first packed genome word; slot j is
+	                  // 4 j bytes further ('+' mates) or back ('-' mates)
+	uint32_t sdst;    // byte position of sequence slot 0 (16 * (P >> 4))
+	uint32_t ns;      // sequence slots | meta << 16; meta = RF_* | genome phase << 8 | quality phase << 12
+	uint32_t area;    // shared-memory address of the read's four edge areas
+};
+struct __align__(16) DHotQ {  // what a quality-chunk lane reads
+	uint32_t qsrc;    // quality arena, 16-byte unit of slot 0
+	uint32_t qdst;    // byte position of quality slot 0
+	uint32_t nq;      // quality slots | meta << 16
+	uint32_t area;
+};
+struct __align__(8) DPos {
 	uint32_t P;       // byte position of the first sequence byte
 	uint32_t L;       // body length
 };
@@ -91,62 +98,62 @@ struct __align__(16) DGen {  // general path only
 	uint32_t nseg;
 	uint32_t pad[2];
 };
-// what a staging slot holds: chunks [s0, s0 + nS) -- from the previous record's last quality chunk to
-// this record's first sequence chunk -- and chunks [t0, t0 + nT): last sequence chunk .. first quality chunk
+// A staging slot holds the IMAGE (names, separators) of the record's edge chunks: chunks [s0, s0 + nS) --
+// from the previous record's last quality chunk to this record's first sequence chunk -- and chunks
+// [t0, t0 + nT): last sequence chunk .. first quality chunk.  The string bytes of those chunks are staged
+// whole in the read's four AREAS (first / last chunk of the sequence, first / last chunk of the qualities)
+// and merged over the image when the slot is shipped.
 struct __align__(16) DShip {
-	uint32_t s0, nS, t0, nT;
+	uint32_t s0, t0;
+	uint32_t n;       // nS | nT << 8 | (1 << 16 when the slot is the one after the tile's last record)
+	uint32_t rstart;  // byte position of the record's '@'
 };
-
-// words of a 16-byte chunk that hold at least one byte of output positions [0, L); k0 = output position
-// of the chunk's first byte.  The word's other bytes belong to the name or a separator: the same lane
-// writes those afterwards.
-__device__ __forceinline__ void store_words(unsigned char *chunk, const uint4 &v, int k0, int L) {
-	uint32_t *cp = (uint32_t *)chunk;
-	const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-	for (int w = 0; w < 4; w++) {
-		const int lo = k0 + 4 * w;
-		if (lo < L && lo + 4 > 0) cp[w] = vw[w];
-	}
-}
-// same, but a word that also holds bytes past L gets only its own bytes (the neighbouring bytes belong
-// to the next record's name, which another lane writes)
-__device__ __forceinline__ void store_words_exact_end(unsigned char *chunk, const uint4 &v, int k0, int L) {
-	uint32_t *cp = (uint32_t *)chunk;
-	const uint32_t vw[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-	for (int w = 0; w < 4; w++) {
-		const int lo = k0 + 4 * w;
-		if (lo + 4 <= L) {
-			if (lo + 4 > 0) cp[w] = vw[w];
-		} else {
-#pragma unroll
-			for (int b = 0; b < 3; b++)
-				if (lo + b < L) chunk[4 * w + b] = (unsigned char)(vw[w] >> (8 * b));
-		}
-	}
-}
+enum { AREA_SEQ_HEAD = 0, AREA_SEQ_TAIL = 1, AREA_QUAL_HEAD = 2, AREA_QUAL_TAIL = 3 };
 
 // reference base at genome position gp as the reference's mutate() sees it: 0..3, or 4 for N and
-// for positions past the record end
-__device__ __forceinline__ uint32_t ref_code_at(const DevGenome &g, uint64_t gp, uint64_t gend, bool checked) {
-	if (checked) {
-		if (gp >= gend) return 4u;
-		if ((__ldg(&g.nmask[gp >> 5]) >> (gp & 31)) & 1u) return 4u;
-	}
+// for positions past the record end; general-path reads only
+__device__ __forceinline__ uint32_t ref_code_at(const DevGenome &g, uint64_t gp, uint64_t gend) {
+	if (gp >= gend) return 4u;
+	if ((__ldg(&g.nmask[gp >> 5]) >> (gp & 31)) & 1u) return 4u;
 	return (__ldg(&g.bases[gp >> 4]) >> (2 * (gp & 15))) & 3u;
 }
 
+// out = out with bytes [lo, hi) of the chunk replaced by v's
+__device__ __forceinline__ void overlay(uint4 &out, const uint4 &v, const uint4 *lowmask, int lo, int hi) {
+	const uint4 m = range_mask(lowmask, lo, hi);
+	out.x = (out.x & ~m.x) | (v.x & m.x);
+	out.y = (out.y & ~m.y) | (v.y & m.y);
+	out.z = (out.z & ~m.z) | (v.z & m.z);
+	out.w = (out.w & ~m.w) | (v.w & m.w);
+}
+
+// shared memory through 32-bit shared-window addresses: one instruction per access, no generic-address arithmetic
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+	uint4 v;
+	asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+	return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+	asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 template <int MODE, int CAT>
-__global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulate_direct(SimArgs a, int RW, int lgG, int rounds,
-                                                                                          int lgH, int hrounds, uint32_t s_bytes,
-                                                                                          uint32_t warp_smem) {
+__global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulate_direct(SimArgs a, int RW, int K, uint32_t kmagic,
+                                                                                          int PMAX, uint32_t pmagic, int lgH,
+                                                                                          int hrounds, uint32_t s_bytes,
+                                                                                          uint32_t warp_smem, int skip) {
 	constexpr int NS = CAT == CAT_U ? 1 : 2;                    // output streams
 	constexpr int NM = (CAT == CAT_C || CAT == CAT_D) ? 2 : 1;  // aligned mates per read
 	extern __shared__ __align__(16) unsigned char smem[];
-	__shared__ uint4 s_lowmask[17];
 
 	const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+	__shared__ uint4 s_lowmask[17];
 	if (tid < 17) {
 		uint32_t w[4];
 #pragma unroll
@@ -164,12 +171,19 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 	const int nr = (int)((a.nreads - r0) < (uint64_t)RW ? (a.nreads - r0) : (uint64_t)RW);
 
 	const uint32_t slot_bytes = s_bytes + T_BYTES;
+	const int GROW = 4 * PMAX;  // words per s_gbuf row
 	unsigned char *wsm = smem + (size_t)wib * warp_smem;
-	unsigned char *s_edge = wsm;                                                  // [NS][RW + 1] slots
-	DHot *s_hot = (DHot *)(s_edge + (size_t)NS * (RW + 1) * slot_bytes);          // [NS][RW]
-	DGen *s_gen = (DGen *)(s_hot + (size_t)NS * RW);                              // [NS][RW]
+	unsigned char *s_edge = wsm;                                                  // [NS][RW + 1] slot images
+	uint4 *s_area = (uint4 *)(s_edge + (size_t)NS * (RW + 1) * slot_bytes);       // [NS][RW][4]
+	uint32_t *s_gbuf = (uint32_t *)(s_area + (size_t)NS * RW * 4);                // [NS][RW][GROW] packed genome
+	DHot *s_hot = (DHot *)(s_gbuf + (size_t)NS * RW * GROW);                      // [NS][RW]
+	DHotQ *s_hotq = (DHotQ *)(s_hot + (size_t)NS * RW);                           // [NS][RW]
+	DGen *s_gen = (DGen *)(s_hotq + (size_t)NS * RW);                             // [NS][RW]
 	DShip *s_ship = (DShip *)(s_gen + (size_t)NS * RW);                           // [NS][RW + 1]
 	uint32_t *s_ops = (uint32_t *)(s_ship + (size_t)NS * (RW + 1));               // [NM][DT_OPS][RW]
+	uint32_t *s_gunit = s_ops + (size_t)NM * DT_OPS * RW;                         // [NS][RW] 16-byte unit of bases[] at the row's start
+	uint32_t *s_gb0 = s_gunit + (size_t)NS * RW;                                  // [NS][RW]
+	DPos *s_pos = (DPos *)(s_gb0 + (size_t)NS * RW);                              // [NS][RW]
 
 	const uint64_t *offs[2] = {a.off0, a.off1};
 	const uint64_t *tots[2] = {a.tot0, a.tot1};
@@ -182,8 +196,8 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 	const bool act = lane < nr;
 	const uint64_t ri = r0 + (uint64_t)(act ? lane : 0);
 
-	// ---------------- step A (lane = read) ----------------
-	char *tb[NS];          // tile base in the output stream (16-byte aligned)
+	// ---------------- step A (lane = read): geometry ----------------
+	char *tb[NS];               // tile base in the output stream (16-byte aligned)
 	uint32_t ph[NS], tend[NS];  // tile-relative position of the tile's first byte / one past its last
 	uint32_t rstart[NS], rlen[NS];
 #pragma unroll
@@ -200,25 +214,22 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 		rlen[s] = (uint32_t)(nxt - myoff);
 	}
 	const PlanRec pr = a.plan[ri];
-	uint32_t nops[NM];
-	uint32_t fwbits = 0;  // bit m: mate m is '+'
-	bool s0_random = false;
-	if (act) {
-		const TmplDesc *tp = a.c.t + pr.tmpl;
-		const uint4 *recp4 = (const uint4 *)(a.g.recs + pr.record);
-		const uint4 rec_a = __ldg(recp4), rec_b = __ldg(recp4 + 1);
-		const uint64_t rec_gstart = (uint64_t)rec_a.x | ((uint64_t)rec_a.y << 32);
-		const uint64_t gend = rec_gstart + ((uint64_t)rec_a.z | ((uint64_t)rec_a.w << 32));
-		const uint32_t rec_name_off = rec_b.x, rl = rec_b.y;
-		const TmplTail tt = load_tail(tp);
-		MateHot mh[NM];
+	const TmplDesc *tp = a.c.t + pr.tmpl;
+	const uint4 *recp4 = (const uint4 *)(a.g.recs + pr.record);
+	const uint4 rec_a = __ldg(recp4), rec_b = __ldg(recp4 + 1), rec_c = __ldg(recp4 + 2);
+	const uint64_t rec_gstart = (uint64_t)rec_a.x | ((uint64_t)rec_a.y << 32);
+	const uint64_t gend = rec_gstart + ((uint64_t)rec_a.z | ((uint64_t)rec_a.w << 32));
+	const TmplTail tt = load_tail(tp);
+	MateHot mh[NM];
 #pragma unroll
-		for (int m = 0; m < NM; m++) mh[m] = load_mate(&tp->m[m]);
-		const uint64_t ro[2] = {pr.refoff + tt.delta[0], pr.refoff + tt.delta[1]};
-		s0_random = CAT == CAT_B && !tt.aligned_is_mate1;
+	for (int m = 0; m < NM; m++) mh[m] = load_mate(&tp->m[m]);
+	const uint64_t ro[2] = {pr.refoff + tt.delta[0], pr.refoff + tt.delta[1]};
+	const bool s0_random = CAT == CAT_B && !tt.aligned_is_mate1;
+	uint32_t nl = 0;
+	if (act) {
 		// which mates need the general path: indel segments, reaching past the record end, or any N in the
 		// 64-base blocks of the N-mask summary the mate touches (bases outside the mate only ever land on
-		// bytes that are not stored)
+		// bytes that are masked away)
 		bool general[NM];
 #pragma unroll
 		for (int m = 0; m < NM; m++) {
@@ -234,23 +245,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 				for (uint64_t b = b0; b <= b1; b++) anyn |= ((__ldg(&a.g.nblk[b >> 5]) >> (b & 31)) & 1u) != 0;
 			}
 			general[m] = anyn || !mh[m].single || (gpos + mh[m].rflen > gend);
-			// L2 prefetch of the packed genome lines the chunk lanes are about to read
-			const uintptr_t gl = ((uintptr_t)a.g.bases + ((gpos - 16) >> 2)) & ~(uintptr_t)127;
-			const uintptr_t gh = (uintptr_t)a.g.bases + ((gpos + mh[m].rflen + 32) >> 2);
-			for (uintptr_t p = gl; p <= gh; p += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-			// the first draw ops, X ops with their reference base in place of the reference offset
-			nops[m] = mh[m].nops;
-			fwbits |= mh[m].fw ? (1u << m) : 0u;
-#pragma unroll
-			for (int j = 0; j < DT_OPS; j++)
-				if (j < (int)mh[m].nops) {
-					uint32_t e = __ldg(&a.c.ops[mh[m].ops_off + j]);
-					if ((e & 3u) == OP_X) e = (e & 0x1ffffu) | (ref_code_at(a.g, gpos + (e >> 17), gend, general[m]) << 17);
-					s_ops[(m * DT_OPS + j) * RW + lane] = e;
-				}
 		}
-		uint32_t nl = 0;
-		unsigned char *name0 = nullptr;
 #pragma unroll
 		for (int s = 0; s < NS; s++) {
 			const int mate = CAT == CAT_B ? 0 : s;
@@ -265,19 +260,30 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 			const uint32_t A0 = md.qual_out_off + 16u * (uint32_t)q_first - Pq;  // arena byte of the first quality chunk, >= 1
 			const uint64_t gadj = md.fw ? gpos + (uint64_t)(int64_t)md.ref0 - (P & 15u)
 			                            : gpos + (uint64_t)(int64_t)md.ref0 + (P & 15u) - 15u;
-			const uint32_t w0 = (uint32_t)(gadj >> 4);
+			const uint32_t ns = random ? 0u : (uint32_t)(c_last - c_first + 1);
+			const bool fast = !random && !general[mate];
+			// the read's row of packed genome words starts at a 16-byte unit of bases[]
+			const uint64_t wmin = md.fw ? (gadj >> 4) : (gadj >> 4) - (uint64_t)(ns ? ns - 1u : 0u);
+			const uint32_t gunit = (uint32_t)(wmin >> 2);
+			s_gunit[s * RW + lane] = fast ? gunit : 0xffffffffu;
+			s_gb0[s * RW + lane] = (uint32_t)(gpos - 64ull * gunit);
 			const uint32_t meta = (md.fw ? RF_FW : 0u) | (random ? RF_RANDOM : 0u) | (general[mate] ? RF_GENERAL : 0u) |
 			                      ((uint32_t)(gadj & 15u) << 8) | ((A0 & 15u) << 12);
+			const uint32_t w0 = (uint32_t)((gadj >> 4) - 4ull * gunit);  // word of slot 0 in the read's row
 			DHot h;
-			h.sdst = 16u * (uint32_t)(c_first + 1);
-			h.w0 = md.fw ? w0 + 1u : w0 - 1u;
-			h.qdst = 16u * (uint32_t)(q_first + 1);
-			h.qsrc = (A0 >> 4) + 1u;
-			h.nsq = (random ? 0u : (uint32_t)(c_last - c_first - 1)) | ((uint32_t)(q_last - q_first - 1) << 16);
-			h.meta = meta;
-			h.P = P;
-			h.L = L;
+			h.grow = smem_u32(s_gbuf + ((size_t)s * RW + lane) * GROW) + 4u * w0;
+			h.sdst = 16u * (uint32_t)c_first;
+			h.ns = ns | (meta << 16);
+			h.area = smem_u32(s_area + ((size_t)s * RW + lane) * 4);
 			s_hot[s * RW + lane] = h;
+			DHotQ hq;
+			hq.qsrc = A0 >> 4;
+			hq.qdst = 16u * (uint32_t)q_first;
+			hq.nq = (uint32_t)(q_last - q_first + 1) | (meta << 16);
+			hq.area = h.area;
+			s_hotq[s * RW + lane] = hq;
+			s_pos[s * RW + lane] = DPos{P, L};
+			QD_CHK(ns <= (uint32_t)K && (uint32_t)(q_last - q_first + 1) <= (uint32_t)K && (!fast || w0 + ns + 1 <= (uint32_t)(4 * PMAX)), 9, ns, K);
 			if (general[mate]) {
 				DGen g;
 				g.gpos = gpos;
@@ -287,52 +293,79 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 				g.pad[0] = g.pad[1] = 0;
 				s_gen[s * RW + lane] = g;
 			}
-			// staging: this record's slot, and the head of the next slot (our last quality chunk and final '\n')
 			const uint32_t s0c = lane == 0 ? 0u : (rstart[s] - 2u) >> 4;
-			unsigned char *slot = s_edge + ((size_t)s * (RW + 1) + lane) * slot_bytes;
-			unsigned char *sS = slot - 16u * s0c;                       // S space: + tile-relative byte position
-			unsigned char *sT = slot + s_bytes - 16u * (uint32_t)c_last;  // T space
-			unsigned char *sN = slot + slot_bytes - 16u * (uint32_t)q_last;  // next slot's S space
 			DShip sh;
 			sh.s0 = s0c;
-			sh.nS = (uint32_t)c_first - s0c + 1u;
 			sh.t0 = (uint32_t)c_last;
-			sh.nT = (uint32_t)(q_first - c_last) + 1u;
+			sh.n = ((uint32_t)c_first - s0c + 1u) | (((uint32_t)(q_first - c_last) + 1u) << 8);
+			sh.rstart = rstart[s];
 			s_ship[s * (RW + 1) + lane] = sh;
-			QD_CHK(16u * sh.nS <= s_bytes && sh.nT <= 2u && c_last > c_first && q_last > q_first, 5, sh.nS, sh.nT);
+			QD_CHK(16u * (sh.n & 0xffu) <= s_bytes && (sh.n >> 8) <= 2u && c_last > c_first && q_last > q_first, 5, sh.n, s_bytes);
 			if (lane == nr - 1) {  // the slot after the tile's last record: its last quality chunk and '\n'
 				DShip z;
 				z.s0 = (uint32_t)q_last;
-				z.nS = ((tend[s] - 1u) >> 4) - (uint32_t)q_last + 1u;
 				z.t0 = 0;
-				z.nT = 0;
+				z.n = (((tend[s] - 1u) >> 4) - (uint32_t)q_last + 1u) | (1u << 16);
+				z.rstart = tend[s];
 				s_ship[s * (RW + 1) + nr] = z;
 			}
-			// edge chunks: words that hold string bytes first, then the name / separator bytes over them
-			if (!random) {
-				uint4 vh, vt;
-				if (general[mate]) {
-					vh = seq16_general(gv, s_lowmask, a.c.segs + md.seg_off, (int)md.nseg, md.fw, (int)L, gpos, gend, 16 * c_first - (int)P);
-					vt = seq16_general(gv, s_lowmask, a.c.segs + md.seg_off, (int)md.nseg, md.fw, (int)L, gpos, gend, 16 * c_last - (int)P);
-				} else {
-					const SeqLoad lh = seq_issue(a.g.bases, w0, meta, 0), lt = seq_issue(a.g.bases, w0, meta, c_last - c_first);
-					vh = seq_finish(lh, meta);
-					vt = seq_finish(lt, meta);
+		}
+	}
+	__syncwarp();
+
+	// ---------------- step A2 (lane = 16-byte piece): the reads' packed genome rows, asynchronously ----------------
+	{
+		const uint32_t nunits = (uint32_t)(a.genome_words >> 2);
+#pragma unroll
+		for (int s = 0; s < NS; s++) {
+			const int nitems = nr * PMAX;
+			for (int q = lane; q < nitems; q += 32) {
+				const int i = (int)__umulhi((uint32_t)q, pmagic), p = q - i * PMAX;
+				const uint32_t unit = s_gunit[s * RW + i];
+				if (unit != 0xffffffffu && unit + (uint32_t)p < nunits) {
+					const uint32_t d = (uint32_t)__cvta_generic_to_shared(s_gbuf + ((size_t)s * RW + i) * GROW + 4 * p);
+					asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"((const uint4 *)a.g.bases + unit + p) : "memory");
 				}
-				store_words(sS + 16 * c_first, vh, 16 * c_first - (int)P, (int)L);
-				store_words(sT + 16 * c_last, vt, 16 * c_last - (int)P, (int)L);
 			}
-			{
-				uint4 vh, vt;
-				if (random) vh = vt = make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u);  // 'I' (simplesim.h:105)
-				else {
-					const QualLoad lh = qual_issue(a.c.qual_out, A0 >> 4), lt = qual_issue(a.c.qual_out, (A0 >> 4) + (uint32_t)(q_last - q_first));
-					vh = qual_finish(lh, A0 & 15u);
-					vt = qual_finish(lt, A0 & 15u);
+		}
+		asm volatile("cp.async.commit_group;" ::: "memory");
+	}
+
+	// ---------------- step A3 (lane = read): draw ops, names and separators into the slot images ----------------
+	if (act) {
+#pragma unroll
+		for (int m = 0; m < NM; m++) {
+			// the first draw ops, four per load (templates.cpp aligns the lists)
+			if (mh[m].nops) {
+				const uint4 *op4 = (const uint4 *)(a.c.ops + mh[m].ops_off);
+				const uint4 o0 = __ldg(op4);
+				uint32_t *so = s_ops + (size_t)m * DT_OPS * RW + lane;
+				so[0] = o0.x;
+				so[RW] = o0.y;
+				so[2 * RW] = o0.z;
+				so[3 * RW] = o0.w;
+				if (mh[m].nops > 4 && DT_OPS > 4) {
+					const uint4 o1 = __ldg(op4 + 1);
+					so[4 * RW] = o1.x;
+					if (DT_OPS > 5) so[5 * RW] = o1.y;
+					if (DT_OPS > 6) so[6 * RW] = o1.z;
+					if (DT_OPS > 7) so[7 * RW] = o1.w;
 				}
-				store_words(sT + 16 * q_first, vh, 16 * q_first - (int)Pq, (int)L);
-				store_words_exact_end(sN + 16 * q_last, vt, 16 * q_last - (int)Pq, (int)L);
 			}
+		}
+		const uint32_t rec_name_off = rec_b.x, rl = rec_b.y;
+		unsigned char *name0 = nullptr;
+#pragma unroll
+		for (int s = 0; s < NS; s++) {
+			const bool random = CAT == CAT_B && ((s == 0) == s0_random);
+			const uint32_t L = random ? tt.opp_len : mh[CAT == CAT_B ? 0 : s].len;
+			const uint32_t P = rstart[s] + nl, Pq = P + L + 3u;
+			const uint32_t c_last = (P + L - 1u) >> 4, q_last = (Pq + L - 1u) >> 4;
+			const uint32_t s0c = lane == 0 ? 0u : (rstart[s] - 2u) >> 4;
+			unsigned char *slot = s_edge + ((size_t)s * (RW + 1) + lane) * slot_bytes;
+			unsigned char *sS = slot - 16u * s0c;                  // S space: + tile-relative byte position
+			unsigned char *sT = slot + s_bytes - 16u * c_last;     // T space
+			unsigned char *sN = slot + slot_bytes - 16u * q_last;  // next slot's S space
 			// name (simplesim.cpp:104-110, :140-150)
 			unsigned char *np = sS + rstart[s];
 			if (s == 0) {
@@ -349,18 +382,18 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 				p += 7;
 				if (CAT == CAT_U) {
 					const uint32_t nd = nl - 13u - rl - mh[0].score_len - tt.typ_len;
-					p = s_origin(p, refid, rl, ro[0], nd, mh[0]);
+					p = s_origin(p, refid, rec_c, rl, ro[0], nd, mh[0]);
 				} else if (CAT == CAT_B) {
 					const uint32_t nd = (nl - 18u - 2u * rl - 2u * mh[0].score_len - tt.typ_len) >> 1;
-					p = s_origin(p, refid, rl, ro[0], nd, mh[0]);
+					p = s_origin(p, refid, rec_c, rl, ro[0], nd, mh[0]);
 					*p++ = ':';
-					p = s_origin(p, refid, rl, ro[0], nd, mh[0]);
+					p = s_origin(p, refid, rec_c, rl, ro[0], nd, mh[0]);
 				} else {
 					const uint32_t nd0 = ndig64(ro[0]);
 					const uint32_t nd1 = nl - 18u - 2u * rl - mh[0].score_len - mh[NM - 1].score_len - tt.typ_len - nd0;
-					p = s_origin(p, refid, rl, ro[0], nd0, mh[0]);
+					p = s_origin(p, refid, rec_c, rl, ro[0], nd0, mh[0]);
 					*p++ = ':';
-					p = s_origin(p, refid, rl, ro[1], nd1, mh[NM - 1]);
+					p = s_origin(p, refid, rec_c, rl, ro[1], nd1, mh[NM - 1]);
 				}
 				p[0] = ':';
 				p[1] = (char)(tt.typ & 0xffu);
@@ -377,69 +410,116 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 			sN[Pq + L] = '\n';
 		}
 	}
-	__syncwarp();
+	if (skip & 1) return;  // attribution runs only (QTIPSIM_SKIP): output incomplete
 
-	// ---------------- step B (lane = interior chunk): G lanes per read, `rounds` passes of G slots ----------------
-	{
-		const int G = 1 << lgG, rpi = 32 >> lgG;  // reads per iteration
-		const int sub = lane >> lgG, jl = lane & (G - 1);
+	// ---------------- step Bq (lane = quality chunk): item q = read * K + slot, read-major ----------------
 #pragma unroll
-		for (int s = 0; s < NS; s++) {
-			char *tbs = tb[s];
-			const DHot *hot = s_hot + s * RW;
-			for (int rd = 0; rd < rounds; rd++) {
-				const int j = rd * G + jl;
-				for (int i0 = 0; i0 < nr; i0 += DT_UNROLL * rpi) {
-					SeqLoad sl[DT_UNROLL];
-					QualLoad ql[DT_UNROLL];
-					uint4 sgen[DT_UNROLL];
-					uint32_t meta[DT_UNROLL], sdst[DT_UNROLL], qdst[DT_UNROLL];
-					bool slive[DT_UNROLL], qlive[DT_UNROLL];
+	for (int s = 0; s < NS; s++) {
+		char *tbs = tb[s];
+		const uint32_t hot_a = smem_u32(s_hotq + s * RW);
+		const int nitems = nr * K;
+		for (int q0 = lane; q0 < nitems && !(skip & 8); q0 += 32 * DT_UNROLL) {
+			QualLoad ql[DT_UNROLL];
+			uint32_t meta[DT_UNROLL], dst[DT_UNROLL], ar[DT_UNROLL];  // ar: area address for a string's first / last chunk, else 0
+			bool live[DT_UNROLL];
 #pragma unroll
-					for (int u = 0; u < DT_UNROLL; u++) {
-						const int i = i0 + u * rpi + sub;
-						slive[u] = qlive[u] = false;
-						meta[u] = 0;
-						if (i < nr) {
-							const uint4 h4 = *(const uint4 *)&hot[i];          // sdst | w0 | qdst | qsrc
-							const uint2 h2 = *((const uint2 *)&hot[i] + 2);    // nsq | meta
-							meta[u] = h2.y;
-							sdst[u] = h4.x + 16u * (uint32_t)j;
-							qdst[u] = h4.z + 16u * (uint32_t)j;
-							slive[u] = j < (int)(h2.x & 0xffffu);
-							qlive[u] = j < (int)(h2.x >> 16);
-							if (slive[u]) {
-								if (meta[u] & RF_GENERAL) {
-									const DHot &hh = hot[i];
-									const DGen &gg = s_gen[s * RW + i];
-									sgen[u] = seq16_general(gv, s_lowmask, a.c.segs + gg.segoff, (int)gg.nseg, (meta[u] & RF_FW) != 0,
-									                        (int)hh.L, gg.gpos, gg.gend, (int)sdst[u] - (int)hh.P);
-								} else sl[u] = seq_issue(a.g.bases, h4.y, meta[u], j);
-							}
-							if (qlive[u] && !(meta[u] & RF_RANDOM)) ql[u] = qual_issue(a.c.qual_out, h4.w + (uint32_t)j);
-						}
-					}
-#pragma unroll
-					for (int u = 0; u < DT_UNROLL; u++) {
-						if (slive[u]) {
-							QD_CHK(sdst[u] + 16u <= tend[s], 3, sdst[u], tend[s]);
-							*(uint4 *)(tbs + sdst[u]) = (meta[u] & RF_GENERAL) ? sgen[u] : seq_finish(sl[u], meta[u]);
-						}
-						if (qlive[u]) {
-							QD_CHK(qdst[u] + 16u <= tend[s], 4, qdst[u], tend[s]);
-							*(uint4 *)(tbs + qdst[u]) =
-							    (meta[u] & RF_RANDOM) ? make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u)
-							                          : qual_finish(ql[u], (meta[u] >> 12) & 15u);
-						}
-					}
+			for (int u = 0; u < DT_UNROLL; u++) {
+				const int q = q0 + 32 * u;
+				live[u] = false;
+				if (q < nitems) {
+					const int i = (int)__umulhi((uint32_t)q, kmagic), j = q - i * K;
+					const uint4 h4 = lds128(hot_a + 16u * (uint32_t)i);  // qsrc | qdst | nq, meta | area
+					const int nq = (int)(h4.z & 0xffffu);
+					meta[u] = h4.z >> 16;
+					live[u] = j < nq;
+					dst[u] = h4.y + 16u * (uint32_t)j;
+					ar[u] = j == 0 ? h4.w + 16u * AREA_QUAL_HEAD : (j == nq - 1 ? h4.w + 16u * AREA_QUAL_TAIL : 0u);
+					if (live[u] && !(meta[u] & RF_RANDOM)) ql[u] = qual_issue(a.c.qual_out, (skip & 64) ? (uint32_t)lane : h4.x + (uint32_t)j);
 				}
+			}
+#pragma unroll
+			for (int u = 0; u < DT_UNROLL; u++) {
+				if (!live[u]) continue;
+				const uint4 v = (meta[u] & RF_RANDOM) ? make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u)  // 'I' (simplesim.h:105)
+				                                      : qual_finish(ql[u], (meta[u] >> 12) & 15u);
+				if (ar[u]) sts128(ar[u], v);
+				else if (!(skip & 32)) {
+					QD_CHK(dst[u] + 16u <= tend[s], 4, dst[u], tend[s]);
+					*(uint4 *)(tbs + dst[u]) = v;
+				} else if (v.x == 0x12345678u) tbs[dst[u]] = 1;
 			}
 		}
 	}
+	asm volatile("cp.async.wait_group 0;" ::: "memory");
 	__syncwarp();
 
-	// ---------------- step C (lane = read): draws, patched over staging slots / HBM ----------------
+	// ---------------- step Bs (lane = sequence chunk): genome words from the rows in shared memory ----------------
+#pragma unroll
+	for (int s = 0; s < NS; s++) {
+		char *tbs = tb[s];
+		const uint32_t hot_a = smem_u32(s_hot + s * RW);
+		const int nitems = nr * K;
+		for (int q = lane; q < nitems && !(skip & 16); q += 32) {
+			const int i = (int)__umulhi((uint32_t)q, kmagic), j = q - i * K;
+			const uint4 h4 = lds128(hot_a + 16u * (uint32_t)i);  // grow | sdst | ns, meta | area
+			const int ns = (int)(h4.z & 0xffffu);
+			const uint32_t meta = h4.z >> 16;
+			if (j >= ns) continue;
+			const uint32_t dst = h4.y + 16u * (uint32_t)j;
+			uint4 v;
+			if (meta & RF_GENERAL) {
+				const DPos pp = s_pos[s * RW + i];
+				const DGen &gg = s_gen[s * RW + i];
+				v = seq16_general(gv, s_lowmask, a.c.segs + gg.segoff, (int)gg.nseg, (meta & RF_FW) != 0, (int)pp.L, gg.gpos, gg.gend,
+				                  (int)dst - (int)pp.P);
+			} else {
+				const uint32_t wa = (meta & RF_FW) ? h4.x + 4u * (uint32_t)j : h4.x - 4u * (uint32_t)j;
+				SeqLoad sl;
+				sl.lo = lds32(wa);
+				sl.hi = lds32(wa + 4u);
+				v = seq_finish(sl, meta);
+			}
+			if (j == 0 || j == ns - 1) sts128(h4.w + (j ? 16u * AREA_SEQ_TAIL : 16u * AREA_SEQ_HEAD), v);
+			else if (!(skip & 32)) {
+				QD_CHK(dst + 16u <= tend[s], 3, dst, tend[s]);
+				*(uint4 *)(tbs + dst) = v;
+			} else if (v.x == 0x12345678u) tbs[dst] = 1;
+		}
+	}
+	__syncwarp();
+	if (skip & 2) return;
+
+	// ---------------- step C (lane = read): edge chunks merged into the slot images, then the draws ----------------
 	if (act) {
+		// the four areas hold whole chunks; only the bytes inside the string go into the image (names and
+		// separators are already there).  The last quality chunk belongs to the next slot's first chunk.
+#pragma unroll
+		for (int s = 0; s < NS; s++) {
+			const DPos pp = s_pos[s * RW + lane];
+			const uint32_t P = pp.P, L = pp.L, Pq = P + L + 3u;
+			const uint32_t c_first = P >> 4, c_last = (P + L - 1u) >> 4, q_first = Pq >> 4, q_last = (Pq + L - 1u) >> 4;
+			const uint32_t s0c = s_ship[s * (RW + 1) + lane].s0;
+			unsigned char *slot = s_edge + ((size_t)s * (RW + 1) + lane) * slot_bytes;
+			const uint4 *ar = s_area + ((size_t)s * RW + lane) * 4;
+			uint4 *img;
+			uint4 v;
+			img = (uint4 *)(slot + 16u * (c_first - s0c));  // first sequence chunk: bytes from P on
+			v = *img;
+			overlay(v, ar[AREA_SEQ_HEAD], s_lowmask, (int)P - 16 * (int)c_first, 16);
+			*img = v;
+			img = (uint4 *)(slot + s_bytes);  // last sequence chunk: bytes before P + L
+			v = *img;
+			overlay(v, ar[AREA_SEQ_TAIL], s_lowmask, 0, (int)(P + L) - 16 * (int)c_last);
+			*img = v;
+			img = (uint4 *)(slot + s_bytes + 16u * (q_first - c_last));  // first quality chunk: bytes from Pq on
+			v = *img;
+			overlay(v, ar[AREA_QUAL_HEAD], s_lowmask, (int)Pq - 16 * (int)q_first, 16);
+			*img = v;
+			img = (uint4 *)(slot + slot_bytes);  // last quality chunk: bytes before Pq + L
+			v = *img;
+			overlay(v, ar[AREA_QUAL_TAIL], s_lowmask, 0, (int)(Pq + L) - 16 * (int)q_last);
+			*img = v;
+		}
 		LState st{pr.s1, pr.s2};
 		const uint64_t gi = a.read_index_base + ri;
 		uint32_t dk = 0;
@@ -461,7 +541,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 			return draw16() >> 14;
 		};
 		// where output position k of stream s's sequence lives: first chunk -> slot S space, last chunk ->
-		// slot T space, interior -> HBM (already stored by step B: same warp, ordered by __syncwarp)
+		// slot T space, interior -> HBM (already stored by step Bs: same warp, ordered by __syncwarp)
 		auto put_base = [&](int s, uint32_t P, uint32_t c_first, uint32_t c_last, uint32_t s0c, uint32_t k, uint32_t ch) {
 			const uint32_t x = P + k, cx = x >> 4;
 			unsigned char *slot = s_edge + ((size_t)s * (RW + 1) + lane) * slot_bytes;
@@ -472,37 +552,31 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 #pragma unroll
 		for (int m = 0; m < NM; m++) {
 			const int s = CAT == CAT_B ? (s0_random ? 1 : 0) : m;  // stream that holds aligned mate m
-			const DHot &hh = s_hot[s * RW + lane];
-			const uint32_t P = hh.P, L = hh.L;
+			const uint32_t n = mh[m].nops;
+			if (!n) continue;
+			const DPos pp = s_pos[s * RW + lane];
+			const uint32_t P = pp.P, L = pp.L;
 			const uint32_t c_first = P >> 4, c_last = (P + L - 1u) >> 4, s0c = s_ship[s * (RW + 1) + lane].s0;
-			const bool fw = (fwbits >> m) & 1u;
+			const bool fw = mh[m].fw;
+			const bool gen = ((s_hot[s * RW + lane].ns >> 16) & RF_GENERAL) != 0;
 			const uint32_t T = fw ? TBL_FW : TBL_RC;
-			const uint32_t n = nops[m];
+			const uint32_t gb0 = s_gb0[s * RW + lane];
+			const uint32_t *row = s_gbuf + ((size_t)s * RW + lane) * GROW;
+			const uint32_t *ops = a.c.ops + mh[m].ops_off;
 			for (uint32_t j = 0; j < n; j++) {
-				uint32_t e;
-				if (j < (uint32_t)DT_OPS) e = s_ops[(m * DT_OPS + j) * RW + lane];
-				else {  // long draw-op lists: from the template, reference base looked up here
-					const TmplDesc *tp = a.c.t + pr.tmpl;
-					e = __ldg(&a.c.ops[tp->m[m].ops_off + j]);
-					if ((e & 3u) == OP_X) {
-						const DGen &gg = s_gen[s * RW + lane];
-						const bool gen = (hh.meta & RF_GENERAL) != 0;
-						uint64_t gpos, gend = 0;
-						if (gen) {
-							gpos = gg.gpos;
-							gend = gg.gend;
-						} else {
-							const RecDev &rc = a.g.recs[pr.record];
-							gpos = rc.gstart + pr.refoff + tp->delta[m];
-						}
-						e = (e & 0x1ffffu) | (ref_code_at(a.g, gpos + (e >> 17), gend, gen) << 17);
-					}
-				}
+				const uint32_t e = j < (uint32_t)DT_OPS ? s_ops[(m * DT_OPS + j) * RW + lane] : __ldg(&ops[j]);
 				const uint32_t outp = (e >> 2) & 0x7fffu;
 				QD_CHK(outp < L, 7, outp, L);
 				uint32_t code;
 				if ((e & 3u) == OP_X) {
-					const uint32_t ref = e >> 17;
+					uint32_t ref;
+					if (gen) {
+						const DGen &gg = s_gen[s * RW + lane];
+						ref = ref_code_at(a.g, gg.gpos + (e >> 17), gg.gend);
+					} else {
+						const uint32_t t = gb0 + (e >> 17);
+						ref = (row[t >> 4] >> (2u * (t & 15u))) & 3u;
+					}
 					if (MODE == QTIPSIM_RNG_REPLAY) {
 						do code = draw_code();  // simplesim.cpp:47-49
 						while (code == ref);
@@ -517,10 +591,10 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 		if (CAT == CAT_B) {
 			// init_random (simplesim.h:89-117): opp_len draws, printed with the aligned mate's strand
 			const int s = s0_random ? 0 : 1;
-			const DHot &hh = s_hot[s * RW + lane];
-			const uint32_t P = hh.P, L = hh.L;
+			const DPos pp = s_pos[s * RW + lane];
+			const uint32_t P = pp.P, L = pp.L;
 			const uint32_t c_first = P >> 4, c_last = (P + L - 1u) >> 4, s0c = s_ship[s * (RW + 1) + lane].s0;
-			const bool fw = fwbits & 1u;
+			const bool fw = mh[0].fw;
 			const uint32_t T = fw ? TBL_FW : TBL_RC;
 			for (uint32_t j = 0; j < L; j++) {
 				const uint32_t code = draw_code();
@@ -529,8 +603,9 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 		}
 	}
 	__syncwarp();
+	if (skip & 4) return;
 
-	// ---------------- step D (lane = edge chunk): staging slots -> HBM ----------------
+	// ---------------- step D (lane = edge chunk): slot images -> HBM ----------------
 	{
 		const int H = 1 << lgH, spi = 32 >> lgH;  // slots per iteration
 		const int sub = lane >> lgH, jl = lane & (H - 1);
@@ -544,16 +619,11 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 					const int i = i0 + sub;
 					if (i > nr) continue;
 					const DShip sh = s_ship[s * (RW + 1) + i];
+					const uint32_t nS = sh.n & 0xffu, nT = (sh.n >> 8) & 0xffu;
+					if (j >= nS + nT) continue;
 					const unsigned char *slot = s_edge + ((size_t)s * (RW + 1) + i) * slot_bytes;
-					uint32_t chunk;
-					const unsigned char *src;
-					if (j < sh.nS) {
-						chunk = sh.s0 + j;
-						src = slot + 16u * j;
-					} else if (j < sh.nS + sh.nT) {
-						chunk = sh.t0 + (j - sh.nS);
-						src = slot + s_bytes + 16u * (j - sh.nS);
-					} else continue;
+					const uint32_t chunk = j < nS ? sh.s0 + j : sh.t0 + (j - nS);
+					const unsigned char *src = j < nS ? slot + 16u * j : slot + s_bytes + 16u * (j - nS);
 					char *dst = tbs + 16u * (size_t)chunk;
 					if (chunk == 0 && phs) {  // shared with the previous tile
 						for (uint32_t b = phs; b < 16u; b++) dst[b] = (char)src[b];
@@ -577,29 +647,29 @@ static bool launch_cat(const SimArgs &a, uint32_t max_name, uint32_t max_body, c
 		e = getenv("QTIPSIM_WARPS");
 		env_warps = e ? atoi(e) : 0;
 	}
+	// chunks a string of max_body bytes can touch at any alignment
+	const uint32_t K = (max_body + 14u) / 16u + 1u;
+	const uint32_t kmagic = (uint32_t)((0x100000000ull + K - 1) / K);  // q / K == umulhi(q, kmagic) for q < 2^16
+	// 16-byte pieces of packed genome per read: K + 1 words plus up to 3 of alignment
+	const uint32_t PMAX = (K + 1u + 3u + 3u) / 4u;
+	const uint32_t pmagic = (uint32_t)((0x100000000ull + PMAX - 1) / PMAX);
 	// S part of a slot: from the chunk of (record start - 2) to the chunk of the first sequence byte
 	const uint32_t s_bytes = ((max_name + 2u + 15u + 15u) & ~15u) + 16u;
 	auto warp_bytes = [&](int rw) -> uint32_t {
 		return NS * (uint32_t)(rw + 1) * (s_bytes + T_BYTES + (uint32_t)sizeof(DShip)) +
-		       (uint32_t)rw * (NS * (uint32_t)(sizeof(DHot) + sizeof(DGen)) + NM * DT_OPS * 4u);
+		       (uint32_t)rw * (NS * (uint32_t)(sizeof(DHot) + sizeof(DHotQ) + sizeof(DGen) + sizeof(DPos) + 64u + 16u * PMAX + 8u) + NM * DT_OPS * 4u);
 	};
 	const uint32_t sm_budget = 200u * 1024u;
 	int rw = env_rw > 0 ? env_rw : 32;
 	if (rw > 32) rw = 32;
 	if (env_rw <= 0)
-		while (rw > 4 && warp_bytes(rw) * 16u > sm_budget) rw >>= 1;
-	if (warp_bytes(rw) + 1024 > sm_budget) return false;
+		while (rw > 4 && warp_bytes(rw) * 24u > sm_budget) rw >>= 1;  // at least 24 resident warps per SM
+	if (warp_bytes(rw) + 1024 > sm_budget || (uint64_t)rw * K >= 65536u) return false;
 	int warps = env_warps > 0 ? env_warps : DT_MAX_WARPS;
 	if (warps > DT_MAX_WARPS) warps = DT_MAX_WARPS;
 	while (warps > 1 && warp_bytes(rw) * (uint32_t)warps + 1024 > sm_budget) warps >>= 1;
 	const uint32_t wb = warp_bytes(rw);
 	const size_t smem = (size_t)wb * warps;
-	// step B: interior chunks of a string of max_body bytes at any alignment: at most floor((max_body + 14) / 16) - 1
-	int slots = (int)((max_body + 14u) / 16u) - 1;
-	if (slots < 1) slots = 1;
-	int lgG = 0;
-	while ((1 << lgG) < slots && lgG < 5) lgG++;
-	const int rounds = (slots + (1 << lgG) - 1) >> lgG;
 	// step D: chunks per staging slot
 	const int hslots = (int)(s_bytes / 16u) + 2;
 	int lgH = 0;
@@ -613,7 +683,12 @@ static bool launch_cat(const SimArgs &a, uint32_t max_name, uint32_t max_body, c
 	}
 	const uint64_t ntiles = (a.nreads + rw - 1) / rw;
 	const uint64_t nblocks = (ntiles + warps - 1) / warps;
-	kern<<<(unsigned)nblocks, warps * 32, smem, st>>>(a, rw, lgG, rounds, lgH, hrounds, s_bytes, wb);
+	static int skip = -1;  // QTIPSIM_SKIP (attribution runs only): bit 0 stop after step A, 1 after B, 2 after C
+	if (skip < 0) {
+		const char *e = getenv("QTIPSIM_SKIP");
+		skip = e ? atoi(e) : 0;
+	}
+	kern<<<(unsigned)nblocks, warps * 32, smem, st>>>(a, rw, (int)K, kmagic, (int)PMAX, pmagic, lgH, hrounds, s_bytes, wb, skip);
 	kernels_count_launch();
 	return true;
 }

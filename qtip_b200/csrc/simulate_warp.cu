@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(WT_MAX_WARPS * 32, QT_WT_MIN_BLOCKS) k_simulat
 	const PlanRec pr = a.plan[ri];
 	const TmplDesc *tp = a.c.t + pr.tmpl;
 	const uint4 *recp4 = (const uint4 *)(a.g.recs + pr.record);
-	const uint4 rec_a = __ldg(recp4), rec_b = __ldg(recp4 + 1);
+	const uint4 rec_a = __ldg(recp4), rec_b = __ldg(recp4 + 1), rec_c = __ldg(recp4 + 2);
 	const uint64_t rec_gstart = (uint64_t)rec_a.x | ((uint64_t)rec_a.y << 32);
 	const uint64_t gend = rec_gstart + ((uint64_t)rec_a.z | ((uint64_t)rec_a.w << 32));
 	const uint32_t rec_name_off = rec_b.x, rl = rec_b.y;
@@ -339,18 +339,18 @@ __global__ void __launch_bounds__(WT_MAX_WARPS * 32, QT_WT_MIN_BLOCKS) k_simulat
 			p += 7;
 			if (CAT == CAT_U) {
 				const uint32_t nd = nl - 13u - rl - mh[0].score_len - tt.typ_len;
-				p = s_origin(p, refid, rl, ro[0], nd, mh[0]);
+				p = s_origin(p, refid, rec_c, rl, ro[0], nd, mh[0]);
 			} else if (CAT == CAT_B) {
 				const uint32_t nd = (nl - 18u - 2u * rl - 2u * mh[0].score_len - tt.typ_len) >> 1;
-				p = s_origin(p, refid, rl, ro[0], nd, mh[0]);
+				p = s_origin(p, refid, rec_c, rl, ro[0], nd, mh[0]);
 				*p++ = ':';
-				p = s_origin(p, refid, rl, ro[0], nd, mh[0]);
+				p = s_origin(p, refid, rec_c, rl, ro[0], nd, mh[0]);
 			} else {
 				const uint32_t nd0 = ndig64(ro[0]);
 				const uint32_t nd1 = nl - 18u - 2u * rl - mh[0].score_len - mh[NM - 1].score_len - tt.typ_len - nd0;
-				p = s_origin(p, refid, rl, ro[0], nd0, mh[0]);
+				p = s_origin(p, refid, rec_c, rl, ro[0], nd0, mh[0]);
 				*p++ = ':';
-				p = s_origin(p, refid, rl, ro[1], nd1, mh[NM - 1]);
+				p = s_origin(p, refid, rec_c, rl, ro[1], nd1, mh[NM - 1]);
 			}
 			p[0] = ':';
 			p[1] = (char)(tt.typ & 0xffu);

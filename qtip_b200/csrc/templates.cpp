@@ -62,6 +62,7 @@ bool add_mate(Category &c, MateDesc &m, HostMateProg &hp, const char *qual, cons
 	else
 		for (uint32_t i = 0; i < m.len; i++) c.qual_out.push_back(qual[m.len - 1 - i]);
 	while (c.qual_out.size() % 16) c.qual_out.push_back('\0');
+	while (c.ops.size() % 4) c.ops.push_back(0u);  // 16-byte aligned lists: the kernel reads four ops per load
 	m.ops_off = (uint32_t)c.ops.size();
 	m.seg_off = (uint32_t)c.segs.size();
 	if (ok && rd == m.len && m.len <= COMPILED_MAX_LEN && rf <= COMPILED_MAX_LEN) {
