@@ -40,15 +40,17 @@ UNIT = "reads/s"
 
 # ------------------------------------------------------------------ workload --
 
-def workload(n_gpus: int, scale: float):
+def workload(n_gpus: int, scale: float, which: str = "auto", cats: str = "bcd"):
     """Returns dict(name, records, templates, targets) for the bench configuration."""
     recs = synth.grch38_like_records(scale)
-    if n_gpus == 1:
+    if which in ("c3", "auto"):
+        # weak scaling: 10M reads per GPU over the same genome, windows sharded across the ranks
         tu = synth.templates_unpaired(30000, 250, seed=3003, max_x=5)
+        per = f", x{n_gpus} GPUs (windows sharded by rank)" if n_gpus > 1 else ""
         return dict(name=f"C3: GRCh38-sized synthetic {sum(l for _, l in recs) / 1e9:.2f} Gbp ref (24 records, 10 kbp "
-                         f"leading N each), {10 * scale:.3g}M unpaired 250 bp reads from 30k templates (0-5 X)",
+                         f"leading N each), {10 * scale:.3g}M unpaired 250 bp reads per GPU from 30k templates (0-5 X){per}",
                     records=recs, lead_n=10000, tu=tu, tb=[], tc=[], td=[],
-                    kw=dict(fraction=float(int(10_000_000 * scale)), function=3, min_u=1, min_c=1, min_d=1, min_b=1),
+                    kw=dict(fraction=float(int(10_000_000 * scale) * n_gpus), function=3, min_u=1, min_c=1, min_d=1, min_b=1),
                     unit="reads/s", genome_seed=3001)
     tc = synth.templates_paired(30000, 150, seed=4002, frag_mean=400, frag_sd=40, max_x=4)
     td = synth.templates_paired(30000, 150, seed=4003, discordant=True, max_fraglen=50000)
@@ -56,6 +58,9 @@ def workload(n_gpus: int, scale: float):
     total = int(12_500_000 * n_gpus * scale)
     # 70 / 15 / 15 mix through `added` and the linear function: target = added
     added = (0, int(total * 0.15), int(total * 0.70), int(total * 0.15))
+    if set(cats) != set("bcd"):  # diagnostic runs: one category at a time
+        tb, tc, td = (tb if "b" in cats else []), (tc if "c" in cats else []), (td if "d" in cats else [])
+        added = (0, added[1] if "b" in cats else 0, added[2] if "c" in cats else 0, added[3] if "d" in cats else 0)
     return dict(name=f"C4: GRCh38-sized synthetic {sum(l for _, l in recs) / 1e9:.2f} Gbp ref, {total / 1e6:.3g}M pairs "
                      f"70/15/15 concordant/discordant/bad-end 2x150, sharded across {n_gpus} GPU(s)",
                 records=recs, lead_n=10000, tu=[], tb=tb, tc=tc, td=td, added=added,
@@ -189,6 +194,10 @@ def main():
                     help="shrink genome and read counts together (1.0 = the BASELINE.json configuration)")
     ap.add_argument("--mode", default="native", choices=["replay", "native"],
                     help="RNG mode of the primary numbers; the other mode is measured too (1 step) and reported alongside")
+    ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c4"],
+                    help="auto / c3: BASELINE config 3 (10M unpaired 250 bp reads per GPU, weak scaling); c4: the pair mix of "
+                         "config 4 (12.5M pairs per GPU), a secondary measurement")
+    ap.add_argument("--cats", default="bcd", help="diagnostic: pair categories kept in the C4 mix (subset of 'bcd')")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -197,7 +206,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_gpus = args.gpus
-    wl = workload(n_gpus, args.scale)
+    wl = workload(n_gpus, args.scale, args.workload, args.cats)
 
     if args.impl == "reference":
         if rank != 0:

@@ -83,6 +83,16 @@ struct qtipsim {
 	bool have_jt = false;
 
 	DevBuf d_win, d_ncount, d_cum;
+	// window table + per-window N counts: functions of (genome, chunksz, olap) only, kept across runs
+	std::vector<Window> win_cache;
+	std::vector<uint32_t> ncount_cache;
+	uint64_t win_cache_chunksz = 0, win_cache_olap = ~0ull;
+	bool win_cache_ok = false;
+	// binomial set-ups per window class: functions of the above plus the targets and the shard's window range
+	std::vector<BinomSetup> setup_cache;
+	std::vector<uint32_t> pclass_cache;
+	uint64_t setup_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	bool setup_cache_ok = false;
 	DevBuf d_plan[NCAT], d_len0, d_len1, d_off0[NCAT], d_off1[NCAT], d_scan_tmp, d_small;
 	DevBuf d_out[NOUT];
 	uint64_t out_bytes[NOUT] = {0, 0, 0, 0, 0, 0, 0};
@@ -204,6 +214,8 @@ static int upload_genome(qtipsim *h) {
 	}
 	CK(cudaStreamSynchronize(h->st));
 	h->have_genome = true;
+	h->win_cache_ok = false;
+	h->setup_cache_ok = false;
 	h->host_packed = true;
 	h->have_result = false;
 	return QTIPSIM_OK;
@@ -357,6 +369,8 @@ static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
 	cudaEventDestroy(e0);
 	cudaEventDestroy(e1);
 	h->have_genome = true;
+	h->win_cache_ok = false;
+	h->setup_cache_ok = false;
 	h->host_packed = false;
 	h->have_result = false;
 	return QTIPSIM_OK;
@@ -464,6 +478,8 @@ int qtipsim_genome_adopt(qtipsim_t *h, const void *blob, uint64_t blob_bytes, co
 	CK(cudaMemcpyAsync(h->hg.nmask.data(), h->d_nmask.p, need_n, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
 	h->have_genome = true;
+	h->win_cache_ok = false;
+	h->setup_cache_ok = false;
 	h->host_packed = true;
 	h->have_result = false;
 	return QTIPSIM_OK;
@@ -540,8 +556,13 @@ static void window_setups(const std::vector<Window> &win, uint64_t olap, const P
 	std::map<uint32_t, uint32_t> pclass_of;  // float bits of p -> class
 	pclass.assign(win.size(), 0);
 	setups.clear();
+	uint32_t last_retsz = 0xffffffffu, last_class = 0;
 	for (uint32_t w = lo; w < hi; w++) {
 		if (win[w].retsz < olap) continue;
+		if (win[w].retsz == last_retsz) {  // nearly every window is a full one
+			pclass[w] = last_class;
+			continue;
+		}
 		const float bp = window_binom_p(win[w].retsz, olap, pp.tot_fasta_len);
 		uint32_t pb;
 		memcpy(&pb, &bp, 4);
@@ -551,8 +572,27 @@ static void window_setups(const std::vector<Window> &win, uint64_t olap, const P
 			for (int c = 0; c < NCAT; c++) setups.push_back(binom_setup((int32_t)pp.target[c], bp));
 		}
 		pclass[w] = it->second;
+		last_retsz = win[w].retsz;
+		last_class = it->second;
 	}
 	if (setups.empty()) setups.resize(NCAT);
+}
+
+// window classes + binomial set-ups on the device (d_pclass, d_setups), recomputed only when their inputs change
+static int ensure_setups(qtipsim *h, const std::vector<Window> &win, uint64_t olap, const PlanParams &pp, uint32_t lo, uint32_t hi) {
+	const uint64_t key[8] = {pp.target[0], pp.target[1], pp.target[2], pp.target[3], olap, pp.chunksz, ((uint64_t)lo << 32) | hi,
+	                         pp.tot_fasta_len};
+	if (h->setup_cache_ok && memcmp(key, h->setup_key, sizeof(key)) == 0) return QTIPSIM_OK;
+	window_setups(win, olap, pp, lo, hi, h->pclass_cache, h->setup_cache);
+	const size_t nwin = win.size();
+	CK(h->d_setups.ensure(h->setup_cache.size() * sizeof(BinomSetup)));
+	CK(h->d_pclass.ensure(nwin * 4 + 16));
+	CK(cudaMemcpyAsync(h->d_setups.p, h->setup_cache.data(), h->setup_cache.size() * sizeof(BinomSetup), cudaMemcpyHostToDevice, h->st));
+	if (nwin) CK(cudaMemcpyAsync(h->d_pclass.p, h->pclass_cache.data(), nwin * 4, cudaMemcpyHostToDevice, h->st));
+	CK(cudaStreamSynchronize(h->st));  // the cache vectors may be rebuilt by the next call
+	memcpy(h->setup_key, key, sizeof(key));
+	h->setup_cache_ok = true;
+	return QTIPSIM_OK;
 }
 
 int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
@@ -598,12 +638,35 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 	for (auto &e : ev) CK(cudaEventCreate(&e));
 	CK(cudaEventRecord(ev[0], h->st));
 
-	// ---- window table + N counts ----
-	std::vector<Window> win = h->hg.windows(p->chunksz, olap);
+	// ---- window table + N counts (cached: they depend on the genome, chunksz and olap only) ----
+	if (!h->win_cache_ok || h->win_cache_chunksz != p->chunksz || h->win_cache_olap != olap) {
+		h->win_cache = h->hg.windows(p->chunksz, olap);
+		const uint32_t nw = (uint32_t)h->win_cache.size();
+		h->ncount_cache.assign(nw, 0);
+		if (nw) {
+			DevGenome dg0;
+			dg0.bases = h->d_bases.as<uint32_t>();
+			dg0.nmask = h->d_nmask.as<uint32_t>();
+			dg0.nblk = h->d_nblk.as<uint32_t>();
+			dg0.recs = h->d_recs.as<RecDev>();
+			dg0.names = h->d_names.as<char>();
+			dg0.nrecs = (uint32_t)h->hg.recs.size();
+			CK(h->d_win.ensure(nw * sizeof(Window)));
+			CK(h->d_ncount.ensure(nw * 4));
+			CK(cudaMemcpyAsync(h->d_win.p, h->win_cache.data(), nw * sizeof(Window), cudaMemcpyHostToDevice, h->st));
+			launch_window_ncount(dg0, h->d_win.as<Window>(), nw, h->d_ncount.as<uint32_t>(), h->st);
+			CK(cudaMemcpyAsync(h->ncount_cache.data(), h->d_ncount.p, nw * 4, cudaMemcpyDeviceToHost, h->st));
+			CK(cudaStreamSynchronize(h->st));
+		}
+		h->win_cache_chunksz = p->chunksz;
+		h->win_cache_olap = olap;
+		h->win_cache_ok = true;
+	}
+	const std::vector<Window> &win = h->win_cache;
 	const uint32_t nwin = (uint32_t)win.size();
 	pp.win_lo = (uint64_t)p->shard_rank * nwin / p->shard_count;
 	pp.win_hi = (uint64_t)(p->shard_rank + 1) * nwin / p->shard_count;
-	std::vector<uint32_t> ncount(nwin, 0);
+	const std::vector<uint32_t> &ncount = h->ncount_cache;
 	DevGenome dg;
 	dg.bases = h->d_bases.as<uint32_t>();
 	dg.nmask = h->d_nmask.as<uint32_t>();
@@ -611,14 +674,6 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 	dg.recs = h->d_recs.as<RecDev>();
 	dg.names = h->d_names.as<char>();
 	dg.nrecs = (uint32_t)h->hg.recs.size();
-	if (nwin) {
-		CK(h->d_win.ensure(nwin * sizeof(Window)));
-		CK(h->d_ncount.ensure(nwin * 4));
-		CK(cudaMemcpyAsync(h->d_win.p, win.data(), nwin * sizeof(Window), cudaMemcpyHostToDevice, h->st));
-		launch_window_ncount(dg, h->d_win.as<Window>(), nwin, h->d_ncount.as<uint32_t>(), h->st);
-		CK(cudaMemcpyAsync(ncount.data(), h->d_ncount.p, nwin * 4, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaStreamSynchronize(h->st));
-	}
 
 	// ---- plan ----
 	const double t_plan0 = now_ms();
@@ -630,14 +685,9 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 	if (p->rng_mode == QTIPSIM_RNG_REPLAY && !host_planner) {
 		// ---- K2 on the device: speculative resolution of the draw chain (resolve.cu) ----
 		// binomial set-ups per distinct window probability, computed with the host's libm
-		std::vector<BinomSetup> setups;
-		std::vector<uint32_t> pclass;
-		window_setups(win, olap, pp, (uint32_t)pp.win_lo, (uint32_t)pp.win_hi, pclass, setups);
-		CK(h->d_setups.ensure(setups.size() * sizeof(BinomSetup)));
-		CK(h->d_pclass.ensure((size_t)nwin * 4 + 16));
+		rc = ensure_setups(h, win, olap, pp, (uint32_t)pp.win_lo, (uint32_t)pp.win_hi);
+		if (rc) return rc;
 		CK(h->d_rsresult.ensure(8 * 8));
-		CK(cudaMemcpyAsync(h->d_setups.p, setups.data(), setups.size() * sizeof(BinomSetup), cudaMemcpyHostToDevice, h->st));
-		if (nwin) CK(cudaMemcpyAsync(h->d_pclass.p, pclass.data(), (size_t)nwin * 4, cudaMemcpyHostToDevice, h->st));
 		double grow = 1.0;
 		for (int attempt = 0;; attempt++) {
 			ResolveArgs ra;
@@ -701,13 +751,8 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 	} else {
 		// ---- PHILOX: per-window counts ~ Binomial(target, p_window) drawn on the device from a Philox
 		// stream keyed by (seed, window, category); prefix sums give each read's window ----
-		std::vector<BinomSetup> setups;
-		std::vector<uint32_t> pclass;
-		window_setups(win, olap, pp, 0, nwin, pclass, setups);
-		CK(h->d_setups.ensure(setups.size() * sizeof(BinomSetup)));
-		CK(h->d_pclass.ensure((size_t)nwin * 4 + 16));
-		CK(cudaMemcpyAsync(h->d_setups.p, setups.data(), setups.size() * sizeof(BinomSetup), cudaMemcpyHostToDevice, h->st));
-		if (nwin) CK(cudaMemcpyAsync(h->d_pclass.p, pclass.data(), (size_t)nwin * 4, cudaMemcpyHostToDevice, h->st));
+		rc = ensure_setups(h, win, olap, pp, 0, nwin);
+		if (rc) return rc;
 		CK(h->d_len0.ensure((size_t)nwin * 4 + 16));
 		CK(h->d_scan_tmp.ensure(((size_t)nwin / 1024 + 4) * 8));
 		CK(h->d_cum.ensure(((size_t)nwin + 1) * 8 * NCAT));
