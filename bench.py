@@ -296,12 +296,20 @@ def main():
     state_buf = torch.zeros(2, dtype=torch.int64, device="cuda")
     host_out = [None] * _abi.NOUT
 
+    trace = os.environ.get("QTIP_BENCH_TRACE") == "1"
+
     def one_step(seed, rng_mode, e2e=False):
         """Runs one step on this rank's shard; returns stats."""
+        tr0 = time.perf_counter()
         if e2e:
             if rank == 0 and world == 1:
-                eng.load_fasta_bytes(fa_pinned.numpy())  # H2D of the FASTA text + device pack
-            set_templates()
+                eng.load_fasta_bytes_async(fa_pinned.numpy())  # H2D of the FASTA text + device pack ...
+            tr1 = time.perf_counter()
+            set_templates()                                    # ... while the host compiles the templates
+            eng.wait_genome()
+            if trace:
+                print(f"[trace] load_fasta {1e3 * (tr1 - tr0):.1f} ms, set_templates {1e3 * (time.perf_counter() - tr1):.1f} ms",
+                      file=sys.stderr)
         cg = cli_seed(seed)
         chain = world > 1 and rng_mode == _abi.RNG_REPLAY
         if chain and rank > 0:
@@ -309,7 +317,9 @@ def main():
             cg = (int(state_buf[0].item()), int(state_buf[1].item()))
         p = sim.make_params(CHUNKSZ, kw["fraction"], kw["function"], kw["min_u"], kw["min_c"], kw["min_d"], kw["min_b"],
                             rng_mode, cg=cg, philox_seed=seed, shard_rank=rank, shard_count=world)
+        tr2 = time.perf_counter()
         st = eng.run(p)
+        tr3 = time.perf_counter()
         if chain and rank < world - 1:
             state_buf[0], state_buf[1] = p.cg1, p.cg2
             dist.send(state_buf, dst=rank + 1)
@@ -321,6 +331,9 @@ def main():
                     if host_out[s] is None or host_out[s].numel() < n:
                         host_out[s] = torch.empty(int(n * 1.05) + 4096, dtype=torch.uint8).pin_memory()
                     eng.check(eng.lib.qtipsim_result_copy(eng.h, s, C.c_void_p(host_out[s].data_ptr()), host_out[s].numel()))
+            if trace:
+                print(f"[trace] run {1e3 * (tr3 - tr2):.1f} ms (pack {st.ms_pack:.1f}), result_copy {1e3 * (time.perf_counter() - tr3):.1f} ms",
+                      file=sys.stderr)
         return st
 
     def barrier():

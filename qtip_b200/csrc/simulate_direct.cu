@@ -64,6 +64,9 @@ __device__ unsigned long long g_qd_violation[4];
 #ifndef QT_DT_MIN_BLOCKS
 #define QT_DT_MIN_BLOCKS 8
 #endif
+#ifndef QT_DT_MIN_BLOCKS_PAIR
+#define QT_DT_MIN_BLOCKS_PAIR 6
+#endif
 #ifndef QT_DT_UNROLL
 #define QT_DT_UNROLL 2
 #endif
@@ -109,6 +112,9 @@ struct __align__(16) DShip {
 	uint32_t rstart;  // byte position of the record's '@'
 };
 enum { AREA_SEQ_HEAD = 0, AREA_SEQ_TAIL = 1, AREA_QUAL_HEAD = 2, AREA_QUAL_TAIL = 3 };
+// Per-read strides in shared memory are odd multiples of 16 bytes: when lane = read, the 32 lanes' accesses then
+// spread over all eight 16-byte bank groups instead of piling onto two or four of them.
+static constexpr int AREA_STRIDE = 5;  // uint4 per read (four areas + one of padding)
 
 // reference base at genome position gp as the reference's mutate() sees it: 0..3, or 4 for N and
 // for positions past the record end; general-path reads only
@@ -144,7 +150,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
 }
 
 template <int MODE, int CAT>
-__global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulate_direct(SimArgs a, int RW, int K, uint32_t kmagic,
+__global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BLOCKS : QT_DT_MIN_BLOCKS_PAIR) k_simulate_direct(SimArgs a, int RW, int K, uint32_t kmagic,
                                                                                           int PMAX, uint32_t pmagic, int lgH,
                                                                                           int hrounds, uint32_t s_bytes,
                                                                                           uint32_t warp_smem, int skip) {
@@ -174,8 +180,8 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 	const int GROW = 4 * PMAX;  // words per s_gbuf row
 	unsigned char *wsm = smem + (size_t)wib * warp_smem;
 	unsigned char *s_edge = wsm;                                                  // [NS][RW + 1] slot images
-	uint4 *s_area = (uint4 *)(s_edge + (size_t)NS * (RW + 1) * slot_bytes);       // [NS][RW][4]
-	uint32_t *s_gbuf = (uint32_t *)(s_area + (size_t)NS * RW * 4);                // [NS][RW][GROW] packed genome
+	uint4 *s_area = (uint4 *)(s_edge + (size_t)NS * (RW + 1) * slot_bytes);       // [NS][RW][AREA_STRIDE]
+	uint32_t *s_gbuf = (uint32_t *)(s_area + (size_t)NS * RW * AREA_STRIDE);                // [NS][RW][GROW] packed genome
 	DHot *s_hot = (DHot *)(s_gbuf + (size_t)NS * RW * GROW);                      // [NS][RW]
 	DHotQ *s_hotq = (DHotQ *)(s_hot + (size_t)NS * RW);                           // [NS][RW]
 	DGen *s_gen = (DGen *)(s_hotq + (size_t)NS * RW);                             // [NS][RW]
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 			h.grow = smem_u32(s_gbuf + ((size_t)s * RW + lane) * GROW) + 4u * w0;
 			h.sdst = 16u * (uint32_t)c_first;
 			h.ns = ns | (meta << 16);
-			h.area = smem_u32(s_area + ((size_t)s * RW + lane) * 4);
+			h.area = smem_u32(s_area + ((size_t)s * RW + lane) * AREA_STRIDE);
 			s_hot[s * RW + lane] = h;
 			DHotQ hq;
 			hq.qsrc = A0 >> 4;
@@ -500,7 +506,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 			const uint32_t c_first = P >> 4, c_last = (P + L - 1u) >> 4, q_first = Pq >> 4, q_last = (Pq + L - 1u) >> 4;
 			const uint32_t s0c = s_ship[s * (RW + 1) + lane].s0;
 			unsigned char *slot = s_edge + ((size_t)s * (RW + 1) + lane) * slot_bytes;
-			const uint4 *ar = s_area + ((size_t)s * RW + lane) * 4;
+			const uint4 *ar = s_area + ((size_t)s * RW + lane) * AREA_STRIDE;
 			uint4 *img;
 			uint4 v;
 			img = (uint4 *)(slot + 16u * (c_first - s0c));  // first sequence chunk: bytes from P on
@@ -613,6 +619,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 		for (int s = 0; s < NS; s++) {
 			char *tbs = tb[s];
 			const uint32_t end = tend[s], phs = ph[s];
+			const uint32_t last_chunk = end >> 4;  // shared with the next tile when end & 15 != 0 (else nothing of ours)
 			for (int rd = 0; rd < hrounds; rd++) {
 				const uint32_t j = (uint32_t)(rd * H + jl);
 				for (int i0 = 0; i0 <= nr; i0 += spi) {
@@ -624,13 +631,19 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, QT_DT_MIN_BLOCKS) k_simulat
 					const unsigned char *slot = s_edge + ((size_t)s * (RW + 1) + i) * slot_bytes;
 					const uint32_t chunk = j < nS ? sh.s0 + j : sh.t0 + (j - nS);
 					const unsigned char *src = j < nS ? slot + 16u * j : slot + s_bytes + 16u * (j - nS);
-					char *dst = tbs + 16u * (size_t)chunk;
-					if (chunk == 0 && phs) {  // shared with the previous tile
-						for (uint32_t b = phs; b < 16u; b++) dst[b] = (char)src[b];
-					} else if (chunk == (end >> 4)) {  // shared with the next tile (end & 15 != 0, or nothing to ship)
-						for (uint32_t b = 0; b < (end & 15u); b++) dst[b] = (char)src[b];
-					} else *(uint4 *)dst = *(const uint4 *)src;
+					if ((chunk == 0 && phs) || chunk == last_chunk) continue;  // the tile's ragged ends: below
+					*(uint4 *)(tbs + 16u * (size_t)chunk) = *(const uint4 *)src;
 				}
+			}
+			// the tile's first and last chunk are shared with the neighbouring tiles: one byte per lane
+			{
+				const DShip z = s_ship[s * (RW + 1) + nr];
+				const unsigned char *head = s_edge + (size_t)s * (RW + 1) * slot_bytes;                                   // slot 0, chunk 0
+				const unsigned char *tail = s_edge + ((size_t)s * (RW + 1) + nr) * slot_bytes + 16u * (last_chunk - z.s0);  // in the last slot
+				const uint32_t b = (uint32_t)lane & 15u;
+				if (lane < 16) {
+					if (phs && b >= phs) tbs[b] = (char)head[b];
+				} else if (b < (end & 15u)) tbs[16u * (size_t)last_chunk + b] = (char)tail[b];
 			}
 		}
 	}
@@ -651,19 +664,20 @@ static bool launch_cat(const SimArgs &a, uint32_t max_name, uint32_t max_body, c
 	const uint32_t K = (max_body + 14u) / 16u + 1u;
 	const uint32_t kmagic = (uint32_t)((0x100000000ull + K - 1) / K);  // q / K == umulhi(q, kmagic) for q < 2^16
 	// 16-byte pieces of packed genome per read: K + 1 words plus up to 3 of alignment
-	const uint32_t PMAX = (K + 1u + 3u + 3u) / 4u;
+	const uint32_t PMAX = ((K + 1u + 3u + 3u) / 4u) | 1u;  // odd: see AREA_STRIDE
 	const uint32_t pmagic = (uint32_t)((0x100000000ull + PMAX - 1) / PMAX);
 	// S part of a slot: from the chunk of (record start - 2) to the chunk of the first sequence byte
-	const uint32_t s_bytes = ((max_name + 2u + 15u + 15u) & ~15u) + 16u;
+	uint32_t s_bytes = ((max_name + 2u + 15u + 15u) & ~15u) + 16u;
+	if ((((s_bytes + T_BYTES) >> 4) & 1u) == 0) s_bytes += 16u;  // slot stride: an odd multiple of 16 bytes (see AREA_STRIDE)
 	auto warp_bytes = [&](int rw) -> uint32_t {
 		return NS * (uint32_t)(rw + 1) * (s_bytes + T_BYTES + (uint32_t)sizeof(DShip)) +
-		       (uint32_t)rw * (NS * (uint32_t)(sizeof(DHot) + sizeof(DHotQ) + sizeof(DGen) + sizeof(DPos) + 64u + 16u * PMAX + 8u) + NM * DT_OPS * 4u);
+		       (uint32_t)rw * (NS * (uint32_t)(sizeof(DHot) + sizeof(DHotQ) + sizeof(DGen) + sizeof(DPos) + 16u * AREA_STRIDE + 16u * PMAX + 8u) + NM * DT_OPS * 4u);
 	};
-	const uint32_t sm_budget = 200u * 1024u;
+	const uint32_t sm_budget = 216u * 1024u;
 	int rw = env_rw > 0 ? env_rw : 32;
 	if (rw > 32) rw = 32;
 	if (env_rw <= 0)
-		while (rw > 4 && warp_bytes(rw) * 24u > sm_budget) rw >>= 1;  // at least 24 resident warps per SM
+		while (rw > 4 && warp_bytes(rw) * (NS == 1 ? 24u : 16u) > sm_budget) rw >>= 1;  // resident warps per SM: 24 (16 for pairs)
 	if (warp_bytes(rw) + 1024 > sm_budget || (uint64_t)rw * K >= 65536u) return false;
 	int warps = env_warps > 0 ? env_warps : DT_MAX_WARPS;
 	if (warps > DT_MAX_WARPS) warps = DT_MAX_WARPS;

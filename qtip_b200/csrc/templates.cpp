@@ -58,10 +58,12 @@ bool add_mate(Category &c, MateDesc &m, HostMateProg &hp, const char *qual, cons
 	// qualities as they are printed (simplesim.cpp:119-125): reversed for '-' mates
 	if (c.qual_out.empty()) c.qual_out.assign(16, '\0');
 	m.qual_out_off = (uint32_t)c.qual_out.size();
-	if (fw) c.qual_out.append(qual, m.len);
-	else
-		for (uint32_t i = 0; i < m.len; i++) c.qual_out.push_back(qual[m.len - 1 - i]);
-	while (c.qual_out.size() % 16) c.qual_out.push_back('\0');
+	{
+		const size_t at = c.qual_out.size();
+		c.qual_out.resize(at + ((size_t)m.len + 15) / 16 * 16, '\0');
+		if (fw) memcpy(&c.qual_out[at], qual, m.len);
+		else std::reverse_copy(qual, qual + m.len, &c.qual_out[at]);
+	}
 	while (c.ops.size() % 4) c.ops.push_back(0u);  // 16-byte aligned lists: the kernel reads four ops per load
 	m.ops_off = (uint32_t)c.ops.size();
 	m.seg_off = (uint32_t)c.segs.size();
@@ -140,6 +142,12 @@ int TemplateStore::set_unpaired(int ci, const qtipsim_tmpl_unp *v, size_t kept, 
 	c.added = added;
 	c.t.resize(kept);
 	c.prog.resize(2 * kept);
+	if (kept) {  // arenas sized from the first template: one allocation instead of a doubling chain
+		const size_t l0 = v[0].qual ? strlen(v[0].qual) : 0;
+		c.qual.reserve(kept * (l0 + 8));
+		c.xs.reserve(kept * (l0 + 8));
+		c.qual_out.reserve(kept * (l0 + 24) + 64);
+	}
 	double bytes = 0, draws = 0;
 	for (size_t i = 0; i < kept; i++) {
 		TmplDesc &t = c.t[i];
@@ -192,6 +200,12 @@ int TemplateStore::set_paired(int ci, const qtipsim_tmpl_pair *v, size_t kept, u
 	c.added = added;
 	c.t.resize(kept);
 	c.prog.resize(2 * kept);
+	if (kept) {
+		const size_t l0 = (v[0].qual_1 ? strlen(v[0].qual_1) : 0) + (v[0].qual_2 ? strlen(v[0].qual_2) : 0);
+		c.qual.reserve(kept * (l0 + 16));
+		c.xs.reserve(kept * (l0 + 16));
+		c.qual_out.reserve(kept * (l0 + 48) + 64);
+	}
 	double bytes = 0, draws = 0;
 	for (size_t i = 0; i < kept; i++) {
 		TmplDesc &t = c.t[i];

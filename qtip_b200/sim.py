@@ -121,6 +121,30 @@ class Engine:
             a = np.ascontiguousarray(data, dtype=np.uint8)
             self.check(self.lib.qtipsim_load_fasta_bytes(self.h, C.c_void_p(a.ctypes.data), a.size))
 
+    def load_fasta_bytes_async(self, data):
+        """Starts load_fasta_bytes on a worker thread (ctypes releases the GIL during the call) so that the host
+        can compile the templates while the FASTA text crosses PCIe and is packed; join with wait_genome()."""
+        import threading
+        box = {}
+
+        def work():
+            try:
+                self.load_fasta_bytes(data)
+            except BaseException as e:  # re-raised by wait_genome
+                box["err"] = e
+
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        self._genome_job = (th, box)
+
+    def wait_genome(self) -> None:
+        job = getattr(self, "_genome_job", None)
+        if job:
+            job[0].join()
+            self._genome_job = None
+            if "err" in job[1]:
+                raise job[1]["err"]
+
     def _marshalled(self, cat: int, ts, fn):
         # the ctypes array for a template list is built once and reused (the C call itself is cheap)
         key = (cat, id(ts), len(ts))
