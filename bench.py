@@ -344,12 +344,14 @@ def main():
 
     def measure(rng_mode, steps, warmup, with_clocks):
         """Device-resident arm + end-to-end arm for one RNG mode; returns a dict (rank 0) of reduced numbers."""
-        for i in range(warmup):
-            one_step(100 + i, rng_mode)
+        # clocks / throttle reasons are sampled (nvidia-smi, every 100 ms) from the warm-up through the
+        # end-to-end arm: the device-timed region alone lasts only a few milliseconds per step
         sampler = ClockSampler(local_rank) if with_clocks else None
-        barrier()
         if sampler:
             sampler.start()
+        for i in range(warmup):
+            one_step(100 + i, rng_mode)
+        barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         t0 = time.perf_counter()
@@ -367,7 +369,6 @@ def main():
         torch.cuda.synchronize()
         wall_ms = (time.perf_counter() - t0) * 1e3
         ev_ms = ev0.elapsed_time(ev1)
-        clocks = sampler.stop() if sampler else None
         barrier()
         # end-to-end arm (host buffers; H2D of the FASTA text and templates, D2H of the FASTQ bytes inside)
         one_step(300, rng_mode, e2e=True)  # warm (allocates the pinned result buffers)
@@ -383,6 +384,7 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         e2e_ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
         barrier()
         t = torch.tensor([ev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
         w = torch.tensor([agg["reads"], agg["bytes"], agg["alg"], agg["launches"], e2e_reads, e2e_d2h], dtype=torch.float64, device="cuda")
@@ -419,6 +421,14 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+        # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture (same workload only)
+        traffic = None
+        if args.scale == 1.0 and args.workload in ("auto", "c3") and args.mode == "native":
+            try:
+                with open(os.path.join(ROOT, "profiles", "r01_k_simulate_direct_traffic.json")) as fh:
+                    traffic = json.load(fh)["traffic_bytes_per_launch"]
+            except Exception:
+                traffic = None
         names = {"native": "philox (native counter-based RNG: the product default)",
                  "replay": "replay (consumes the reference's rnglib/ranlib stream: bit-exact with the reference)"}
         other = "replay" if args.mode == "native" else "native"
@@ -434,7 +444,7 @@ def main():
             "wall_ms_per_step": m["wall_ms_per_step"],
             "phase_ms_per_step_rank0": m["phase"],
             "roofline": {"bound": "hbm", "kernel": "k_simulate_direct", "achieved": m["achieved"], "peak": peak, "unit": "GB/s",
-                         "frac": m["achieved"] / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "frac": m["achieved"] / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_step": m["alg_step"]},
             "e2e": m["e2e"],
             "gpu_launches": m["launches"],
