@@ -696,6 +696,12 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 			ra.ncount = h->d_ncount.as<uint32_t>();
 			ra.pclass = h->d_pclass.as<uint32_t>();
 			ra.setups = h->d_setups.as<BinomSetup>();
+			ra.nwin = nwin;
+			{
+				uint32_t mr = 0;
+				for (int c = 0; c < NCAT; c++) mr = std::max(mr, h->ts.cat[c].max_rflen);
+				ra.n_skip_ok = p->chunksz - olap >= (uint64_t)mr;
+			}
 			ra.win_lo = (uint32_t)pp.win_lo;
 			ra.win_hi = (uint32_t)pp.win_hi;
 			ra.olap = olap;

@@ -16,6 +16,8 @@ struct ResolveArgs {
 	const uint32_t *pclass;       // per window: row of the binomial set-up table
 	const BinomSetup *setups;     // [npclass][NCAT]
 	uint32_t win_lo, win_hi;
+	uint32_t nwin;                // windows in the table
+	bool n_skip_ok;               // chunksz - olap >= longest reference span: a mate never reaches past the next window
 	uint64_t olap;
 	// per category
 	const TmplDesc *t[NCAT];

@@ -307,6 +307,17 @@ def test_staged_kernel_path_still_bit_exact(name, workdir, monkeypatch):
     assert nat_s == nat_d  # both kernels consume the Philox stream identically
 
 
+@pytest.mark.parametrize("name", ["mixed_small", "c4_mix_small", "inversion"])
+def test_single_cta_resolver_equals_cluster_resolver(name, workdir, monkeypatch):
+    """K2 has two forms: the thread-block-cluster resolver (default) and the single-CTA one it grew out of
+    (QTIPSIM_RESOLVER=cta).  Same plan, same draws, same exit state."""
+    case = cases.CASES[name]()
+    a, sta, pa = util.run_cuda(case, workdir, name)
+    monkeypatch.setenv("QTIPSIM_RESOLVER", "cta")
+    b, stb, pb = util.run_cuda(case, workdir, name)
+    assert a == b and sta.draws == stb.draws and (pa.cg1, pa.cg2) == (pb.cg1, pb.cg2)
+
+
 def test_host_pack_path_equals_device_pack(workdir, monkeypatch):
     """K0 on the device (default) and the host FASTA packer produce the same reads."""
     case = cases.CASES["edges"]()
