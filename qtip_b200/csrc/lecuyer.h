@@ -47,7 +47,21 @@ struct LState {
 	uint32_t s1, s2;
 };
 
-QT_HD LState lstep(LState s) { return LState{mulmod1(s.s1, LA1), mulmod2(s.s2, LA2)}; }
+// (a*w) mod m for a CONSTANT multiplier w with wp = floor(w * 2^32 / m) precomputed (Shoup): one high and two low
+// multiplies and a conditional subtract instead of two 62-bit foldings.  Exact for a < m < 2^31.
+QT_HD uint32_t mulmod_const(uint32_t a, uint32_t w, uint32_t wp, uint32_t m) {
+#if defined(__CUDA_ARCH__)
+	const uint32_t q = __umulhi(a, wp);
+#else
+	const uint32_t q = (uint32_t)(((uint64_t)a * wp) >> 32);
+#endif
+	const uint32_t r = a * w - q * m;
+	return r >= m ? r - m : r;
+}
+static constexpr uint32_t LA1P = 80028u;  // floor(40014 * 2^32 / (2^31 - 85))
+static constexpr uint32_t LA2P = 81384u;  // floor(40692 * 2^32 / (2^31 - 249))
+
+QT_HD LState lstep(LState s) { return LState{mulmod_const(s.s1, LA1, LA1P, LM1), mulmod_const(s.s2, LA2, LA2P, LM2)}; }
 
 // i4_uni's output for the state *after* the step (rnglib.cpp:667-672)
 QT_HD int32_t lout(LState s) {

@@ -295,6 +295,8 @@ struct ClusterShared {
 	uint32_t err;
 	uint64_t nc, nd;
 	uint32_t total;
+	uint32_t w, region;               // window and region (category) being resolved
+	uint32_t fresh, done;
 };
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -324,14 +326,76 @@ __global__ void __cluster_dims__(CL_NC, 1, 1) __launch_bounds__(CL_T, 1) k_resol
 		for (int c = 0; c < NCAT; c++) own->count[c] = 0;
 		own->draws = 0;
 		own->err = 0;
+		own->n = 0;
+		own->w = a.win_lo;
+		own->region = 0;
+		own->fresh = 1;
+		own->done = 0;
 	}
-	cluster_sync_all();
 
-	for (uint32_t w = a.win_lo; w < a.win_hi; w++) {
+	for (;;) {
+		cluster_sync_all();  // everyone has left the previous region's rounds before its state is rewritten
+		// ---- thread 0 of CTA 0 walks the reference's sequence of binomial draws (simplesim.cpp:216-397) up
+		// to the next region that has reads: regions without reads cost one draw and no barrier ----
+		if (lead && tid == 0) {
+			LState S = own->S;
+			unsigned long long nd = 0;
+			auto nx = [&]() {
+				S = lstep(S);
+				nd++;
+				return lfloat(lout(S));
+			};
+			uint32_t w = own->w, region = own->region;
+			if (!own->fresh) region++;  // the region just resolved
+			own->fresh = 0;
+			uint64_t n = 0;
+			for (;;) {
+				if (region == 4) {
+					w++;
+					region = 0;
+				}
+				if (w >= a.win_hi) {
+					own->done = 1;
+					break;
+				}
+				const Window wn = a.win[w];
+				if (region == 0 && (wn.retsz < a.olap || (int)a.ncount[w] > (int)(0.9 * (double)wn.retsz))) {
+					w++;  // simplesim.cpp:221-223, :228-234: the window is skipped, no draws
+					continue;
+				}
+				const BinomSetup *su = a.setups + (size_t)a.pclass[w] * NCAT;
+				if (region <= 1) {
+					n = (uint64_t)binom_sample(su[region], nx);
+				} else if (region == 2) {
+					own->nc = (uint64_t)binom_sample(su[CAT_C], nx);
+					own->nd = (uint64_t)binom_sample(su[CAT_D], nx);
+					n = own->nc;
+				} else {
+					n = own->nd;
+				}
+				if (n) {
+					if (region == 0 && (uint64_t)wn.retsz - a.olap == 0) own->err = 1;  // assert(nslots > 0), simplesim.cpp:252
+					if (a.ntmpl[region] == 0) own->err = 2;
+					if (own->count[region] + n > a.cap[region]) own->err = 3;  // plan buffer too small: host retries larger
+					break;
+				}
+				region++;
+			}
+			own->S = S;
+			own->draws += nd;
+			own->p0 = 0;
+			own->n = n;
+			own->w = w;
+			own->region = region;
+		}
+		cluster_sync_all();
+		if (sh->done || sh->err) break;
+		const uint32_t w = sh->w;
+		const int cat = (int)sh->region;
 		const Window wn = a.win[w];
-		if (wn.retsz < a.olap) continue;                                                  // simplesim.cpp:221-223
-		if ((int)a.ncount[w] > (int)(0.9 * (double)wn.retsz)) continue;                   // simplesim.cpp:228-234
 		const uint64_t nslots = (uint64_t)wn.retsz - a.olap;
+		// N mask reads are skipped when neither this window nor the next one of the record holds an N (a mate
+		// whose reference span exceeds its fragment can reach past its window, SURVEY Q9, but never past the next)
 		bool has_n = true;
 		if (a.n_skip_ok && a.ncount[w] == 0) {
 			const bool next_same = w + 1 < a.nwin && a.win[w + 1].record == wn.record;
@@ -340,171 +404,137 @@ __global__ void __cluster_dims__(CL_NC, 1, 1) __launch_bounds__(CL_T, 1) k_resol
 		const RecDev rec = a.g.recs[wn.record];
 		const uint64_t gwin = rec.gstart + wn.refoff;
 		const uint64_t gend = rec.gstart + rec.len;
-		const BinomSetup *su = a.setups + (size_t)a.pclass[w] * NCAT;
+		const TmplDesc *tdesc = a.t[cat];
+		const XStep *xs = a.xsteps[cat];
+		const HostMateProg *prog = a.prog[cat];
+		const uint32_t ntm = a.ntmpl[cat];
 
-		for (int region = 0; region < 4; region++) {
-			const int cat = region;
-			cluster_sync_all();  // everyone has left the previous region's loop before its state is rewritten
-			if (lead && tid == 0) {
-				LState S = own->S;
-				unsigned long long nd = 0;
-				auto nx = [&]() {
-					S = lstep(S);
-					nd++;
-					return lfloat(lout(S));
-				};
-				if (region <= 1) {
-					own->n = (uint64_t)binom_sample(su[cat], nx);
-				} else if (region == 2) {
-					own->nc = (uint64_t)binom_sample(su[CAT_C], nx);
-					own->nd = (uint64_t)binom_sample(su[CAT_D], nx);
-					own->n = own->nc;
-				} else {
-					own->n = own->nd;
-				}
-				own->S = S;
-				own->draws += nd;
-				own->p0 = 0;
-				if (region == 0 && own->n && nslots == 0) own->err = 1;  // assert(nslots > 0), simplesim.cpp:252
-				if (own->n && a.ntmpl[cat] == 0) own->err = 2;
-				if (own->count[cat] + own->n > a.cap[cat]) own->err = 3;  // plan buffer too small: host retries larger
-			}
-			cluster_sync_all();
-			if (sh->err) break;
-			const TmplDesc *tdesc = a.t[cat];
-			const XStep *xs = a.xsteps[cat];
-			const HostMateProg *prog = a.prog[cat];
-			const uint32_t ntm = a.ntmpl[cat];
-
-			while (sh->n > 0) {  // uniform over the cluster: read after a cluster barrier, rewritten only before the next
-				const uint32_t p0 = sh->p0;
-				if (p0 >= (uint32_t)CL_N) {
-					// the previous read ran past this whole round (very long transcript): move on
-					cluster_sync_all();
-					if (lead && tid == 0) {
-						own->S = jump_tbl(own->S, (uint32_t)CL_N, a.jt1, a.jt2);
-						own->draws += CL_N;
-						own->p0 -= (uint32_t)CL_N;
-					}
-					cluster_sync_all();
-					continue;
-				}
-				// ---- speculate: a read starting at stream position pos (relative to S) ----
-				const LState S = sh->S;
-				const uint64_t n_left = sh->n;
-				const uint64_t base = sh->count[cat];
-				LState s = jump_tbl(S, pos, a.jt1, a.jt2);
-				s = lstep(s);
-				const uint32_t ti = (uint32_t)lindex(lfloat(lout(s)), ntm);
-				s = lstep(s);
-				const uint64_t off = lindex(lfloat(lout(s)), nslots);
-				const LState after2 = s;
-				uint32_t len = 2;
-				{
-					uint32_t d0 = 0, d1 = 0;
-					if (cat >= CAT_C) {
-						d0 = tdesc[ti].delta[0];
-						d1 = tdesc[ti].delta[1];
-					}
-					len += walk_mate_dev(s, a.g, xs, prog[2 * ti], gwin + off + d0, gend, has_n, a.jt1, a.jt2);
-					if (cat >= CAT_C) len += walk_mate_dev(s, a.g, xs, prog[2 * ti + 1], gwin + off + d1, gend, has_n, a.jt1, a.jt2);
-					if (cat == CAT_B) len += tdesc[ti].opp_len;  // init_random, simplesim.h:108-113
-				}
-				const uint32_t J = pos + len;
-				sh->jump[0][pos] = (uint16_t)(J < (uint32_t)CL_N ? J : (uint32_t)CL_N);
-				sh->mark[pos] = 0;
+		while (sh->n > 0) {  // uniform over the cluster: read after a cluster barrier, rewritten only before the next
+			const uint32_t p0 = sh->p0;
+			if (p0 >= (uint32_t)CL_N) {
+				// the previous read ran past this whole round (very long transcript): move on
 				cluster_sync_all();
-				// ---- CTA 0: orbit of p0 under J ----
-				if (lead) {
-					for (int r = 1; r <= CL_LOG; r++) {  // pointer doubling: jump[r] = J^(2^r)
-#pragma unroll
-						for (int m = 0; m < CL_PER; m++) {
-							const int e = tid + m * CL_T;
-							const uint32_t h = own->jump[r - 1][e];
-							own->jump[r][e] = h < (uint32_t)CL_N ? own->jump[r - 1][h] : (uint16_t)CL_N;
-						}
-						__syncthreads();
-					}
-					if (tid == 0) own->mark[p0] = 1;
-					__syncthreads();
-					for (int r = CL_LOG; r >= 0; r--) {  // mark all J^d(p0), d < 2^(CL_LOG+1)
-#pragma unroll
-						for (int m = 0; m < CL_PER; m++) {
-							const int e = tid + m * CL_T;
-							if (own->mark[e]) {
-								const uint32_t h = own->jump[r][e];
-								if (h < (uint32_t)CL_N) own->mark[h] = 1;
-							}
-						}
-						__syncthreads();
-					}
-					// number the marked positions (orbit order == position order): thread tid owns positions
-					// [tid * CL_PER, (tid + 1) * CL_PER)
-					uint32_t mine = 0;
-#pragma unroll
-					for (int m = 0; m < CL_PER; m++) mine += own->mark[tid * CL_PER + m];
-					uint32_t x = mine;
-					for (int o = 1; o < 32; o <<= 1) {
-						const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-						if (lane >= (uint32_t)o) x += y;
-					}
-					if (lane == 31) own->wsum[wid] = x;
-					__syncthreads();
-					if (wid == 0) {
-						const uint32_t v = lane < (uint32_t)(CL_T / 32) ? own->wsum[lane] : 0u;
-						uint32_t z = v;
-						for (int o = 1; o < 32; o <<= 1) {
-							const uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
-							if (lane >= (uint32_t)o) z += y;
-						}
-						if (lane < (uint32_t)(CL_T / 32)) own->wsum[lane] = z - v;  // exclusive prefix over warps
-						if (lane == (uint32_t)(CL_T / 32) - 1) own->total = z;
-					}
-					__syncthreads();
-					uint32_t run = own->wsum[wid] + x - mine;  // marked positions before tid * CL_PER
+				if (lead && tid == 0) {
+					own->S = jump_tbl(own->S, (uint32_t)CL_N, a.jt1, a.jt2);
+					own->draws += CL_N;
+					own->p0 -= (uint32_t)CL_N;
+				}
+				cluster_sync_all();
+				continue;
+			}
+			// ---- speculate: a read starting at stream position pos (relative to S) ----
+			const LState S = sh->S;
+			const uint64_t n_left = sh->n;
+			const uint64_t base = sh->count[cat];
+			LState s = jump_tbl(S, pos, a.jt1, a.jt2);
+			s = lstep(s);
+			const uint32_t ti = (uint32_t)lindex(lfloat(lout(s)), ntm);
+			s = lstep(s);
+			const uint64_t off = lindex(lfloat(lout(s)), nslots);
+			const LState after2 = s;
+			uint32_t len = 2;
+			{
+				uint32_t d0 = 0, d1 = 0;  // the mates' offsets from the drawn position are 0 for U and B
+				if (cat >= CAT_C) {
+					d0 = tdesc[ti].delta[0];
+					d1 = tdesc[ti].delta[1];
+				}
+				len += walk_mate_dev(s, a.g, xs, prog[2 * ti], gwin + off + d0, gend, has_n, a.jt1, a.jt2);
+				if (cat >= CAT_C) len += walk_mate_dev(s, a.g, xs, prog[2 * ti + 1], gwin + off + d1, gend, has_n, a.jt1, a.jt2);
+				if (cat == CAT_B) len += tdesc[ti].opp_len;  // init_random, simplesim.h:108-113
+			}
+			const uint32_t J = pos + len;
+			sh->jump[0][pos] = (uint16_t)(J < (uint32_t)CL_N ? J : (uint32_t)CL_N);
+			sh->mark[pos] = 0;
+			cluster_sync_all();
+			// ---- CTA 0: orbit of p0 under J ----
+			if (lead) {
+				for (int r = 1; r <= CL_LOG; r++) {  // pointer doubling: jump[r] = J^(2^r)
 #pragma unroll
 					for (int m = 0; m < CL_PER; m++) {
-						own->rank[tid * CL_PER + m] = (uint16_t)run;
-						run += own->mark[tid * CL_PER + m];
+						const int e = tid + m * CL_T;
+						const uint32_t h = own->jump[r - 1][e];
+						own->jump[r][e] = h < (uint32_t)CL_N ? own->jump[r - 1][h] : (uint16_t)CL_N;
 					}
+					__syncthreads();
 				}
-				cluster_sync_all();
-				// ---- every thread: is my position on the orbit, and which read is it? ----
-				const uint32_t total_marked = sh->total;
-				const uint32_t mk = sh->mark[pos];
-				const uint32_t rank = sh->rank[pos];
-				const bool take = mk && (uint64_t)rank < n_left;
-				if (take) {
-					PlanRec pr;
-					pr.tmpl = ti;
-					pr.record = wn.record;
-					pr.refoff = wn.refoff + off;
-					pr.s1 = after2.s1;
-					pr.s2 = after2.s2;
-					a.plan[cat][base + rank] = pr;
-				}
-				// ---- advance: the last taken read's end is the next position ----
-				const uint64_t ntake = n_left < (uint64_t)total_marked ? n_left : (uint64_t)total_marked;
-				cluster_sync_all();  // everyone has read S, n, count, total, marks: they may be rewritten now
-				if (take && (uint64_t)rank == ntake - 1) {
-					const uint32_t endpos = pos + len;  // may exceed CL_N
-					if (ntake == n_left) {  // region finished inside this round
-						sh->S = jump_tbl(S, endpos, a.jt1, a.jt2);
-						sh->draws += endpos;
-						sh->p0 = 0;
-					} else {
-						sh->S = jump_tbl(S, (uint32_t)CL_N, a.jt1, a.jt2);
-						sh->draws += CL_N;
-						sh->p0 = endpos - (uint32_t)CL_N;  // >= 0: the orbit left the round here
+				if (tid == 0) own->mark[p0] = 1;
+				__syncthreads();
+				for (int r = CL_LOG; r >= 0; r--) {  // mark all J^d(p0), d < 2^(CL_LOG+1)
+#pragma unroll
+					for (int m = 0; m < CL_PER; m++) {
+						const int e = tid + m * CL_T;
+						if (own->mark[e]) {
+							const uint32_t h = own->jump[r][e];
+							if (h < (uint32_t)CL_N) own->mark[h] = 1;
+						}
 					}
-					sh->n = n_left - ntake;
-					sh->count[cat] = base + ntake;
+					__syncthreads();
 				}
-				cluster_sync_all();
+				// number the marked positions (orbit order == position order): thread tid owns positions
+				// [tid * CL_PER, (tid + 1) * CL_PER)
+				uint32_t mine = 0;
+#pragma unroll
+				for (int m = 0; m < CL_PER; m++) mine += own->mark[tid * CL_PER + m];
+				uint32_t x = mine;
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+					if (lane >= (uint32_t)o) x += y;
+				}
+				if (lane == 31) own->wsum[wid] = x;
+				__syncthreads();
+				if (wid == 0) {
+					const uint32_t v = lane < (uint32_t)(CL_T / 32) ? own->wsum[lane] : 0u;
+					uint32_t z = v;
+					for (int o = 1; o < 32; o <<= 1) {
+						const uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
+						if (lane >= (uint32_t)o) z += y;
+					}
+					if (lane < (uint32_t)(CL_T / 32)) own->wsum[lane] = z - v;  // exclusive prefix over warps
+					if (lane == (uint32_t)(CL_T / 32) - 1) own->total = z;
+				}
+				__syncthreads();
+				uint32_t run = own->wsum[wid] + x - mine;  // marked positions before tid * CL_PER
+#pragma unroll
+				for (int m = 0; m < CL_PER; m++) {
+					own->rank[tid * CL_PER + m] = (uint16_t)run;
+					run += own->mark[tid * CL_PER + m];
+				}
 			}
-			if (sh->err) break;
+			cluster_sync_all();
+			// ---- every thread: is my position on the orbit, and which read is it? ----
+			const uint32_t total_marked = sh->total;
+			const uint32_t mk = sh->mark[pos];
+			const uint32_t rank = sh->rank[pos];
+			const bool take = mk && (uint64_t)rank < n_left;
+			if (take) {
+				PlanRec pr;
+				pr.tmpl = ti;
+				pr.record = wn.record;
+				pr.refoff = wn.refoff + off;
+				pr.s1 = after2.s1;
+				pr.s2 = after2.s2;
+				a.plan[cat][base + rank] = pr;
+			}
+			// ---- advance: the last taken read's end is the next position ----
+			const uint64_t ntake = n_left < (uint64_t)total_marked ? n_left : (uint64_t)total_marked;
+			cluster_sync_all();  // everyone has read S, n, count, total, marks: they may be rewritten now
+			if (take && (uint64_t)rank == ntake - 1) {
+				const uint32_t endpos = pos + len;  // may exceed CL_N
+				if (ntake == n_left) {  // region finished inside this round
+					sh->S = jump_tbl(S, endpos, a.jt1, a.jt2);
+					sh->draws += endpos;
+					sh->p0 = 0;
+				} else {
+					sh->S = jump_tbl(S, (uint32_t)CL_N, a.jt1, a.jt2);
+					sh->draws += CL_N;
+					sh->p0 = endpos - (uint32_t)CL_N;  // >= 0: the orbit left the round here
+				}
+				sh->n = n_left - ntake;
+				sh->count[cat] = base + ntake;
+			}
+			cluster_sync_all();
 		}
-		if (sh->err) break;
 	}
 	cluster_sync_all();
 	if (lead && tid == 0) {
