@@ -764,6 +764,8 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 		CK(h->d_cum.ensure(((size_t)nwin + 1) * 8 * NCAT));
 		uint64_t edge[NCAT][2];
 		for (int c = 0; c < NCAT; c++) {
+			edge[c][0] = edge[c][1] = 0;
+			if (!pp.target[c]) continue;  // Binomial(0, p) = 0 in every window: nothing to launch
 			uint64_t *cum = h->d_cum.as<uint64_t>() + (size_t)c * (nwin + 1);
 			launch_philox_counts(h->d_win.as<Window>(), h->d_ncount.as<uint32_t>(), h->d_pclass.as<uint32_t>(),
 			                     h->d_setups.as<BinomSetup>(), nwin, olap, pp.target[c], p->philox_seed, c,
@@ -778,10 +780,8 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 			read_base[c] = edge[c][0];
 			if (!nreads[c]) continue;
 			const uint64_t *cum = h->d_cum.as<uint64_t>() + (size_t)c * (nwin + 1);
-			CK(h->d_plan[c].ensure(nreads[c] * sizeof(PlanRec)));
-			launch_plan_philox(h->d_win.as<Window>() + pp.win_lo, cum + pp.win_lo, (uint32_t)(pp.win_hi - pp.win_lo), olap,
-			                   (uint32_t)h->ts.cat[c].t.size(), c, p->philox_seed, h->d_plan[c].as<PlanRec>(), nreads[c],
-			                   read_base[c], h->st);
+			CK(h->d_plan[c].ensure(nreads[c] * sizeof(PlanRec)));  // filled together with the record lengths below
+			(void)cum;
 		}
 	}
 	const double t_plan_host = now_ms() - t_plan0;
@@ -822,7 +822,15 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 		const int s0 = cat_stream0(c);
 		CK(h->d_off0[c].ensure(nreads[c] * 8));
 		if (c != CAT_U) CK(h->d_off1[c].ensure(nreads[c] * 8));
-		launch_read_lengths(a, h->d_len0.as<uint32_t>(), c != CAT_U ? h->d_len1.as<uint32_t>() : nullptr, d_gb, h->st);
+		if (p->rng_mode == QTIPSIM_RNG_PHILOX) {
+			// native plan and record lengths in one pass (the read's window by binary search over the cumulative counts)
+			const uint64_t *cum = h->d_cum.as<uint64_t>() + (size_t)c * (nwin + 1);
+			launch_plan_philox_lengths(h->d_win.as<Window>() + pp.win_lo, cum + pp.win_lo, (uint32_t)(pp.win_hi - pp.win_lo), olap,
+			                           (uint32_t)h->ts.cat[c].t.size(), p->philox_seed, a, h->d_plan[c].as<PlanRec>(),
+			                           h->d_len0.as<uint32_t>(), c != CAT_U ? h->d_len1.as<uint32_t>() : nullptr, d_gb, h->st);
+		} else {
+			launch_read_lengths(a, h->d_len0.as<uint32_t>(), c != CAT_U ? h->d_len1.as<uint32_t>() : nullptr, d_gb, h->st);
+		}
 		launch_scan(h->d_len0.as<uint32_t>(), h->d_off0[c].as<uint64_t>(), nreads[c], h->d_scan_tmp.as<uint64_t>(), d_tot + s0, h->st);
 		if (c != CAT_U)
 			launch_scan(h->d_len1.as<uint32_t>(), h->d_off1[c].as<uint64_t>(), nreads[c], h->d_scan_tmp.as<uint64_t>(), d_tot + s0 + 1, h->st);

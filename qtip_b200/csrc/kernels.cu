@@ -315,6 +315,59 @@ __global__ void __launch_bounds__(256) k_plan_philox(const Window *win, const ui
 	plan[r] = pr;
 }
 
+// the same, fused with k_read_lengths: the thread that plans read r also computes its FASTQ record length(s)
+// (a = the category's SimArgs: a.plan is written here, templates and records are read)
+__global__ void __launch_bounds__(256) k_plan_philox_lengths(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap,
+                                                              uint32_t ntmpl, uint64_t seed, SimArgs a, PlanRec *plan,
+                                                              uint32_t *len0, uint32_t *len1, unsigned long long *gbytes) {
+	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t gb = 0;
+	if (r < a.nreads) {
+		const uint64_t gi = a.read_index_base + r;
+		uint32_t lo = 0, hi = nwin;  // invariant: cum[lo] <= gi < cum[hi]
+		while (hi - lo > 1) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if (cum[mid] <= gi) lo = mid;
+			else hi = mid;
+		}
+		const Window w = win[lo];
+		const Philox4 x = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), 0u, PHILOX_DOM_PLAN | (uint32_t)a.cat,
+		                             (uint32_t)seed, (uint32_t)(seed >> 32));
+		const uint64_t nslots = (uint64_t)w.retsz - olap;
+		PlanRec pr;
+		pr.tmpl = __umulhi(x.v[0], ntmpl);
+		pr.record = w.record;
+		pr.refoff = w.refoff + (nslots ? (uint64_t)__umulhi(x.v[1], (uint32_t)nslots) : 0);
+		pr.s1 = 0;
+		pr.s2 = 0;
+		plan[r] = pr;
+		const TmplDesc &t = a.c.t[pr.tmpl];
+		const ReadGeom gm = read_geom(a, pr, t);
+		len0[r] = gm.name_len + 2u * gm.body0 + 4u;
+		if (len1) len1[r] = gm.name_len + 2u * gm.body1 + 4u;
+		gb = (t.m[0].rflen + 3u) / 4u;
+		if (t.nmates == 2) gb += (t.m[1].rflen + 3u) / 4u;
+	}
+	for (int o = 16; o; o >>= 1) gb += __shfl_xor_sync(0xffffffffu, gb, o);
+	__shared__ uint32_t ws[8];
+	if (lane_id() == 0) ws[threadIdx.x >> 5] = gb;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		unsigned long long s = 0;
+		for (int i = 0; i < 8; i++) s += ws[i];
+		if (s) atomicAdd(gbytes, s);
+	}
+}
+
+void launch_plan_philox_lengths(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap, uint32_t ntmpl, uint64_t seed,
+                                const SimArgs &a, PlanRec *plan, uint32_t *len0, uint32_t *len1, unsigned long long *gbytes,
+                                cudaStream_t st) {
+	if (!a.nreads) return;
+	k_plan_philox_lengths<<<(unsigned)((a.nreads + 255) / 256), 256, 0, st>>>(win, cum, nwin, olap, ntmpl, seed, a, plan, len0, len1,
+	                                                                        gbytes);
+	g_launches++;
+}
+
 void launch_plan_philox(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap, uint32_t ntmpl,
                         int cat, uint64_t seed, PlanRec *plan, uint64_t n, uint64_t read_index_base,
                         cudaStream_t st) {

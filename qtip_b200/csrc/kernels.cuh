@@ -101,6 +101,11 @@ void launch_pack_units(const uint8_t *text, const uint64_t *seg_start, const uin
                        const int64_t *seg_gbase, uint32_t *bases, uint32_t *nmask, cudaStream_t st);
 void launch_fill_n(const uint64_t *lo, const uint64_t *hi, uint32_t n, uint32_t *nmask, cudaStream_t st);
 
+// plan + record lengths in one pass over the reads (PHILOX)
+void launch_plan_philox_lengths(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap, uint32_t ntmpl, uint64_t seed,
+                                const SimArgs &a, PlanRec *plan, uint32_t *len0, uint32_t *len1, unsigned long long *gbytes,
+                                cudaStream_t st);
+
 int kernels_launch_count();  // kernels launched through the wrappers above since process start
 
 }  // namespace qt
