@@ -272,28 +272,59 @@ __device__ __forceinline__ char *s_put_dec(char *p, uint64_t v, uint32_t n) {
 	}
 	return p + n;
 }
+// decimal of v, n digits, also written d2 bytes further when TWO (the same name goes to both files of a pair)
+template <bool TWO>
+__device__ __forceinline__ char *s_put_dec2(char *p, ptrdiff_t d2, uint64_t v, uint32_t n) {
+	if (v <= 0xffffffffull) {
+		uint32_t x = (uint32_t)v;
+		for (int i = (int)n - 1; i >= 0; i--) {
+			const uint32_t q = x / 10u;
+			const char ch = (char)('0' + (int)(x - q * 10u));
+			p[i] = ch;
+			if (TWO) p[i + d2] = ch;
+			x = q;
+		}
+	} else {
+		for (int i = (int)n - 1; i >= 0; i--) {
+			const char ch = (char)('0' + (int)(v % 10));
+			p[i] = ch;
+			if (TWO) p[i + d2] = ch;
+			v /= 10;
+		}
+	}
+	return p + n;
+}
 // "<refid>:<+|->:<off>:<score>" (simplesim.cpp:104-110); the score and refids of up to 16 bytes come
-// from registers (n16 = RecDev::name16)
-__device__ __forceinline__ char *s_origin(char *p, const char *__restrict__ refid, const uint4 &n16, uint32_t rl, uint64_t off,
-                                          uint32_t nd, const MateHot &m) {
+// from registers (n16 = RecDev::name16).  TWO: every byte is also stored d2 bytes further (second file).
+template <bool TWO>
+__device__ __forceinline__ char *s_origin2(char *p, ptrdiff_t d2, const char *__restrict__ refid, const uint4 &n16, uint32_t rl,
+                                           uint64_t off, uint32_t nd, const MateHot &m) {
+	auto put = [&](char *q, char ch) {
+		*q = ch;
+		if (TWO) q[d2] = ch;
+	};
 	if (rl <= 16u) {
 		const uint32_t nw[4] = {n16.x, n16.y, n16.z, n16.w};
 #pragma unroll
 		for (int k = 0; k < 16; k++)
-			if (k < (int)rl) p[k] = (char)(nw[k >> 2] >> (8 * (k & 3)));
+			if (k < (int)rl) put(p + k, (char)(nw[k >> 2] >> (8 * (k & 3))));
 	} else {
-		for (uint32_t i = 0; i < rl; i++) p[i] = refid[i];
+		for (uint32_t i = 0; i < rl; i++) put(p + i, refid[i]);
 	}
 	p += rl;
-	p[0] = ':';
-	p[1] = m.fw ? '+' : '-';
-	p[2] = ':';
-	p = s_put_dec(p + 3, off, nd);
-	p[0] = ':';
+	put(p, ':');
+	put(p + 1, m.fw ? '+' : '-');
+	put(p + 2, ':');
+	p = s_put_dec2<TWO>(p + 3, d2, off, nd);
+	put(p, ':');
 #pragma unroll
 	for (int k = 0; k < 11; k++)
-		if (k < (int)m.score_len) p[1 + k] = (char)(m.score[k >> 2] >> (8 * (k & 3)));
+		if (k < (int)m.score_len) put(p + 1 + k, (char)(m.score[k >> 2] >> (8 * (k & 3))));
 	return p + 1 + m.score_len;
+}
+__device__ __forceinline__ char *s_origin(char *p, const char *__restrict__ refid, const uint4 &n16, uint32_t rl, uint64_t off,
+                                          uint32_t nd, const MateHot &m) {
+	return s_origin2<false>(p, 0, refid, n16, rl, off, nd, m);
 }
 
 // ASCII base as staged -> 2-bit code of the REFERENCE base (4 for N); '-' mates are staged complemented

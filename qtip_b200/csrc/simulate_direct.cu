@@ -360,7 +360,6 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 			}
 		}
 		const uint32_t rec_name_off = rec_b.x, rl = rec_b.y;
-		unsigned char *name0 = nullptr;
 #pragma unroll
 		for (int s = 0; s < NS; s++) {
 			const bool random = CAT == CAT_B && ((s == 0) == s0_random);
@@ -372,42 +371,50 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 			unsigned char *sS = slot - 16u * s0c;                  // S space: + tile-relative byte position
 			unsigned char *sT = slot + s_bytes - 16u * c_last;     // T space
 			unsigned char *sN = slot + slot_bytes - 16u * q_last;  // next slot's S space
-			// name (simplesim.cpp:104-110, :140-150)
+			// name (simplesim.cpp:104-110, :140-150): composed once, every byte stored to both files of a pair
 			unsigned char *np = sS + rstart[s];
 			if (s == 0) {
-				name0 = np;
+				constexpr bool TWO = NS == 2;
+				ptrdiff_t d2 = 0;
+				if (TWO) {
+					const uint32_t s0c1 = lane == 0 ? 0u : (rstart[NS - 1] - 2u) >> 4;
+					unsigned char *np1 = s_edge + ((size_t)(NS - 1) * (RW + 1) + lane) * slot_bytes - 16u * s0c1 + rstart[NS - 1];
+					d2 = np1 - np;
+				}
+				auto put = [&](char *q, char ch) {
+					*q = ch;
+					if (TWO) q[d2] = ch;
+				};
 				const char *refid = a.g.names + rec_name_off;
 				char *p = (char *)np;
-				p[0] = '@';
-				p[1] = 'q';
-				p[2] = 't';
-				p[3] = 'i';
-				p[4] = 'p';
-				p[5] = '!';
-				p[6] = ':';
+				put(p, '@');
+				put(p + 1, 'q');
+				put(p + 2, 't');
+				put(p + 3, 'i');
+				put(p + 4, 'p');
+				put(p + 5, '!');
+				put(p + 6, ':');
 				p += 7;
 				if (CAT == CAT_U) {
 					const uint32_t nd = nl - 13u - rl - mh[0].score_len - tt.typ_len;
-					p = s_origin(p, refid, rec_c, rl, ro[0], nd, mh[0]);
+					p = s_origin2<TWO>(p, d2, refid, rec_c, rl, ro[0], nd, mh[0]);
 				} else if (CAT == CAT_B) {
 					const uint32_t nd = (nl - 18u - 2u * rl - 2u * mh[0].score_len - tt.typ_len) >> 1;
-					p = s_origin(p, refid, rec_c, rl, ro[0], nd, mh[0]);
-					*p++ = ':';
-					p = s_origin(p, refid, rec_c, rl, ro[0], nd, mh[0]);
+					p = s_origin2<TWO>(p, d2, refid, rec_c, rl, ro[0], nd, mh[0]);
+					put(p++, ':');
+					p = s_origin2<TWO>(p, d2, refid, rec_c, rl, ro[0], nd, mh[0]);
 				} else {
 					const uint32_t nd0 = ndig64(ro[0]);
 					const uint32_t nd1 = nl - 18u - 2u * rl - mh[0].score_len - mh[NM - 1].score_len - tt.typ_len - nd0;
-					p = s_origin(p, refid, rec_c, rl, ro[0], nd0, mh[0]);
-					*p++ = ':';
-					p = s_origin(p, refid, rec_c, rl, ro[1], nd1, mh[NM - 1]);
+					p = s_origin2<TWO>(p, d2, refid, rec_c, rl, ro[0], nd0, mh[0]);
+					put(p++, ':');
+					p = s_origin2<TWO>(p, d2, refid, rec_c, rl, ro[1], nd1, mh[NM - 1]);
 				}
-				p[0] = ':';
-				p[1] = (char)(tt.typ & 0xffu);
-				if (tt.typ_len > 1) p[2] = (char)(tt.typ >> 8);
-				p[1 + tt.typ_len] = '\n';
+				put(p, ':');
+				put(p + 1, (char)(tt.typ & 0xffu));
+				if (tt.typ_len > 1) put(p + 2, (char)(tt.typ >> 8));
+				put(p + 1 + tt.typ_len, '\n');
 				QD_CHK(p + 2 + tt.typ_len == (char *)np + nl, 6, (uint32_t)(p - (char *)np), nl);
-			} else {
-				for (uint32_t j = 0; j < nl; j++) np[j] = name0[j];
 			}
 			// separators
 			sT[P + L] = '\n';
@@ -677,7 +684,9 @@ static bool launch_cat(const SimArgs &a, uint32_t max_name, uint32_t max_body, c
 	int rw = env_rw > 0 ? env_rw : 32;
 	if (rw > 32) rw = 32;
 	if (env_rw <= 0)
-		while (rw > 4 && warp_bytes(rw) * (NS == 1 ? 24u : 16u) > sm_budget) rw >>= 1;  // resident warps per SM: 24 (16 for pairs)
+		// resident warps per SM wanted: 24; 12 for concordant / discordant pairs (their lane = read steps are long
+		// and want full half-warps more than they want occupancy: measured)
+		while (rw > 4 && warp_bytes(rw) * ((CAT == CAT_C || CAT == CAT_D) ? 12u : 24u) > sm_budget) rw >>= 1;
 	if (warp_bytes(rw) + 1024 > sm_budget || (uint64_t)rw * K >= 65536u) return false;
 	int warps = env_warps > 0 ? env_warps : DT_MAX_WARPS;
 	if (warps > DT_MAX_WARPS) warps = DT_MAX_WARPS;
