@@ -63,6 +63,11 @@ static constexpr uint32_t LA2P = 81384u;  // floor(40692 * 2^32 / (2^31 - 249))
 
 QT_HD LState lstep(LState s) { return LState{mulmod_const(s.s1, LA1, LA1P, LM1), mulmod_const(s.s2, LA2, LA2P, LM2)}; }
 
+// one step BACK: multiplication by a^-1 mod m (the stream is a group, so it can be walked in either direction)
+static constexpr uint32_t LB1 = 2082061899u, LB1P = 4164123962u;  // 40014^-1 mod (2^31 - 85), floor(LB1 * 2^32 / m1)
+static constexpr uint32_t LB2 = 1481316021u, LB2P = 2962632385u;  // 40692^-1 mod (2^31 - 249)
+QT_HD LState lstep_back(LState s) { return LState{mulmod_const(s.s1, LB1, LB1P, LM1), mulmod_const(s.s2, LB2, LB2P, LM2)}; }
+
 // i4_uni's output for the state *after* the step (rnglib.cpp:667-672)
 QT_HD int32_t lout(LState s) {
 	int32_t z = (int32_t)s.s1 - (int32_t)s.s2;

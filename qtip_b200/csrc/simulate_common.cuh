@@ -4,6 +4,7 @@
 #pragma once
 #include <stdint.h>
 #include "kernels.cuh"
+#include "lecuyer.h"
 
 namespace qt {
 
@@ -325,6 +326,20 @@ __device__ __forceinline__ char *s_origin2(char *p, ptrdiff_t d2, const char *__
 __device__ __forceinline__ char *s_origin(char *p, const char *__restrict__ refid, const uint4 &n16, uint32_t rl, uint64_t off,
                                           uint32_t nd, const MateHot &m) {
 	return s_origin2<false>(p, 0, refid, n16, rl, off, nd, m);
+}
+
+// state k steps ahead, from the tables of a^j mod m (j < JUMP_TBL) in global memory
+__device__ __forceinline__ LState ljump_tbl(LState s, uint32_t k, const uint32_t *jt1, const uint32_t *jt2) {
+	while (k >= (uint32_t)JUMP_TBL) {
+		s.s1 = mulmod1(s.s1, __ldg(&jt1[JUMP_TBL - 1]));
+		s.s2 = mulmod2(s.s2, __ldg(&jt2[JUMP_TBL - 1]));
+		k -= (uint32_t)(JUMP_TBL - 1);
+	}
+	if (k) {
+		s.s1 = mulmod1(s.s1, __ldg(&jt1[k]));
+		s.s2 = mulmod2(s.s2, __ldg(&jt2[k]));
+	}
+	return s;
 }
 
 // ASCII base as staged -> 2-bit code of the REFERENCE base (4 for N); '-' mates are staged complemented

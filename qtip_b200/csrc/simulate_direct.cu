@@ -90,6 +90,12 @@ struct __align__(16) DHotQ {  // what a quality-chunk lane reads
 	uint32_t nq;      // quality slots | meta << 16
 	uint32_t area;
 };
+// bad-end pairs: what the chunk lanes of step Br need to draw a read's random mate
+struct __align__(8) DRnd {
+	uint32_t r0, r1;  // REPLAY: generator state before the mate's first draw; PHILOX: index of its first draw, 0
+	uint32_t flags;   // bit 0: stream of the random mate, bit 1: printed on the '+' strand
+	uint32_t pad;
+};
 struct __align__(8) DPos {
 	uint32_t P;       // byte position of the first sequence byte
 	uint32_t L;       // body length
@@ -190,6 +196,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 	uint32_t *s_gunit = s_ops + (size_t)NM * DT_OPS * RW;                         // [NS][RW] 16-byte unit of bases[] at the row's start
 	uint32_t *s_gb0 = s_gunit + (size_t)NS * RW;                                  // [NS][RW]
 	DPos *s_pos = (DPos *)(s_gb0 + (size_t)NS * RW);                              // [NS][RW]
+	DRnd *s_rnd = (DRnd *)(s_pos + (size_t)NS * RW);                              // [RW] (bad-end pairs only)
 
 	const uint64_t *offs[2] = {a.off0, a.off1};
 	const uint64_t *tots[2] = {a.tot0, a.tot1};
@@ -516,14 +523,16 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 			const uint4 *ar = s_area + ((size_t)s * RW + lane) * AREA_STRIDE;
 			uint4 *img;
 			uint4 v;
-			img = (uint4 *)(slot + 16u * (c_first - s0c));  // first sequence chunk: bytes from P on
-			v = *img;
-			overlay(v, ar[AREA_SEQ_HEAD], s_lowmask, (int)P - 16 * (int)c_first, 16);
-			*img = v;
-			img = (uint4 *)(slot + s_bytes);  // last sequence chunk: bytes before P + L
-			v = *img;
-			overlay(v, ar[AREA_SEQ_TAIL], s_lowmask, 0, (int)(P + L) - 16 * (int)c_last);
-			*img = v;
+			if (!(CAT == CAT_B && ((s == 0) == s0_random))) {  // (a random mate's sequence is drawn in step Br)
+				img = (uint4 *)(slot + 16u * (c_first - s0c));  // first sequence chunk: bytes from P on
+				v = *img;
+				overlay(v, ar[AREA_SEQ_HEAD], s_lowmask, (int)P - 16 * (int)c_first, 16);
+				*img = v;
+				img = (uint4 *)(slot + s_bytes);  // last sequence chunk: bytes before P + L
+				v = *img;
+				overlay(v, ar[AREA_SEQ_TAIL], s_lowmask, 0, (int)(P + L) - 16 * (int)c_last);
+				*img = v;
+			}
 			img = (uint4 *)(slot + s_bytes + 16u * (q_first - c_last));  // first quality chunk: bytes from Pq on
 			v = *img;
 			overlay(v, ar[AREA_QUAL_HEAD], s_lowmask, (int)Pq - 16 * (int)q_first, 16);
@@ -602,17 +611,88 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 			}
 		}
 		if (CAT == CAT_B) {
-			// init_random (simplesim.h:89-117): opp_len draws, printed with the aligned mate's strand
+			// the random mate (init_random, simplesim.h:89-117) follows in the draw stream: hand the generator to step Br
+			DRnd rd;
+			rd.r0 = MODE == QTIPSIM_RNG_REPLAY ? st.s1 : dk;
+			rd.r1 = MODE == QTIPSIM_RNG_REPLAY ? st.s2 : 0u;
+			rd.flags = (s0_random ? 0u : 1u) | (mh[0].fw ? 2u : 0u);
+			rd.pad = 0;
+			s_rnd[lane] = rd;
+		}
+	}
+	if (CAT == CAT_B) {
+		__syncwarp();
+		// ---------------- step Br (lane = 16-byte chunk of a random mate): opp_len draws per read, 16 per lane ----------------
+		// Both generators are addressable: draw j of the mate is Philox draw (first + j), or the L'Ecuyer state
+		// (j + 1) steps past the handed-over one (jump tables), walked forwards for '+' mates and backwards -- a
+		// multiplication by a^-1 -- for '-' mates, whose bases are printed in reverse (simplesim.h:108-113).
+		const int nitems = nr * K;
+		for (int q = lane; q < nitems; q += 32) {
+			const int i = (int)__umulhi((uint32_t)q, kmagic), j = q - i * K;
+			const DRnd rd = s_rnd[i];
+			const int sr = (int)(rd.flags & 1u);
+			const bool fw = (rd.flags & 2u) != 0;
+			const DPos pp = s_pos[sr * RW + i];
+			const int P = (int)pp.P, L = (int)pp.L;
+			const int c_first = P >> 4, ns = ((P + L - 1) >> 4) - c_first + 1;
+			if (j >= ns) continue;
+			const int k0 = 16 * (c_first + j) - P;       // output position of the chunk's first byte
+			const int t_first = k0 < 0 ? -k0 : 0;        // first byte of the chunk inside the mate
+			const uint32_t T = fw ? TBL_FW : TBL_RC;
+			uint32_t w[4] = {0u, 0u, 0u, 0u};
+			if (MODE == QTIPSIM_RNG_REPLAY) {
+				const int jd0 = fw ? k0 + t_first : L - 1 - (k0 + t_first);  // draw of the first byte inside
+				LState st = ljump_tbl(LState{rd.r0, rd.r1}, (uint32_t)(fw ? jd0 : jd0 + 1), a.jt1, a.jt2);
+#pragma unroll
+				for (int t = 0; t < 16; t++) {
+					if (t >= t_first && k0 + t < L) {
+						if (fw) st = lstep(st);
+						const uint32_t code = lbase_code(lfloat(lout(st)));
+						w[t >> 2] |= ((T >> (8u * code)) & 0xffu) << (8 * (t & 3));
+						if (!fw) st = lstep_back(st);
+					}
+				}
+			} else {
+				const uint64_t gi = a.read_index_base + r0 + (uint64_t)i;
+				uint32_t curb = 0xffffffffu;
+				Philox4 blk{};
+#pragma unroll
+				for (int t = 0; t < 16; t++) {
+					if (t >= t_first && k0 + t < L) {
+						const uint32_t d = rd.r0 + (uint32_t)(fw ? k0 + t : L - 1 - (k0 + t));
+						if ((d >> 3) != curb) {
+							curb = d >> 3;
+							blk = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), curb, PHILOX_DOM_BASE | (uint32_t)CAT,
+							                 (uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32));
+						}
+						const uint32_t wi = (d >> 1) & 3u;
+						const uint32_t x = wi == 0 ? blk.v[0] : wi == 1 ? blk.v[1] : wi == 2 ? blk.v[2] : blk.v[3];
+						const uint32_t code = ((d & 1u) ? (x >> 16) : (x & 0xffffu)) >> 14;
+						w[t >> 2] |= ((T >> (8u * code)) & 0xffu) << (8 * (t & 3));
+					}
+				}
+			}
+			const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
+			if (j == 0 || j == ns - 1) s_area[((size_t)sr * RW + i) * AREA_STRIDE + (j ? AREA_SEQ_TAIL : AREA_SEQ_HEAD)] = v;
+			else *(uint4 *)((sr ? tb[NS - 1] : tb[0]) + 16u * (size_t)(c_first + j)) = v;
+		}
+		__syncwarp();
+		// ---------------- step C2 (lane = read): the random mate's first and last chunk into the slot image ----------------
+		if (act) {
 			const int s = s0_random ? 0 : 1;
 			const DPos pp = s_pos[s * RW + lane];
 			const uint32_t P = pp.P, L = pp.L;
 			const uint32_t c_first = P >> 4, c_last = (P + L - 1u) >> 4, s0c = s_ship[s * (RW + 1) + lane].s0;
-			const bool fw = mh[0].fw;
-			const uint32_t T = fw ? TBL_FW : TBL_RC;
-			for (uint32_t j = 0; j < L; j++) {
-				const uint32_t code = draw_code();
-				put_base(s, P, c_first, c_last, s0c, fw ? j : L - 1 - j, (T >> (8u * code)) & 0xffu);
-			}
+			unsigned char *slot = s_edge + ((size_t)s * (RW + 1) + lane) * slot_bytes;
+			const uint4 *ar = s_area + ((size_t)s * RW + lane) * AREA_STRIDE;
+			uint4 *img = (uint4 *)(slot + 16u * (c_first - s0c));
+			uint4 v = *img;
+			overlay(v, ar[AREA_SEQ_HEAD], s_lowmask, (int)P - 16 * (int)c_first, 16);
+			*img = v;
+			img = (uint4 *)(slot + s_bytes);
+			v = *img;
+			overlay(v, ar[AREA_SEQ_TAIL], s_lowmask, 0, (int)(P + L) - 16 * (int)c_last);
+			*img = v;
 		}
 	}
 	__syncwarp();
@@ -678,7 +758,7 @@ static bool launch_cat(const SimArgs &a, uint32_t max_name, uint32_t max_body, c
 	if ((((s_bytes + T_BYTES) >> 4) & 1u) == 0) s_bytes += 16u;  // slot stride: an odd multiple of 16 bytes (see AREA_STRIDE)
 	auto warp_bytes = [&](int rw) -> uint32_t {
 		return NS * (uint32_t)(rw + 1) * (s_bytes + T_BYTES + (uint32_t)sizeof(DShip)) +
-		       (uint32_t)rw * (NS * (uint32_t)(sizeof(DHot) + sizeof(DHotQ) + sizeof(DGen) + sizeof(DPos) + 16u * AREA_STRIDE + 16u * PMAX + 8u) + NM * DT_OPS * 4u);
+		       (uint32_t)rw * (NS * (uint32_t)(sizeof(DHot) + sizeof(DHotQ) + sizeof(DGen) + sizeof(DPos) + 16u * AREA_STRIDE + 16u * PMAX + 8u) + NM * DT_OPS * 4u + (CAT == CAT_B ? (uint32_t)sizeof(DRnd) : 0u));
 	};
 	const uint32_t sm_budget = 216u * 1024u;
 	int rw = env_rw > 0 ? env_rw : 32;
