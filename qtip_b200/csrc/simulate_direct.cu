@@ -707,19 +707,35 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 			char *tbs = tb[s];
 			const uint32_t end = tend[s], phs = ph[s];
 			const uint32_t last_chunk = end >> 4;  // shared with the next tile when end & 15 != 0 (else nothing of ours)
-			for (int rd = 0; rd < hrounds; rd++) {
+			// hrounds < 0: the lane groups cover the S chunks only; the (one or two) T chunks of a slot go in a second
+			// loop with two lanes per slot (launcher: when S + T would not fit the same power-of-two group)
+			const bool split = hrounds < 0;
+			const int hr = split ? -hrounds : hrounds;
+			for (int rd = 0; rd < hr; rd++) {
 				const uint32_t j = (uint32_t)(rd * H + jl);
 				for (int i0 = 0; i0 <= nr; i0 += spi) {
 					const int i = i0 + sub;
 					if (i > nr) continue;
 					const DShip sh = s_ship[s * (RW + 1) + i];
-					const uint32_t nS = sh.n & 0xffu, nT = (sh.n >> 8) & 0xffu;
+					const uint32_t nS = sh.n & 0xffu, nT = split ? 0u : (sh.n >> 8) & 0xffu;
 					if (j >= nS + nT) continue;
 					const unsigned char *slot = s_edge + ((size_t)s * (RW + 1) + i) * slot_bytes;
 					const uint32_t chunk = j < nS ? sh.s0 + j : sh.t0 + (j - nS);
 					const unsigned char *src = j < nS ? slot + 16u * j : slot + s_bytes + 16u * (j - nS);
 					if ((chunk == 0 && phs) || chunk == last_chunk) continue;  // the tile's ragged ends: below
 					*(uint4 *)(tbs + 16u * (size_t)chunk) = *(const uint4 *)src;
+				}
+			}
+			if (split) {
+				for (int i0 = 0; i0 < nr; i0 += 16) {
+					const int i = i0 + (lane >> 1);
+					if (i >= nr) continue;
+					const DShip sh = s_ship[s * (RW + 1) + i];
+					const uint32_t jt = (uint32_t)lane & 1u;
+					if (jt >= ((sh.n >> 8) & 0xffu)) continue;
+					const uint32_t chunk = sh.t0 + jt;
+					if (chunk == last_chunk) continue;
+					*(uint4 *)(tbs + 16u * (size_t)chunk) = *(const uint4 *)(s_edge + ((size_t)s * (RW + 1) + i) * slot_bytes + s_bytes + 16u * jt);
 				}
 			}
 			// the tile's first and last chunk are shared with the neighbouring tiles: one byte per lane
@@ -774,10 +790,14 @@ static bool launch_cat(const SimArgs &a, uint32_t max_name, uint32_t max_body, c
 	const uint32_t wb = warp_bytes(rw);
 	const size_t smem = (size_t)wb * warps;
 	// step D: chunks per staging slot
-	const int hslots = (int)(s_bytes / 16u) + 2;
+	// step D: lane groups of 2^lgH per slot; if the S chunks alone fill a power of two, the T chunks go separately
+	const int hS = (int)(s_bytes / 16u);
 	int lgH = 0;
-	while ((1 << lgH) < hslots && lgH < 5) lgH++;
-	const int hrounds = (hslots + (1 << lgH) - 1) >> lgH;
+	while ((1 << lgH) < hS && lgH < 5) lgH++;
+	const bool split = hS + 2 > (1 << lgH);
+	const int hslots = split ? hS : hS + 2;
+	int hrounds = (hslots + (1 << lgH) - 1) >> lgH;
+	if (split) hrounds = -hrounds;
 	auto kern = k_simulate_direct<MODE, CAT>;
 	static bool attr_set = false;
 	if (!attr_set) {
