@@ -141,6 +141,16 @@ def case_short_reads():
                 kw=dict(fraction=400.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(81)))
 
 
+def case_long_reads():
+    """20 kbp reads (1250 output chunks per string): substitution-only templates on the fast path and
+    indel-heavy ones on the general path, both strands; tiles shrink to a few reads per warp."""
+    fa = synth.make_fasta([("ctgL", 400000), ("ctgM", 150000)], seed=91, lead_n=500)
+    tu = synth.templates_unpaired(12, 20000, 92, max_x=40) + synth.templates_unpaired(8, 20000, 93, indel=True)
+    tc = synth.templates_paired(6, 9000, 94, frag_mean=25000, frag_sd=500, max_x=20)
+    return dict(fasta=fa, tu=tu, tb=[], tc=tc, td=[],
+                kw=dict(fraction=60.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(91)))
+
+
 CASES = {
     "c1_lambda": case_c1_lambda,
     "mixed_small": case_mixed_small,
@@ -152,6 +162,7 @@ CASES = {
     "inversion": case_inversion,
     "long_refid": case_long_refid,
     "short_reads": case_short_reads,
+    "long_reads": case_long_reads,
 }
 
 
