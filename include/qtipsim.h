@@ -136,7 +136,11 @@ const char *qtipsim_last_error(const qtipsim_t *h); /* h may be NULL: last creat
  * Only the first path of a multi-file list has defined behaviour in the reference
  * (SURVEY Q13); more than one path is rejected with QTIPSIM_EINVAL. */
 int qtipsim_load_fasta(qtipsim_t *h, const char *const *paths, size_t npaths);
-/* Same, from FASTA text already in host memory (pinned or pageable). */
+/* Same, from FASTA text already in host memory (pinned or pageable).
+ * Threading: a handle is single-threaded like the reference (qtip_parse.cpp:73), with one exception a host may
+ * use to overlap its own work with the upload: one thread may be inside qtipsim_load_fasta* while another calls
+ * qtipsim_set_templates_* on the same handle (they touch disjoint state); both must have returned before
+ * qtipsim_run. */
 int qtipsim_load_fasta_bytes(qtipsim_t *h, const void *bytes, size_t nbytes);
 /* size_t num_estimated_bases() const, simplesim.h:263-265 (= FASTA file bytes) */
 uint64_t qtipsim_num_estimated_bases(const qtipsim_t *h);

@@ -3,7 +3,7 @@
 //   k_window_ncount : N count per FASTA window            (simplesim.cpp:228-234)
 //   k_read_lengths  : FASTQ record length per read        (simplesim.cpp:102-171 byte counts)
 //   k_scan_*        : exclusive scan of lengths -> byte offsets in the output streams
-//   k_plan_philox   : native-RNG plan (template, window, offset per read)
+//   k_plan_philox_lengths : native-RNG plan (template, window, offset per read) + record lengths
 //   k_simulate      : SimulatedRead::init/mutate/init_random + write/write_pair
 //                     (simplesim.h:68-117, simplesim.cpp:31-71, :102-171)
 #include "kernels.cuh"
@@ -287,36 +287,11 @@ void launch_philox_counts(const Window *win, const uint32_t *ncount, const uint3
 	g_launches++;
 }
 
-__global__ void __launch_bounds__(256) k_plan_philox(const Window *win, const uint64_t *cum, uint32_t nwin,
-                                                      uint64_t olap, uint32_t ntmpl, int cat, uint64_t seed,
-                                                      PlanRec *plan, uint64_t n, uint64_t read_index_base) {
-	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= n) return;
-	// window of read r: last w with cum[w] <= global index (the length-weighted choice was made when the
-	// per-window counts were drawn; this is the binary search over their prefix sums).
-	// cum[] holds GLOBAL cumulative counts for this shard's windows; read_index_base = cum[0].
-	const uint64_t gi = read_index_base + r;
-	uint32_t lo = 0, hi = nwin;  // invariant: cum[lo] <= gi < cum[hi]
-	while (hi - lo > 1) {
-		const uint32_t mid = (lo + hi) >> 1;
-		if (cum[mid] <= gi) lo = mid;
-		else hi = mid;
-	}
-	const Window w = win[lo];
-	const Philox4 x = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), 0u, PHILOX_DOM_PLAN | (uint32_t)cat,
-	                             (uint32_t)seed, (uint32_t)(seed >> 32));
-	const uint64_t nslots = (uint64_t)w.retsz - olap;
-	PlanRec pr;
-	pr.tmpl = __umulhi(x.v[0], ntmpl);
-	pr.record = w.record;
-	pr.refoff = w.refoff + (nslots ? (uint64_t)__umulhi(x.v[1], (uint32_t)nslots) : 0);
-	pr.s1 = 0;
-	pr.s2 = 0;
-	plan[r] = pr;
-}
-
-// the same, fused with k_read_lengths: the thread that plans read r also computes its FASTQ record length(s)
-// (a = the category's SimArgs: a.plan is written here, templates and records are read)
+// Native plan, fused with k_read_lengths: the thread that plans read r (window by binary search over the
+// cumulative per-window counts -- the length-weighted choice was made when those were drawn -- then template
+// and offset from one Philox block) also computes its FASTQ record length(s).  cum[] holds GLOBAL cumulative
+// counts for this shard's windows; a = the category's SimArgs: a.plan is written here, templates and records
+// are read; a.read_index_base = cum[0].
 __global__ void __launch_bounds__(256) k_plan_philox_lengths(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap,
                                                               uint32_t ntmpl, uint64_t seed, SimArgs a, PlanRec *plan,
                                                               uint32_t *len0, uint32_t *len1, unsigned long long *gbytes) {
@@ -368,14 +343,6 @@ void launch_plan_philox_lengths(const Window *win, const uint64_t *cum, uint32_t
 	g_launches++;
 }
 
-void launch_plan_philox(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap, uint32_t ntmpl,
-                        int cat, uint64_t seed, PlanRec *plan, uint64_t n, uint64_t read_index_base,
-                        cudaStream_t st) {
-	if (!n) return;
-	k_plan_philox<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(win, cum, nwin, olap, ntmpl, cat, seed, plan, n,
-	                                                          read_index_base);
-	g_launches++;
-}
 
 // ------------------------------------------------------------------ simulate --
 

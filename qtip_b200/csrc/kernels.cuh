@@ -67,14 +67,10 @@ void launch_scan(const uint32_t *len, uint64_t *off, uint64_t n, uint64_t *tmp, 
 // simulate + emit (SimulatedRead::init/mutate/init_random/write/write_pair)
 // generic path: one warp per read, byte-granular
 void launch_simulate(const SimArgs &a, cudaStream_t st);
-// tiled path: a CTA stages a tile of consecutive records in shared memory, 16 output bytes
-// per lane per step, then streams the tile to HBM with aligned 16-byte stores.
-// max_rec_bytes = upper bound on one FASTQ record of this category.  Returns false when the
-// category cannot use it (record too large for the staging buffer) -- caller falls back.
-bool launch_simulate_tiled(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, uint32_t max_rflen,
-                           cudaStream_t st);
-// warp-autonomous path (simulate_warp.cu): a warp stages a tile of consecutive records in its own slice of
-// shared memory and ships it with one bulk copy; no CTA barriers.  Same contract as the tiled path.
+// staged path (simulate_warp.cu): a warp stages a tile of consecutive records in its own slice of shared
+// memory and ships it with one bulk copy; no CTA barriers.  max_rec_bytes = upper bound on one FASTQ record of
+// this category.  Returns false when the category cannot use it (record too large for the staging buffer) --
+// the caller falls back to the generic kernel.
 bool launch_simulate_warp(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max_body, cudaStream_t st);
 // direct path (simulate_direct.cu): interior chunks go from registers to HBM, only a record's edge chunks are
 // staged.  max_name bounds the read name; returns false when the category cannot use it (caller falls back).
@@ -86,12 +82,6 @@ void kernels_count_launch();
 void launch_philox_counts(const Window *win, const uint32_t *ncount, const uint32_t *pclass, const BinomSetup *setups,
                           uint32_t nwin, uint64_t olap, uint64_t target, uint64_t seed, int cat, uint32_t *counts,
                           cudaStream_t st);
-// PHILOX planning: fills plan[] for reads [0, n) of one category from per-window
-// cumulative counts (cum[w] = reads before window w, cum[nwin] = n).
-void launch_plan_philox(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap,
-                        uint32_t ntmpl, int cat, uint64_t seed, PlanRec *plan, uint64_t n,
-                        uint64_t read_index_base, cudaStream_t st);
-
 // K0: FASTA text -> packed genome (pack.cu)
 void launch_find_gt(const uint8_t *text, uint64_t n, uint64_t *list, uint32_t cap, uint32_t *count, cudaStream_t st);
 void launch_count_bases(const uint8_t *text, const uint64_t *seg_start, const uint64_t *seg_end,
