@@ -70,6 +70,13 @@ __device__ unsigned long long g_qd_violation[4];
 #ifndef QT_DT_UNROLL
 #define QT_DT_UNROLL 2
 #endif
+// 16-byte stores of FASTQ chunks to HBM: written once, never read back by the kernel
+// (streaming, evict-first: they should not push templates and quality strings out of L2)
+#ifndef QT_DT_NO_STCS
+#define ST16(ptr, v) __stcs((uint4 *)(ptr), (v))
+#else
+#define ST16(ptr, v) (*(uint4 *)(ptr) = (v))
+#endif
 static constexpr int DT_MAX_WARPS = QT_DT_MAX_WARPS;
 static constexpr int DT_OPS = 6;                 // draw ops per mate kept in shared memory from step A
 static constexpr int DT_UNROLL = QT_DT_UNROLL;   // step B: chunk iterations with their loads in flight together
@@ -465,7 +472,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 				if (ar[u]) sts128(ar[u], v);
 				else if (!(skip & 32)) {
 					QD_CHK(dst[u] + 16u <= tend[s], 4, dst[u], tend[s]);
-					*(uint4 *)(tbs + dst[u]) = v;
+					ST16(tbs + dst[u], v);
 				} else if (v.x == 0x12345678u) tbs[dst[u]] = 1;
 			}
 		}
@@ -502,7 +509,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 			if (j == 0 || j == ns - 1) sts128(h4.w + (j ? 16u * AREA_SEQ_TAIL : 16u * AREA_SEQ_HEAD), v);
 			else if (!(skip & 32)) {
 				QD_CHK(dst + 16u <= tend[s], 3, dst, tend[s]);
-				*(uint4 *)(tbs + dst) = v;
+				ST16(tbs + dst, v);
 			} else if (v.x == 0x12345678u) tbs[dst] = 1;
 		}
 	}
@@ -674,7 +681,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 			}
 			const uint4 v = make_uint4(w[0], w[1], w[2], w[3]);
 			if (j == 0 || j == ns - 1) s_area[((size_t)sr * RW + i) * AREA_STRIDE + (j ? AREA_SEQ_TAIL : AREA_SEQ_HEAD)] = v;
-			else *(uint4 *)((sr ? tb[NS - 1] : tb[0]) + 16u * (size_t)(c_first + j)) = v;
+			else ST16((sr ? tb[NS - 1] : tb[0]) + 16u * (size_t)(c_first + j), v);
 		}
 		__syncwarp();
 		// ---------------- step C2 (lane = read): the random mate's first and last chunk into the slot image ----------------
@@ -723,7 +730,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 					const uint32_t chunk = j < nS ? sh.s0 + j : sh.t0 + (j - nS);
 					const unsigned char *src = j < nS ? slot + 16u * j : slot + s_bytes + 16u * (j - nS);
 					if ((chunk == 0 && phs) || chunk == last_chunk) continue;  // the tile's ragged ends: below
-					*(uint4 *)(tbs + 16u * (size_t)chunk) = *(const uint4 *)src;
+					ST16(tbs + 16u * (size_t)chunk, *(const uint4 *)src);
 				}
 			}
 			if (split) {
@@ -735,7 +742,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 					if (jt >= ((sh.n >> 8) & 0xffu)) continue;
 					const uint32_t chunk = sh.t0 + jt;
 					if (chunk == last_chunk) continue;
-					*(uint4 *)(tbs + 16u * (size_t)chunk) = *(const uint4 *)(s_edge + ((size_t)s * (RW + 1) + i) * slot_bytes + s_bytes + 16u * jt);
+					ST16(tbs + 16u * (size_t)chunk, *(const uint4 *)(s_edge + ((size_t)s * (RW + 1) + i) * slot_bytes + s_bytes + 16u * jt));
 				}
 			}
 			// the tile's first and last chunk are shared with the neighbouring tiles: one byte per lane
