@@ -461,19 +461,19 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 					live[u] = j < nq;
 					dst[u] = h4.y + 16u * (uint32_t)j;
 					ar[u] = j == 0 ? h4.w + 16u * AREA_QUAL_HEAD : (j == nq - 1 ? h4.w + 16u * AREA_QUAL_TAIL : 0u);
-					if (live[u] && !(meta[u] & RF_RANDOM)) ql[u] = qual_issue(a.c.qual_out, (skip & 64) ? (uint32_t)lane : h4.x + (uint32_t)j);
+					if (live[u] && !(CAT == CAT_B && (meta[u] & RF_RANDOM))) ql[u] = qual_issue(a.c.qual_out, h4.x + (uint32_t)j);
 				}
 			}
 #pragma unroll
 			for (int u = 0; u < DT_UNROLL; u++) {
 				if (!live[u]) continue;
-				const uint4 v = (meta[u] & RF_RANDOM) ? make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u)  // 'I' (simplesim.h:105)
+				const uint4 v = (CAT == CAT_B && (meta[u] & RF_RANDOM)) ? make_uint4(0x49494949u, 0x49494949u, 0x49494949u, 0x49494949u)  // 'I' (simplesim.h:105)
 				                                      : qual_finish(ql[u], (meta[u] >> 12) & 15u);
 				if (ar[u]) sts128(ar[u], v);
-				else if (!(skip & 32)) {
+				else {
 					QD_CHK(dst[u] + 16u <= tend[s], 4, dst[u], tend[s]);
 					ST16(tbs + dst[u], v);
-				} else if (v.x == 0x12345678u) tbs[dst[u]] = 1;
+				}
 			}
 		}
 	}
@@ -507,10 +507,10 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 				v = seq_finish(sl, meta);
 			}
 			if (j == 0 || j == ns - 1) sts128(h4.w + (j ? 16u * AREA_SEQ_TAIL : 16u * AREA_SEQ_HEAD), v);
-			else if (!(skip & 32)) {
+			else {
 				QD_CHK(dst + 16u <= tend[s], 3, dst, tend[s]);
 				ST16(tbs + dst, v);
-			} else if (v.x == 0x12345678u) tbs[dst] = 1;
+			}
 		}
 	}
 	__syncwarp();
