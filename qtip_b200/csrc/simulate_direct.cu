@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 	const uint64_t ro[2] = {pr.refoff + tt.delta[0], pr.refoff + tt.delta[1]};
 	const bool s0_random = CAT == CAT_B && !tt.aligned_is_mate1;
 	uint32_t nl = 0;
+	bool my_general = false;
 	if (act) {
 		// which mates need the general path: indel segments, reaching past the record end, or any N in the
 		// 64-base blocks of the N-mask summary the mate touches (bases outside the mate only ever land on
@@ -265,6 +266,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 				for (uint64_t b = b0; b <= b1; b++) anyn |= ((__ldg(&a.g.nblk[b >> 5]) >> (b & 31)) & 1u) != 0;
 			}
 			general[m] = anyn || !mh[m].single || (gpos + mh[m].rflen > gend);
+			my_general |= general[m];
 		}
 #pragma unroll
 		for (int s = 0; s < NS; s++) {
@@ -332,6 +334,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 		}
 	}
 	__syncwarp();
+	const bool any_general = __any_sync(0xffffffffu, my_general);
 
 	// ---------------- step A2 (lane = 16-byte piece): the reads' packed genome rows, asynchronously ----------------
 	{
@@ -481,6 +484,8 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 	__syncwarp();
 
 	// ---------------- step Bs (lane = sequence chunk): genome words from the rows in shared memory ----------------
+	// Two loops, so that the hot one holds no call: fast-path reads first, then -- only in tiles that have any --
+	// the reads of the general path (N, past the record end, indel segments).
 #pragma unroll
 	for (int s = 0; s < NS; s++) {
 		char *tbs = tb[s];
@@ -491,25 +496,32 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 			const uint4 h4 = lds128(hot_a + 16u * (uint32_t)i);  // grow | sdst | ns, meta | area
 			const int ns = (int)(h4.z & 0xffffu);
 			const uint32_t meta = h4.z >> 16;
-			if (j >= ns) continue;
-			const uint32_t dst = h4.y + 16u * (uint32_t)j;
-			uint4 v;
-			if (meta & RF_GENERAL) {
-				const DPos pp = s_pos[s * RW + i];
-				const DGen &gg = s_gen[s * RW + i];
-				v = seq16_general(gv, s_lowmask, a.c.segs + gg.segoff, (int)gg.nseg, (meta & RF_FW) != 0, (int)pp.L, gg.gpos, gg.gend,
-				                  (int)dst - (int)pp.P);
-			} else {
-				const uint32_t wa = (meta & RF_FW) ? h4.x + 4u * (uint32_t)j : h4.x - 4u * (uint32_t)j;
-				SeqLoad sl;
-				sl.lo = lds32(wa);
-				sl.hi = lds32(wa + 4u);
-				v = seq_finish(sl, meta);
-			}
+			if (j >= ns || (meta & RF_GENERAL)) continue;
+			const uint32_t wa = (meta & RF_FW) ? h4.x + 4u * (uint32_t)j : h4.x - 4u * (uint32_t)j;
+			SeqLoad sl;
+			sl.lo = lds32(wa);
+			sl.hi = lds32(wa + 4u);
+			const uint4 v = seq_finish(sl, meta);
 			if (j == 0 || j == ns - 1) sts128(h4.w + (j ? 16u * AREA_SEQ_TAIL : 16u * AREA_SEQ_HEAD), v);
 			else {
-				QD_CHK(dst + 16u <= tend[s], 3, dst, tend[s]);
-				ST16(tbs + dst, v);
+				QD_CHK(h4.y + 16u * (uint32_t)j + 16u <= tend[s], 3, h4.y, tend[s]);
+				ST16(tbs + h4.y + 16u * (uint32_t)j, v);
+			}
+		}
+		if (any_general) {
+			for (int q = lane; q < nitems && !(skip & 16); q += 32) {
+				const int i = (int)__umulhi((uint32_t)q, kmagic), j = q - i * K;
+				const uint4 h4 = lds128(hot_a + 16u * (uint32_t)i);
+				const int ns = (int)(h4.z & 0xffffu);
+				const uint32_t meta = h4.z >> 16;
+				if (j >= ns || !(meta & RF_GENERAL)) continue;
+				const uint32_t dst = h4.y + 16u * (uint32_t)j;
+				const DPos pp = s_pos[s * RW + i];
+				const DGen &gg = s_gen[s * RW + i];
+				const uint4 v = seq16_general(gv, s_lowmask, a.c.segs + gg.segoff, (int)gg.nseg, (meta & RF_FW) != 0, (int)pp.L, gg.gpos,
+				                              gg.gend, (int)dst - (int)pp.P);
+				if (j == 0 || j == ns - 1) sts128(h4.w + (j ? 16u * AREA_SEQ_TAIL : 16u * AREA_SEQ_HEAD), v);
+				else ST16(tbs + dst, v);
 			}
 		}
 	}
