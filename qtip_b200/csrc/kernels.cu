@@ -297,14 +297,25 @@ __global__ void __launch_bounds__(256) k_plan_philox_lengths(const Window *win, 
                                                               uint32_t *len0, uint32_t *len1, unsigned long long *gbytes) {
 	const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t gb = 0;
+	// window of the warp's first read by binary search (lane 0), then every lane walks forward from there: the 32
+	// consecutive reads of a warp lie in the same or the next few windows (invariant: cum[lo] <= gi < cum[lo + 1])
+	uint32_t lo = 0;
+	{
+		const uint64_t r_first = r - lane_id();
+		if (lane_id() == 0 && r_first < a.nreads) {
+			const uint64_t g0 = a.read_index_base + r_first;
+			uint32_t hi = nwin;
+			while (hi - lo > 1) {
+				const uint32_t mid = (lo + hi) >> 1;
+				if (cum[mid] <= g0) lo = mid;
+				else hi = mid;
+			}
+		}
+		lo = __shfl_sync(0xffffffffu, lo, 0);
+	}
 	if (r < a.nreads) {
 		const uint64_t gi = a.read_index_base + r;
-		uint32_t lo = 0, hi = nwin;  // invariant: cum[lo] <= gi < cum[hi]
-		while (hi - lo > 1) {
-			const uint32_t mid = (lo + hi) >> 1;
-			if (cum[mid] <= gi) lo = mid;
-			else hi = mid;
-		}
+		while (lo + 1 < nwin && cum[lo + 1] <= gi) lo++;
 		const Window w = win[lo];
 		const Philox4 x = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), 0u, PHILOX_DOM_PLAN | (uint32_t)a.cat,
 		                             (uint32_t)seed, (uint32_t)(seed >> 32));
