@@ -28,6 +28,11 @@ __device__ __forceinline__ uint32_t fetch_code(const DevGenome &g, uint64_t gp, 
 }
 
 __device__ __forceinline__ uint32_t ndigits_u64(uint64_t v) {
+	if (v <= 0xffffffffull) {  // offsets fit 32 bits in practice: a compare chain, no 64-bit divisions
+		const uint32_t x = (uint32_t)v;
+		return x < 10u ? 1u : x < 100u ? 2u : x < 1000u ? 3u : x < 10000u ? 4u : x < 100000u ? 5u : x < 1000000u ? 6u
+		     : x < 10000000u ? 7u : x < 100000000u ? 8u : x < 1000000000u ? 9u : 10u;
+	}
 	uint32_t d = 1;
 	while (v >= 10) {
 		v /= 10;
