@@ -247,40 +247,51 @@ def main():
         fa_pinned.numpy()[:] = fa
         del fa
         eng.load_fasta_bytes(fa_pinned.numpy())
-    if world > 1:
-        # replicate the packed genome: rank 0 packed it, NCCL broadcast over NVLink, others adopt
-        meta = [None]
-        if rank == 0:
-            bl = eng.lib.qtipsim_genome_export
-            import ctypes as C
-            ptrs = []
-            for which in (0, 1, 2):
-                p, n, isd = C.c_void_p(), C.c_uint64(), C.c_int()
-                eng.check(bl(eng.h, which, C.byref(p), C.byref(n), C.byref(isd)))
-                ptrs.append((p.value, n.value))
-            blob = (C.c_char * ptrs[2][1]).from_address(ptrs[2][0]).raw
-            meta = [(ptrs[0][1], ptrs[1][1], blob)]
-        dist.broadcast_object_list(meta, src=0)
-        nb_bytes, nm_bytes, blob = meta[0]
+    repl_state = {}
+
+    def replicate_genome():
+        """Rank 0 has packed the genome on its GPU: NCCL broadcast of the packed arrays over NVLink, the others adopt."""
+        import ctypes as C
+        if "meta" not in repl_state:  # sizes and record table: the same for every step
+            meta = [None]
+            if rank == 0:
+                ptrs = []
+                for which in (0, 1, 2):
+                    p, n, isd = C.c_void_p(), C.c_uint64(), C.c_int()
+                    eng.check(eng.lib.qtipsim_genome_export(eng.h, which, C.byref(p), C.byref(n), C.byref(isd)))
+                    ptrs.append((p.value, n.value))
+                blob = (C.c_char * ptrs[2][1]).from_address(ptrs[2][0]).raw
+                meta = [(ptrs[0][1], ptrs[1][1], blob)]
+            dist.broadcast_object_list(meta, src=0)
+            repl_state["meta"] = meta[0]
+        nb_bytes, nm_bytes, blob = repl_state["meta"]
 
         class _Raw:
             def __init__(self, ptr, n):
                 self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 3}
 
         if rank == 0:
-            tb_ = torch.as_tensor(_Raw(ptrs[0][0], nb_bytes), device="cuda")
-            tn_ = torch.as_tensor(_Raw(ptrs[1][0], nm_bytes), device="cuda")
+            ptrs = []
+            for which in (0, 1):
+                p, n, isd = C.c_void_p(), C.c_uint64(), C.c_int()
+                eng.check(eng.lib.qtipsim_genome_export(eng.h, which, C.byref(p), C.byref(n), C.byref(isd)))
+                ptrs.append(p.value)
+            tb_ = torch.as_tensor(_Raw(ptrs[0], nb_bytes), device="cuda")
+            tn_ = torch.as_tensor(_Raw(ptrs[1], nm_bytes), device="cuda")
         else:
-            tb_ = torch.empty(nb_bytes, dtype=torch.uint8, device="cuda")
-            tn_ = torch.empty(nm_bytes, dtype=torch.uint8, device="cuda")
+            if "bufs" not in repl_state:
+                repl_state["bufs"] = (torch.empty(nb_bytes, dtype=torch.uint8, device="cuda"),
+                                      torch.empty(nm_bytes, dtype=torch.uint8, device="cuda"))
+            tb_, tn_ = repl_state["bufs"]
         dist.broadcast(tb_, src=0)
         dist.broadcast(tn_, src=0)
         torch.cuda.synchronize()
         if rank != 0:
-            import ctypes as C
             eng.check(eng.lib.qtipsim_genome_adopt(eng.h, blob, len(blob), C.c_void_p(tb_.data_ptr()), nb_bytes,
                                                    C.c_void_p(tn_.data_ptr()), nm_bytes))
-            del tb_, tn_
+
+    if world > 1:
+        replicate_genome()
     added = wl.get("added") or (len(wl["tu"]), len(wl["tb"]), len(wl["tc"]), len(wl["td"]))
 
     def set_templates():
@@ -302,11 +313,13 @@ def main():
         """Runs one step on this rank's shard; returns stats."""
         tr0 = time.perf_counter()
         if e2e:
-            if rank == 0 and world == 1:
+            if rank == 0:
                 eng.load_fasta_bytes_async(fa_pinned.numpy())  # H2D of the FASTA text + device pack ...
             tr1 = time.perf_counter()
             set_templates()                                    # ... while the host compiles the templates
             eng.wait_genome()
+            if world > 1:
+                replicate_genome()                             # N > 1: rank 0's packed genome to every GPU (NCCL)
             if trace:
                 print(f"[trace] load_fasta {1e3 * (tr1 - tr0):.1f} ms, set_templates {1e3 * (time.perf_counter() - tr1):.1f} ms",
                       file=sys.stderr)
@@ -396,9 +409,8 @@ def main():
         sim_ms_step = agg["ms_sim"] / steps
         alg_step_rank0 = agg["alg"] / steps
         achieved = alg_step_rank0 / (sim_ms_step * 1e-3) / 1e9 if sim_ms_step > 0 else 0.0
-        h2d = 0
-        if world == 1:
-            h2d = sum(l for _, l in wl["records"]) * 71 // 70 + 64 * len(wl["records"])  # FASTA text bytes
+        # FASTA text bytes: uploaded by rank 0 every e2e step (N > 1: then broadcast GPU to GPU as packed arrays)
+        h2d = sum(l for _, l in wl["records"]) * 71 // 70 + 64 * len(wl["records"])
         return dict(value=reads / (ev_ms * 1e-3), ms_per_step=ev_ms / steps, wall_ms_per_step=wall_ms / steps,
                     output_gb_per_s=obytes / (ev_ms * 1e-3) / 1e9, reads_per_step=reads / steps,
                     phase={"plan": agg["ms_plan"] / steps, "simulate": sim_ms_step, "total": agg["ms_total"] / steps},

@@ -471,16 +471,14 @@ int qtipsim_genome_adopt(qtipsim_t *h, const void *blob, uint64_t blob_bytes, co
 	CK(cudaMemcpyAsync(h->d_recs.p, h->hg.recs.data(), h->hg.recs.size() * sizeof(RecDev), cudaMemcpyHostToDevice, h->st));
 	if (!h->hg.names.empty())
 		CK(cudaMemcpyAsync(h->d_names.p, h->hg.names.data(), h->hg.names.size(), cudaMemcpyHostToDevice, h->st));
-	// the host replay planner reads reference bases at X positions: keep a host copy too
-	h->hg.bases.resize((size_t)(need_b / 4));
-	h->hg.nmask.resize((size_t)(need_n / 4));
-	CK(cudaMemcpyAsync(h->hg.bases.data(), h->d_bases.p, need_b, cudaMemcpyDeviceToHost, h->st));
-	CK(cudaMemcpyAsync(h->hg.nmask.data(), h->d_nmask.p, need_n, cudaMemcpyDeviceToHost, h->st));
+	// (the host replay planner fetches a host copy of the packed arrays on demand: ensure_host_packed)
+	h->hg.bases.clear();
+	h->hg.nmask.clear();
 	CK(cudaStreamSynchronize(h->st));
 	h->have_genome = true;
 	h->win_cache_ok = false;
 	h->setup_cache_ok = false;
-	h->host_packed = true;
+	h->host_packed = false;
 	h->have_result = false;
 	return QTIPSIM_OK;
 }
