@@ -615,6 +615,88 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 				else tb[0][x] = (char)ch;
 			}
 		}
+	} else if ((CAT == CAT_C || CAT == CAT_D) && MODE == QTIPSIM_RNG_PHILOX && RW <= 16) {
+		// Pairs with the native generator: lanes 0-15 serve the first file and mate, lanes 16-31 the second (the
+		// second mate's draws start at index nops of the first: addressable)
+		const int sx = NS == 2 ? (lane >> 4) : 0, rl_ = lane & 15;
+		const uint32_t n0 = __shfl_sync(0xffffffffu, mh[0].nops, rl_), n1 = __shfl_sync(0xffffffffu, mh[NM - 1].nops, rl_);
+		const uint32_t o0 = __shfl_sync(0xffffffffu, mh[0].ops_off, rl_), o1 = __shfl_sync(0xffffffffu, mh[NM - 1].ops_off, rl_);
+		const uint32_t f0 = __shfl_sync(0xffffffffu, mh[0].fw ? 1u : 0u, rl_), f1 = __shfl_sync(0xffffffffu, mh[NM - 1].fw ? 1u : 0u, rl_);
+		const uint32_t c_nops = sx ? n1 : n0, c_opsoff = sx ? o1 : o0, c_fw = sx ? f1 : f0, d_first = sx ? n0 : 0u;
+		uint32_t P = 0, L = 0, c_first = 0, c_last = 0, s0c = 0;
+		unsigned char *slot = s_edge + ((size_t)sx * (RW + 1) + rl_) * slot_bytes;
+		if (rl_ < nr) {
+			const DPos pp = s_pos[sx * RW + rl_];
+			P = pp.P;
+			L = pp.L;
+			const uint32_t Pq = P + L + 3u;
+			c_first = P >> 4;
+			c_last = (P + L - 1u) >> 4;
+			const uint32_t q_first = Pq >> 4, q_last = (Pq + L - 1u) >> 4;
+			s0c = s_ship[sx * (RW + 1) + rl_].s0;
+			const uint4 *ar = s_area + ((size_t)sx * RW + rl_) * AREA_STRIDE;
+			uint4 *img;
+			uint4 v;
+			img = (uint4 *)(slot + 16u * (c_first - s0c));
+			v = *img;
+			overlay(v, ar[AREA_SEQ_HEAD], s_lowmask, (int)P - 16 * (int)c_first, 16);
+			*img = v;
+			img = (uint4 *)(slot + s_bytes);
+			v = *img;
+			overlay(v, ar[AREA_SEQ_TAIL], s_lowmask, 0, (int)(P + L) - 16 * (int)c_last);
+			*img = v;
+			img = (uint4 *)(slot + s_bytes + 16u * (q_first - c_last));
+			v = *img;
+			overlay(v, ar[AREA_QUAL_HEAD], s_lowmask, (int)Pq - 16 * (int)q_first, 16);
+			*img = v;
+			img = (uint4 *)(slot + slot_bytes);
+			v = *img;
+			overlay(v, ar[AREA_QUAL_TAIL], s_lowmask, 0, (int)(Pq + L) - 16 * (int)q_last);
+			*img = v;
+			if (c_nops) {  // (same lane merged this stream's images: program order suffices)
+				const uint64_t gi = a.read_index_base + r0 + (uint64_t)rl_;
+				const bool fw = c_fw != 0;
+				const bool gen = ((s_hot[sx * RW + rl_].ns >> 16) & RF_GENERAL) != 0;
+				const uint32_t T = fw ? TBL_FW : TBL_RC;
+				const uint32_t gb0 = s_gb0[sx * RW + rl_];
+				const uint32_t *row = s_gbuf + ((size_t)sx * RW + rl_) * GROW;
+				const uint32_t *ops = a.c.ops + c_opsoff;
+				char *tbx = sx ? tb[NS - 1] : tb[0];
+				uint32_t curb = 0xffffffffu;
+				Philox4 blk{};
+				for (uint32_t j = 0; j < c_nops; j++) {
+					const uint32_t e = j < (uint32_t)DT_OPS ? s_ops[(sx * DT_OPS + j) * RW + rl_] : __ldg(&ops[j]);
+					const uint32_t outp = (e >> 2) & 0x7fffu;
+					QD_CHK(outp < L, 7, outp, L);
+					const uint32_t d = d_first + j;  // draw index within the pair
+					if ((d >> 3) != curb) {
+						curb = d >> 3;
+						blk = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), curb, PHILOX_DOM_BASE | (uint32_t)CAT, (uint32_t)a.philox_seed,
+						                 (uint32_t)(a.philox_seed >> 32));
+					}
+					const uint32_t wi = (d >> 1) & 3u;
+					const uint32_t wv = wi == 0 ? blk.v[0] : wi == 1 ? blk.v[1] : wi == 2 ? blk.v[2] : blk.v[3];
+					const uint32_t b = (d & 1u) ? (wv >> 16) : (wv & 0xffffu);
+					uint32_t code;
+					if ((e & 3u) == OP_X) {
+						uint32_t ref;
+						if (gen) {
+							const DGen &gg = s_gen[sx * RW + rl_];
+							ref = ref_code_at(a.g, gg.gpos + (e >> 17), gg.gend);
+						} else {
+							const uint32_t t = gb0 + (e >> 17);
+							ref = (row[t >> 4] >> (2u * (t & 15u))) & 3u;
+						}
+						code = ref < 4u ? ((ref + 1u + ((b * 3u) >> 16)) & 3u) : (b >> 14);
+					} else code = b >> 14;
+					const uint32_t ch = (T >> (8u * code)) & 0xffu;
+					const uint32_t x = P + outp, cx = x >> 4;
+					if (cx == c_first) slot[x - 16u * s0c] = (unsigned char)ch;
+					else if (cx == c_last) slot[s_bytes + x - 16u * c_last] = (unsigned char)ch;
+					else tbx[x] = (char)ch;
+				}
+			}
+		}
 	} else if (act) {
 		// the four areas hold whole chunks; only the bytes inside the string go into the image (names and
 		// separators are already there).  The last quality chunk belongs to the next slot's first chunk.
