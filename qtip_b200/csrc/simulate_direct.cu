@@ -12,26 +12,33 @@
 // bytes next to name / separator bytes ("edge" chunks).  A warp owns a tile of RW consecutive
 // records and never meets another warp at a barrier:
 //
-//   step A  lane = read: plan record + template -> chunk geometry (shared memory); L2 prefetch
-//           of the read's packed genome lines; the read's draw ops with their reference base
-//           looked up; the record's EDGE chunks composed exactly in a small per-read staging
-//           slot: name, separators, first / last chunk of the sequence and of the qualities
-//   step B  lane = interior chunk, G lanes per read (consecutive lanes = consecutive chunks of one
-//           read => coalesced genome / quality loads and 16-byte global stores):
-//             sequence   32 bits of 2-bit genome funnel-shifted from two packed words (reversed for
-//                        '-' mates), expanded to 16 ASCII bases with PRMT ("ACGT" / "TGCA" as the
-//                        byte table)
-//             qualities  two aligned 16-byte loads of the template's pre-oriented quality string,
-//                        re-aligned to the output phase (branch-free word mux)
-//   step C  lane = read: the read's random draws patched over the sequence, byte stores into the
-//           staging slot or HBM (REPLAY: the reference's L'Ecuyer stream stepped from the plan's
-//           state, with X redraws against the reference base; PHILOX: counter-based)
-//   step D  lane = edge chunk: staging slots -> HBM, 16 bytes per lane; the tile's first and last
-//           chunk, shared with the neighbouring tiles, byte by byte
+//   step A   lane = read: plan record + template (16-byte descriptor blocks) -> chunk geometry in
+//            shared memory; the N-block summary decides fast / general path per mate
+//   step A2  lane = 16-byte piece: each read's packed genome span -> its row in shared memory,
+//            cp.async, coalesced over the tile
+//   step A3  lane = read, while those copies fly: the read's first draw ops, its name and the
+//            separators into the slot IMAGE (the staged picture of the record's edge chunks)
+//   step Bq  lane = quality chunk (item = read * K + slot, read-major: consecutive lanes = consecutive
+//            chunks of one read => coalesced loads and 16-byte stores): two aligned 16-byte loads of
+//            the template's pre-oriented quality string, re-aligned to the output phase by a
+//            branch-free word mux
+//   step Bs  lane = sequence chunk: two words of the row funnel-shifted to 32 bits of 2-bit genome,
+//            expanded to 16 ASCII bases with PRMT; strand = byte table ("ACGT" / "TGCA") + reversed
+//            interleave selectors after one rotate.  General-path reads (N, past the record end, indel
+//            segments) take a second loop with the segment-merging generator, only in tiles that have any.
+//            In both B steps interior chunks go from registers straight to HBM (streaming 16-byte
+//            stores); a string's first / last chunk goes whole into one of the read's four AREAS
+//   step C   lane = read (two lanes per read or pair in the native mode): the areas' in-string bytes
+//            overlaid onto the image, then the read's draws patched over image or HBM bytes (REPLAY:
+//            the reference's L'Ecuyer stream stepped from the plan's state, with X redraws against the
+//            reference base read from the row; PHILOX: addressed by draw index)
+//   step Br  bad-end pairs only, lane = chunk of the random mate: init_random's draws, 16 per lane
+//            (Philox by index; L'Ecuyer by jump table, backwards for '-' mates); step C2 merges its edges
+//   step D   lane = edge chunk: slot images -> HBM, 16 bytes per lane; the tile's first and last
+//            chunk, shared with the neighbouring tiles, one byte per lane
 //
-// Reads that contain N, reach past their record, or have indel segments take the general chunk
-// generator (segment merge + N mask) in steps A and B.  Categories with a body shorter than 17
-// bytes (edge chunks of one string could coincide) use the staged kernel in simulate_warp.cu.
+// Categories with a body shorter than 17 bytes (the edge chunks of one string could coincide) use the
+// staged kernel in simulate_warp.cu; records too large for either use the generic kernel (kernels.cu).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
