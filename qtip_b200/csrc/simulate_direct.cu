@@ -978,7 +978,7 @@ static bool launch_cat(const SimArgs &a, uint32_t max_name, uint32_t max_body, c
 		// and want full half-warps more than they want occupancy: measured)
 		while (rw > 4 && warp_bytes(rw) * ((CAT == CAT_C || CAT == CAT_D) ? 12u : 24u) > sm_budget) rw >>= 1;
 	if (warp_bytes(rw) + 1024 > sm_budget || (uint64_t)rw * K >= 65536u) return false;
-	int warps = env_warps > 0 ? env_warps : DT_MAX_WARPS;
+	int warps = env_warps > 0 ? env_warps : (NS == 1 ? 1 : DT_MAX_WARPS);  // tiles per CTA: measured (QTIPSIM_WARPS overrides)
 	if (warps > DT_MAX_WARPS) warps = DT_MAX_WARPS;
 	while (warps > 1 && warp_bytes(rw) * (uint32_t)warps + 1024 > sm_budget) warps >>= 1;
 	const uint32_t wb = warp_bytes(rw);
