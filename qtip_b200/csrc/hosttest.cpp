@@ -9,6 +9,7 @@
 #include "../../include/qtipsim.h"
 #include "genome.h"
 #include "lecuyer.h"
+#include "pack_swar.h"
 #include "planner.h"
 #include "templates.h"
 
@@ -145,6 +146,69 @@ uint64_t qthost_logf_sweep(uint32_t lo, uint32_t hi, uint32_t step) {
 		bad += memcmp(&a, &g, 4) != 0;
 	}
 	return bad;
+}
+
+
+// ---- K0's word-parallel classification (pack_swar.h), checked byte by byte by tests/test_host_logic.py ----
+
+// bytes [a, b) of one 16-byte vector: squeezed codes / N bits, returns the count of non-whitespace bytes
+uint32_t qthost_swar_vec(const uint8_t *bytes16, uint32_t a, uint32_t b, uint32_t *codes, uint32_t *nbits, uint32_t *ws) {
+	uint32_t w[4];
+	memcpy(w, bytes16, 16);
+	VecClass vc = classify_vec(w[0], w[1], w[2], w[3]);
+	*ws = vc.ws;
+	const uint32_t cnt = squeeze_vec(vc, a, b);
+	*codes = vc.codes;
+	*nbits = vc.nbits;
+	return cnt;
+}
+
+// The arithmetic of pack.cu's k_pack_units for one unit, lanes run one after the other: text [t0, t1) (text is
+// 16-byte aligned and padded), first base at genome position g; ORs into bases[] / nmask[] like the kernel's
+// image + ship steps.  Returns the number of bases.
+uint64_t qthost_swar_pack_unit(const uint8_t *text, uint64_t t0, uint64_t t1, uint64_t g, uint32_t *bases, uint32_t *nmask) {
+	const uint64_t g_first = g;
+	for (uint64_t tile = t0 & ~(uint64_t)15; tile < t1; tile += 512) {
+		uint32_t img_b[36] = {0}, img_n[20] = {0};
+		uint32_t excl = 0;
+		const uint32_t gph = (uint32_t)(g & 15u), gpn = (uint32_t)(g & 31u);
+		for (uint32_t lane = 0; lane < 32; lane++) {
+			const uint64_t i = tile + lane * 16;
+			if (i >= t1) continue;
+			const uint32_t a = t0 > i ? (uint32_t)(t0 - i) : 0u;
+			const uint32_t b = t1 - i < 16u ? (uint32_t)(t1 - i) : 16u;
+			uint32_t w[4];
+			memcpy(w, text + i, 16);
+			VecClass vc = classify_vec(w[0], w[1], w[2], w[3]);
+			const uint32_t cnt = squeeze_vec(vc, a, b);
+			if (vc.codes) {
+				const uint32_t ob = 2u * (gph + excl);
+				const uint64_t x = (uint64_t)vc.codes << (ob & 31u);
+				img_b[ob >> 5] |= (uint32_t)x;
+				if ((uint32_t)(x >> 32)) img_b[(ob >> 5) + 1] |= (uint32_t)(x >> 32);
+			}
+			if (vc.nbits) {
+				const uint32_t on = gpn + excl;
+				const uint64_t x = (uint64_t)vc.nbits << (on & 31u);
+				img_n[on >> 5] |= (uint32_t)x;
+				if ((uint32_t)(x >> 32)) img_n[(on >> 5) + 1] |= (uint32_t)(x >> 32);
+			}
+			excl += cnt;
+		}
+		const uint32_t total = excl;
+		const uint32_t nwords = (gph + total + 15u) >> 4, nmw = (gpn + total + 31u) >> 5;
+		for (uint32_t wl = 0; wl < nwords; wl++) {
+			if (wl != 0 && wl + 1 != nwords) bases[(g >> 4) + wl] = img_b[wl];  // interior word: plain store
+			else bases[(g >> 4) + wl] |= img_b[wl];
+		}
+		for (uint32_t wl = 0; wl < nmw; wl++) nmask[(g >> 5) + wl] |= img_n[wl];
+		for (uint32_t wl = nwords; wl < 36; wl++)
+			if (img_b[wl]) return ~0ull;  // bits beyond the round's words: would be lost by the kernel
+		for (uint32_t wl = nmw; wl < 20; wl++)
+			if (img_n[wl]) return ~0ull;
+		g += total;
+	}
+	return g - g_first;
 }
 
 }  // extern "C"

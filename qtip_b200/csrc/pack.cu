@@ -6,12 +6,14 @@
 // packed by the GPU:
 //
 //   k_find_gt      positions of every '>' in the text (rare) -> host resolves header lines
-//   k_count_bases  per 4 KiB unit of sequence text: number of non-whitespace bytes
+//   k_count_bases  per 4 KiB unit of sequence text: number of non-whitespace bytes (word-parallel
+//                  classification, pack_swar.h; all loads of a unit in flight together)
 //   (scan)         exclusive prefix over units -> base index of every unit
-//   k_pack_units   one warp per unit: 16 text bytes per lane per step, warp-scan compaction of
-//                  the non-whitespace bytes through shared memory, then word-parallel assembly
-//                  of 2-bit words and N-mask words, merged into HBM with RED.OR (unit boundaries
-//                  fall inside words)
+//   k_pack_units   one warp per unit: 16 text bytes per lane per round classified four bytes per
+//                  instruction (pack_swar.h), whitespace squeezed out of the lane's bit strings in
+//                  registers, warp scan -> bit offsets, lanes OR their bits into a shared-memory
+//                  image of the output words; interior words are plain coalesced stores, the two
+//                  words a round shares with its neighbours are merged into HBM with RED.OR
 //   k_fill_n       N padding in front of / between / after records
 //
 // Same classification as the reference: A/C/G/T in either case are bases, every other
@@ -20,21 +22,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "kernels.cuh"
+#include "pack_swar.h"
 
 namespace qt {
 
 static constexpr uint32_t UNIT_BYTES = 4096;
-
-// class of a text byte: 0..3 = A C G T, 4 = N, 5 = whitespace
-__device__ __forceinline__ uint32_t classify(uint32_t c) {
-	const uint32_t u = c & 0xdfu;  // fold case
-	if (u == 'A') return 0u;
-	if (u == 'C') return 1u;
-	if (u == 'G') return 2u;
-	if (u == 'T') return 3u;
-	if (c == ' ' || (c >= 9u && c <= 13u)) return 5u;
-	return 4u;
-}
 
 __global__ void __launch_bounds__(256) k_find_gt(const uint8_t *__restrict__ text, uint64_t n, uint64_t *list,
                                                   uint32_t cap, uint32_t *count) {
@@ -79,6 +71,19 @@ __device__ __forceinline__ uint32_t unit_segment(const SegTable &st, uint64_t u)
 	return lo;
 }
 
+// 16 text bytes of a unit for one lane: the aligned vector at i, or blanks when it starts at or past t1
+__device__ __forceinline__ uint4 load_text16(const uint8_t *__restrict__ text, uint64_t i, uint64_t t1) {
+	if (i < t1) return *(const uint4 *)(text + i);
+	return make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
+}
+// which bytes of the vector at i belong to [t0, t1): [a, b), b > a for every vector that starts below t1
+__device__ __forceinline__ void vec_range(uint64_t i, uint64_t t0, uint64_t t1, uint32_t &a, uint32_t &b) {
+	a = t0 > i ? (uint32_t)(t0 - i) : 0u;
+	b = t1 - i < 16u ? (uint32_t)(t1 - i) : 16u;
+}
+
+static constexpr int UNIT_ROUNDS = UNIT_BYTES / 512 + 1;  // 512-byte warp rounds per unit (+1: t0 is not 16-aligned)
+
 __global__ void __launch_bounds__(256) k_count_bases(const uint8_t *__restrict__ text, SegTable st, uint64_t nunits,
                                                       uint32_t *counts) {
 	const uint64_t u = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -87,19 +92,21 @@ __global__ void __launch_bounds__(256) k_count_bases(const uint8_t *__restrict__
 	const uint32_t s = unit_segment(st, u);
 	const uint64_t t0 = st.seg_start[s] + (u - st.unit_base[s]) * UNIT_BYTES;
 	const uint64_t t1 = t0 + UNIT_BYTES < st.seg_end[s] ? t0 + UNIT_BYTES : st.seg_end[s];
+	// aligned 16-byte loads from the 16-byte boundary at or below t0 (the text buffer is padded, so the last load
+	// may run past n); all of the unit's loads are issued before the first is looked at
+	const uint64_t i0 = (t0 & ~(uint64_t)15) + lane * 16;
+	uint4 v[UNIT_ROUNDS];
+#pragma unroll
+	for (int r = 0; r < UNIT_ROUNDS; r++) v[r] = load_text16(text, i0 + 512u * r, t1);
 	uint32_t cnt = 0;
-	// aligned 16-byte loads from the 16-byte boundary at or below t0; bytes outside [t0, t1) are ignored
-	// (the text buffer is padded, so the last load may run past n)
-	for (uint64_t i = (t0 & ~(uint64_t)15) + lane * 16; i < t1; i += 32 * 16) {
-		const uint4 v = *(const uint4 *)(text + i);
-		const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-		for (int k = 0; k < 4; k++)
-#pragma unroll
-			for (int b = 0; b < 4; b++) {
-				const uint64_t p = i + 4 * k + b;
-				cnt += (p >= t0 && p < t1 && classify((w[k] >> (8 * b)) & 0xffu) != 5u) ? 1u : 0u;
-			}
+	for (int r = 0; r < UNIT_ROUNDS; r++) {
+		const uint64_t i = i0 + 512u * r;
+		if (i >= t1) continue;
+		uint32_t a, b;
+		vec_range(i, t0, t1, a, b);
+		const uint32_t ws = (ws_vec(v[r].x, v[r].y, v[r].z, v[r].w) >> a) & sw_low(b - a);
+		cnt += (b - a) - sw_popc(ws);
 	}
 	for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
 	if (lane == 0) counts[u] = cnt;
@@ -108,11 +115,21 @@ __global__ void __launch_bounds__(256) k_count_bases(const uint8_t *__restrict__
 // One warp per unit.  base_of_unit[u] = bases of the whole text before unit u (exclusive scan of
 // counts); seg_gbase[s] = genome position of the segment's first base minus base_of_unit of its
 // first unit, so that genome position = seg_gbase[s] + base_of_unit[u] + (bases before, in unit).
+//
+// Per round of 512 text bytes: every lane classifies its 16 bytes word-parallel (pack_swar.h) and squeezes the
+// whitespace out of its 32 bits of codes / 16 N bits; an exclusive warp scan of the lanes' base counts gives each lane
+// its bit offset in the round's output, the lanes OR their bits into a small shared-memory image of the output
+// words (ATOMS.OR: a lane's bits straddle at most two words), and lane l ships image word l.  Words that lie
+// wholly inside the round are plain stores; the first and the last one, shared with the neighbouring round or
+// unit, are merged into HBM with RED.OR.
+static constexpr int PK_BW = 36;  // image words per warp: 2-bit codes, (15 + 512 + 15) / 16 + spill
+static constexpr int PK_NW = 20;  // N-mask words, (31 + 512 + 31) / 32 + spill
+
 __global__ void __launch_bounds__(256) k_pack_units(const uint8_t *__restrict__ text, SegTable st, uint64_t nunits,
                                                      const uint64_t *__restrict__ base_of_unit,
                                                      const int64_t *__restrict__ seg_gbase, uint32_t *bases,
                                                      uint32_t *nmask) {
-	__shared__ uint8_t s_codes[8][512 + 16];
+	__shared__ uint32_t s_img[8][PK_BW + PK_NW];
 	const uint32_t wib = threadIdx.x >> 5, lane = threadIdx.x & 31u;
 	const uint64_t u = (uint64_t)blockIdx.x * 8 + wib;
 	if (u >= nunits) return;
@@ -120,20 +137,22 @@ __global__ void __launch_bounds__(256) k_pack_units(const uint8_t *__restrict__ 
 	const uint64_t t0 = st.seg_start[s] + (u - st.unit_base[s]) * UNIT_BYTES;
 	const uint64_t t1 = t0 + UNIT_BYTES < st.seg_end[s] ? t0 + UNIT_BYTES : st.seg_end[s];
 	uint64_t g = (uint64_t)(seg_gbase[s] + (int64_t)base_of_unit[u]);  // genome position of the unit's first base
-	uint8_t *codes = s_codes[wib];
+	uint32_t *img_b = s_img[wib], *img_n = img_b + PK_BW;
+	for (uint32_t k = lane; k < (uint32_t)(PK_BW + PK_NW); k += 32) img_b[k] = 0;
+	__syncwarp();
+	const uint64_t i0 = (t0 & ~(uint64_t)15) + lane * 16;
+	uint4 nxt = load_text16(text, i0, t1);
 	for (uint64_t tile = t0 & ~(uint64_t)15; tile < t1; tile += 512) {
-		// classify 16 bytes per lane (one aligned 16-byte load; bytes outside [t0, t1) count as whitespace)
 		const uint64_t i = tile + lane * 16;
-		uint32_t cls[16];
+		const uint4 v = nxt;
+		nxt = load_text16(text, i + 512, t1);  // next round's bytes fly while this round is packed
 		uint32_t cnt = 0;
-		uint4 v = make_uint4(0x20202020u, 0x20202020u, 0x20202020u, 0x20202020u);
-		if (i < t1) v = *(const uint4 *)(text + i);
-		const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-		for (int k = 0; k < 16; k++) {
-			const uint64_t p = i + k;
-			cls[k] = (p >= t0 && p < t1) ? classify((w[k >> 2] >> (8 * (k & 3))) & 0xffu) : 5u;
-			cnt += cls[k] != 5u;
+		VecClass vc{0u, 0u, 0u};
+		if (i < t1) {
+			uint32_t a, b;
+			vec_range(i, t0, t1, a, b);
+			vc = classify_vec(v.x, v.y, v.z, v.w);
+			cnt = squeeze_vec(vc, a, b);
 		}
 		// exclusive warp scan of the counts
 		uint32_t incl = cnt;
@@ -142,38 +161,38 @@ __global__ void __launch_bounds__(256) k_pack_units(const uint8_t *__restrict__ 
 			if (lane >= (uint32_t)o) incl += y;
 		}
 		const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-		uint32_t off = incl - cnt;
-#pragma unroll
-		for (int k = 0; k < 16; k++)
-			if (cls[k] != 5u) codes[off++] = (uint8_t)cls[k];
+		const uint32_t excl = incl - cnt;
+		const uint32_t gph = (uint32_t)(g & 15u), gpn = (uint32_t)(g & 31u);
+		if (vc.codes) {
+			const uint32_t ob = 2u * (gph + excl);
+			const uint64_t x = (uint64_t)vc.codes << (ob & 31u);
+			if ((uint32_t)x) atomicOr(&img_b[ob >> 5], (uint32_t)x);
+			if ((uint32_t)(x >> 32)) atomicOr(&img_b[(ob >> 5) + 1], (uint32_t)(x >> 32));
+		}
+		if (vc.nbits) {
+			const uint32_t on = gpn + excl;
+			const uint64_t x = (uint64_t)vc.nbits << (on & 31u);
+			if ((uint32_t)x) atomicOr(&img_n[on >> 5], (uint32_t)x);
+			if ((uint32_t)(x >> 32)) atomicOr(&img_n[(on >> 5) + 1], (uint32_t)(x >> 32));
+		}
 		__syncwarp();
-		// word-parallel assembly: lane l builds 2-bit word (g>>4)+l (+32 for a possible 33rd word)
+		// lane l ships image words l and l + 32 and clears them for the next round
 		const uint64_t W0 = g >> 4;
-		const uint32_t nwords = (uint32_t)(((g + total + 15) >> 4) - W0);
+		const uint32_t nwords = (gph + total + 15u) >> 4;
 		for (uint32_t wl = lane; wl < nwords; wl += 32) {
-			const int64_t first = (int64_t)((W0 + wl) << 4) - (int64_t)g;  // index in codes[] of the word's base 0
-			uint32_t v = 0;
-#pragma unroll
-			for (int t = 0; t < 16; t++) {
-				const int64_t idx = first + t;
-				if (idx >= 0 && idx < (int64_t)total) {
-					const uint32_t c = codes[idx];
-					if (c < 4u) v |= c << (2 * t);
-				}
-			}
-			if (v) atomicOr(&bases[W0 + wl], v);
+			const uint32_t x = img_b[wl];
+			img_b[wl] = 0;
+			if (wl != 0 && wl + 1 != nwords) bases[W0 + wl] = x;
+			else if (x) atomicOr(&bases[W0 + wl], x);
 		}
 		const uint64_t M0 = g >> 5;
-		const uint32_t nmw = (uint32_t)(((g + total + 31) >> 5) - M0);
+		const uint32_t nmw = (gpn + total + 31u) >> 5;
 		for (uint32_t wl = lane; wl < nmw; wl += 32) {
-			const int64_t first = (int64_t)((M0 + wl) << 5) - (int64_t)g;
-			uint32_t v = 0;
-#pragma unroll
-			for (int t = 0; t < 32; t++) {
-				const int64_t idx = first + t;
-				if (idx >= 0 && idx < (int64_t)total && codes[idx] == 4u) v |= 1u << t;
+			const uint32_t x = img_n[wl];
+			if (x) {
+				img_n[wl] = 0;
+				atomicOr(&nmask[M0 + wl], x);
 			}
-			if (v) atomicOr(&nmask[M0 + wl], v);
 		}
 		__syncwarp();
 		g += total;

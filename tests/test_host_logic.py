@@ -144,3 +144,107 @@ def test_bad_transcripts_flagged():
     hs = util.HostSide(bad_len)
     assert hs.L.qthost_cat_valid(hs.h, 0) == 0
     hs.close()
+
+
+# ---- K0's word-parallel byte classification (qtip_b200/csrc/pack_swar.h) ----
+
+def _byte_class(c: int) -> int:
+    """dna_upper + isspace of the reference's parser (fasta.cpp:18-35,113): 0..3 = ACGT, 4 = N, 5 = whitespace."""
+    if c in b"Aa":
+        return 0
+    if c in b"Cc":
+        return 1
+    if c in b"Gg":
+        return 2
+    if c in b"Tt":
+        return 3
+    if c == 0x20 or 9 <= c <= 13:
+        return 5
+    return 4
+
+
+def _swar_vec(L, data16: bytes, a: int, b: int):
+    codes, nbits, ws = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    buf = (C.c_uint8 * 16).from_buffer_copy(data16)
+    cnt = L.qthost_swar_vec(buf, a, b, C.byref(codes), C.byref(nbits), C.byref(ws))
+    return cnt, codes.value, nbits.value, ws.value
+
+
+def _want_vec(data16: bytes, a: int, b: int):
+    cls = [_byte_class(c) for c in data16]
+    ws = sum(1 << k for k in range(16) if cls[k] == 5)
+    kept = [c for c in cls[a:b] if c != 5]
+    codes = sum((c if c < 4 else 0) << (2 * j) for j, c in enumerate(kept))
+    nbits = sum(1 << j for j, c in enumerate(kept) if c == 4)
+    return len(kept), codes, nbits, ws
+
+
+def test_swar_classification_every_byte_value_every_position():
+    L = util.hosttest()
+    L.qthost_swar_vec.restype = C.c_uint32
+    for c in range(256):
+        for k in range(16):
+            v = bytearray(b"ACGTacgtNn\n\t xR-")  # neighbours of every class around the byte under test
+            v[k] = c
+            assert _swar_vec(L, bytes(v), 0, 16) == _want_vec(bytes(v), 0, 16), (c, k)
+
+
+def test_swar_squeeze_random_vectors_and_ranges():
+    L = util.hosttest()
+    L.qthost_swar_vec.restype = C.c_uint32
+    rng = np.random.default_rng(2024)
+    alphabet = np.frombuffer(b"ACGTacgtNnRYKM-*\n\r\t \x0b\x0c\x00\x7f\x80\xa0\xc1\xff>", dtype=np.uint8)
+    for it in range(4000):
+        p_ws = (0.0, 0.05, 0.3, 0.9)[it % 4]
+        v = alphabet[rng.integers(0, alphabet.size, 16)].copy()
+        v[rng.random(16) < p_ws] = (0x0a, 0x20, 0x0d, 0x09)[it % 4]
+        a = int(rng.integers(0, 16))
+        b = int(rng.integers(a + 1, 17))
+        if it % 3 == 0:
+            a, b = 0, 16
+        assert _swar_vec(L, v.tobytes(), a, b) == _want_vec(v.tobytes(), a, b), (v.tobytes(), a, b)
+
+
+def test_swar_pack_unit_arithmetic_matches_bytewise_pack():
+    """The bit-offset / image / ship arithmetic of k_pack_units, run lane by lane on the host, for units at every
+    text phase and genome phase, against a byte-at-a-time pack."""
+    L = util.hosttest()
+    L.qthost_swar_pack_unit.restype = C.c_uint64
+    L.qthost_swar_pack_unit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(7)
+    letters = np.frombuffer(b"ACGTACGTACGTacgtNnRY", dtype=np.uint8)
+    for it in range(300):
+        n = int(rng.integers(1, 4097)) if it % 5 else 4096
+        width = (60, 70, 1, 17, 4096)[it % 5]
+        body = letters[rng.integers(0, letters.size, n)]
+        lines = [body[i:i + width].tobytes() for i in range(0, n, width)]
+        text = (b"\r\n" if it % 7 == 0 else b"\n").join(lines)[:4096]
+        if it % 11 == 0:
+            text = b" \n\n" + text[:4000] + b"\n\n"
+        lead = int(rng.integers(0, 40))
+        g = 64 + int(rng.integers(0, 64))
+        raw = np.full(lead + len(text) + 600, ord(">"), dtype=np.uint8)  # bytes outside [t0, t1) must be ignored
+        raw[lead:lead + len(text)] = np.frombuffer(text, dtype=np.uint8)
+        buf = np.zeros(raw.size + 16, dtype=np.uint8)
+        off = (-buf.ctypes.data) % 16
+        buf[off:off + raw.size] = raw
+        base_ptr = buf.ctypes.data + off
+        cls = [_byte_class(c) for c in text]
+        kept = [c for c in cls if c != 5]
+        nb = len(kept)
+        bases = np.zeros((g + nb) // 16 + 4, dtype=np.uint32)
+        nmask = np.zeros((g + nb) // 32 + 4, dtype=np.uint32)
+        # neighbours' bits already in the shared first / last words must survive
+        bases[g >> 4] = (1 << (2 * (g & 15))) - 1
+        got = L.qthost_swar_pack_unit(base_ptr, lead, lead + len(text), g, bases.ctypes.data, nmask.ctypes.data)
+        assert got == nb
+        wb = np.zeros_like(bases)
+        wn = np.zeros_like(nmask)
+        wb[g >> 4] = (1 << (2 * (g & 15))) - 1
+        for j, c in enumerate(kept):
+            p = g + j
+            if c < 4:
+                wb[p >> 4] |= np.uint32(c << (2 * (p & 15)))
+            else:
+                wn[p >> 5] |= np.uint32(1 << (p & 31))
+        assert np.array_equal(bases, wb) and np.array_equal(nmask, wn), it
