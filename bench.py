@@ -308,10 +308,24 @@ def main():
     host_out = [None] * _abi.NOUT
 
     trace = os.environ.get("QTIP_BENCH_TRACE") == "1"
+    stream_ready = [False]  # pinned result buffers sized by a first (one-shot) end-to-end step
 
     def one_step(seed, rng_mode, e2e=False):
         """Runs one step on this rank's shard; returns stats."""
         tr0 = time.perf_counter()
+        if e2e and world == 1 and stream_ready[0] and os.environ.get("QTIP_BENCH_STREAM") == "1":
+            # opt-in (QTIP_BENCH_STREAM=1): the streaming path -- chunked upload, record-by-record pack + simulate,
+            # download of earlier records' reads while later text is still uploading.  Bit-exact with the one-shot
+            # path but not faster yet on this box (DESIGN.md section 6), so the default e2e arm stays one-shot.
+            eng.stream_begin(fa_pinned.numpy())
+            set_templates()                                    # the host compiles the templates while the text uploads
+            p = sim.make_params(CHUNKSZ, kw["fraction"], kw["function"], kw["min_u"], kw["min_c"], kw["min_d"], kw["min_b"],
+                                rng_mode, cg=cli_seed(seed), philox_seed=seed, shard_rank=0, shard_count=1)
+            st = eng.stream_run(p, [t.data_ptr() if t is not None else 0 for t in host_out],
+                                [t.numel() if t is not None else 0 for t in host_out])
+            if trace:
+                print(f"[trace] streaming e2e step {1e3 * (time.perf_counter() - tr0):.1f} ms", file=sys.stderr)
+            return st
         if e2e:
             if rank == 0:
                 eng.load_fasta_bytes_async(fa_pinned.numpy())  # H2D of the FASTA text + device pack ...
@@ -342,7 +356,7 @@ def main():
                 n = int(st.bytes[s])
                 if n:
                     if host_out[s] is None or host_out[s].numel() < n:
-                        host_out[s] = torch.empty(int(n * 1.05) + 4096, dtype=torch.uint8).pin_memory()
+                        host_out[s] = torch.empty(int(n * 1.05) + (1 << 20), dtype=torch.uint8).pin_memory()
                     eng.check(eng.lib.qtipsim_result_copy(eng.h, s, C.c_void_p(host_out[s].data_ptr()), host_out[s].numel()))
             if trace:
                 print(f"[trace] run {1e3 * (tr3 - tr2):.1f} ms (pack {st.ms_pack:.1f}), result_copy {1e3 * (time.perf_counter() - tr3):.1f} ms",
@@ -385,6 +399,9 @@ def main():
         barrier()
         # end-to-end arm (host buffers; H2D of the FASTA text and templates, D2H of the FASTQ bytes inside)
         one_step(300, rng_mode, e2e=True)  # warm (allocates the pinned result buffers)
+        stream_ready[0] = True
+        if os.environ.get("QTIP_BENCH_STREAM") == "1":
+            one_step(301, rng_mode, e2e=True)  # warm (the path the timed steps take)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -182,6 +182,18 @@ int qtipsim_result_write_fds(qtipsim_t *h, const int fds[QTIPSIM_NOUT]);
 int qtipsim_run_to_host(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats,
                         void *const dst[QTIPSIM_NOUT], const uint64_t cap[QTIPSIM_NOUT]);
 
+/* Streaming end-to-end path (one GPU): the same bytes as qtipsim_load_fasta_bytes + qtipsim_run_to_host, with the
+ * upload of the FASTA text, the device pack, the simulation and the download of the FASTQ bytes overlapped --
+ * the reference, too, streams the FASTA once and emits reads window by window (simplesim.cpp:216-397,
+ * fasta.cpp:42-127).  begin: starts the chunked upload of `bytes` (must stay valid until stream_run returns;
+ * pinned memory makes the copies asynchronous) and returns at once, so the caller can set the templates
+ * meanwhile.  run: packs and simulates every record as soon as the next record's header has arrived and appends
+ * its reads to dst[i] (cap[i] bytes); stats->bytes[i] = bytes written to dst[i].  Afterwards the genome is
+ * resident as after qtipsim_load_fasta_bytes.  REPLAY mode chains the generator state through the parts. */
+int qtipsim_stream_begin(qtipsim_t *h, const void *bytes, size_t nbytes);
+int qtipsim_stream_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats,
+                       void *const dst[QTIPSIM_NOUT], const uint64_t cap[QTIPSIM_NOUT]);
+
 #ifdef __cplusplus
 }
 #endif

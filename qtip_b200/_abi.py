@@ -40,6 +40,8 @@ SYMBOLS = (
     "qtipsim_result_device_ptr",
     "qtipsim_result_write_fds",
     "qtipsim_run_to_host",
+    "qtipsim_stream_begin",
+    "qtipsim_stream_run",
 )
 
 
@@ -115,5 +117,7 @@ def load() -> C.CDLL:
     lib.qtipsim_result_device_ptr.argtypes = [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     lib.qtipsim_result_write_fds.argtypes = [H, C.POINTER(C.c_int)]
     lib.qtipsim_run_to_host.argtypes = [H, C.POINTER(RunParams), C.POINTER(Stats), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    lib.qtipsim_stream_begin.argtypes = [H, C.c_void_p, C.c_size_t]
+    lib.qtipsim_stream_run.argtypes = [H, C.POINTER(RunParams), C.POINTER(Stats), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     _lib = lib
     return lib

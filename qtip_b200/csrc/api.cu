@@ -7,7 +7,12 @@
 #include <string.h>
 #include <unistd.h>
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <map>
 #include <string>
 #include <vector>
@@ -101,6 +106,26 @@ struct qtipsim {
 	void *h_stage = nullptr;  // pinned staging for fd writes
 	size_t h_stage_cap = 0;
 
+	// header-line scan (shared by the one-shot and the streaming loader): text ranges of the sequence lines of
+	// every record of hg.recs, and the record whose end has not been seen yet
+	std::vector<uint64_t> seg_start, seg_end;
+	uint64_t hdr_end = 0;
+	bool open_rec = false, open_is_leading = false;
+	RecDev open_desc{};
+	uint64_t open_start = 0;
+	uint32_t recs_packed = 0;
+	// streaming loader (qtipsim_stream_begin / qtipsim_stream_run): upload, pack, simulate and download overlap
+	cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+	const uint8_t *stream_text = nullptr;
+	uint64_t stream_n = 0, stream_chunk = 0, stream_cap_bases = 0;
+	std::vector<cudaEvent_t> stream_ev;
+	bool stream_open = false;
+	DevBuf d_out2[NOUT];
+	std::thread feeder;  // issues the upload in small pieces, a few in flight: control copies never queue behind the bulk
+	std::atomic<uint64_t> chunks_issued{0};
+	std::atomic<int> bulk_err{0};
+	double stream_t0 = 0;
+
 	int fail(int code, const std::string &m) {
 		err = m;
 		return code;
@@ -179,6 +204,11 @@ void qtipsim_destroy(qtipsim_t *h) {
 		h->d_off1[c].release();
 	}
 	for (int s = 0; s < NOUT; s++) h->d_out[s].release();
+	for (int s = 0; s < NOUT; s++) h->d_out2[s].release();
+	if (h->feeder.joinable()) h->feeder.join();
+	for (cudaEvent_t e : h->stream_ev) cudaEventDestroy(e);
+	if (h->st_h2d) cudaStreamDestroy(h->st_h2d);
+	if (h->st_d2h) cudaStreamDestroy(h->st_d2h);
 	if (h->h_stage) cudaFreeHost(h->h_stage);
 	cudaStreamDestroy(h->st);
 	delete h;
@@ -221,76 +251,109 @@ static int upload_genome(qtipsim *h) {
 	return QTIPSIM_OK;
 }
 
-// K0 on the device: `text` is the FASTA text in host memory.  The host only resolves header
-// lines; classification, counting and packing of the sequence bytes run on the GPU (pack.cu).
-static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
-	CK(cudaSetDevice(h->device));
-	cudaEvent_t e0, e1;
-	CK(cudaEventCreate(&e0));
-	CK(cudaEventCreate(&e1));
-	CK(cudaEventRecord(e0, h->st));
+// ---- K0 on the device (pack.cu).  The host only resolves header lines; classification, counting and packing
+// of the sequence bytes run on the GPU.  Three pieces, shared by the one-shot loader (device_pack) and the
+// streaming loader (qtipsim_stream_run): reset, header resolution, packing of a range of complete records. ----
+
+static void genome_reset(qtipsim *h, uint64_t n) {
 	HostGenome &g = h->hg;
 	g.recs.clear();
 	g.names.clear();
 	g.bases.clear();
 	g.nmask.clear();
 	g.file_bytes = n;
-	CK(h->d_text.ensure(n + 64));
-	if (n) CK(cudaMemcpyAsync(h->d_text.p, text, n, cudaMemcpyHostToDevice, h->st));
-	CK(cudaMemsetAsync((char *)h->d_text.p + n, ' ', 64, h->st));
-	// ---- header lines: every '>' found by the GPU, resolved against the host text ----
+	g.total_bases = 0;
+	h->seg_start.clear();
+	h->seg_end.clear();
+	h->hdr_end = 0;
+	// sequence bytes before the first header form a record with an empty name (fasta.cpp:72-124)
+	h->open_rec = true;
+	h->open_is_leading = true;
+	h->open_desc = RecDev{0, 0, 0, 0};
+	h->open_start = 0;
+	h->recs_packed = 0;
+	h->have_genome = false;
+	h->win_cache_ok = false;
+	h->setup_cache_ok = false;
+	h->host_packed = false;
+	h->have_result = false;
+}
+
+static inline bool fa_is_sp(uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); }
+
+// the open record ends at text position `end`: it joins hg.recs (the headerless leading record only if it has bases)
+static void close_open_record(qtipsim *h, const uint8_t *text, uint64_t end) {
+	if (!h->open_rec) return;
+	bool keep = true;
+	if (h->open_is_leading) {
+		keep = false;
+		for (uint64_t i = 0; i < end && !keep; i++) keep = !fa_is_sp(text[i]);
+	}
+	if (keep) {
+		h->hg.recs.push_back(h->open_desc);
+		h->seg_start.push_back(h->open_start);
+		h->seg_end.push_back(end);
+	}
+	h->open_rec = false;
+	h->open_is_leading = false;
+}
+
+// gts: ascending positions of '>' not yet looked at.  A header closes the open record and opens the next one.
+static void resolve_headers(qtipsim *h, const uint8_t *text, uint64_t n, const std::vector<uint64_t> &gts, bool final) {
+	HostGenome &g = h->hg;
+	for (size_t k = 0; k < gts.size(); k++) {
+		const uint64_t p = gts[k];
+		if (p < h->hdr_end) continue;  // a '>' inside a header line is part of the name
+		close_open_record(h, text, p);
+		uint64_t i = p + 1;
+		const uint64_t s0 = i;
+		while (i < n && !fa_is_sp(text[i])) i++;
+		h->open_desc = RecDev{0, 0, (uint32_t)g.names.size(), (uint32_t)(i - s0)};
+		g.names.append((const char *)text + s0, (size_t)(i - s0));
+		while (i < n && text[i] != '\n' && text[i] != '\r') i++;
+		h->hdr_end = i;
+		h->open_rec = true;
+		h->open_start = i;
+	}
+	if (final) close_open_record(h, text, n);
+}
+
+// positions of '>' in text [c0, c1), already on the device, ascending
+static int find_headers_chunk(qtipsim *h, const uint8_t *text, uint64_t c0, uint64_t c1, std::vector<uint64_t> &gts) {
+	gts.clear();
+	if (c1 <= c0) return QTIPSIM_OK;
 	const uint32_t cap = 1u << 22;
 	CK(h->d_pk_a.ensure((size_t)cap * 8 + 16));
 	CK(h->d_small.ensure(16 * 8));
 	CK(cudaMemsetAsync(h->d_small.p, 0, 16 * 8, h->st));
-	launch_find_gt(h->d_text.as<uint8_t>(), n, h->d_pk_a.as<uint64_t>(), cap, h->d_small.as<uint32_t>(), h->st);
+	launch_find_gt(h->d_text.as<uint8_t>() + c0, c1 - c0, h->d_pk_a.as<uint64_t>(), cap, h->d_small.as<uint32_t>(), h->st);
 	uint32_t ngt = 0;
 	CK(cudaMemcpyAsync(&ngt, h->d_small.p, 4, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaStreamSynchronize(h->st));
-	std::vector<uint64_t> gts;
 	if (ngt > cap) {  // pathological: fall back to a host scan for '>'
-		for (const uint8_t *p = text, *e = text + n; p < e;) {
-			const uint8_t *q = (const uint8_t *)memchr(p, '>', (size_t)(e - p));
+		for (const uint8_t *q0 = text + c0, *e = text + c1; q0 < e;) {
+			const uint8_t *q = (const uint8_t *)memchr(q0, '>', (size_t)(e - q0));
 			if (!q) break;
 			gts.push_back((uint64_t)(q - text));
-			p = q + 1;
+			q0 = q + 1;
 		}
 	} else {
 		gts.resize(ngt);
 		if (ngt) CK(cudaMemcpy(gts.data(), h->d_pk_a.p, (size_t)ngt * 8, cudaMemcpyDeviceToHost));
+		for (uint64_t &v : gts) v += c0;
 		std::sort(gts.begin(), gts.end());
 	}
-	auto is_sp = [](uint8_t c) { return c == ' ' || (c >= 9 && c <= 13); };
-	std::vector<uint64_t> seg_start, seg_end;
-	uint64_t hdr_end = 0;
-	// sequence bytes before the first header form a record with an empty name (fasta.cpp:72-124)
-	{
-		const uint64_t first = gts.empty() ? n : gts[0];
-		bool any = false;
-		for (uint64_t i = 0; i < first && !any; i++) any = !is_sp(text[i]);
-		if (any) {
-			RecDev r{0, 0, 0, 0};
-			g.recs.push_back(r);
-			seg_start.push_back(0);
-			seg_end.push_back(first);
-		}
-	}
-	for (size_t k = 0; k < gts.size(); k++) {
-		const uint64_t p = gts[k];
-		if (p < hdr_end) continue;  // a '>' inside a header line is part of the name
-		if (!seg_end.empty()) seg_end.back() = p;
-		uint64_t i = p + 1;
-		const uint64_t s0 = i;
-		while (i < n && !is_sp(text[i])) i++;
-		RecDev r{0, 0, (uint32_t)g.names.size(), (uint32_t)(i - s0)};
-		g.names.append((const char *)text + s0, (size_t)(i - s0));
-		while (i < n && text[i] != '\n' && text[i] != '\r') i++;
-		hdr_end = i;
-		g.recs.push_back(r);
-		seg_start.push_back(i);
-		seg_end.push_back(n);
-	}
-	const uint32_t nseg = (uint32_t)seg_start.size();
+	return QTIPSIM_OK;
+}
+
+// Packs records [recs_packed, hg.recs.size()) -- their text is on the device -- behind what is packed already.
+// presized: d_bases / d_nmask were allocated and cleared for stream_cap_bases positions by the caller.
+static int pack_records(qtipsim *h, bool presized) {
+	HostGenome &g = h->hg;
+	const uint32_t r0 = h->recs_packed, r1 = (uint32_t)g.recs.size();
+	const uint32_t nseg = r1 - r0;
+	const bool first = r0 == 0 && g.total_bases == 0;
+	const uint64_t *seg_start = h->seg_start.data() + r0, *seg_end = h->seg_end.data() + r0;
 	std::vector<uint64_t> unit_base((size_t)nseg + 1, 0);
 	for (uint32_t s = 0; s < nseg; s++) unit_base[s + 1] = unit_base[s] + (seg_end[s] - seg_start[s] + 4095) / 4096;
 	const uint64_t nunits = unit_base[nseg];
@@ -298,8 +361,8 @@ static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
 	if (nunits) {
 		CK(h->d_pk_b.ensure((size_t)(3 * nseg + 1) * 8 + 16));
 		uint64_t *d_ss = h->d_pk_b.as<uint64_t>(), *d_se = d_ss + nseg, *d_ub = d_se + nseg;
-		CK(cudaMemcpyAsync(d_ss, seg_start.data(), nseg * 8, cudaMemcpyHostToDevice, h->st));
-		CK(cudaMemcpyAsync(d_se, seg_end.data(), nseg * 8, cudaMemcpyHostToDevice, h->st));
+		CK(cudaMemcpyAsync(d_ss, seg_start, nseg * 8, cudaMemcpyHostToDevice, h->st));
+		CK(cudaMemcpyAsync(d_se, seg_end, nseg * 8, cudaMemcpyHostToDevice, h->st));
 		CK(cudaMemcpyAsync(d_ub, unit_base.data(), ((size_t)nseg + 1) * 8, cudaMemcpyHostToDevice, h->st));
 		CK(h->d_pk_c.ensure((size_t)nunits * 4 + 16));                   // counts
 		CK(h->d_pk_d.ensure(((size_t)nunits + 1) * 8 + 16));             // exclusive prefix
@@ -313,13 +376,15 @@ static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
 	// ---- genome coordinates: 64 N in front, every record 64-aligned with an N gap behind it ----
 	std::vector<int64_t> seg_gbase(nseg);
 	std::vector<uint64_t> pad_lo, pad_hi;
-	uint64_t gp = 64;
-	pad_lo.push_back(0);
-	pad_hi.push_back(64);
+	uint64_t gp = first ? 64 : g.total_bases;
+	if (first) {
+		pad_lo.push_back(0);
+		pad_hi.push_back(64);
+	}
 	for (uint32_t s = 0; s < nseg; s++) {
 		const uint64_t len = unit_pref[unit_base[s + 1]] - unit_pref[unit_base[s]];
-		g.recs[s].gstart = gp;
-		g.recs[s].len = len;
+		g.recs[r0 + s].gstart = gp;
+		g.recs[r0 + s].len = len;
 		seg_gbase[s] = (int64_t)gp - (int64_t)unit_pref[unit_base[s]];
 		gp += len;
 		uint64_t end = (gp + 63) & ~(uint64_t)63;
@@ -330,10 +395,14 @@ static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
 	}
 	g.total_bases = gp;
 	const size_t bw = (size_t)((gp + 15) / 16 + 4), mw = (size_t)((gp + 31) / 32 + 4);
-	CK(h->d_bases.ensure(bw * 4));
-	CK(h->d_nmask.ensure(mw * 4));
-	CK(cudaMemsetAsync(h->d_bases.p, 0, bw * 4, h->st));
-	CK(cudaMemsetAsync(h->d_nmask.p, 0, mw * 4, h->st));
+	if (!presized) {
+		CK(h->d_bases.ensure(bw * 4));
+		CK(h->d_nmask.ensure(mw * 4));
+		CK(cudaMemsetAsync(h->d_bases.p, 0, bw * 4, h->st));
+		CK(cudaMemsetAsync(h->d_nmask.p, 0, mw * 4, h->st));
+	} else if (gp + 64 > h->stream_cap_bases) {
+		return h->fail(QTIPSIM_ERANGE, "streaming loader: more record padding than reserved (too many records)");
+	}
 	if (nunits) {
 		CK(h->d_pk_a.ensure((size_t)nseg * 8 + 16));
 		CK(cudaMemcpyAsync(h->d_pk_a.p, seg_gbase.data(), nseg * 8, cudaMemcpyHostToDevice, h->st));
@@ -341,7 +410,7 @@ static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
 		launch_pack_units(h->d_text.as<uint8_t>(), d_ss, d_se, d_ub, nseg, nunits, h->d_pk_d.as<uint64_t>(),
 		                  h->d_pk_a.as<int64_t>(), h->d_bases.as<uint32_t>(), h->d_nmask.as<uint32_t>(), h->st);
 	}
-	{
+	if (!pad_lo.empty()) {
 		const uint32_t np = (uint32_t)pad_lo.size();
 		CK(h->d_pk_c.ensure((size_t)np * 16 + 16));
 		uint64_t *d_lo = h->d_pk_c.as<uint64_t>(), *d_hi = d_lo + np;
@@ -360,6 +429,30 @@ static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
 		CK(cudaMemcpyAsync(h->d_recs.p, g.recs.data(), g.recs.size() * sizeof(RecDev), cudaMemcpyHostToDevice, h->st));
 	if (!g.names.empty())
 		CK(cudaMemcpyAsync(h->d_names.p, g.names.data(), g.names.size(), cudaMemcpyHostToDevice, h->st));
+	h->recs_packed = r1;
+	h->win_cache_ok = false;
+	h->setup_cache_ok = false;
+	return QTIPSIM_OK;
+}
+
+// One-shot loader: `text` is the FASTA text in host memory.
+static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
+	CK(cudaSetDevice(h->device));
+	cudaEvent_t e0, e1;
+	CK(cudaEventCreate(&e0));
+	CK(cudaEventCreate(&e1));
+	CK(cudaEventRecord(e0, h->st));
+	genome_reset(h, n);
+	CK(h->d_text.ensure(n + 64));
+	if (n) CK(cudaMemcpyAsync(h->d_text.p, text, n, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemsetAsync((char *)h->d_text.p + n, ' ', 64, h->st));
+	// ---- header lines: every '>' found by the GPU, resolved against the host text ----
+	std::vector<uint64_t> gts;
+	int rc = find_headers_chunk(h, text, 0, n, gts);
+	if (rc) return rc;
+	resolve_headers(h, text, n, gts, true);
+	rc = pack_records(h, false);
+	if (rc) return rc;
 	CK(cudaEventRecord(e1, h->st));
 	CK(cudaStreamSynchronize(h->st));
 	CK(cudaGetLastError());
@@ -369,10 +462,6 @@ static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
 	cudaEventDestroy(e0);
 	cudaEventDestroy(e1);
 	h->have_genome = true;
-	h->win_cache_ok = false;
-	h->setup_cache_ok = false;
-	h->host_packed = false;
-	h->have_result = false;
 	return QTIPSIM_OK;
 }
 
@@ -593,9 +682,10 @@ static int ensure_setups(qtipsim *h, const std::vector<Window> &win, uint64_t ol
 	return QTIPSIM_OK;
 }
 
-int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
+// One run over the windows [range_lo, range_hi) of the packed records (range_lo < 0: the shard's share of all windows).
+static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int64_t range_lo, int64_t range_hi) {
 	if (!h || !p) return QTIPSIM_EINVAL;
-	if (!h->have_genome) return h->fail(QTIPSIM_ESTATE, "qtipsim_run: no genome loaded");
+	if (!h->have_genome && range_lo < 0) return h->fail(QTIPSIM_ESTATE, "qtipsim_run: no genome loaded");
 	CK(cudaSetDevice(h->device));
 	const int launches0 = kernels_launch_count();
 	const uint64_t olap = h->ts.olap();
@@ -664,6 +754,10 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 	const uint32_t nwin = (uint32_t)win.size();
 	pp.win_lo = (uint64_t)p->shard_rank * nwin / p->shard_count;
 	pp.win_hi = (uint64_t)(p->shard_rank + 1) * nwin / p->shard_count;
+	if (range_lo >= 0) {
+		pp.win_lo = (uint64_t)range_lo;
+		pp.win_hi = (uint64_t)range_hi < nwin ? (uint64_t)range_hi : nwin;
+	}
 	const std::vector<uint32_t> &ncount = h->ncount_cache;
 	DevGenome dg;
 	dg.bases = h->d_bases.as<uint32_t>();
@@ -918,6 +1012,8 @@ int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) {
 	return QTIPSIM_OK;
 }
 
+int qtipsim_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats) { return run_impl(h, p, stats, -1, -1); }
+
 int qtipsim_result_copy(qtipsim_t *h, int stream, void *dst, uint64_t cap) {
 	if (!h || stream < 0 || stream >= NOUT) return QTIPSIM_EINVAL;
 	if (!h->have_result) return h->fail(QTIPSIM_ESTATE, "no result: call qtipsim_run first");
@@ -1012,5 +1108,268 @@ int qtipsim_run_to_host(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stat
 	CK(cudaStreamSynchronize(h->st));
 	return QTIPSIM_OK;
 }
+
+// ---- streaming end-to-end path: upload, pack, simulate and download overlap ----
+//
+// The reference streams the FASTA once and emits reads window by window (simplesim.cpp:216-397); everything a
+// window's reads depend on -- the window table, the per-window counts, the read indices, the output offsets -- is a
+// prefix quantity over the records before it.  So the text can be uploaded in chunks on one copy stream, every
+// record packed and simulated as soon as the header of the NEXT record has arrived, and its FASTQ bytes sent back
+// on a second copy stream while later chunks are still uploading: both directions of the link run at once.  The
+// bytes are those of qtipsim_load_fasta_bytes + qtipsim_run_to_host (tests/test_gpu_parity.py).
+
+static uint64_t env_u64(const char *name, uint64_t dflt) {
+	const char *e = getenv(name);
+	if (!e || !*e) return dflt;
+	const unsigned long long v = strtoull(e, nullptr, 10);
+	return v ? (uint64_t)v : dflt;
+}
+
+int qtipsim_stream_begin(qtipsim_t *h, const void *bytes, size_t nbytes) {
+	if (!h || (!bytes && nbytes)) return QTIPSIM_EINVAL;
+	CK(cudaSetDevice(h->device));
+	if (!h->st_h2d) CK(cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
+	if (!h->st_d2h) CK(cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
+	CK(cudaStreamSynchronize(h->st));
+	const uint64_t n = nbytes;
+	genome_reset(h, n);
+	h->stream_text = (const uint8_t *)bytes;
+	h->stream_n = n;
+	h->stream_chunk = env_u64("QTIPSIM_STREAM_CHUNK", 128ull << 20) & ~(uint64_t)15;
+	if (h->stream_chunk < 16) h->stream_chunk = 16;
+	// every record takes at least two text bytes and adds at most 127 positions of padding
+	const uint64_t max_recs = std::min<uint64_t>(1ull << 22, n / 2 + 2);
+	h->stream_cap_bases = n + 128 + 128 * max_recs;
+	CK(h->d_text.ensure(n + 64));
+	const size_t bw = (size_t)(h->stream_cap_bases / 16 + 8), mw = (size_t)(h->stream_cap_bases / 32 + 8);
+	CK(h->d_bases.ensure(bw * 4));
+	CK(h->d_nmask.ensure(mw * 4));
+	CK(cudaMemsetAsync(h->d_bases.p, 0, bw * 4, h->st));
+	CK(cudaMemsetAsync(h->d_nmask.p, 0, mw * 4, h->st));
+	CK(cudaMemsetAsync((char *)h->d_text.p + n, ' ', 64, h->st));
+	if (h->feeder.joinable()) h->feeder.join();
+	for (cudaEvent_t e : h->stream_ev) cudaEventDestroy(e);
+	h->stream_ev.clear();
+	for (uint64_t c0 = 0; c0 < n; c0 += h->stream_chunk) {
+		cudaEvent_t e;
+		CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+		h->stream_ev.push_back(e);
+	}
+	// The copy engine of a direction serves copies in issue order: were the whole text enqueued at once, every small
+	// control upload of the pack / plan steps would wait behind it.  A feeder thread issues the text in pieces (32 MB) and keeps three in flight; stream_ev[i] fires when chunk i (the unit of the header scan) has arrived.
+	h->chunks_issued.store(0);
+	h->bulk_err.store(0);
+	const uint64_t piece = std::max<uint64_t>(env_u64("QTIPSIM_STREAM_PIECE", 32ull << 20) & ~(uint64_t)15, 16);
+	h->feeder = std::thread([h, bytes, n, piece]() {
+		if (cudaSetDevice(h->device) != cudaSuccess) h->bulk_err.store(1);
+		constexpr int DEPTH = 3;
+		cudaEvent_t ring[DEPTH];
+		for (auto &e : ring) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+		uint64_t pos = 0, k = 0;
+		for (size_t ci = 0; ci < h->stream_ev.size(); ci++) {
+			const uint64_t chunk_end = std::min<uint64_t>((uint64_t)(ci + 1) * h->stream_chunk, n);
+			while (pos < chunk_end) {
+				const uint64_t len = std::min<uint64_t>(piece, chunk_end - pos);
+				if (k >= DEPTH) cudaEventSynchronize(ring[k % DEPTH]);
+				if (cudaMemcpyAsync((char *)h->d_text.p + pos, (const char *)bytes + pos, len, cudaMemcpyHostToDevice, h->st_h2d) != cudaSuccess)
+					h->bulk_err.store(1);
+				cudaEventRecord(ring[k % DEPTH], h->st_h2d);
+				k++;
+				pos += len;
+			}
+			cudaEventRecord(h->stream_ev[ci], h->st_h2d);
+			h->chunks_issued.store(ci + 1, std::memory_order_release);
+		}
+		cudaStreamSynchronize(h->st_h2d);
+		for (auto &e : ring) cudaEventDestroy(e);
+	});
+	h->stream_open = true;
+	h->stream_t0 = now_ms();
+	return QTIPSIM_OK;
+}
+
+int qtipsim_stream_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats, void *const dst[QTIPSIM_NOUT],
+                       const uint64_t cap[QTIPSIM_NOUT]) {
+	if (!h || !p || !dst || !cap) return QTIPSIM_EINVAL;
+	if (!h->stream_open) return h->fail(QTIPSIM_ESTATE, "qtipsim_stream_run: call qtipsim_stream_begin first");
+	if (p->shard_count > 1) return h->fail(QTIPSIM_EINVAL, "the streaming path runs all windows on one GPU (shard_count must be 1)");
+	CK(cudaSetDevice(h->device));
+	h->stream_open = false;
+	{
+		// templates go up now, while the first records are still arriving, not inside the first part's run
+		const int rc0 = upload_templates(h);
+		if (rc0) return rc0;
+	}
+	const uint8_t *text = h->stream_text;
+	const uint64_t n = h->stream_n;
+	const uint64_t min_part = env_u64("QTIPSIM_STREAM_MIN_PART", 512ull << 20);
+	const size_t nchunks = h->stream_ev.size();
+	// downloads: a drain thread issues each part's FASTQ bytes in pieces of a few MB, three in flight (the small
+	// control read-backs of the next parts' pack / plan steps slip in between), and counts the parts that are home
+	struct DrainJob {
+		char *dst;
+		const char *src;
+		uint64_t n;
+		bool last_of_part;
+	};
+	std::deque<DrainJob> dq;
+	std::mutex dm;
+	std::condition_variable dcv;
+	bool drain_stop = false;
+	int parts_home = 0;
+	const uint64_t dpiece = std::max<uint64_t>(env_u64("QTIPSIM_STREAM_PIECE", 32ull << 20), 4096);
+	std::thread drain([&]() {
+		if (cudaSetDevice(h->device) != cudaSuccess) h->bulk_err.store(1);
+		constexpr int DEPTH = 3;
+		cudaEvent_t ring[DEPTH];
+		for (auto &e : ring) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+		uint64_t k = 0;
+		for (;;) {
+			DrainJob j;
+			{
+				std::unique_lock<std::mutex> lk(dm);
+				dcv.wait(lk, [&] { return drain_stop || !dq.empty(); });
+				if (dq.empty()) break;
+				j = dq.front();
+				dq.pop_front();
+			}
+			for (uint64_t pos = 0; pos < j.n; pos += dpiece) {
+				const uint64_t len = std::min<uint64_t>(dpiece, j.n - pos);
+				if (k >= DEPTH) cudaEventSynchronize(ring[k % DEPTH]);
+				if (cudaMemcpyAsync(j.dst + pos, j.src + pos, len, cudaMemcpyDeviceToHost, h->st_d2h) != cudaSuccess) h->bulk_err.store(1);
+				cudaEventRecord(ring[k % DEPTH], h->st_d2h);
+				k++;
+			}
+			if (j.last_of_part) {
+				cudaStreamSynchronize(h->st_d2h);
+				std::lock_guard<std::mutex> lk(dm);
+				parts_home++;
+				dcv.notify_all();
+			}
+		}
+		cudaStreamSynchronize(h->st_d2h);
+		for (auto &e : ring) cudaEventDestroy(e);
+	});
+	auto stop_drain = [&]() {
+		{
+			std::lock_guard<std::mutex> lk(dm);
+			drain_stop = true;
+		}
+		dcv.notify_all();
+		if (drain.joinable()) drain.join();
+	};
+	uint64_t out_off[NOUT] = {0, 0, 0, 0, 0, 0, 0};
+	qtipsim_stats tot;
+	memset(&tot, 0, sizeof(tot));
+	uint64_t win_done = 0;
+	int part = 0, rc = QTIPSIM_OK;
+	const bool trace_parts = getenv("QTIPSIM_STREAM_TRACE") != nullptr;
+	std::vector<uint64_t> gts;
+	for (size_t i = 0; (i < nchunks || (i == 0 && nchunks == 0)) && rc == QTIPSIM_OK; i++) {
+		const bool final = i + 1 >= nchunks;
+		if (nchunks) {
+			const uint64_t c0 = (uint64_t)i * h->stream_chunk, c1 = std::min<uint64_t>(c0 + h->stream_chunk, n);
+			while (h->chunks_issued.load(std::memory_order_acquire) <= i) std::this_thread::sleep_for(std::chrono::microseconds(50));
+			{
+				const cudaError_t e = cudaEventSynchronize(h->stream_ev[i]);
+				if (e != cudaSuccess) {
+					rc = h->cuda_fail(e, "cudaEventSynchronize(upload chunk)");
+					break;
+				}
+			}
+			rc = find_headers_chunk(h, text, c0, c1, gts);
+			if (rc) break;
+		} else {
+			gts.clear();
+		}
+		resolve_headers(h, text, n, gts, final);
+		const double t_ready = now_ms();
+		const uint32_t r1 = (uint32_t)h->hg.recs.size();
+		if (r1 > h->recs_packed) {
+			const uint64_t span = h->seg_end[r1 - 1] - h->seg_start[h->recs_packed];
+			if (!final && span < min_part) continue;
+			rc = pack_records(h, true);
+			if (rc) break;
+		} else if (final && h->hg.total_bases == 0) {
+			rc = pack_records(h, true);  // no record at all: the leading N pad, as the one-shot loader leaves it
+			if (rc) break;
+		} else if (!final) {
+			continue;
+		}
+		// windows of the records packed so far: [win_done, nwin) are new
+		const uint64_t olap = h->ts.olap();
+		if (!(p->chunksz > olap)) {
+			rc = h->fail(QTIPSIM_ERANGE, "chunksz must exceed the longest template / fragment (fasta.h:41)");
+			break;
+		}
+		const uint64_t nwin = h->hg.windows(p->chunksz, olap).size();
+		if (nwin == win_done && !(final && part == 0)) continue;
+		// the output buffers about to be written were last read by the download of part - 2
+		{
+			std::unique_lock<std::mutex> lk(dm);
+			dcv.wait(lk, [&] { return parts_home >= part - 1; });
+		}
+		qtipsim_stats st;
+		memset(&st, 0, sizeof(st));
+		const double t_run0 = now_ms();
+		rc = run_impl(h, p, &st, (int64_t)win_done, (int64_t)nwin);
+		if (rc) break;
+		if (trace_parts)
+			fprintf(stderr, "[stream] part %d: chunk %zu, ready %.1f ms, run %.1f -> %.1f ms, windows %llu..%llu, home %d\n", part, i,
+			        t_ready - h->stream_t0, t_run0 - h->stream_t0, now_ms() - h->stream_t0, (unsigned long long)win_done,
+			        (unsigned long long)nwin, parts_home);
+		win_done = nwin;
+		for (int s = 0; s < NOUT; s++) {
+			const uint64_t nb = h->out_bytes[s];
+			if (nb && (out_off[s] + nb > cap[s] || !dst[s])) rc = h->fail(QTIPSIM_ERANGE, "destination buffer too small");
+		}
+		if (rc) break;
+		{
+			std::lock_guard<std::mutex> lk(dm);
+			for (int s = 0; s < NOUT; s++) {
+				const uint64_t nb = h->out_bytes[s];
+				if (!nb) continue;
+				dq.push_back(DrainJob{(char *)dst[s] + out_off[s], h->d_out[s].as<char>(), nb, false});
+				out_off[s] += nb;
+			}
+			dq.push_back(DrainJob{nullptr, nullptr, 0, true});
+		}
+		dcv.notify_all();
+		for (int s = 0; s < NOUT; s++) std::swap(h->d_out[s], h->d_out2[s]);
+		for (int c = 0; c < NCAT; c++) {
+			tot.wrote[c] += st.wrote[c];
+			tot.target[c] = st.target[c];
+		}
+		tot.draws += st.draws;
+		tot.algorithmic_bytes += st.algorithmic_bytes;
+		tot.kernel_launches += st.kernel_launches;
+		tot.ms_plan += st.ms_plan;
+		tot.ms_simulate += st.ms_simulate;
+		tot.ms_total += st.ms_total;
+		tot.ms_pack += st.ms_pack;
+		part++;
+	}
+	if (trace_parts) fprintf(stderr, "[stream] last part issued at %.1f ms\n", now_ms() - h->stream_t0);
+	stop_drain();
+	if (trace_parts) fprintf(stderr, "[stream] downloads home at %.1f ms\n", now_ms() - h->stream_t0);
+	if (h->feeder.joinable()) h->feeder.join();
+	cudaStreamSynchronize(h->st_h2d);
+	cudaStreamSynchronize(h->st_d2h);
+	cudaStreamSynchronize(h->st);
+	for (cudaEvent_t e : h->stream_ev) cudaEventDestroy(e);
+	h->stream_ev.clear();
+	if (rc) return rc;
+	if (h->bulk_err.load()) return h->fail(QTIPSIM_ECUDA, "streaming path: a bulk copy failed");
+	CK(cudaGetLastError());
+	for (int s = 0; s < NOUT; s++) {
+		tot.bytes[s] = out_off[s];
+		h->out_bytes[s] = 0;
+	}
+	h->have_result = false;  // the parts' buffers were recycled: the bytes are in dst
+	h->have_genome = true;   // the whole genome is packed: qtipsim_run works from here on
+	if (stats) *stats = tot;
+	return QTIPSIM_OK;
+}
+
 
 }  // extern "C"

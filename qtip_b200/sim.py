@@ -121,6 +121,26 @@ class Engine:
             a = np.ascontiguousarray(data, dtype=np.uint8)
             self.check(self.lib.qtipsim_load_fasta_bytes(self.h, C.c_void_p(a.ctypes.data), a.size))
 
+    def stream_begin(self, data) -> None:
+        """Streaming end-to-end path, step 1: starts the chunked upload of the FASTA text (a numpy uint8 array, pinned
+        for asynchronous copies; it must stay alive until stream_run returns) and returns at once."""
+        a = np.ascontiguousarray(data, dtype=np.uint8)
+        self._stream_text = a
+        self.check(self.lib.qtipsim_stream_begin(self.h, C.c_void_p(a.ctypes.data), a.size))
+
+    def stream_run(self, params: _abi.RunParams, dst_ptrs: Sequence[int], caps: Sequence[int]) -> _abi.Stats:
+        """Step 2 (templates set): packs and simulates record by record while later text is still uploading and earlier
+        reads are downloading; appends every stream's FASTQ bytes to the host buffer at dst_ptrs[i] (caps[i] bytes).
+        Returns the stats (bytes[i] = bytes written to buffer i).  Same bytes as load_fasta_bytes + run + result."""
+        st = _abi.Stats()
+        d = (C.c_void_p * _abi.NOUT)(*[C.c_void_p(int(x) if x else None) for x in dst_ptrs])
+        c = (C.c_uint64 * _abi.NOUT)(*[int(x) for x in caps])
+        try:
+            self.check(self.lib.qtipsim_stream_run(self.h, C.byref(params), C.byref(st), d, c))
+        finally:
+            self._stream_text = None
+        return st
+
     def load_fasta_bytes_async(self, data):
         """Starts load_fasta_bytes on a worker thread (ctypes releases the GIL during the call) so that the host
         can compile the templates while the FASTA text crosses PCIe and is packed; join with wait_genome()."""

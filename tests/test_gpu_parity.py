@@ -337,3 +337,28 @@ def test_host_planner_path_still_bit_exact(name, workdir, monkeypatch):
     assert dev == host
     assert (p_d.cg1, p_d.cg2) == (p_h.cg1, p_h.cg2)
     assert st_d.draws == st_h.draws
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk,min_part", [(4096, 1), (65536, 100000), (0, 0)])
+@pytest.mark.parametrize("name", ["mixed_small", "edges", "c3_shape_small", "c4_mix_small"])
+def test_streaming_path_equals_one_shot_path(name, chunk, min_part, workdir, monkeypatch):
+    """qtipsim_stream_begin / qtipsim_stream_run (upload, pack, simulate and download overlapped, record by record) give
+    the bytes of load + run: replay mode against the oracle / golden, native mode against the one-shot path; with
+    upload chunks small enough that records span chunks and every case runs in several parts."""
+    if chunk:
+        monkeypatch.setenv("QTIPSIM_STREAM_CHUNK", str(chunk))
+        monkeypatch.setenv("QTIPSIM_STREAM_MIN_PART", str(min_part))
+    case = cases.CASES[name]()
+    want, st0, p0 = util.run_cuda(case, workdir, name, via="bytes")
+    got, st, p, again = util.run_cuda_streaming(case)
+    for i in range(7):
+        assert got[i] == want[i], (name, i)
+        assert again[i] == want[i], (name, i)
+    assert (p.cg1, p.cg2) == (p0.cg1, p0.cg2)
+    assert list(st.wrote) == list(st0.wrote) and list(st.bytes) == list(st0.bytes)
+    wantn, _, _ = util.run_cuda(case, workdir, name, rng_mode=1, philox_seed=77, via="bytes")
+    gotn, _, _, againn = util.run_cuda_streaming(case, rng_mode=1, philox_seed=77)
+    for i in range(7):
+        assert gotn[i] == wantn[i], (name, i)
+        assert againn[i] == wantn[i], (name, i)

@@ -166,3 +166,34 @@ def run_cuda(case, workdir, name, rng_mode=0, philox_seed=0, shard=(0, 1), via="
         return streams, st, p
     finally:
         eng.close()
+
+
+def run_cuda_streaming(case, rng_mode=0, philox_seed=0, cg=None):
+    """The case through the streaming end-to-end path (qtipsim_stream_begin / qtipsim_stream_run); returns
+    (streams, stats, params) like run_cuda."""
+    import numpy as np
+    from qtip_b200 import sim
+    eng = sim.Engine()
+    try:
+        fa = np.ascontiguousarray(np.frombuffer(bytes(case["fasta"]), dtype=np.uint8))
+        eng.stream_begin(fa)
+        added = case.get("added") or (len(case["tu"]), len(case["tb"]), len(case["tc"]), len(case["td"]))
+        eng.set_unpaired(0, case["tu"], added[0])
+        eng.set_unpaired(1, case["tb"], added[1])
+        eng.set_paired(2, case["tc"], added[2])
+        eng.set_paired(3, case["td"], added[3])
+        kw = case["kw"]
+        p = sim.make_params(case.get("chunksz", 128 * 1024), kw["fraction"], kw["function"], kw["min_u"], kw["min_c"],
+                            kw["min_d"], kw["min_b"], rng_mode, cg=cg or kw["cg"], philox_seed=philox_seed)
+        cap = 64 << 20
+        bufs = [np.zeros(cap, dtype=np.uint8) for _ in range(7)]
+        st = eng.stream_run(p, [b.ctypes.data for b in bufs], [cap] * 7)
+        streams = [bufs[i][:int(st.bytes[i])].tobytes() for i in range(7)]
+        # the genome is resident afterwards: a plain run on the same engine gives the same bytes again
+        p2 = sim.make_params(case.get("chunksz", 128 * 1024), kw["fraction"], kw["function"], kw["min_u"], kw["min_c"],
+                             kw["min_d"], kw["min_b"], rng_mode, cg=cg or kw["cg"], philox_seed=philox_seed)
+        st2 = eng.run(p2)
+        again = eng.results(st2)
+        return streams, st, p, again
+    finally:
+        eng.close()
