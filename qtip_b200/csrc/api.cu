@@ -256,6 +256,9 @@ static int upload_genome(qtipsim *h) {
 // streaming loader (qtipsim_stream_run): reset, header resolution, packing of a range of complete records. ----
 
 static void genome_reset(qtipsim *h, uint64_t n) {
+	// an upload started by qtipsim_stream_begin and never consumed must be over before its buffers are reused
+	if (h->feeder.joinable()) h->feeder.join();
+	h->stream_open = false;
 	HostGenome &g = h->hg;
 	g.recs.clear();
 	g.names.clear();
@@ -486,6 +489,8 @@ static bool use_host_pack() {
 int qtipsim_load_fasta_bytes(qtipsim_t *h, const void *bytes, size_t nbytes) {
 	if (!h || (!bytes && nbytes)) return QTIPSIM_EINVAL;
 	if (!use_host_pack()) return device_pack(h, (const uint8_t *)bytes, nbytes);
+	if (h->feeder.joinable()) h->feeder.join();
+	h->stream_open = false;
 	h->hg.parse((const uint8_t *)bytes, nbytes);
 	return upload_genome(h);
 }
