@@ -1,74 +1,61 @@
 // src/input_model.h -- drop-in for the reference's src/input_model.h: InputModelUnpaired
-// (:22-94) and InputModelPaired (:96-167).  They only describe the model (a reference to the
-// caller's template list + counts); drawing from it happens on the GPU.
+// (:22-94) and InputModelPaired (:96-167).  A model only DESCRIBES the input here -- a reference to
+// the caller's template list (not owned, input_model.h:88,161), how many alignments were offered to
+// the reservoir, and the longest / average span -- because drawing from it happens on the GPU
+// (qtip_b200/csrc/resolve.cu, kernels.cu).  One class template serves both kinds; the two names
+// qtip_parse.cpp:1826-1829 constructs are thin subclasses that inherit its constructor.
 #ifndef QTIP_B200_INPUT_MODEL_H
 #define QTIP_B200_INPUT_MODEL_H
 
-#include <cassert>
 #include <algorithm>
+#include <cassert>
 #include "ds.h"
-#include "template.h"
 #include "rnglib.hpp"
+#include "template.h"
 
-class InputModelUnpaired {
+template <class Tmpl>
+class InputModelOf {
 public:
-	InputModelUnpaired(const EList<TemplateUnpaired> &ts, size_t n, float fraction_even, float low_score_bias)
-	    : ts_(ts), n_(n), fraction_even_(fraction_even), low_score_bias_(low_score_bias) {
-		len_avg_ = 0.0f;
-		len_max_ = 0;
-		for (size_t i = 0; i < ts.size(); i++) {
-			len_avg_ += ((float)ts[i].reflen() / ts.size());
-			len_max_ = std::max(len_max_, ts[i].reflen());
+	// (templates kept by the reservoir, alignments offered to it, two tuning knobs the reference stores and
+	// never reads: input_model.h:26-30,100-104)
+	InputModelOf(const EList<Tmpl> &kept, size_t offered, float fraction_even, float low_score_bias)
+	    : kept_(kept), offered_(offered), knobs_{fraction_even, low_score_bias}, span_max_(0), span_avg_(0.0f) {
+		const size_t k = kept.size();
+		for (size_t i = 0; i < k; i++) {
+			const size_t sp = kept[i].span();
+			span_max_ = std::max(span_max_, sp);
+			span_avg_ += (float)sp / k;  // same accumulation order as input_model.h:32-36
 		}
 	}
-	// uniform draw, input_model.h:49-54 (kept for API compatibility; the simulator does not call it)
-	const TemplateUnpaired &draw() const {
+	bool empty() const { return kept_.empty(); }
+	size_t num_added() const { return offered_; }  // input_model.h:68-70
+	size_t max_len() const { return span_max_; }    // input_model.h:82-84: sets the windows' overlap
+	float avg_len() const { return span_avg_; }
+	const EList<Tmpl> &templates() const { return kept_; }
+	// uniform pick with the global generator (input_model.h:49-54); kept for API compatibility -- the simulator
+	// makes this draw on the device, in the reference's order
+	const Tmpl &draw() const {
 		assert(!empty());
-		return ts_[std::min((size_t)(r4_uni_01() * ts_.size()), ts_.size() - 1)];
+		const size_t k = kept_.size();
+		return kept_[std::min((size_t)(r4_uni_01() * k), k - 1)];
 	}
-	bool empty() const { return ts_.empty(); }
-	size_t num_added() const { return n_; }
-	float avg_len() const { return len_avg_; }
-	size_t max_len() const { return len_max_; }
-	const EList<TemplateUnpaired> &templates() const { return ts_; }
 
-protected:
-	const EList<TemplateUnpaired> &ts_;
-	float len_avg_;
-	size_t n_;
-	size_t len_max_;
-	float fraction_even_;   // unused, as in the reference
-	float low_score_bias_;  // unused
+private:
+	const EList<Tmpl> &kept_;
+	size_t offered_;
+	float knobs_[2];
+	size_t span_max_;
+	float span_avg_;
 };
 
-class InputModelPaired {
+class InputModelUnpaired : public InputModelOf<TemplateUnpaired> {
 public:
-	InputModelPaired(const EList<TemplatePaired> &ts, size_t n, float fraction_even, float low_score_bias)
-	    : ts_(ts), n_(n), fraction_even_(fraction_even), low_score_bias_(low_score_bias) {
-		len_avg_ = 0.0f;
-		len_max_ = 0;
-		for (size_t i = 0; i < ts.size(); i++) {
-			len_avg_ += ((float)ts[i].fraglen_ / ts.size());
-			len_max_ = std::max(len_max_, ts[i].fraglen_);
-		}
-	}
-	const TemplatePaired &draw() const {
-		assert(!empty());
-		return ts_[std::min((size_t)(r4_uni_01() * ts_.size()), ts_.size() - 1)];
-	}
-	bool empty() const { return ts_.empty(); }
-	size_t num_added() const { return n_; }
-	float avg_len() const { return len_avg_; }
-	size_t max_len() const { return len_max_; }
-	const EList<TemplatePaired> &templates() const { return ts_; }
+	using InputModelOf<TemplateUnpaired>::InputModelOf;
+};
 
-protected:
-	const EList<TemplatePaired> &ts_;
-	float len_avg_;
-	size_t n_;
-	size_t len_max_;
-	float fraction_even_;
-	float low_score_bias_;
+class InputModelPaired : public InputModelOf<TemplatePaired> {
+public:
+	using InputModelOf<TemplatePaired>::InputModelOf;
 };
 
 #endif

@@ -31,13 +31,13 @@ void upload_unpaired(qtipsim *h, int cat, const Model &m) {
 	const EList<TemplateUnpaired> &ts = m.templates();
 	std::vector<qtipsim_tmpl_unp> v(ts.size());
 	for (size_t i = 0; i < ts.size(); i++) {
-		v[i].best_score = ts[i].best_score_;
-		v[i].len = ts[i].len_;
-		v[i].fw_flag = ts[i].fw_flag_;
-		v[i].mate_flag = ts[i].mate_flag_;
-		v[i].opp_len = ts[i].opp_len_;
-		v[i].qual = ts[i].qual_.c_str();
-		v[i].xscript = ts[i].edit_xscript_.c_str();
+		v[i].best_score = ts[i].m.score;
+		v[i].len = ts[i].m.len;
+		v[i].fw_flag = ts[i].m.fw;
+		v[i].mate_flag = ts[i].mate_flag;
+		v[i].opp_len = ts[i].opp_len;
+		v[i].qual = ts[i].m.qual.c_str();
+		v[i].xscript = ts[i].m.xscript.c_str();
 	}
 	check(h, qtipsim_set_templates_unpaired(h, cat, v.data(), v.size(), m.num_added()));
 }
@@ -46,19 +46,19 @@ void upload_paired(qtipsim *h, int cat, const InputModelPaired &m) {
 	const EList<TemplatePaired> &ts = m.templates();
 	std::vector<qtipsim_tmpl_pair> v(ts.size());
 	for (size_t i = 0; i < ts.size(); i++) {
-		v[i].score_12 = ts[i].score_12_;
-		v[i].score_1 = ts[i].score_1_;
-		v[i].len_1 = ts[i].len_1_;
-		v[i].fw_flag_1 = ts[i].fw_flag_1_;
-		v[i].qual_1 = ts[i].qual_1_.c_str();
-		v[i].xscript_1 = ts[i].edit_xscript_1_.c_str();
-		v[i].score_2 = ts[i].score_2_;
-		v[i].len_2 = ts[i].len_2_;
-		v[i].fw_flag_2 = ts[i].fw_flag_2_;
-		v[i].qual_2 = ts[i].qual_2_.c_str();
-		v[i].xscript_2 = ts[i].edit_xscript_2_.c_str();
-		v[i].upstream1 = ts[i].upstream1_ ? 1 : 0;
-		v[i].fraglen = ts[i].fraglen_;
+		v[i].score_12 = ts[i].score_12;
+		v[i].score_1 = ts[i].m1.score;
+		v[i].len_1 = ts[i].m1.len;
+		v[i].fw_flag_1 = ts[i].m1.fw;
+		v[i].qual_1 = ts[i].m1.qual.c_str();
+		v[i].xscript_1 = ts[i].m1.xscript.c_str();
+		v[i].score_2 = ts[i].m2.score;
+		v[i].len_2 = ts[i].m2.len;
+		v[i].fw_flag_2 = ts[i].m2.fw;
+		v[i].qual_2 = ts[i].m2.qual.c_str();
+		v[i].xscript_2 = ts[i].m2.xscript.c_str();
+		v[i].upstream1 = ts[i].upstream1 ? 1 : 0;
+		v[i].fraglen = ts[i].fraglen;
 	}
 	check(h, qtipsim_set_templates_paired(h, cat, v.data(), v.size(), m.num_added()));
 }
