@@ -316,7 +316,7 @@ def main():
         if e2e and world == 1 and stream_ready[0] and os.environ.get("QTIP_BENCH_STREAM") == "1":
             # opt-in (QTIP_BENCH_STREAM=1): the streaming path -- chunked upload, record-by-record pack + simulate,
             # download of earlier records' reads while later text is still uploading.  Bit-exact with the one-shot
-            # path but not faster yet on this box (DESIGN.md section 6), so the default e2e arm stays one-shot.
+            # path but not faster yet on this box (DESIGN.md section 8), so the default e2e arm stays one-shot.
             eng.stream_begin(fa_pinned.numpy())
             set_templates()                                    # the host compiles the templates while the text uploads
             p = sim.make_params(CHUNKSZ, kw["fraction"], kw["function"], kw["min_u"], kw["min_c"], kw["min_d"], kw["min_b"],

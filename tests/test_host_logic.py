@@ -248,3 +248,57 @@ def test_swar_pack_unit_arithmetic_matches_bytewise_pack():
             else:
                 wn[p >> 5] |= np.uint32(1 << (p & 31))
         assert np.array_equal(bases, wb) and np.array_equal(nmask, wn), it
+
+
+@pytest.mark.parametrize("name", ["edges", "mixed_small"])
+def test_swar_pack_whole_fasta_matches_host_packer(name):
+    """K0's unit arithmetic over whole FASTA files (4 KiB units cut anywhere in a line, CRLF, IUPAC, blank lines,
+    headerless leading bases): every record's sequence lines packed unit by unit with the kernel's arithmetic on
+    the host equal the host packer's record (which is pinned against the oracle above)."""
+    case = cases.CASES[name]()
+    hs = util.HostSide(case)
+    L = hs.L
+    L.qthost_swar_pack_unit.restype = C.c_uint64
+    L.qthost_swar_pack_unit.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]
+    text = bytes(np.ascontiguousarray(case["fasta"]).tobytes())
+    n = len(text)
+    # header lines as the loader resolves them: '>' outside a header line starts one, it ends at '\n' or '\r'
+    segs, i, hdr_end = [], 0, 0
+    first = text.find(b">")
+    lead_end = n if first < 0 else first
+    if any(_byte_class(c) != 5 for c in text[:lead_end]):
+        segs.append([0, lead_end])
+    pos = first
+    while pos >= 0:
+        if pos >= hdr_end:
+            if segs:
+                segs[-1][1] = min(segs[-1][1], pos)
+            j = pos
+            while j < n and text[j] not in b"\n\r":
+                j += 1
+            hdr_end = j
+            segs.append([j, n])
+        pos = text.find(b">", pos + 1)
+    recs = hs.records()
+    assert len(segs) == len(recs)
+    buf = np.full(n + 64 + 16, 0x20, dtype=np.uint8)
+    off = (-buf.ctypes.data) % 16
+    buf[off:off + n] = np.frombuffer(text, dtype=np.uint8)
+    base_ptr = buf.ctypes.data + off
+    total = max(gs + ln for _, ln, gs in recs) + 128
+    bases = np.zeros(total // 16 + 8, dtype=np.uint32)
+    nmask = np.zeros(total // 32 + 8, dtype=np.uint32)
+    for (s0, s1), (nm, ln, gs) in zip(segs, recs):
+        g = gs
+        for t0 in range(s0, s1, 4096):
+            got = L.qthost_swar_pack_unit(base_ptr, t0, min(t0 + 4096, s1), g, bases.ctypes.data, nmask.ctypes.data)
+            assert got != 2 ** 64 - 1
+            g += got
+        assert g - gs == ln, nm
+        p = np.arange(gs, gs + ln, dtype=np.int64)
+        codes = (bases[p >> 4] >> (2 * (p & 15)).astype(np.uint32)) & 3
+        isn = (nmask[p >> 5] >> (p & 31).astype(np.uint32)) & 1
+        seq = np.where(isn == 1, ord("N"), np.frombuffer(b"ACGT", dtype=np.uint8)[codes]).astype(np.uint8).tobytes()
+        assert seq == hs.unpack(gs, ln), nm
+        assert not np.any((codes != 0) & (isn == 1)), nm  # N positions carry code 0, as the kernels expect
+    hs.close()
