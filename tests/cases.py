@@ -166,6 +166,37 @@ CASES = {
 }
 
 
+def random_case(seed: int) -> dict:
+    """A small configuration drawn from the seed: record layout (incl. a record below the overlap), line width,
+    lower-case fraction, window size (down to longest template + 1), target function with `added` counts, read
+    length, indel / soft-clipped transcripts and the category mix."""
+    import random
+    rnd = random.Random(seed)
+    L = rnd.choice([30, 75, 100, 151])
+    recs = [(f"r{k}", rnd.randint(200, 60000)) for k in range(rnd.randint(1, 5))]
+    recs.insert(rnd.randint(0, len(recs)), ("short", rnd.randint(1, L)))
+    fa = synth.make_fasta(recs, seed=seed, lead_n=rnd.choice([0, 0, 50, 700]), width=rnd.choice([50, 60, 70, 80]),
+                          lowercase_frac=rnd.choice([0.0, 0.2]))
+    indel = rnd.random() < 0.5
+    tu = synth.templates_unpaired(rnd.randint(0, 40), L, seed, max_x=4, indel=indel, len_jitter=rnd.choice([0, 10]))
+    tb = synth.templates_badend(rnd.randint(0, 20), L, seed + 1, opp_len=rnd.choice([20, L])) if rnd.random() < 0.7 else []
+    tc = synth.templates_paired(rnd.randint(0, 30), L, seed + 2, frag_mean=3 * L, frag_sd=L / 4, indel=indel) if rnd.random() < 0.7 else []
+    td = synth.templates_paired(rnd.randint(0, 20), L, seed + 3, discordant=True, max_fraglen=2000) if rnd.random() < 0.7 else []
+    if not (tu or tb or tc or td):
+        tu = synth.templates_unpaired(5, L, seed, max_x=2)
+    longest = max([t.reflen() for t in tu + tb] + [t.fraglen for t in tc + td])
+    chunksz = rnd.choice([longest + 1, longest + 17, 2 * longest + 3, 4096 + longest, 128 * 1024])
+    function = rnd.choice([1, 2, 3])
+    fraction = {1: rnd.choice([0.5, 2.0, 7.5]), 2: rnd.choice([3.0, 45.0]), 3: rnd.choice([1.0, 200.0, 1500.0])}[function]
+    added = (len(tu) * rnd.randint(1, 30), len(tb) * rnd.randint(1, 30), len(tc) * rnd.randint(1, 30), len(td) * rnd.randint(1, 30))
+    return dict(fasta=fa, tu=tu, tb=tb, tc=tc, td=td, chunksz=chunksz, added=added,
+                kw=dict(fraction=fraction, function=function, min_u=rnd.choice([0, 1, 300]), min_c=rnd.choice([0, 1, 300]),
+                        min_d=rnd.choice([0, 1, 100]), min_b=rnd.choice([0, 1, 100]), cg=cli_seed(seed)))
+
+
+RANDOM_SEEDS = list(range(100, 148))
+
+
 def sim_kwargs(case: dict) -> dict:
     kw = dict(case["kw"])
     kw["chunksz"] = case.get("chunksz", 128 * 1024)

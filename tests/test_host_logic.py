@@ -111,6 +111,30 @@ def test_replay_plan_matches_oracle_trace(name, workdir):
     hs.close()
 
 
+@pytest.mark.parametrize("seed", cases.RANDOM_SEEDS)
+def test_replay_plan_matches_oracle_trace_random_configs(seed, workdir):
+    """The product's host logic (FASTA parse, window table, template flattening, replay chain walk) on the randomised
+    configurations the oracle is pinned on against the unmodified reference (test_oracle_pin.py)."""
+    case = cases.random_case(seed)
+    kw = cases.sim_kwargs(case)
+    name = f"rand{seed}"
+    r = po.oracle_simulate(util.write_fasta(case, workdir, name), tu=case["tu"], tb=case["tb"], tc=case["tc"],
+                           td=case["td"], want_trace=True, **kw)
+    assert r.rc == 0
+    hs = util.HostSide(case)
+    rc, cg, draws, nreads = hs.plan(kw)
+    assert rc == 0
+    assert cg == tuple(r.cg)
+    assert draws == r.draws
+    assert nreads == r.wrote
+    wins = hs.windows(kw["chunksz"], int(hs.L.qthost_olap(hs.h)))
+    for cat in range(4):
+        want = [(t[1], wins[t[2]][0], wins[t[2]][1] + t[3]) for t in r.trace if t[0] == cat]
+        got = [(p[0], p[1], p[2]) for p in hs.plan_recs(cat, nreads[cat])]
+        assert got == want, (seed, cat)
+    hs.close()
+
+
 def test_sharded_plans_concatenate(workdir):
     """Shards walk the same chain and emit disjoint, ordered slices of the plan."""
     case = cases.CASES["c3_shape_small"]()

@@ -182,38 +182,17 @@ def test_apply_function():
 
 
 @pytest.mark.skipif(not po.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("seed", list(range(100, 112)))
+@pytest.mark.parametrize("seed", cases.RANDOM_SEEDS)
 def test_oracle_matches_reference_random_configs(seed, workdir):
-    """Randomised pin: record layout, window size, target function (sqrt / linear / const with `added` counts), read
-    lengths, indel / soft-clipped transcripts and the category mix all drawn from the seed; the oracle must produce the
-    unmodified reference's seven streams and exit state byte for byte."""
-    import random
-    rnd = random.Random(seed)
-    L = rnd.choice([30, 75, 100, 151])
-    recs = [(f"r{k}", rnd.randint(200, 60000)) for k in range(rnd.randint(1, 5))]
-    recs.insert(rnd.randint(0, len(recs)), ("short", rnd.randint(1, L)))  # a record below the overlap
-    fa = synth.make_fasta(recs, seed=seed, lead_n=rnd.choice([0, 0, 50, 700]), width=rnd.choice([50, 60, 70, 80]),
-                          lowercase_frac=rnd.choice([0.0, 0.2]))
+    """Randomised pin (cases.random_case): record layout, window size, target function (sqrt / linear / const with
+    `added` counts), read lengths, indel / soft-clipped transcripts and the category mix all drawn from the seed; the
+    oracle must produce the unmodified reference's seven streams and exit state byte for byte."""
+    case = cases.random_case(seed)
     p = os.path.join(workdir, f"rand{seed}.fa")
-    fa.tofile(p)
-    indel = rnd.random() < 0.5
-    tu = synth.templates_unpaired(rnd.randint(0, 40), L, seed, max_x=4, indel=indel, len_jitter=rnd.choice([0, 10]))
-    tb = synth.templates_badend(rnd.randint(0, 20), L, seed + 1, opp_len=rnd.choice([20, L])) if rnd.random() < 0.7 else []
-    tc = synth.templates_paired(rnd.randint(0, 30), L, seed + 2, frag_mean=3 * L, frag_sd=L / 4, indel=indel) if rnd.random() < 0.7 else []
-    td = synth.templates_paired(rnd.randint(0, 20), L, seed + 3, discordant=True, max_fraglen=2000) if rnd.random() < 0.7 else []
-    if not (tu or tb or tc or td):
-        tu = synth.templates_unpaired(5, L, seed, max_x=2)
-    longest = max([t.reflen() for t in tu + tb] + [t.fraglen for t in tc + td])
-    chunksz = rnd.choice([longest + 1, longest + 17, 2 * longest + 3, 4096 + longest, 128 * 1024])
-    function = rnd.choice([1, 2, 3])
-    fraction = {1: rnd.choice([0.5, 2.0, 7.5]), 2: rnd.choice([3.0, 45.0]), 3: rnd.choice([1.0, 200.0, 1500.0])}[function]
-    added = (len(tu) * rnd.randint(1, 30), len(tb) * rnd.randint(1, 30), len(tc) * rnd.randint(1, 30), len(td) * rnd.randint(1, 30))
-    kw = dict(tu=tu, tb=tb, tc=tc, td=td, added=added, chunksz=chunksz, fraction=fraction, function=function,
-              min_u=rnd.choice([0, 1, 300]), min_c=rnd.choice([0, 1, 300]), min_d=rnd.choice([0, 1, 100]),
-              min_b=rnd.choice([0, 1, 100]), cg=cases.cli_seed(seed))
+    case["fasta"].tofile(p)
+    kw = dict(tu=case["tu"], tb=case["tb"], tc=case["tc"], td=case["td"], **cases.sim_kwargs(case))
     a = po.ref_simulate(p, **kw)
     b = po.oracle_simulate(p, **kw)
-    assert a.rc == b.rc
-    if a.rc == 0:
-        assert a.streams == b.streams
-        assert a.cg == b.cg
+    assert a.rc == 0 and b.rc == 0
+    assert a.streams == b.streams
+    assert a.cg == b.cg
