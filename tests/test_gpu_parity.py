@@ -362,3 +362,24 @@ def test_streaming_path_equals_one_shot_path(name, chunk, min_part, workdir, mon
     for i in range(7):
         assert gotn[i] == wantn[i], (name, i)
         assert againn[i] == wantn[i], (name, i)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("QTIP_TEST_RANDOM_GPU") != "1",
+                    reason="opt-in until it has run once on a B200 (written after round 1's GPU budget was spent): "
+                           "QTIP_TEST_RANDOM_GPU=1")
+@pytest.mark.parametrize("seed", cases.RANDOM_SEEDS)
+def test_replay_bit_exact_random_configs(seed, workdir):
+    """The randomised configurations the oracle is pinned on (test_oracle_pin.py) through the CUDA path, replay mode:
+    all seven streams and the generator state equal the oracle's."""
+    from oracle import pyoracle as po
+    case = cases.random_case(seed)
+    name = f"rand{seed}"
+    o = po.oracle_simulate(util.write_fasta(case, workdir, name), tu=case["tu"], tb=case["tb"], tc=case["tc"],
+                           td=case["td"], **cases.sim_kwargs(case))
+    assert o.rc == 0
+    got, st, p = util.run_cuda(case, workdir, name, via="bytes")
+    for i in range(7):
+        assert got[i] == o.streams[i], (seed, i)
+    assert (p.cg1, p.cg2) == tuple(o.cg)
+    assert list(st.wrote) == list(o.wrote)
