@@ -274,12 +274,12 @@ def test_swar_pack_unit_arithmetic_matches_bytewise_pack():
         assert np.array_equal(bases, wb) and np.array_equal(nmask, wn), it
 
 
-@pytest.mark.parametrize("name", ["edges", "mixed_small"])
+@pytest.mark.parametrize("name", ["edges", "mixed_small"] + [f"rand{s}" for s in cases.RANDOM_SEEDS[:10]])
 def test_swar_pack_whole_fasta_matches_host_packer(name):
     """K0's unit arithmetic over whole FASTA files (4 KiB units cut anywhere in a line, CRLF, IUPAC, blank lines,
     headerless leading bases): every record's sequence lines packed unit by unit with the kernel's arithmetic on
     the host equal the host packer's record (which is pinned against the oracle above)."""
-    case = cases.CASES[name]()
+    case = cases.random_case(int(name[4:])) if name.startswith("rand") else cases.CASES[name]()
     hs = util.HostSide(case)
     L = hs.L
     L.qthost_swar_pack_unit.restype = C.c_uint64
