@@ -166,6 +166,56 @@ CASES = {
 }
 
 
+# ---- BASELINE.json configurations at their stated sizes (tests/golden/make_golden_full.py runs the unmodified
+# reference on them; tests/test_gpu_fullsize.py compares the CUDA path's streams with those digests) ----
+
+def full_c2():
+    """BASELINE config 2 at full size: 4.6 Mbp single record, 30 k concordant 2x150 templates (fraglen N(400,40),
+    0-4 X), const 1 M pairs."""
+    fa = synth.make_fasta([("ecoli_like", 4_600_000)], seed=2021)
+    tc = synth.templates_paired(30000, 150, 2022, frag_mean=400, frag_sd=40, max_x=4)
+    return dict(fasta=fa, tu=[], tb=[], tc=tc, td=[],
+                kw=dict(fraction=1_000_000.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(20202)))
+
+
+def full_c5():
+    """BASELINE config 5 at full size: 4.6 Mbp genome, 10 k unpaired 1 kbp indel-heavy templates, const 200 k."""
+    fa = synth.make_fasta([("ecoli_like", 4_600_000)], seed=5051)
+    tu = synth.templates_unpaired(10000, 1000, 5052, indel=True)
+    return dict(fasta=fa, tu=tu, tb=[], tc=[], td=[],
+                kw=dict(fraction=200_000.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(50505)))
+
+
+def _from_bench(which, n_gpus, scale, seed):
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench
+    wl = bench.workload(n_gpus, scale, which)
+    fa = synth.make_fasta(wl["records"], seed=wl["genome_seed"], lead_n=wl["lead_n"])
+    case = dict(fasta=fa, tu=wl["tu"], tb=wl["tb"], tc=wl["tc"], td=wl["td"], kw=dict(wl["kw"], cg=cli_seed(seed)))
+    if wl.get("added"):
+        case["added"] = wl["added"]
+    return case
+
+
+def full_c3():
+    """BASELINE config 3 at full size = the benchmark's N=1 workload: 3.1 Gbp in 24 records, 30 k unpaired 250 bp
+    templates (0-5 X), const 10 M."""
+    return _from_bench("c3", 1, 1.0, 30303)
+
+
+def full_c4_tenth():
+    """BASELINE config 4 at 1/10: 0.31 Gbp, 10 M pairs, 70/15/15 concordant / discordant / bad-end 2x150 -- the
+    benchmark's N=8 workload with genome and targets scaled by 0.1."""
+    return _from_bench("c4", 8, 0.1, 40404)
+
+
+FULL_CASES = {"c2_full": full_c2, "c5_full": full_c5, "c3_full": full_c3, "c4_tenth": full_c4_tenth}
+
+
 def random_case(seed: int) -> dict:
     """A small configuration drawn from the seed: record layout (incl. a record below the overlap), line width,
     lower-case fraction, window size (down to longest template + 1), target function with `added` counts, read

@@ -365,9 +365,6 @@ def test_streaming_path_equals_one_shot_path(name, chunk, min_part, workdir, mon
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("QTIP_TEST_RANDOM_GPU") != "1",
-                    reason="opt-in until it has run once on a B200 (written after round 1's GPU budget was spent): "
-                           "QTIP_TEST_RANDOM_GPU=1")
 @pytest.mark.parametrize("seed", cases.RANDOM_SEEDS)
 def test_replay_bit_exact_random_configs(seed, workdir):
     """The randomised configurations the oracle is pinned on (test_oracle_pin.py) through the CUDA path, replay mode:
