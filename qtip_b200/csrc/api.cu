@@ -84,8 +84,11 @@ struct qtipsim {
 	DevBuf d_t[NCAT], d_qual[NCAT], d_xs[NCAT], d_qual_out[NCAT], d_ops[NCAT], d_segs[NCAT], d_xsteps[NCAT], d_prog[NCAT];
 	DevBuf d_setups, d_pclass, d_rsresult;
 
-	DevBuf d_jt1, d_jt2;
+	DevBuf d_jt1, d_jt2, d_jh1, d_jh2;
 	bool have_jt = false;
+	// band-speculative replay resolver (resolve2.cu)
+	DevBuf d_r2_aw, d_r2_cum, d_r2_anchor, d_r2_counter, d_r2_slot, d_r2_end, d_r2_cn, d_r2_wres, d_r2_cnt, d_r2_off, d_r2_misc;
+	uint32_t r2_stages_last = 0;  // stage launches of the last replay run (diagnostics)
 
 	DevBuf d_win, d_ncount, d_cum;
 	// window table + per-window N counts: functions of (genome, chunksz, olap) only, kept across runs
@@ -95,6 +98,8 @@ struct qtipsim {
 	bool win_cache_ok = false;
 	// binomial set-ups per window class: functions of the above plus the targets and the shard's window range
 	std::vector<BinomSetup> setup_cache;
+	std::vector<BinomTables> tab_cache;  // BTPE acceptance bounds per set-up (lecuyer.h), for the band resolver
+	DevBuf d_tabs;
 	std::vector<uint32_t> pclass_cache;
 	uint64_t setup_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	bool setup_cache_ok = false;
@@ -187,7 +192,8 @@ void qtipsim_destroy(qtipsim_t *h) {
 	if (!h) return;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->st);
-	DevBuf *all[] = {&h->d_setups, &h->d_pclass, &h->d_rsresult, &h->d_text, &h->d_pk_a, &h->d_pk_b, &h->d_pk_c, &h->d_pk_d, &h->d_pk_e, &h->d_bases, &h->d_nmask, &h->d_nblk, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
+	DevBuf *all[] = {&h->d_tabs, &h->d_jh1, &h->d_jh2, &h->d_r2_aw, &h->d_r2_cum, &h->d_r2_anchor, &h->d_r2_counter, &h->d_r2_slot, &h->d_r2_end, &h->d_r2_cn,
+	                 &h->d_r2_wres, &h->d_r2_cnt, &h->d_r2_off, &h->d_r2_misc, &h->d_setups, &h->d_pclass, &h->d_rsresult, &h->d_text, &h->d_pk_a, &h->d_pk_b, &h->d_pk_c, &h->d_pk_d, &h->d_pk_e, &h->d_bases, &h->d_nmask, &h->d_nblk, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
 	                 &h->d_ncount, &h->d_cum, &h->d_len0, &h->d_len1, &h->d_scan_tmp, &h->d_small};
 	for (DevBuf *b : all) b->release();
 	for (int c = 0; c < NCAT; c++) {
@@ -635,7 +641,19 @@ static int upload_templates(qtipsim *h) {
 		CK(h->d_jt2.ensure(JUMP_TBL * 4));
 		CK(cudaMemcpyAsync(h->d_jt1.p, j1.data(), JUMP_TBL * 4, cudaMemcpyHostToDevice, h->st));
 		CK(cudaMemcpyAsync(h->d_jt2.p, j2.data(), JUMP_TBL * 4, cudaMemcpyHostToDevice, h->st));
-		CK(cudaStreamSynchronize(h->st));  // j1/j2 are stack-lifetime
+		// a^(4096 k): the high digit of a two-level jump (resolve2.cu)
+		std::vector<uint32_t> g1(JUMP_TBL), g2(JUMP_TBL);
+		const uint32_t b1 = mulmod1(j1[JUMP_TBL - 1], LA1), b2 = mulmod2(j2[JUMP_TBL - 1], LA2);
+		g1[0] = g2[0] = 1;
+		for (int i = 1; i < JUMP_TBL; i++) {
+			g1[i] = mulmod1(g1[i - 1], b1);
+			g2[i] = mulmod2(g2[i - 1], b2);
+		}
+		CK(h->d_jh1.ensure(JUMP_TBL * 4));
+		CK(h->d_jh2.ensure(JUMP_TBL * 4));
+		CK(cudaMemcpyAsync(h->d_jh1.p, g1.data(), JUMP_TBL * 4, cudaMemcpyHostToDevice, h->st));
+		CK(cudaMemcpyAsync(h->d_jh2.p, g2.data(), JUMP_TBL * 4, cudaMemcpyHostToDevice, h->st));
+		CK(cudaStreamSynchronize(h->st));  // the vectors are stack-lifetime
 		h->have_jt = true;
 	}
 	return QTIPSIM_OK;
@@ -678,12 +696,202 @@ static int ensure_setups(qtipsim *h, const std::vector<Window> &win, uint64_t ol
 	window_setups(win, olap, pp, lo, hi, h->pclass_cache, h->setup_cache);
 	const size_t nwin = win.size();
 	CK(h->d_setups.ensure(h->setup_cache.size() * sizeof(BinomSetup)));
+	h->tab_cache.resize(h->setup_cache.size());
+	for (size_t i = 0; i < h->setup_cache.size(); i++) binom_tables(h->setup_cache[i], h->tab_cache[i]);
+	CK(h->d_tabs.ensure(h->tab_cache.size() * sizeof(BinomTables)));
+	CK(cudaMemcpyAsync(h->d_tabs.p, h->tab_cache.data(), h->tab_cache.size() * sizeof(BinomTables), cudaMemcpyHostToDevice, h->st));
 	CK(h->d_pclass.ensure(nwin * 4 + 16));
 	CK(cudaMemcpyAsync(h->d_setups.p, h->setup_cache.data(), h->setup_cache.size() * sizeof(BinomSetup), cudaMemcpyHostToDevice, h->st));
 	if (nwin) CK(cudaMemcpyAsync(h->d_pclass.p, h->pclass_cache.data(), nwin * 4, cudaMemcpyHostToDevice, h->st));
 	CK(cudaStreamSynchronize(h->st));  // the cache vectors may be rebuilt by the next call
 	memcpy(h->setup_key, key, sizeof(key));
 	h->setup_cache_ok = true;
+	return QTIPSIM_OK;
+}
+
+static void fill_resolve_args(qtipsim *h, const qtipsim_run_params *p, const PlanParams &pp, const DevGenome &dg, uint32_t nwin,
+                              uint64_t olap, ResolveArgs &ra) {
+	ra.g = dg;
+	ra.win = h->d_win.as<Window>();
+	ra.ncount = h->d_ncount.as<uint32_t>();
+	ra.pclass = h->d_pclass.as<uint32_t>();
+	ra.setups = h->d_setups.as<BinomSetup>();
+	ra.nwin = nwin;
+	uint32_t mr = 0;
+	for (int c = 0; c < NCAT; c++) mr = std::max(mr, h->ts.cat[c].max_rflen);
+	ra.n_skip_ok = p->chunksz - olap >= (uint64_t)mr;
+	ra.win_lo = (uint32_t)pp.win_lo;
+	ra.win_hi = (uint32_t)pp.win_hi;
+	ra.olap = olap;
+	for (int c = 0; c < NCAT; c++) {
+		ra.t[c] = h->d_t[c].as<TmplDesc>();
+		ra.xsteps[c] = h->d_xsteps[c].as<XStep>();
+		ra.prog[c] = h->d_prog[c].as<HostMateProg>();
+		ra.ntmpl[c] = (uint32_t)h->ts.cat[c].t.size();
+		ra.target[c] = pp.target[c];
+		ra.cap[c] = 0;
+		ra.plan[c] = nullptr;
+	}
+	ra.jt1 = h->d_jt1.as<uint32_t>();
+	ra.jt2 = h->d_jt2.as<uint32_t>();
+	ra.s1 = (uint32_t)p->cg1;
+	ra.s2 = (uint32_t)p->cg2;
+	ra.result = nullptr;
+}
+
+// K2, second generation (resolve2.cu): stages of band-speculated windows, then counts, offsets and the plan records.
+// done = false (with rc OK): the resolver declined or got stuck -- the caller runs the first-generation kernel, which
+// also produces the reference's error for the window in question.
+static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanParams &pp, const DevGenome &dg, uint32_t nwin, uint64_t olap,
+                               uint64_t nreads[NCAT], uint64_t &draws, bool &done) {
+	done = false;
+	const std::vector<Window> &win = h->win_cache;
+	const std::vector<uint32_t> &ncount = h->ncount_cache;
+	// ---- the shard's live windows and the statistics of the draws each one consumes ----
+	std::vector<uint32_t> aw;
+	std::vector<double> cum;  // [0 .. na]: mean, [na + 1 .. 2 na + 1]: variance
+	for (uint64_t w = pp.win_lo; w < pp.win_hi; w++)
+		if (window_live(win[w].retsz, olap, ncount[w])) aw.push_back((uint32_t)w);
+	const uint32_t na = (uint32_t)aw.size();
+	Resolve2Args a2;
+	memset((void *)&a2, 0, sizeof(a2));
+	fill_resolve_args(h, p, pp, dg, nwin, olap, a2.ra);
+	for (int c = 0; c < NCAT; c++) {
+		const Category &cg = h->ts.cat[c];
+		a2.m1[c] = (float)cg.draw_m1;
+		a2.v1[c] = (float)cg.draw_v1;
+		a2.maxfixed[c] = cg.draw_max_fixed;
+		if (cg.draw_max_fixed > 16000u) return QTIPSIM_OK;  // a read of this many draws does not fit the u16 tables: first-generation kernel
+	}
+	cum.assign(2 * (size_t)na + 2, 0.0);
+	double typical = 0;
+	for (uint32_t i = 0; i < na; i++) {
+		const BinomSetup *su = &h->setup_cache[(size_t)h->pclass_cache[aw[i]] * NCAT];
+		double m = 0, v = 0, big = 0;
+		for (int c = 0; c < NCAT; c++) {
+			const double np = (double)su[c].n * (double)su[c].pp, q = 1.0 - (double)su[c].pp;
+			m += 1.5 + np * a2.m1[c];
+			v += np * q * (double)a2.m1[c] * a2.m1[c] + np * a2.v1[c] + 2.0;
+			big = std::max(big, np * a2.m1[c]);
+		}
+		cum[i + 1] = cum[i] + m;
+		cum[na + 1 + i + 1] = cum[na + 1 + i] + v;
+		typical = std::max(typical, big);
+	}
+	auto envu = [](const char *nm, uint32_t dflt) {
+		const char *e = getenv(nm);
+		return e && *e ? (uint32_t)strtoul(e, nullptr, 10) : dflt;
+	};
+	int nsm = 148;
+	cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, h->device);
+	a2.rcap = std::min<uint32_t>(R2_RCAP_MAX, std::max<uint32_t>(1024u, envu("QTIPSIM_R2_RCAP", R2_RCAP_MAX)));
+	a2.rcap_emit = std::min<uint32_t>(R2_RCAP_MAX, std::max<uint32_t>(1024u, envu("QTIPSIM_R2_RCAP_EMIT", 8192u)));
+	a2.nbmax = std::max<uint32_t>(64u, envu("QTIPSIM_R2_NBMAX", 24576u));
+	{
+		const char *e = getenv("QTIPSIM_R2_SIGMA");
+		a2.band_sigma = e && *e ? (float)atof(e) : 5.0f;
+	}
+	uint32_t K = std::min<uint32_t>(R2_KMAX, std::max<uint32_t>(1u, envu("QTIPSIM_R2_K", (uint32_t)nsm)));
+	// windows whose reads cannot fit one dense table are resolved one per stage in exact mode: no point in speculating
+	if (typical + 64.0 > (double)a2.rcap) K = 1;
+	if (na && K > na) K = na;
+	if (!na) {
+		for (int c = 0; c < NCAT; c++) nreads[c] = 0;
+		draws = 0;
+		done = true;
+		return QTIPSIM_OK;
+	}
+	const uint32_t max_launch = na + 8;
+	CK(h->d_r2_aw.ensure((size_t)na * 4));
+	CK(h->d_r2_cum.ensure(cum.size() * 8));
+	CK(h->d_r2_anchor.ensure(((size_t)max_launch + 1) * sizeof(StageAnchor)));
+	CK(h->d_r2_counter.ensure((size_t)max_launch * 4));
+	CK(h->d_r2_slot.ensure((size_t)K * sizeof(uint2)));
+	CK(h->d_r2_end.ensure((size_t)NCAT * K * a2.nbmax * 4));
+	CK(h->d_r2_cn.ensure((size_t)2 * K * a2.nbmax * 4));
+	CK(h->d_r2_wres.ensure((size_t)na * sizeof(WinResolved)));
+	CK(h->d_r2_cnt.ensure((size_t)2 * NCAT * na * 4));
+	CK(h->d_r2_off.ensure((size_t)NCAT * ((size_t)na + 1) * 8));
+	CK(h->d_r2_misc.ensure(64));
+	CK(h->d_scan_tmp.ensure(((size_t)na / 1024 + 4) * 8));
+	CK(cudaMemcpyAsync(h->d_r2_aw.p, aw.data(), (size_t)na * 4, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemcpyAsync(h->d_r2_cum.p, cum.data(), cum.size() * 8, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemsetAsync(h->d_r2_counter.p, 0, (size_t)max_launch * 4, h->st));
+	CK(cudaMemsetAsync(h->d_r2_misc.p, 0, 64, h->st));
+	StageAnchor a0;
+	memset(&a0, 0, sizeof(a0));
+	a0.s1 = (uint32_t)p->cg1;
+	a0.s2 = (uint32_t)p->cg2;
+	a0.status = R2_RUNNING;
+	CK(cudaMemcpyAsync(h->d_r2_anchor.p, &a0, sizeof(a0), cudaMemcpyHostToDevice, h->st));
+	a2.jh1 = h->d_jh1.as<uint32_t>();
+	a2.jh2 = h->d_jh2.as<uint32_t>();
+	a2.tabs = h->d_tabs.as<BinomTables>();
+	a2.aw = h->d_r2_aw.as<uint32_t>();
+	a2.na = na;
+	a2.cumM = h->d_r2_cum.as<double>();
+	a2.cumV = h->d_r2_cum.as<double>() + na + 1;
+	a2.anchor = h->d_r2_anchor.as<StageAnchor>();
+	a2.counter = h->d_r2_counter.as<uint32_t>();
+	a2.slot = h->d_r2_slot.as<uint2>();
+	a2.end = h->d_r2_end.as<uint32_t>();
+	a2.cn = h->d_r2_cn.as<uint32_t>();
+	a2.cnd = a2.cn + (size_t)K * a2.nbmax;
+	a2.wres = h->d_r2_wres.as<WinResolved>();
+
+	// ---- stages: launched in batches without host round trips; a batch ends with a look at the last anchor ----
+	uint32_t launched = 0;
+	StageAnchor fin;
+	memset(&fin, 0, sizeof(fin));
+	for (;;) {
+		const uint32_t left = na - fin.first;
+		uint32_t batch = (left + K - 1) / K + 2;
+		if (launched + batch > max_launch) batch = max_launch - launched;
+		if (!batch) return h->fail(QTIPSIM_ERANGE, "replay resolver made no progress");
+		for (uint32_t b = 0; b < batch; b++) launch_resolve2_stage(a2, launched + b, K, h->st);
+		launched += batch;
+		CK(cudaMemcpyAsync(&fin, a2.anchor + launched, sizeof(fin), cudaMemcpyDeviceToHost, h->st));
+		CK(cudaStreamSynchronize(h->st));
+		if (fin.status != R2_RUNNING) break;
+	}
+	h->r2_stages_last = launched;
+	if (getenv("QTIPSIM_R2_TRACE"))
+		fprintf(stderr, "[resolve2] %u live windows, K = %u, %u stage launches, status %u, first %u, draws %llu\n", na, K, launched,
+		        fin.status, fin.first, (unsigned long long)fin.abs);
+	if (fin.status == R2_STUCK) return QTIPSIM_OK;  // done stays false: first-generation kernel
+
+	// ---- counts per (window, category), offsets, totals ----
+	uint32_t *d_cnt = h->d_r2_cnt.as<uint32_t>();
+	uint32_t *d_start = d_cnt + (size_t)NCAT * na;
+	uint32_t *d_err = h->d_r2_misc.as<uint32_t>();
+	launch_resolve2_counts(a2, d_cnt, d_start, d_err, h->st);
+	R2Offsets offs;
+	for (int c = 0; c < NCAT; c++) {
+		uint64_t *off = h->d_r2_off.as<uint64_t>() + (size_t)c * ((size_t)na + 1);
+		launch_scan(d_cnt + (size_t)c * na, off, na, h->d_scan_tmp.as<uint64_t>(), off + na, h->st);
+		offs.p[c] = off;
+	}
+	uint64_t tot[NCAT];
+	uint32_t errw = 0;
+	for (int c = 0; c < NCAT; c++)
+		CK(cudaMemcpyAsync(&tot[c], offs.p[c] + na, 8, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(&errw, d_err, 4, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	if (errw) return QTIPSIM_OK;  // the first-generation kernel reports the reference's error for it
+	for (int c = 0; c < NCAT; c++) {
+		if (tot[c]) CK(h->d_plan[c].ensure(tot[c] * sizeof(PlanRec)));
+		a2.ra.plan[c] = h->d_plan[c].as<PlanRec>();
+		a2.ra.cap[c] = tot[c];
+	}
+	launch_resolve2_emit(a2, d_cnt, d_start, offs, d_err, h->st);
+	CK(cudaMemcpyAsync(&errw, d_err, 4, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaStreamSynchronize(h->st));
+	if (errw) return QTIPSIM_OK;
+	for (int c = 0; c < NCAT; c++) nreads[c] = tot[c];
+	p->cg1 = (int32_t)fin.s1;
+	p->cg2 = (int32_t)fin.s2;
+	draws = fin.abs;
+	done = true;
 	return QTIPSIM_OK;
 }
 
@@ -784,56 +992,66 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 		// binomial set-ups per distinct window probability, computed with the host's libm
 		rc = ensure_setups(h, win, olap, pp, (uint32_t)pp.win_lo, (uint32_t)pp.win_hi);
 		if (rc) return rc;
-		CK(h->d_rsresult.ensure(8 * 8));
-		double grow = 1.0;
-		for (int attempt = 0;; attempt++) {
-			ResolveArgs ra;
-			ra.g = dg;
-			ra.win = h->d_win.as<Window>();
-			ra.ncount = h->d_ncount.as<uint32_t>();
-			ra.pclass = h->d_pclass.as<uint32_t>();
-			ra.setups = h->d_setups.as<BinomSetup>();
-			ra.nwin = nwin;
-			{
-				uint32_t mr = 0;
-				for (int c = 0; c < NCAT; c++) mr = std::max(mr, h->ts.cat[c].max_rflen);
-				ra.n_skip_ok = p->chunksz - olap >= (uint64_t)mr;
+		// default: the band-speculative resolver (resolve2.cu); QTIPSIM_RESOLVER=cluster|cta forces the first-generation
+		// kernel, which is also what a declined / stuck run falls back to
+		const char *rsv = getenv("QTIPSIM_RESOLVER");
+		bool band_done = false;
+		if (!rsv || !*rsv || strcmp(rsv, "band") == 0) {
+			rc = resolve_replay_band(h, p, pp, dg, nwin, olap, nreads, draws, band_done);
+			if (rc) return rc;
+		}
+		if (!band_done) {
+			CK(h->d_rsresult.ensure(8 * 8));
+			double grow = 1.0;
+			for (int attempt = 0;; attempt++) {
+				ResolveArgs ra;
+				ra.g = dg;
+				ra.win = h->d_win.as<Window>();
+				ra.ncount = h->d_ncount.as<uint32_t>();
+				ra.pclass = h->d_pclass.as<uint32_t>();
+				ra.setups = h->d_setups.as<BinomSetup>();
+				ra.nwin = nwin;
+				{
+					uint32_t mr = 0;
+					for (int c = 0; c < NCAT; c++) mr = std::max(mr, h->ts.cat[c].max_rflen);
+					ra.n_skip_ok = p->chunksz - olap >= (uint64_t)mr;
+				}
+				ra.win_lo = (uint32_t)pp.win_lo;
+				ra.win_hi = (uint32_t)pp.win_hi;
+				ra.olap = olap;
+				const double share = nwin ? (double)(pp.win_hi - pp.win_lo) / (double)nwin : 1.0;
+				for (int c = 0; c < NCAT; c++) {
+					ra.t[c] = h->d_t[c].as<TmplDesc>();
+					ra.xsteps[c] = h->d_xsteps[c].as<XStep>();
+					ra.prog[c] = h->d_prog[c].as<HostMateProg>();
+					ra.ntmpl[c] = (uint32_t)h->ts.cat[c].t.size();
+					ra.target[c] = pp.target[c];
+					// expected reads <= 1.1 * target * (this shard's share of the windows); generous margin
+					ra.cap[c] = pp.target[c] ? (uint64_t)((1.25 * share * (double)pp.target[c] + 65536.0) * grow) : 0;
+					if (ra.cap[c]) CK(h->d_plan[c].ensure(ra.cap[c] * sizeof(PlanRec)));
+					ra.plan[c] = h->d_plan[c].as<PlanRec>();
+				}
+				ra.jt1 = h->d_jt1.as<uint32_t>();
+				ra.jt2 = h->d_jt2.as<uint32_t>();
+				ra.s1 = (uint32_t)p->cg1;
+				ra.s2 = (uint32_t)p->cg2;
+				ra.result = h->d_rsresult.as<unsigned long long>();
+				launch_resolve_replay(ra, h->st);
+				unsigned long long res[8];
+				CK(cudaMemcpyAsync(res, h->d_rsresult.p, sizeof(res), cudaMemcpyDeviceToHost, h->st));
+				CK(cudaStreamSynchronize(h->st));
+				if (res[7] == 3 && attempt < 6) {  // plan buffer too small: retry larger
+					grow *= 2.0;
+					continue;
+				}
+				if (res[7] == 1) return h->fail(QTIPSIM_ERANGE, "window with zero slots (assert(nslots > 0), simplesim.cpp:252)");
+				if (res[7]) return h->fail(QTIPSIM_ERANGE, "replay resolver failed");
+				for (int c = 0; c < NCAT; c++) nreads[c] = res[c];
+				p->cg1 = (int32_t)res[4];
+				p->cg2 = (int32_t)res[5];
+				draws = res[6];
+				break;
 			}
-			ra.win_lo = (uint32_t)pp.win_lo;
-			ra.win_hi = (uint32_t)pp.win_hi;
-			ra.olap = olap;
-			const double share = nwin ? (double)(pp.win_hi - pp.win_lo) / (double)nwin : 1.0;
-			for (int c = 0; c < NCAT; c++) {
-				ra.t[c] = h->d_t[c].as<TmplDesc>();
-				ra.xsteps[c] = h->d_xsteps[c].as<XStep>();
-				ra.prog[c] = h->d_prog[c].as<HostMateProg>();
-				ra.ntmpl[c] = (uint32_t)h->ts.cat[c].t.size();
-				ra.target[c] = pp.target[c];
-				// expected reads <= 1.1 * target * (this shard's share of the windows); generous margin
-				ra.cap[c] = pp.target[c] ? (uint64_t)((1.25 * share * (double)pp.target[c] + 65536.0) * grow) : 0;
-				if (ra.cap[c]) CK(h->d_plan[c].ensure(ra.cap[c] * sizeof(PlanRec)));
-				ra.plan[c] = h->d_plan[c].as<PlanRec>();
-			}
-			ra.jt1 = h->d_jt1.as<uint32_t>();
-			ra.jt2 = h->d_jt2.as<uint32_t>();
-			ra.s1 = (uint32_t)p->cg1;
-			ra.s2 = (uint32_t)p->cg2;
-			ra.result = h->d_rsresult.as<unsigned long long>();
-			launch_resolve_replay(ra, h->st);
-			unsigned long long res[8];
-			CK(cudaMemcpyAsync(res, h->d_rsresult.p, sizeof(res), cudaMemcpyDeviceToHost, h->st));
-			CK(cudaStreamSynchronize(h->st));
-			if (res[7] == 3 && attempt < 6) {  // plan buffer too small: retry larger
-				grow *= 2.0;
-				continue;
-			}
-			if (res[7] == 1) return h->fail(QTIPSIM_ERANGE, "window with zero slots (assert(nslots > 0), simplesim.cpp:252)");
-			if (res[7]) return h->fail(QTIPSIM_ERANGE, "replay resolver failed");
-			for (int c = 0; c < NCAT; c++) nreads[c] = res[c];
-			p->cg1 = (int32_t)res[4];
-			p->cg2 = (int32_t)res[5];
-			draws = res[6];
-			break;
 		}
 	} else if (p->rng_mode == QTIPSIM_RNG_REPLAY) {
 		rc = ensure_host_packed(h);

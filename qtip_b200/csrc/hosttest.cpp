@@ -133,6 +133,21 @@ int qthost_ignbin(uint32_t *s1, uint32_t *s2, int n, float p) {
 	*s2 = s.s2;
 	return v;
 }
+// the table-driven sampler the device resolver uses (lecuyer.h: binom_tables / binom_sample_tab)
+int qthost_ignbin_tab(uint32_t *s1, uint32_t *s2, int n, float p) {
+	LState s{*s1, *s2};
+	BinomSetup b = binom_setup(n, p);
+	static BinomTables t;
+	binom_tables(b, t);
+	auto nx = [&]() {
+		s = lstep(s);
+		return lfloat(lout(s));
+	};
+	int v = binom_sample_tab(b, t, nx);
+	*s1 = s.s1;
+	*s2 = s.s2;
+	return v;
+}
 float qthost_logf(float x) { return logf_glibc(x); }
 // compares logf_glibc with the host libm over [lo, hi) bit patterns; returns mismatches
 uint64_t qthost_logf_sweep(uint32_t lo, uint32_t hi, uint32_t step) {

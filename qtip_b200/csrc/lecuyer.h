@@ -189,16 +189,27 @@ QT_HD LState ljump(LState s, uint64_t k) {
 // the fused and unfused evaluations agree after rounding to float on all of them.
 // Valid for positive normal x, which is all ignbin ever passes.
 // ---------------------------------------------------------------------------
+#define QT_LOGF_TABLE                                                                                  \
+	{{0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},     \
+	 {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},     \
+	 {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},        \
+	 {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},     \
+	 {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},                                  \
+	 {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},       \
+	 {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},       \
+	 {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}}
+#if defined(__CUDACC__)
+// constant memory on the device: a table in the function body would be rebuilt on the stack at every call
+static __constant__ double qt_logf_tab_dev[16][2] = QT_LOGF_TABLE;
+#endif
+static const double qt_logf_tab_host[16][2] = QT_LOGF_TABLE;
+
 QT_HD float logf_glibc(float x) {
-	const double T[16][2] = {
-		{0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
-		{0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2},  {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
-		{0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
-		{0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
-		{0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
-		{0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5},  {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
-		{0x1.b2036576afce6p-1, 0x1.526e57720db08p-3},  {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
-		{0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2},  {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+#if defined(__CUDA_ARCH__)
+	const double(*T)[2] = qt_logf_tab_dev;
+#else
+	const double(*T)[2] = qt_logf_tab_host;
+#endif
 	const double Ln2 = 0x1.62e42fefa39efp-1;
 	const double A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
 	uint32_t ix;
@@ -299,6 +310,97 @@ QT_HD double stirling_tail(float s2, float s) {
 	return ddiv_rn(ddiv_rn(t, (double)s), 166320.0);
 }
 
+// ---- the three acceptance bounds of BTPE's step 5 (ranlib.cpp:1274-1387): functions of ix (or k = |ix - m|) and the
+// set-up only, so they can be tabulated per set-up (BinomTables) instead of being recomputed for every variate ----
+
+// f(ix) / f(m) by the recurrence, ranlib.cpp:1284-1300
+QT_HD float btpe_explicit_f(const BinomSetup &b, int32_t ix) {
+	float f = 1.0f;
+	float r = fdiv_rn(b.p, b.q);
+	float g = fmul_rn((float)(b.n + 1), r);
+	if (b.m < ix) {
+		for (int32_t i = b.m + 1; i <= ix; i++) f = fmul_rn(f, fsub_rn(fdiv_rn(g, (float)i), r));
+	} else if (ix < b.m) {
+		for (int32_t i = ix + 1; i <= b.m; i++) f = fdiv_rn(f, fsub_rn(fdiv_rn(g, (float)i), r));
+	}
+	return f;
+}
+
+// squeeze bounds on log(v), ranlib.cpp:1315-1334: accept below lo = ynorm - amaxp, reject above hi = ynorm + amaxp
+QT_HD void btpe_squeeze(const BinomSetup &b, int32_t k, float &lo, float &hi) {
+	double dk = (double)k;
+	double inner = dadd_rn(dmul_rn(dk, dadd_rn(ddiv_rn(dk, 3.0), 0.625)), 0.1666666666666);
+	inner = dadd_rn(ddiv_rn(inner, (double)b.xnpq), 0.5);
+	float amaxp = (float)dmul_rn((double)fdiv_rn((float)k, b.xnpq), inner);
+	float ynorm = (float)ddiv_rn((double)(-(float)(k * k)), dmul_rn(2.0, (double)b.xnpq));
+	lo = fsub_rn(ynorm, amaxp);
+	hi = fadd_rn(ynorm, amaxp);
+}
+
+// the final bound on log(v) with Stirling's correction, ranlib.cpp:1340-1387
+QT_HD float btpe_stirling_t(const BinomSetup &b, int32_t ix) {
+	const int32_t n = b.n;
+	float x1 = (float)(ix + 1);
+	float f1 = (float)dadd_rn((double)b.fm, 1.0);
+	float z = fsub_rn((float)(n + 1), b.fm);
+	float w = (float)(n - ix + 1);
+	float z2 = fmul_rn(z, z), x2 = fmul_rn(x1, x1), f2 = fmul_rn(f1, f1), w2 = fmul_rn(w, w);
+	double d = (double)fmul_rn(b.xm, logf_glibc(fdiv_rn(f1, x1)));
+	d = dadd_rn(d, dmul_rn(dadd_rn((double)(n - b.m), 0.5), (double)logf_glibc(fdiv_rn(z, w))));
+	d = dadd_rn(d, (double)fmul_rn((float)(ix - b.m), logf_glibc(fdiv_rn(fmul_rn(w, b.p), fmul_rn(x1, b.q)))));
+	d = dadd_rn(d, stirling_tail(f2, f1));
+	d = dadd_rn(d, stirling_tail(z2, z));
+	d = dadd_rn(d, stirling_tail(x2, x1));
+	d = dadd_rn(d, stirling_tail(w2, w));
+	return (float)d;
+}
+
+// Per BTPE set-up: the bounds above for every ix within BT_KT of the mode.  Built on the host (binom_tables); the
+// device sampler binom_sample_tab reads them -- the values are those the direct computation gives, bit for bit.
+static constexpr int BT_KT = 256;
+struct BinomTables {
+	float expl[41];               // btpe_explicit_f at ix = m - 20 + i
+	float sq_lo[BT_KT];           // btpe_squeeze at k
+	float sq_hi[BT_KT];
+	float stir[2 * BT_KT - 1];    // btpe_stirling_t at ix = m - (BT_KT - 1) + i (0 where ix is outside [0, n])
+};
+
+inline void binom_tables(const BinomSetup &b, BinomTables &t) {
+	memset(&t, 0, sizeof(t));
+	if (b.inversion) return;
+	for (int i = 0; i < 41; i++) t.expl[i] = btpe_explicit_f(b, b.m - 20 + i);
+	for (int k = 0; k < BT_KT; k++) btpe_squeeze(b, k, t.sq_lo[k], t.sq_hi[k]);
+	for (int i = 0; i < 2 * BT_KT - 1; i++) {
+		const int64_t ix = (int64_t)b.m - (BT_KT - 1) + i;
+		if (ix >= 0 && ix <= (int64_t)b.n) t.stir[i] = btpe_stirling_t(b, (int32_t)ix);
+	}
+}
+
+// BTPE steps 1-4 (ranlib.cpp:1252-1273): the candidate ix and the v the acceptance test compares.  Returns 0: accepted
+// outright (triangle), 1: go to step 5, 2: rejected, draw again.
+QT_HD int btpe_candidate(const BinomSetup &b, float u, float &v, int32_t &ix) {
+	if (u < b.p1) {
+		ix = (int32_t)fadd_rn(fsub_rn(b.xm, fmul_rn(b.p1, v)), u);
+		return 0;
+	}
+	if (u <= b.p2) {
+		float x = fadd_rn(b.xl, fdiv_rn(fsub_rn(u, b.p1), b.c));
+		double dv = dsub_rn(dadd_rn((double)fmul_rn(v, b.c), 1.0), (double)fdiv_rn(fabsf(fsub_rn(b.xm, x)), b.p1));
+		v = (float)dv;
+		if ((double)v <= 0.0 || 1.0 < (double)v) return 2;
+		ix = (int32_t)x;
+	} else if (u <= b.p3) {
+		ix = (int32_t)fadd_rn(b.xl, fdiv_rn(logf_glibc(v), b.xll));
+		if (ix < 0) return 2;
+		v = fmul_rn(fmul_rn(v, fsub_rn(u, b.p2)), b.xll);
+	} else {
+		ix = (int32_t)fsub_rn(b.xr, fdiv_rn(logf_glibc(v), b.xlr));
+		if (b.n < ix) return 2;
+		v = fmul_rn(fmul_rn(v, fsub_rn(u, b.p3)), b.xlr);
+	}
+	return 1;
+}
+
 // Draws one Binomial(n, pp) variate from the stream.  `next()` must return the next
 // r4_uni_01 value of the stream (and advance it).
 template <class Next>
@@ -322,62 +424,56 @@ QT_HD int32_t binom_sample(const BinomSetup &b, Next &next) {
 		float u = fmul_rn(next(), b.p4);
 		float v = next();
 		int32_t ix;
-		if (u < b.p1) {
-			ix = (int32_t)fadd_rn(fsub_rn(b.xm, fmul_rn(b.p1, v)), u);
-			return b.flip ? n - ix : ix;
-		}
-		if (u <= b.p2) {
-			float x = fadd_rn(b.xl, fdiv_rn(fsub_rn(u, b.p1), b.c));
-			double dv = dsub_rn(dadd_rn((double)fmul_rn(v, b.c), 1.0),
-			                    (double)fdiv_rn(fabsf(fsub_rn(b.xm, x)), b.p1));
-			v = (float)dv;
-			if ((double)v <= 0.0 || 1.0 < (double)v) continue;
-			ix = (int32_t)x;
-		} else if (u <= b.p3) {
-			ix = (int32_t)fadd_rn(b.xl, fdiv_rn(logf_glibc(v), b.xll));
-			if (ix < 0) continue;
-			v = fmul_rn(fmul_rn(v, fsub_rn(u, b.p2)), b.xll);
-		} else {
-			ix = (int32_t)fsub_rn(b.xr, fdiv_rn(logf_glibc(v), b.xlr));
-			if (n < ix) continue;
-			v = fmul_rn(fmul_rn(v, fsub_rn(u, b.p3)), b.xlr);
-		}
+		const int st = btpe_candidate(b, u, v, ix);
+		if (st == 0) return b.flip ? n - ix : ix;
+		if (st == 2) continue;
 		int32_t k = ix - b.m;
 		if (k < 0) k = -k;
 		if (k <= 20 || dsub_rn(ddiv_rn((double)b.xnpq, 2.0), 1.0) <= (double)k) {
-			float f = 1.0f;
-			float r = fdiv_rn(b.p, b.q);
-			float g = fmul_rn((float)(n + 1), r);
-			if (b.m < ix) {
-				for (int32_t i = b.m + 1; i <= ix; i++) f = fmul_rn(f, fsub_rn(fdiv_rn(g, (float)i), r));
-			} else if (ix < b.m) {
-				for (int32_t i = ix + 1; i <= b.m; i++) f = fdiv_rn(f, fsub_rn(fdiv_rn(g, (float)i), r));
-			}
+			if (v <= btpe_explicit_f(b, ix)) return b.flip ? n - ix : ix;
+		} else {
+			float lo, hi;
+			btpe_squeeze(b, k, lo, hi);
+			float alv = logf_glibc(v);
+			if (alv < lo) return b.flip ? n - ix : ix;
+			if (hi < alv) continue;
+			if (alv <= btpe_stirling_t(b, ix)) return b.flip ? n - ix : ix;
+		}
+	}
+}
+
+// The same variate with step 5's bounds read from the set-up's tables (device resolver: thousands of candidates per
+// window share one set-up, and the direct computation diverges badly across a warp).
+template <class Next>
+QT_HD int32_t binom_sample_tab(const BinomSetup &b, const BinomTables &t, Next &next) {
+	if (b.inversion) return binom_sample(b, next);
+	const int32_t n = b.n;
+	const double khalf = dsub_rn(ddiv_rn((double)b.xnpq, 2.0), 1.0);
+	for (;;) {
+		float u = fmul_rn(next(), b.p4);
+		float v = next();
+		int32_t ix;
+		const int st = btpe_candidate(b, u, v, ix);
+		if (st == 0) return b.flip ? n - ix : ix;
+		if (st == 2) continue;
+		int32_t k = ix - b.m;
+		if (k < 0) k = -k;
+		if (k <= 20 || khalf <= (double)k) {
+			const float f = k <= 20 ? t.expl[ix - b.m + 20] : btpe_explicit_f(b, ix);
 			if (v <= f) return b.flip ? n - ix : ix;
 		} else {
-			double dk = (double)k;
-			double inner = dadd_rn(dmul_rn(dk, dadd_rn(ddiv_rn(dk, 3.0), 0.625)), 0.1666666666666);
-			inner = dadd_rn(ddiv_rn(inner, (double)b.xnpq), 0.5);
-			float amaxp = (float)dmul_rn((double)fdiv_rn((float)k, b.xnpq), inner);
-			float ynorm = (float)ddiv_rn((double)(-(float)(k * k)), dmul_rn(2.0, (double)b.xnpq));
+			float lo, hi;
+			if (k < BT_KT) {
+				lo = t.sq_lo[k];
+				hi = t.sq_hi[k];
+			} else {
+				btpe_squeeze(b, k, lo, hi);
+			}
 			float alv = logf_glibc(v);
-			if (alv < fsub_rn(ynorm, amaxp)) return b.flip ? n - ix : ix;
-			if (fadd_rn(ynorm, amaxp) < alv) continue;
-			float x1 = (float)(ix + 1);
-			float f1 = (float)dadd_rn((double)b.fm, 1.0);
-			float z = fsub_rn((float)(n + 1), b.fm);
-			float w = (float)(n - ix + 1);
-			float z2 = fmul_rn(z, z), x2 = fmul_rn(x1, x1), f2 = fmul_rn(f1, f1), w2 = fmul_rn(w, w);
-			double d = (double)fmul_rn(b.xm, logf_glibc(fdiv_rn(f1, x1)));
-			d = dadd_rn(d, dmul_rn(dadd_rn((double)(n - b.m), 0.5), (double)logf_glibc(fdiv_rn(z, w))));
-			d = dadd_rn(d, (double)fmul_rn((float)(ix - b.m),
-			                               logf_glibc(fdiv_rn(fmul_rn(w, b.p), fmul_rn(x1, b.q)))));
-			d = dadd_rn(d, stirling_tail(f2, f1));
-			d = dadd_rn(d, stirling_tail(z2, z));
-			d = dadd_rn(d, stirling_tail(x2, x1));
-			d = dadd_rn(d, stirling_tail(w2, w));
-			float t = (float)d;
-			if (alv <= t) return b.flip ? n - ix : ix;
+			if (alv < lo) return b.flip ? n - ix : ix;
+			if (hi < alv) continue;
+			const float tt = k < BT_KT ? t.stir[ix - b.m + (BT_KT - 1)] : btpe_stirling_t(b, ix);
+			if (alv <= tt) return b.flip ? n - ix : ix;
 		}
 	}
 }

@@ -22,57 +22,12 @@
 #include "kernels.cuh"
 #include "lecuyer.h"
 #include "resolve.h"
+#include "resolve_dev.cuh"
 
 namespace qt {
 
 static constexpr int RS_T = 1024;    // stream positions speculated per round
 static constexpr int RS_LOG = 10;
-
-__device__ __forceinline__ LState jump_tbl(LState s, uint32_t k, const uint32_t *jt1, const uint32_t *jt2) {
-	while (k >= (uint32_t)JUMP_TBL) {
-		s.s1 = mulmod1(s.s1, __ldg(&jt1[JUMP_TBL - 1]));
-		s.s2 = mulmod2(s.s2, __ldg(&jt2[JUMP_TBL - 1]));
-		k -= (uint32_t)(JUMP_TBL - 1);
-	}
-	if (k) {
-		s.s1 = mulmod1(s.s1, __ldg(&jt1[k]));
-		s.s2 = mulmod2(s.s2, __ldg(&jt2[k]));
-	}
-	return s;
-}
-
-// has_n = the window holds at least one N (its N count is known): only then is the N mask read
-__device__ __forceinline__ uint32_t rs_fetch_code(const DevGenome &g, uint64_t gp, uint64_t gend, bool has_n) {
-	if (gp >= gend) return 4u;
-	if (has_n && ((__ldg(&g.nmask[gp >> 5]) >> (gp & 31)) & 1u)) return 4u;
-	return (__ldg(&g.bases[gp >> 4]) >> (2 * (gp & 15))) & 3u;
-}
-
-// draws consumed by one mate's transcript starting at state s (simplesim.cpp:38-62); advances s
-__device__ __forceinline__ uint32_t walk_mate_dev(LState &s, const DevGenome &g, const XStep *__restrict__ xs,
-                                                  const HostMateProg hp, uint64_t gpos, uint64_t gend, bool has_n,
-                                                  const uint32_t *jt1, const uint32_t *jt2) {
-	uint32_t len = 0;
-	for (uint32_t i = hp.xs_begin; i < hp.xs_end; i++) {
-		const XStep x = xs[i];
-		if (x.skip) {
-			s = jump_tbl(s, x.skip, jt1, jt2);
-			len += x.skip;
-		}
-		const uint32_t ref = rs_fetch_code(g, gpos + x.rf, gend, has_n);
-		uint32_t code;
-		do {
-			s = lstep(s);
-			len++;
-			code = lbase_code(lfloat(lout(s)));
-		} while (code == ref);
-	}
-	if (hp.tail_skip) {
-		s = jump_tbl(s, hp.tail_skip, jt1, jt2);
-		len += hp.tail_skip;
-	}
-	return len;
-}
 
 __global__ void __launch_bounds__(RS_T, 1) k_resolve_replay(ResolveArgs a) {
 	__shared__ uint16_t s_jump[RS_LOG + 1][RS_T];  // J^(2^r), clamped to RS_T (sink)

@@ -1,0 +1,669 @@
+// resolve2.cu -- K2, second generation: the reference's sequential draw chain (REPLAY mode) resolved by
+// band speculation over many windows at once.
+//
+// The chain (simplesim.cpp:216-397): per window four binomial counts (ignbin, ranlib.cpp:1094-1389) and, per read,
+// a template draw, an offset draw and a data-dependent number of base draws, all from ONE generator.  Where window
+// w starts in the stream is only known after window w-1 -- but it is known *approximately*: the draws a window
+// consumes have a mean and a variance that follow from the binomial parameters and the templates, so window w's
+// start lies, with overwhelming probability, in a band of width ~ sigma * sqrt(distance to the last exactly known
+// position).  Because the stream is addressable (lecuyer.h), a window's whole transfer function
+//
+//      T_w : start position  ->  position after the window        (for every start in the band)
+//
+// can be computed without knowing the true start:
+//   1. every candidate start draws its binomial count(s) (one thread per candidate);
+//   2. for each category with reads, "a read starting at stream position q consumes len(q) draws" is evaluated
+//      densely over the range the candidates can reach (one thread per position) into shared memory;
+//   3. five pointer-doubling passes turn len into the 32-read jump length; a candidate then finds the position
+//      after its n reads in n/32 + (n mod 32) shared-memory look-ups.
+// A STAGE is one kernel launch: CTA j builds T for the j-th window after the stage's anchor (the last exactly
+// known position); the last CTA to finish walks the chain through the K tables (one L2 look-up per window),
+// records every window's start and region ends, and publishes the next anchor.  A window whose true start misses
+// its band, or whose candidate ran off the dense table, ends the stage early: it becomes the first window of the
+// next stage, where the band is the single exact position and the table is extended round by round until the
+// window is done (exact mode; this is also how windows too large for one table are resolved).  Nothing is
+// approximate: a table entry is either the exact end position or INVALID.
+//
+// After the last stage k_resolve2_counts re-draws each window's binomial counts at the now known region starts
+// (cheap, parallel), a scan gives every (window, category) its slice of the plan, and k_resolve2_emit -- one CTA
+// per (window, category), all in parallel -- re-evaluates len densely from the known start, marks the orbit and
+// writes the PlanRec of every read on it (template, record, offset, generator state after the two index draws).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include "kernels.cuh"
+#include "lecuyer.h"
+#include "resolve.h"
+#include "resolve_dev.cuh"
+
+namespace qt {
+
+static constexpr int R2_T = 1024;                  // threads of a stage CTA
+static constexpr int R2_TE = 512;                  // threads of an emit CTA
+static constexpr uint32_t R2_SINK = 0xFFFFu;       // table entry: the walk leaves the table / length does not fit
+static constexpr uint32_t R2_INVALID = 0xFFFFFFFFu;
+static constexpr uint32_t R2_POS_LIMIT = 0xE0000000u;  // stage-relative positions stay below this
+static constexpr int R2_STRIDE_LOG = 5;            // the stride table holds 2^5-read jumps
+static constexpr uint32_t R2_MAIN_PTS = R2_RCAP_MAX / 64 + 2;  // stride points of a main orbit (a read is >= 2 draws)
+
+// stream position k (relative) from state s: two table look-ups for k < 2^24, square-and-multiply above
+__device__ __forceinline__ LState jump2(LState s, uint32_t k, const uint32_t *jt1, const uint32_t *jt2, const uint32_t *jh1,
+                                        const uint32_t *jh2) {
+	const uint32_t lo = k & 4095u, hi = (k >> 12) & 4095u, top = k >> 24;
+	if (lo) {
+		s.s1 = mulmod1(s.s1, __ldg(&jt1[lo]));
+		s.s2 = mulmod2(s.s2, __ldg(&jt2[lo]));
+	}
+	if (hi) {
+		s.s1 = mulmod1(s.s1, __ldg(&jh1[hi]));
+		s.s2 = mulmod2(s.s2, __ldg(&jh2[hi]));
+	}
+	if (top) s = ljump(s, (uint64_t)top << 24);
+	return s;
+}
+
+// what a read of one window needs to know about its window
+struct WinCtx {
+	uint32_t record;
+	uint64_t refoff;
+	uint64_t nslots;
+	uint64_t gwin, gend;
+	bool has_n;
+	const BinomSetup *su;
+	const BinomTables *tab;  // may be null (then the direct sampler is used)
+};
+
+__device__ __forceinline__ WinCtx make_winctx(const ResolveArgs &a, uint32_t w, const BinomTables *tabs = nullptr) {
+	WinCtx c;
+	const Window wn = a.win[w];
+	c.record = wn.record;
+	c.refoff = wn.refoff;
+	c.nslots = (uint64_t)wn.retsz - a.olap;
+	// N mask reads are skipped when neither this window nor the next one of the record holds an N (a mate whose
+	// reference span exceeds its fragment can reach past its window, SURVEY Q9, but never past the next)
+	c.has_n = true;
+	if (a.n_skip_ok && a.ncount[w] == 0) {
+		const bool next_same = w + 1 < a.nwin && a.win[w + 1].record == wn.record;
+		c.has_n = next_same && a.ncount[w + 1] != 0;
+	}
+	const RecDev rec = a.g.recs[wn.record];
+	c.gwin = rec.gstart + wn.refoff;
+	c.gend = rec.gstart + rec.len;
+	c.su = a.setups + (size_t)a.pclass[w] * NCAT;
+	c.tab = tabs ? tabs + (size_t)a.pclass[w] * NCAT : nullptr;
+	return c;
+}
+
+// draws consumed by a read / pair of category cat whose template draw is the first draw after state s
+// (simplesim.cpp:243-273, :280-334, :342-397)
+__device__ __forceinline__ uint32_t read_len(const ResolveArgs &a, const WinCtx &wc, int cat, LState s) {
+	const TmplDesc *tdesc = a.t[cat];
+	const HostMateProg *prog = a.prog[cat];
+	s = lstep(s);
+	const uint32_t ti = (uint32_t)lindex(lfloat(lout(s)), a.ntmpl[cat]);
+	s = lstep(s);
+	const uint64_t off = lindex(lfloat(lout(s)), wc.nslots);
+	uint32_t len = 2;
+	uint32_t d0 = 0, d1 = 0;  // the mates' offsets from the drawn position are 0 for U and B
+	if (cat >= CAT_C) {
+		d0 = tdesc[ti].delta[0];
+		d1 = tdesc[ti].delta[1];
+	}
+	len += walk_mate_dev(s, a.g, a.xsteps[cat], prog[2 * ti], wc.gwin + off + d0, wc.gend, wc.has_n, a.jt1, a.jt2);
+	if (cat >= CAT_C) len += walk_mate_dev(s, a.g, a.xsteps[cat], prog[2 * ti + 1], wc.gwin + off + d1, wc.gend, wc.has_n, a.jt1, a.jt2);
+	if (cat == CAT_B) len += tdesc[ti].opp_len;  // init_random, simplesim.h:108-113
+	return len;
+}
+
+// L1[q] = draws of a read starting at relative position q (state S0 = position 0), for q < R
+template <int NT>
+__device__ __forceinline__ void dense_eval(const ResolveArgs &a, const WinCtx &wc, int cat, LState S0, uint32_t R, uint16_t *L1,
+                                           const uint32_t *jh1, const uint32_t *jh2) {
+	const uint32_t tid = threadIdx.x;
+	if (tid >= R) return;
+	LState s = jump2(S0, tid, a.jt1, a.jt2, jh1, jh2);
+	const uint32_t c1 = __ldg(&a.jt1[NT]), c2 = __ldg(&a.jt2[NT]);  // a^NT: this thread's next position
+	for (uint32_t q = tid; q < R; q += NT) {
+		const uint32_t len = read_len(a, wc, cat, s);
+		L1[q] = (uint16_t)(len < R2_SINK ? len : R2_SINK);
+		s.s1 = mulmod1(s.s1, c1);
+		s.s2 = mulmod2(s.s2, c2);
+	}
+}
+
+// five doubling passes: returns the table of 32-read jump lengths (in TA).  Needs L1 complete (barrier before);
+// ends with a barrier.
+template <int NT>
+__device__ __forceinline__ const uint16_t *build_stride(const uint16_t *L1, uint16_t *TA, uint16_t *TB, uint32_t R) {
+	const uint16_t *src = L1;
+	uint16_t *dst = TA;
+	for (int pass = 0; pass < R2_STRIDE_LOG; pass++) {
+		for (uint32_t q = threadIdx.x; q < R; q += NT) {
+			const uint32_t l = src[q];
+			uint32_t r = R2_SINK;
+			if (l != R2_SINK) {
+				const uint32_t q2 = q + l;
+				if (q2 < R) {
+					const uint32_t l2 = src[q2];
+					if (l2 != R2_SINK && l + l2 < R2_SINK) r = l + l2;
+				}
+			}
+			dst[q] = (uint16_t)r;
+		}
+		__syncthreads();
+		src = dst;
+		dst = dst == TA ? TB : TA;
+	}
+	return src;
+}
+
+// n reads forward from relative position p, as far as the tables reach
+__device__ __forceinline__ void advance(const uint16_t *L1, const uint16_t *LS, uint32_t R, uint32_t &p, uint32_t &n) {
+	while (n > 0 && p < R) {
+		if (n >= (1u << R2_STRIDE_LOG)) {
+			const uint32_t l = LS[p];
+			if (l != R2_SINK) {
+				p += l;
+				n -= 1u << R2_STRIDE_LOG;
+				continue;
+			}
+		}
+		const uint32_t l = L1[p];
+		if (l == R2_SINK) break;
+		p += l;
+		n--;
+	}
+}
+
+// block-wide min / max / max; every thread gets the results.  red: 3 * 32 words of shared memory.
+template <int NT>
+__device__ __forceinline__ void block_minmax(uint32_t &mn, uint32_t &mx, uint32_t &mxn, uint32_t *red) {
+	const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	mn = __reduce_min_sync(0xffffffffu, mn);
+	mx = __reduce_max_sync(0xffffffffu, mx);
+	mxn = __reduce_max_sync(0xffffffffu, mxn);
+	__syncthreads();  // red may still be read from the previous call
+	if (lane == 0) {
+		red[wid] = mn;
+		red[32 + wid] = mx;
+		red[64 + wid] = mxn;
+	}
+	__syncthreads();
+	constexpr int NW = NT / 32;
+	uint32_t a = lane < NW ? red[lane] : 0xffffffffu, b = lane < NW ? red[32 + lane] : 0u, c = lane < NW ? red[64 + lane] : 0u;
+	mn = __reduce_min_sync(0xffffffffu, a);
+	mx = __reduce_max_sync(0xffffffffu, b);
+	mxn = __reduce_max_sync(0xffffffffu, c);
+}
+
+// expected reach of n reads beyond their start, generously
+__device__ __forceinline__ uint64_t reach(const Resolve2Args &a, int cat, uint32_t n) {
+	const float fn = (float)n;
+	const float e = fn * a.m1[cat] + 6.0f * sqrtf(fn * a.v1[cat] + 1.0f) + 2.0f * (float)a.maxfixed[cat] + 64.0f;
+	return (uint64_t)e;
+}
+
+// All candidates of one window move over the reads of one category: P[i] = position (stage-relative) of candidate
+// i's next draw, N[i] = reads it still has to pass.  On return P[i] is the position after those reads, or INVALID.
+// exact (a single candidate, the true start): the dense table is extended round by round until the reads are done.
+__device__ __forceinline__ void advance_region(const Resolve2Args &a2, const WinCtx &wc, int cat, LState SA, uint32_t nb, bool exact,
+                                               uint32_t *P, uint32_t *N, uint16_t *L1, uint16_t *TA, uint16_t *TB, uint32_t *red,
+                                               uint32_t *pts) {
+	const ResolveArgs &a = a2.ra;
+	const uint32_t tid = threadIdx.x;
+	for (;;) {
+		uint32_t mn = 0xffffffffu, mx = 0, mxn = 0;
+		for (uint32_t i = tid; i < nb; i += R2_T) {
+			const uint32_t pos = P[i], n = N[i];
+			if (pos != R2_INVALID && n > 0) {
+				mn = min(mn, pos);
+				mx = max(mx, pos);
+				mxn = max(mxn, n);
+			}
+		}
+		block_minmax<R2_T>(mn, mx, mxn, red);
+		if (mxn == 0) break;
+		if (a.ntmpl[cat] == 0) {  // reads of a category without templates: the caller reports it (exact mode: stuck)
+			for (uint32_t i = tid; i < nb; i += R2_T)
+				if (N[i] > 0) {
+					P[i] = R2_INVALID;
+					N[i] = 0;
+				}
+			__syncthreads();
+			break;
+		}
+		const uint32_t rlo = mn;
+		const uint64_t want = (uint64_t)(mx - rlo) + reach(a2, cat, mxn) + 1;
+		const uint32_t R = want < (uint64_t)a2.rcap ? (uint32_t)want : a2.rcap;
+		const LState S0 = jump2(SA, rlo, a.jt1, a.jt2, a2.jh1, a2.jh2);
+		dense_eval<R2_T>(a, wc, cat, S0, R, L1, a2.jh1, a2.jh2);
+		__syncthreads();
+		const uint16_t *LS = build_stride<R2_T>(L1, TA, TB, R);
+		if (!exact) {
+			// ---- every candidate's orbit merges, within a few reads, with the orbit of the lowest position: that one
+			// is enumerated (rank in TB, positions in SEL), a candidate walks single reads until it meets it and looks
+			// its end up by rank.  (Unmerged candidates just keep walking: still exact.) ----
+			for (uint32_t q = tid; q < R; q += R2_T) TB[q] = 0;
+			if (tid == 0) {  // every 32nd read of the main orbit
+				uint32_t p = 0, k = 0;
+				pts[0] = 0;
+				while (p < R && k + 1 < R2_MAIN_PTS) {
+					const uint32_t l = LS[p];
+					if (l == R2_SINK) break;
+					p += l;
+					pts[++k] = p;
+				}
+				pts[R2_MAIN_PTS] = k;
+			}
+			__syncthreads();
+			const uint32_t nfull = pts[R2_MAIN_PTS];
+			uint16_t *SEL = TA;  // the stride table is not needed any more
+			__syncthreads();
+			constexpr uint32_t STR = 1u << R2_STRIDE_LOG;
+			for (uint32_t k = tid; k <= nfull; k += R2_T) {
+				uint32_t p = pts[k], t = 0;
+				const uint32_t lim = k < nfull ? STR : 0xffffffffu;  // the last chunk runs to the table's end
+				for (; t < lim && p < R; t++) {
+					TB[p] = (uint16_t)(STR * k + t + 1);
+					SEL[STR * k + t] = (uint16_t)p;
+					const uint32_t l = L1[p];
+					if (l == R2_SINK) {
+						p = R2_SINK;  // the orbit cannot be followed past this read
+						t++;
+						break;
+					}
+					p += l;
+				}
+				if (k == nfull) {
+					SEL[STR * nfull + t] = (uint16_t)(p < R2_SINK ? p : R2_SINK);  // position after the last read (may lie past the table)
+					pts[R2_MAIN_PTS + 1] = STR * nfull + t;  // reads on the main orbit
+				}
+			}
+			__syncthreads();
+			const uint32_t olen = pts[R2_MAIN_PTS + 1];
+			for (uint32_t i = tid; i < nb; i += R2_T) {
+				const uint32_t pos = P[i];
+				uint32_t n = N[i];
+				if (pos == R2_INVALID || n == 0) continue;
+				uint32_t p = pos - rlo;
+				uint32_t rk = 0;
+				bool ok = true;
+				while (n > 0) {
+					if (p >= R) {
+						ok = false;
+						break;
+					}
+					rk = TB[p];
+					if (rk) break;
+					const uint32_t l = L1[p];
+					if (l == R2_SINK) {
+						ok = false;
+						break;
+					}
+					p += l;
+					n--;
+				}
+				uint32_t endp = p;
+				if (ok && n > 0) {  // met the main orbit at its read rk - 1 with n reads to go
+					const uint32_t idx = rk - 1 + n;
+					if (idx <= olen && SEL[idx] != R2_SINK) endp = SEL[idx];
+					else ok = false;
+				}
+				if (ok && (uint64_t)rlo + endp < (uint64_t)R2_POS_LIMIT) P[i] = rlo + endp;
+				else P[i] = R2_INVALID;
+				N[i] = 0;
+			}
+			__syncthreads();
+			break;
+		}
+		for (uint32_t i = tid; i < nb; i += R2_T) {
+			const uint32_t pos = P[i];
+			uint32_t n = N[i];
+			if (pos == R2_INVALID || n == 0) continue;
+			uint32_t p = pos - rlo;
+			const uint32_t p_in = p;
+			if (p < R) advance(L1, LS, R, p, n);
+			const bool fits = (uint64_t)rlo + p < (uint64_t)R2_POS_LIMIT;
+			if (n == 0 && fits) {
+				P[i] = rlo + p;
+				N[i] = 0;
+			} else if (p != p_in && fits) {
+				P[i] = rlo + p;  // the table ended first: the next round starts here
+				N[i] = n;
+			} else {
+				P[i] = R2_INVALID;
+				N[i] = 0;
+			}
+		}
+		__syncthreads();
+		if (!exact) break;
+	}
+}
+
+__global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uint32_t s) {
+	extern __shared__ __align__(16) unsigned char r2_smem[];
+	uint16_t *L1 = (uint16_t *)r2_smem;
+	uint16_t *TA = L1 + a2.rcap;
+	uint16_t *TB = TA + a2.rcap;
+	__shared__ uint32_t s_red[96];
+	__shared__ uint32_t s_b[4];
+	__shared__ uint32_t s_start[R2_KMAX];
+	__shared__ uint2 s_slot[R2_KMAX];
+	__shared__ uint32_t s_pts[R2_MAIN_PTS + 2];
+
+	const ResolveArgs &a = a2.ra;
+	const uint32_t tid = threadIdx.x;
+	const StageAnchor an = a2.anchor[s];
+	if (an.status != R2_RUNNING) {  // done or stuck: later launches of the batch only pass the verdict on
+		if (blockIdx.x == 0 && tid == 0) a2.anchor[s + 1] = an;
+		return;
+	}
+	const LState SA{an.s1, an.s2};
+	const uint32_t K = gridDim.x;
+	const uint32_t j = blockIdx.x;
+	const uint32_t ai = an.first + j;
+	const size_t nbmax = a2.nbmax;
+
+	if (ai < a2.na) {
+		// ---- this window's band of candidate starts, relative to the anchor ----
+		uint32_t lo = 0, nb = 1;
+		if (j > 0) {
+			const double dM = a2.cumM[ai] - a2.cumM[an.first], dV = a2.cumV[ai] - a2.cumV[an.first];
+			const double h = (double)a2.band_sigma * sqrt(dV) + 16.0;
+			double l = floor(dM - h);
+			double want = 2.0 * h + 2.0;
+			if (want > (double)a2.nbmax) {
+				want = (double)a2.nbmax;
+				l = floor(dM - 0.5 * want);
+			}
+			if (l < 0) l = 0;
+			if (l + want + 1.0 < (double)R2_POS_LIMIT) {
+				lo = (uint32_t)l;
+				nb = (uint32_t)want;
+			} else {
+				nb = 0;  // out of the stage's coordinate range: the walker stops here
+			}
+		}
+		if (tid == 0) a2.slot[j] = make_uint2(lo, nb);
+		const uint32_t w = a2.aw[ai];
+		const WinCtx wc = make_winctx(a, w, a2.tabs);
+		uint32_t *endr[NCAT];
+		for (int r = 0; r < NCAT; r++) endr[r] = a2.end + ((size_t)r * K + j) * nbmax;
+		uint32_t *cn = a2.cn + (size_t)j * nbmax, *cnd = a2.cnd + (size_t)j * nbmax;
+		const bool exact = nb == 1;
+		// a speculated window whose expected reads cannot fit one dense table is left to exact mode
+		bool hopeless = false;
+		if (!exact) {
+			float e = 0;
+			for (int c = 0; c < NCAT; c++) e = fmaxf(e, (float)wc.su[c].n * wc.su[c].pp * a2.m1[c]);
+			hopeless = (double)nb + (double)e > (double)a2.rcap;
+		}
+		if (hopeless) {
+			for (uint32_t i = tid; i < nb; i += R2_T) endr[CAT_D][i] = R2_INVALID;
+		} else {
+			for (int region = 0; region < 3; region++) {  // U, B, then C and D (both counts are drawn before C's reads)
+				const int cat0 = region == 2 ? CAT_C : region;
+				uint32_t *cur = endr[cat0];
+				const uint32_t *prev = region == 0 ? nullptr : endr[cat0 - 1];
+				for (uint32_t i = tid; i < nb; i += R2_T) {
+					uint32_t pos = prev ? prev[i] : lo + i;
+					uint32_t n = 0, nd = 0;
+					if (pos != R2_INVALID) {
+						LState S = jump2(SA, pos, a.jt1, a.jt2, a2.jh1, a2.jh2);
+						uint32_t used = 0;
+						auto nx = [&]() {
+							S = lstep(S);
+							used++;
+							return lfloat(lout(S));
+						};
+						// draw_binomial, simplesim.cpp:242, :279, :340-341
+						n = (uint32_t)(wc.tab ? binom_sample_tab(wc.su[cat0], wc.tab[cat0], nx) : binom_sample(wc.su[cat0], nx));
+						if (region == 2) nd = (uint32_t)(wc.tab ? binom_sample_tab(wc.su[CAT_D], wc.tab[CAT_D], nx) : binom_sample(wc.su[CAT_D], nx));
+						if ((uint64_t)pos + used < (uint64_t)R2_POS_LIMIT) {
+							pos += used;
+						} else {
+							pos = R2_INVALID;
+							n = nd = 0;
+						}
+					}
+					cur[i] = pos;
+					cn[i] = n;
+					if (region == 2) cnd[i] = nd;
+				}
+				__syncthreads();
+				advance_region(a2, wc, cat0, SA, nb, exact, cur, cn, L1, TA, TB, s_red, s_pts);
+				if (region == 2) {
+					uint32_t *ed = endr[CAT_D];
+					for (uint32_t i = tid; i < nb; i += R2_T) ed[i] = cur[i];
+					__syncthreads();
+					advance_region(a2, wc, CAT_D, SA, nb, exact, ed, cnd, L1, TA, TB, s_red, s_pts);
+				}
+			}
+		}
+	}
+
+	// ---- the last CTA to finish walks the chain through the stage's tables ----
+	__threadfence();
+	__syncthreads();
+	if (tid == 0) {
+		const uint32_t prev = atomicAdd(&a2.counter[s], 1u);
+		s_b[0] = prev == gridDim.x - 1;
+	}
+	__syncthreads();
+	if (!s_b[0]) return;
+	__threadfence();
+	const uint32_t nstage = min(K, a2.na - an.first);
+	for (uint32_t jj = tid; jj < nstage; jj += R2_T) s_slot[jj] = __ldcg(&a2.slot[jj]);
+	__syncthreads();
+	if (tid == 0) {
+		uint32_t pos = 0, nres = 0;
+		const uint32_t *eD = a2.end + (size_t)CAT_D * K * nbmax;
+		for (uint32_t jj = 0; jj < nstage; jj++) {
+			const uint2 sl = s_slot[jj];
+			if (pos < sl.x || pos - sl.x >= sl.y) break;  // the true start missed the band
+			const uint32_t e = __ldcg(eD + (size_t)jj * nbmax + (pos - sl.x));
+			if (e == R2_INVALID) break;
+			s_start[jj] = pos;
+			pos = e;
+			nres++;
+		}
+		s_b[1] = nres;
+		s_b[2] = pos;
+	}
+	__syncthreads();
+	const uint32_t nres = s_b[1];
+	for (uint32_t jj = tid; jj < nres; jj += R2_T) {
+		WinResolved wr;
+		wr.stage = s;
+		wr.rel = s_start[jj];
+		const uint32_t idx = s_start[jj] - s_slot[jj].x;
+		for (int r = 0; r < NCAT; r++) wr.end[r] = __ldcg(a2.end + ((size_t)r * K + jj) * nbmax + idx);
+		a2.wres[an.first + jj] = wr;
+	}
+	if (tid == 0) {
+		StageAnchor nx = an;
+		if (nres == 0) {
+			nx.status = R2_STUCK;  // the first window failed in exact mode: the caller falls back / reports
+			nx.stuck_win = a2.aw[an.first];
+		} else {
+			const uint32_t pos = s_b[2];
+			nx.abs = an.abs + pos;
+			const LState S = jump2(SA, pos, a.jt1, a.jt2, a2.jh1, a2.jh2);
+			nx.s1 = S.s1;
+			nx.s2 = S.s2;
+			nx.first = an.first + nres;
+			nx.status = nx.first >= a2.na ? R2_DONE : R2_RUNNING;
+		}
+		a2.anchor[s + 1] = nx;
+	}
+}
+
+// Per resolved window: the four binomial counts, re-drawn at the region starts the walk established, and where each
+// category's reads start.  One thread per active window.
+__global__ void __launch_bounds__(128) k_resolve2_counts(Resolve2Args a2, uint32_t *cnt /*[NCAT][na]*/, uint32_t *start /*[NCAT][na]*/,
+                                                       uint32_t *err) {
+	const ResolveArgs &a = a2.ra;
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a2.na) return;
+	const WinResolved wr = a2.wres[i];
+	const StageAnchor an = a2.anchor[wr.stage];
+	const LState SA{an.s1, an.s2};
+	const uint32_t w = a2.aw[i];
+	const WinCtx wc = make_winctx(a, w);
+	uint32_t n[NCAT], st[NCAT];
+	const uint32_t at[3] = {wr.rel, wr.end[CAT_U], wr.end[CAT_B]};
+	for (int region = 0; region < 3; region++) {
+		LState S = jump2(SA, at[region], a.jt1, a.jt2, a2.jh1, a2.jh2);
+		uint32_t used = 0;
+		auto nx = [&]() {
+			S = lstep(S);
+			used++;
+			return lfloat(lout(S));
+		};
+		const int cat0 = region == 2 ? CAT_C : region;
+		n[cat0] = (uint32_t)binom_sample(wc.su[cat0], nx);
+		if (region == 2) n[CAT_D] = (uint32_t)binom_sample(wc.su[CAT_D], nx);
+		st[cat0] = at[region] + used;
+	}
+	st[CAT_D] = wr.end[CAT_C];
+	for (int c = 0; c < NCAT; c++) {
+		cnt[(size_t)c * a2.na + i] = n[c];
+		start[(size_t)c * a2.na + i] = st[c];
+		if (n[c] && a.ntmpl[c] == 0) atomicMax(err, 2u);
+	}
+	if (n[CAT_U] && wc.nslots == 0) atomicMax(err, 1u);  // assert(nslots > 0), simplesim.cpp:252
+}
+
+// Plan records of one (window, category): the orbit of the known start under "next read", n reads long.
+__global__ void __launch_bounds__(R2_TE) k_resolve2_emit(Resolve2Args a2, const uint32_t *cnt, const uint32_t *start,
+                                                        const R2Offsets offp, uint32_t *err) {
+	extern __shared__ __align__(16) unsigned char r2_smem[];
+	uint16_t *L1 = (uint16_t *)r2_smem;
+	uint16_t *TA = L1 + a2.rcap_emit;
+	uint16_t *TB = TA + a2.rcap_emit;
+	__shared__ uint32_t s_pts[R2_EMIT_PTS];
+	__shared__ uint32_t s_b[4];
+	const ResolveArgs &a = a2.ra;
+	const uint32_t tid = threadIdx.x;
+	const uint32_t i = blockIdx.x;
+	const int cat = (int)blockIdx.y;
+	uint32_t n = cnt[(size_t)cat * a2.na + i];
+	if (n == 0 || a.ntmpl[cat] == 0) return;
+	const WinResolved wr = a2.wres[i];
+	const StageAnchor an = a2.anchor[wr.stage];
+	const LState SA{an.s1, an.s2};
+	const uint32_t w = a2.aw[i];
+	const WinCtx wc = make_winctx(a, w);
+	uint32_t pos = start[(size_t)cat * a2.na + i];
+	uint64_t base = offp.p[cat][i];
+	PlanRec *plan = a.plan[cat];
+	constexpr uint32_t STR = 1u << R2_STRIDE_LOG;
+	while (n > 0) {
+		uint64_t want = reach(a2, cat, n) + 1;
+		const uint32_t R = want < (uint64_t)a2.rcap_emit ? (uint32_t)want : a2.rcap_emit;
+		const LState S0 = jump2(SA, pos, a.jt1, a.jt2, a2.jh1, a2.jh2);
+		dense_eval<R2_TE>(a, wc, cat, S0, R, L1, a2.jh1, a2.jh2);
+		__syncthreads();
+		const uint16_t *LS = build_stride<R2_TE>(L1, TA, TB, R);  // in TA; TB is free for the ranks
+		for (uint32_t q = tid; q < R; q += R2_TE) TB[q] = 0;
+		if (tid == 0) {  // every 32nd read of the orbit
+			uint32_t p = 0, k = 0, rem = n;
+			s_pts[0] = 0;
+			while (rem >= STR && p < R && k + 1 < R2_EMIT_PTS) {
+				const uint32_t l = LS[p];
+				if (l == R2_SINK) break;
+				p += l;
+				rem -= STR;
+				s_pts[++k] = p;
+			}
+			s_b[0] = k;
+		}
+		__syncthreads();
+		const uint32_t nfull = s_b[0];
+		// chunk k: the reads 32 k .. 32 k + 31 of the orbit (the last chunk: as far as the reads / the table go)
+		for (uint32_t k = tid; k <= nfull; k += R2_TE) {
+			uint32_t p = s_pts[k];
+			const uint32_t lim = k < nfull ? STR : n - STR * nfull;
+			uint32_t t = 0;
+			for (; t < lim && p < R; t++) {
+				TB[p] = (uint16_t)(STR * k + t + 1);
+				const uint32_t l = L1[p];
+				if (l == R2_SINK) {  // a read of >= 65535 draws: not representable here (the stage kernel got stuck first)
+					atomicMax(err, 4u);
+					t++;
+					p = R;
+					break;
+				}
+				p += l;
+			}
+			if (k == nfull) {
+				s_b[1] = STR * nfull + t;  // reads taken in this round
+				s_b[2] = p;                // where the next round starts
+			}
+		}
+		__syncthreads();
+		{
+			LState sq = jump2(S0, tid, a.jt1, a.jt2, a2.jh1, a2.jh2);
+			const uint32_t c1 = __ldg(&a.jt1[R2_TE]), c2 = __ldg(&a.jt2[R2_TE]);
+			for (uint32_t q = tid; q < R; q += R2_TE) {
+				const uint32_t rk = TB[q];
+				if (rk) {
+					LState t = lstep(sq);
+					const uint32_t ti = (uint32_t)lindex(lfloat(lout(t)), a.ntmpl[cat]);
+					t = lstep(t);
+					const uint64_t off = lindex(lfloat(lout(t)), wc.nslots);
+					PlanRec pr;
+					pr.tmpl = ti;
+					pr.record = wc.record;
+					pr.refoff = wc.refoff + off;
+					pr.s1 = t.s1;
+					pr.s2 = t.s2;
+					plan[base + rk - 1] = pr;
+				}
+				sq.s1 = mulmod1(sq.s1, c1);
+				sq.s2 = mulmod2(sq.s2, c2);
+			}
+		}
+		const uint32_t taken = s_b[1], endp = s_b[2];
+		__syncthreads();  // s_b, s_pts and the tables are rewritten by the next round
+		if (taken == 0 || (uint64_t)pos + endp >= (uint64_t)R2_POS_LIMIT) {
+			if (tid == 0) atomicMax(err, 5u);
+			break;
+		}
+		pos += endp;
+		n -= taken;
+		base += taken;
+	}
+	// the stage kernel's table-driven walk and this enumeration must agree on where the category's reads end
+	if (tid == 0 && n == 0 && pos != wr.end[cat]) atomicMax(err, 6u);
+}
+
+void launch_resolve2_stage(const Resolve2Args &a, uint32_t s, uint32_t K, cudaStream_t st) {
+	static bool attr = false;
+	if (!attr) {
+		cudaFuncSetAttribute(k_resolve2_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3u * R2_RCAP_MAX * 2u));
+		attr = true;
+	}
+	k_resolve2_stage<<<K, R2_T, (size_t)3 * a.rcap * 2, st>>>(a, s);
+	kernels_count_launch();
+}
+
+void launch_resolve2_counts(const Resolve2Args &a, uint32_t *cnt, uint32_t *start, uint32_t *err, cudaStream_t st) {
+	k_resolve2_counts<<<(a.na + 127) / 128, 128, 0, st>>>(a, cnt, start, err);
+	kernels_count_launch();
+}
+
+void launch_resolve2_emit(const Resolve2Args &a, const uint32_t *cnt, const uint32_t *start, const R2Offsets &offp, uint32_t *err,
+                          cudaStream_t st) {
+	static bool attr = false;
+	if (!attr) {
+		cudaFuncSetAttribute(k_resolve2_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3u * R2_RCAP_MAX * 2u));
+		attr = true;
+	}
+	dim3 grid(a.na, NCAT);
+	k_resolve2_emit<<<grid, R2_TE, (size_t)3 * a.rcap_emit * 2, st>>>(a, cnt, start, offp, err);
+	kernels_count_launch();
+}
+
+}  // namespace qt

@@ -148,7 +148,13 @@ int TemplateStore::set_unpaired(int ci, const qtipsim_tmpl_unp *v, size_t kept, 
 		c.xs.reserve(kept * (l0 + 8));
 		c.qual_out.reserve(kept * (l0 + 24) + 64);
 	}
-	double bytes = 0, draws = 0;
+	double bytes = 0, draws = 0, dsum = 0, dsq = 0;
+	auto draw_stats = [&](double fixed, double nx) {  // per template: mean fixed + 4/3 nx, variance 4/9 nx
+		const double m = fixed + nx * (4.0 / 3.0);
+		dsum += m;
+		dsq += m * m + nx * (4.0 / 9.0);
+		c.draw_max_fixed = std::max<uint32_t>(c.draw_max_fixed, (uint32_t)(fixed + nx));
+	};
 	for (size_t i = 0; i < kept; i++) {
 		TmplDesc &t = c.t[i];
 		memset(&t, 0, sizeof(t));
@@ -175,17 +181,27 @@ int TemplateStore::set_unpaired(int ci, const qtipsim_tmpl_unp *v, size_t kept, 
 			// name (both scores) on both files + two bodies
 			bytes += 2.0 * (7 + 2 * (5 + t.m[0].score_len) + 2 + 1) + 2.0 * t.m[0].len + 2.0 * t.opp_len + 8;
 			draws += 2 + t.m[0].ndraw + t.opp_len;
+			{
+				const double nx = c.prog[2 * i].xs_end - c.prog[2 * i].xs_begin;
+				draw_stats(2.0 + t.m[0].ndraw - nx + t.opp_len, nx);
+			}
 		} else {
 			t.typ[0] = 'u';
 			t.typ_len = 1;
 			bytes += 7 + 5 + t.m[0].score_len + 1 + 1 + 2.0 * t.m[0].len + 4;
 			draws += 2 + t.m[0].ndraw;
+			{
+				const double nx = c.prog[2 * i].xs_end - c.prog[2 * i].xs_begin;
+				draw_stats(2.0 + t.m[0].ndraw - nx, nx);
+			}
 		}
 		c.max_len = std::max<uint64_t>(c.max_len, t.m[0].rflen);  // input_model.h:38-41
 	}
 	if (kept) {
 		c.mean_bytes = bytes / kept;
 		c.mean_draws = draws / kept;
+		c.draw_m1 = dsum / kept;
+		c.draw_v1 = std::max(0.0, dsq / kept - c.draw_m1 * c.draw_m1);
 	}
 	return QTIPSIM_OK;
 }
@@ -206,7 +222,7 @@ int TemplateStore::set_paired(int ci, const qtipsim_tmpl_pair *v, size_t kept, u
 		c.xs.reserve(kept * (l0 + 16));
 		c.qual_out.reserve(kept * (l0 + 48) + 64);
 	}
-	double bytes = 0, draws = 0;
+	double bytes = 0, draws = 0, dsum = 0, dsq = 0;
 	for (size_t i = 0; i < kept; i++) {
 		TmplDesc &t = c.t[i];
 		memset(&t, 0, sizeof(t));
@@ -234,10 +250,20 @@ int TemplateStore::set_paired(int ci, const qtipsim_tmpl_pair *v, size_t kept, u
 		c.max_len = std::max<uint64_t>(c.max_len, fl);  // input_model.h:112-115
 		bytes += 2.0 * (7 + 9 + t.m[0].score_len + t.m[1].score_len + 2) + 2.0 * t.m[0].len + 2.0 * t.m[1].len + 8;
 		draws += 2 + t.m[0].ndraw + t.m[1].ndraw;
+		{
+			const double nx = (double)(c.prog[2 * i].xs_end - c.prog[2 * i].xs_begin) + (double)(c.prog[2 * i + 1].xs_end - c.prog[2 * i + 1].xs_begin);
+			const double fixed = 2.0 + t.m[0].ndraw + t.m[1].ndraw - nx;
+			const double m = fixed + nx * (4.0 / 3.0);
+			dsum += m;
+			dsq += m * m + nx * (4.0 / 9.0);
+			c.draw_max_fixed = std::max<uint32_t>(c.draw_max_fixed, (uint32_t)(fixed + nx));
+		}
 	}
 	if (kept) {
 		c.mean_bytes = bytes / kept;
 		c.mean_draws = draws / kept;
+		c.draw_m1 = dsum / kept;
+		c.draw_v1 = std::max(0.0, dsq / kept - c.draw_m1 * c.draw_m1);
 	}
 	return QTIPSIM_OK;
 }

@@ -45,6 +45,10 @@ struct Category {
 	std::string why;                  // first problem found
 	double mean_bytes = 0;            // expected FASTQ bytes per read, excluding refid/offset digits
 	double mean_draws = 0;            // expected draws per read
+	// draws one read / pair consumes in REPLAY mode, for the band placement of the speculative resolver
+	// (resolve2.cu): 2 index draws + one per I/S (+ opp_len) + Geometric(3/4) per X (simplesim.cpp:45-50)
+	double draw_m1 = 0, draw_v1 = 0;  // mean and variance over a uniformly drawn template
+	uint32_t draw_max_fixed = 0;      // most draws of a template when every X takes one draw
 	void clear() { *this = Category(); }
 };
 

@@ -307,15 +307,36 @@ def test_staged_kernel_path_still_bit_exact(name, workdir, monkeypatch):
     assert nat_s == nat_d  # both kernels consume the Philox stream identically
 
 
-@pytest.mark.parametrize("name", ["mixed_small", "c4_mix_small", "inversion"])
-def test_single_cta_resolver_equals_cluster_resolver(name, workdir, monkeypatch):
-    """K2 has two forms: the thread-block-cluster resolver (default) and the single-CTA one it grew out of
-    (QTIPSIM_RESOLVER=cta).  Same plan, same draws, same exit state."""
+@pytest.mark.parametrize("resolver", ["cluster", "cta"])
+@pytest.mark.parametrize("name", ["mixed_small", "c4_mix_small", "inversion", "edges", "c3_shape_small"])
+def test_first_generation_resolvers_equal_band_resolver(name, resolver, workdir, monkeypatch):
+    """K2 has three forms: the band-speculative staged resolver (default, resolve2.cu), the thread-block-cluster
+    resolver and the single-CTA one it grew out of (QTIPSIM_RESOLVER=cluster|cta).  Same plan, same draws, same
+    exit state."""
     case = cases.CASES[name]()
     a, sta, pa = util.run_cuda(case, workdir, name)
-    monkeypatch.setenv("QTIPSIM_RESOLVER", "cta")
+    monkeypatch.setenv("QTIPSIM_RESOLVER", resolver)
     b, stb, pb = util.run_cuda(case, workdir, name)
     assert a == b and sta.draws == stb.draws and (pa.cg1, pa.cg2) == (pb.cg1, pb.cg2)
+
+
+@pytest.mark.parametrize("knobs", [dict(QTIPSIM_R2_RCAP="1024", QTIPSIM_R2_RCAP_EMIT="1024"),      # many rounds per window
+                                   dict(QTIPSIM_R2_SIGMA="0.3", QTIPSIM_R2_K="16"),                  # bands that miss
+                                   dict(QTIPSIM_R2_NBMAX="64", QTIPSIM_R2_K="7"),                    # clipped bands
+                                   dict(QTIPSIM_R2_K="1"), dict(QTIPSIM_R2_K="400", QTIPSIM_R2_SIGMA="8")])
+@pytest.mark.parametrize("name", ["mixed_small", "c4_mix_small", "c3_shape_small", "edges", "long_reads", "c5_indel"])
+def test_band_resolver_is_exact_under_any_tuning(name, knobs, workdir, monkeypatch):
+    """The band resolver's tables are exact or INVALID whatever the band width, the dense-table size or the stage
+    size: tiny tables force the round-by-round exact mode, narrow bands force early stage ends, and the result is the
+    oracle's every time."""
+    case = cases.CASES[name]()
+    o = _oracle(case, workdir, name)
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    got, st, p = util.run_cuda(case, workdir, name)
+    for i in range(7):
+        assert got[i] == o.streams[i], (name, knobs, i)
+    assert (p.cg1, p.cg2) == tuple(o.cg) and st.draws == o.draws and list(st.wrote) == list(o.wrote)
 
 
 def test_host_pack_path_equals_device_pack(workdir, monkeypatch):

@@ -80,6 +80,24 @@ def test_ignbin_split_matches_oracle():
         assert (s1.value, s2.value) == (st.cg1, st.cg2)
 
 
+def test_ignbin_table_sampler_matches_oracle():
+    """binom_tables + binom_sample_tab (the device resolver's sampler: BTPE's step-5 bounds read from per-set-up
+    tables) == orc_ignbin, value and state, with many variates per set-up so that every branch is taken."""
+    L = util.hosttest()
+    o = po.orc()
+    rng = np.random.default_rng(12)
+    for _ in range(120):
+        n = int(rng.choice([100, 3000, 30000, 1000000, 10000000, 100000000, 2000000000]))
+        p = float(np.float32(rng.choice([4.6e-5, 1e-3, 0.03, 0.3, 0.5, 0.7, 0.97, 0.999])))
+        s = (int(rng.integers(1, 2147483562)), int(rng.integers(1, 2147483398)))
+        st = po.OrcRng()
+        o.orc_rng_set_seed(C.byref(st), *s)
+        s1, s2 = C.c_uint32(s[0]), C.c_uint32(s[1])
+        for _k in range(300):
+            assert L.qthost_ignbin_tab(C.byref(s1), C.byref(s2), n, p) == o.orc_ignbin(C.byref(st), n, p), (n, p, s)
+        assert (s1.value, s2.value) == (st.cg1, st.cg2)
+
+
 def test_logf_matches_libm_sampled():
     """logf_glibc == host logf on a stride over all positive normal floats, and densely over
     (0, 1] where ignbin's arguments live.  (Exhaustive: tests/test_logf_exhaustive.py, -m slow.)"""

@@ -67,6 +67,8 @@ def hosttest() -> C.CDLL:
         L.qthost_rng_jump.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint64]
         L.qthost_ignbin.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.c_float]
         L.qthost_ignbin.restype = C.c_int
+        L.qthost_ignbin_tab.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_int, C.c_float]
+        L.qthost_ignbin_tab.restype = C.c_int
         L.qthost_logf.argtypes = [C.c_float]
         L.qthost_logf.restype = C.c_float
         L.qthost_logf_sweep.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
