@@ -81,7 +81,7 @@ struct qtipsim {
 
 	TemplateStore ts;
 	bool tmpl_dirty[NCAT] = {true, true, true, true};
-	DevBuf d_t[NCAT], d_qual[NCAT], d_xs[NCAT], d_qual_out[NCAT], d_ops[NCAT], d_segs[NCAT], d_xsteps[NCAT], d_prog[NCAT];
+	DevBuf d_t[NCAT], d_qual[NCAT], d_xs[NCAT], d_qual_out[NCAT], d_ops[NCAT], d_segs[NCAT], d_xsteps[NCAT], d_prog[NCAT], d_xprog[NCAT];
 	DevBuf d_setups, d_pclass, d_rsresult;
 
 	DevBuf d_jt1, d_jt2, d_jh1, d_jh2;
@@ -205,6 +205,7 @@ void qtipsim_destroy(qtipsim_t *h) {
 		h->d_segs[c].release();
 		h->d_xsteps[c].release();
 		h->d_prog[c].release();
+		h->d_xprog[c].release();
 		h->d_plan[c].release();
 		h->d_off0[c].release();
 		h->d_off1[c].release();
@@ -627,6 +628,9 @@ static int upload_templates(qtipsim *h) {
 				CK(cudaMemcpyAsync(h->d_xsteps[c].p, cg.xsteps.data(), cg.xsteps.size() * sizeof(XStep), cudaMemcpyHostToDevice, h->st));
 			if (!cg.prog.empty())
 				CK(cudaMemcpyAsync(h->d_prog[c].p, cg.prog.data(), cg.prog.size() * sizeof(HostMateProg), cudaMemcpyHostToDevice, h->st));
+			CK(h->d_xprog[c].ensure(cg.xprog.size() * sizeof(XProgRec) + 64));
+			if (!cg.xprog.empty())
+				CK(cudaMemcpyAsync(h->d_xprog[c].p, cg.xprog.data(), cg.xprog.size() * sizeof(XProgRec), cudaMemcpyHostToDevice, h->st));
 		}
 		h->tmpl_dirty[c] = false;
 	}
@@ -727,6 +731,7 @@ static void fill_resolve_args(qtipsim *h, const qtipsim_run_params *p, const Pla
 		ra.t[c] = h->d_t[c].as<TmplDesc>();
 		ra.xsteps[c] = h->d_xsteps[c].as<XStep>();
 		ra.prog[c] = h->d_prog[c].as<HostMateProg>();
+		ra.xp[c] = getenv("QTIPSIM_R2_NOXPROG") ? nullptr : h->d_xprog[c].as<XProgRec>();
 		ra.ntmpl[c] = (uint32_t)h->ts.cat[c].t.size();
 		ra.target[c] = pp.target[c];
 		ra.cap[c] = 0;
@@ -764,7 +769,7 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 		if (cg.draw_max_fixed > 16000u) return QTIPSIM_OK;  // a read of this many draws does not fit the u16 tables: first-generation kernel
 	}
 	cum.assign(2 * (size_t)na + 2, 0.0);
-	double typical = 0;
+	double typical = 0, vmax = 0, reach_max = 0;
 	for (uint32_t i = 0; i < na; i++) {
 		const BinomSetup *su = &h->setup_cache[(size_t)h->pclass_cache[aw[i]] * NCAT];
 		double m = 0, v = 0, big = 0;
@@ -777,6 +782,12 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 		cum[i + 1] = cum[i] + m;
 		cum[na + 1 + i + 1] = cum[na + 1 + i] + v;
 		typical = std::max(typical, big);
+		vmax = std::max(vmax, v);
+		for (int c = 0; c < NCAT; c++) {
+			const double np = (double)su[c].n * (double)su[c].pp;
+			reach_max = std::max(reach_max, np * a2.m1[c] + 8.0 * sqrt(np * (1.0 - su[c].pp) * a2.m1[c] * a2.m1[c] + np * a2.v1[c] + 1.0) +
+			                                    2.0 * a2.maxfixed[c] + 64.0);
+		}
 	}
 	auto envu = [](const char *nm, uint32_t dflt) {
 		const char *e = getenv(nm);
@@ -789,12 +800,21 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 	a2.nbmax = std::max<uint32_t>(64u, envu("QTIPSIM_R2_NBMAX", 24576u));
 	{
 		const char *e = getenv("QTIPSIM_R2_SIGMA");
-		a2.band_sigma = e && *e ? (float)atof(e) : 5.0f;
+		a2.band_sigma = e && *e ? (float)atof(e) : 4.0f;
 	}
 	uint32_t K = std::min<uint32_t>(R2_KMAX, std::max<uint32_t>(1u, envu("QTIPSIM_R2_K", (uint32_t)nsm)));
 	// windows whose reads cannot fit one dense table are resolved one per stage in exact mode: no point in speculating
 	if (typical + 64.0 > (double)a2.rcap) K = 1;
 	if (na && K > na) K = na;
+	if (K > 1 && !getenv("QTIPSIM_R2_RCAP")) {
+		// the dense tables only need to hold the widest band of a stage plus one window's reads: a smaller table leaves
+		// more of the SM's shared memory to the L1 cache, where the window's packed bases live
+		const double nbw = 2.0 * ((double)a2.band_sigma * sqrt(vmax * (double)(K - 1)) + 16.0) + 2.0;
+		const double need = (std::min(nbw, (double)a2.nbmax) + reach_max) * 1.1;
+		uint32_t rc = (uint32_t)std::min<double>(need, (double)R2_RCAP_MAX);
+		rc = (rc + 1023u) & ~1023u;
+		a2.rcap = std::min<uint32_t>(R2_RCAP_MAX, std::max<uint32_t>(4096u, rc));
+	}
 	if (!na) {
 		for (int c = 0; c < NCAT; c++) nreads[c] = 0;
 		draws = 0;
@@ -856,8 +876,8 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 	}
 	h->r2_stages_last = launched;
 	if (getenv("QTIPSIM_R2_TRACE"))
-		fprintf(stderr, "[resolve2] %u live windows, K = %u, %u stage launches, status %u, first %u, draws %llu\n", na, K, launched,
-		        fin.status, fin.first, (unsigned long long)fin.abs);
+		fprintf(stderr, "[resolve2] %u live windows, K = %u, rcap %u, %u stage launches, status %u, first %u, draws %llu\n", na, K, a2.rcap,
+		        launched, fin.status, fin.first, (unsigned long long)fin.abs);
 	if (fin.status == R2_STUCK) return QTIPSIM_OK;  // done stays false: first-generation kernel
 
 	// ---- counts per (window, category), offsets, totals ----
@@ -1024,6 +1044,7 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 					ra.t[c] = h->d_t[c].as<TmplDesc>();
 					ra.xsteps[c] = h->d_xsteps[c].as<XStep>();
 					ra.prog[c] = h->d_prog[c].as<HostMateProg>();
+					ra.xp[c] = nullptr;
 					ra.ntmpl[c] = (uint32_t)h->ts.cat[c].t.size();
 					ra.target[c] = pp.target[c];
 					// expected reads <= 1.1 * target * (this shard's share of the windows); generous margin

@@ -148,6 +148,26 @@ int qthost_ignbin_tab(uint32_t *s1, uint32_t *s2, int n, float p) {
 	*s2 = s.s2;
 	return v;
 }
+// lbase_code_z against lbase_code(lfloat(z)): re-derives the three thresholds by bisection, then compares the two on
+// +-span around each threshold and on a stride over the whole range; returns the number of disagreements
+uint64_t qthost_base_thresholds(int32_t *t, int32_t span, int32_t stride) {
+	for (int c = 1; c <= 3; c++) {
+		int64_t lo = 1, hi = 2147483562;
+		while (lo < hi) {
+			const int64_t m = (lo + hi) / 2;
+			if ((int)lbase_code(lfloat((int32_t)m)) >= c) hi = m;
+			else lo = m + 1;
+		}
+		t[c - 1] = (int32_t)lo;
+	}
+	uint64_t bad = 0;
+	for (int c = 0; c < 3; c++)
+		for (int64_t z = (int64_t)t[c] - span; z <= (int64_t)t[c] + span; z++)
+			if (z >= 1 && z <= 2147483562 && lbase_code_z((int32_t)z) != lbase_code(lfloat((int32_t)z))) bad++;
+	for (int64_t z = 1; z <= 2147483562; z += stride)
+		if (lbase_code_z((int32_t)z) != lbase_code(lfloat((int32_t)z))) bad++;
+	return bad;
+}
 float qthost_logf(float x) { return logf_glibc(x); }
 // compares logf_glibc with the host libm over [lo, hi) bit patterns; returns mismatches
 uint64_t qthost_logf_sweep(uint32_t lo, uint32_t hi, uint32_t step) {

@@ -151,6 +151,12 @@ QT_HD uint32_t lbase_code(float u) {
 	return (uint32_t)(k < 3 ? k : 3);
 }
 
+// The same code straight from i4_uni's integer z: lbase_code(lfloat(z)) is monotone in z (every step of it is), so it is
+// three comparisons against the smallest z of each code (found by bisection over the exact expression; hosttest.cpp
+// qthost_base_thresholds re-derives them and tests/test_host_logic.py checks them around every threshold).
+static constexpr int32_t LBASE_T1 = 536870865, LBASE_T2 = 1073741729, LBASE_T3 = 1610612672;
+QT_HD uint32_t lbase_code_z(int32_t z) { return (uint32_t)(z >= LBASE_T1) + (uint32_t)(z >= LBASE_T2) + (uint32_t)(z >= LBASE_T3); }
+
 // index draws: min((size_t)(r4 * (float)n), n-1)  (input_model.h:51, simplesim.cpp:253)
 QT_HD uint64_t lindex(float u, uint64_t n) {
 	float prod = fmul_rn(u, (float)n);

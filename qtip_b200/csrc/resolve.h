@@ -23,6 +23,7 @@ struct ResolveArgs {
 	const TmplDesc *t[NCAT];
 	const XStep *xsteps[NCAT];
 	const HostMateProg *prog[NCAT];
+	const XProgRec *xp[NCAT];     // packed draw programs (resolve2.cu); null: walk the XStep lists
 	uint32_t ntmpl[NCAT];
 	uint64_t target[NCAT];
 	PlanRec *plan[NCAT];

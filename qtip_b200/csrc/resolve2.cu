@@ -98,13 +98,35 @@ __device__ __forceinline__ WinCtx make_winctx(const ResolveArgs &a, uint32_t w, 
 // draws consumed by a read / pair of category cat whose template draw is the first draw after state s
 // (simplesim.cpp:243-273, :280-334, :342-397)
 __device__ __forceinline__ uint32_t read_len(const ResolveArgs &a, const WinCtx &wc, int cat, LState s) {
-	const TmplDesc *tdesc = a.t[cat];
-	const HostMateProg *prog = a.prog[cat];
 	s = lstep(s);
 	const uint32_t ti = (uint32_t)lindex(lfloat(lout(s)), a.ntmpl[cat]);
 	s = lstep(s);
 	const uint64_t off = lindex(lfloat(lout(s)), wc.nslots);
 	uint32_t len = 2;
+	const XProgRec *xp = a.xp[cat];
+	if (xp) {
+		// packed programs: one 32-byte load per mate, issued before anything depends on them
+		const uint4 *src = (const uint4 *)(xp + ti);
+		uint32_t w0[8], w1[8];
+		{
+			const uint4 x = __ldg(src), y = __ldg(src + 1);
+			w0[0] = x.x, w0[1] = x.y, w0[2] = x.z, w0[3] = x.w, w0[4] = y.x, w0[5] = y.y, w0[6] = y.z, w0[7] = y.w;
+		}
+		if (cat >= CAT_C) {
+			const uint4 x = __ldg(src + 2), y = __ldg(src + 3);
+			w1[0] = x.x, w1[1] = x.y, w1[2] = x.z, w1[3] = x.w, w1[4] = y.x, w1[5] = y.y, w1[6] = y.z, w1[7] = y.w;
+		}
+		const bool packed = ((w0[5] >> 8) & 0xffu) != 0xffu && (cat < CAT_C || ((w1[5] >> 8) & 0xffu) != 0xffu);
+		if (packed) {
+			const uint32_t d0 = cat >= CAT_C ? w0[7] : 0u;
+			len += walk_mate_xp(s, a.g, w0, wc.gwin + off + d0, wc.gend, wc.has_n, a.jt1, a.jt2);
+			if (cat >= CAT_C) len += walk_mate_xp(s, a.g, w1, wc.gwin + off + w1[6], wc.gend, wc.has_n, a.jt1, a.jt2);
+			if (cat == CAT_B) len += w0[6];  // init_random, simplesim.h:108-113
+			return len;
+		}
+	}
+	const TmplDesc *tdesc = a.t[cat];
+	const HostMateProg *prog = a.prog[cat];
 	uint32_t d0 = 0, d1 = 0;  // the mates' offsets from the drawn position are 0 for U and B
 	if (cat >= CAT_C) {
 		d0 = tdesc[ti].delta[0];

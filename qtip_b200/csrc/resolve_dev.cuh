@@ -45,12 +45,51 @@ __device__ __forceinline__ uint32_t walk_mate_dev(LState &s, const DevGenome &g,
 		do {
 			s = lstep(s);
 			len++;
-			code = lbase_code(lfloat(lout(s)));
+			code = lbase_code_z(lout(s));
 		} while (code == ref);
 	}
 	if (hp.tail_skip) {
 		s = jump_tbl(s, hp.tail_skip, jt1, jt2);
 		len += hp.tail_skip;
+	}
+	return len;
+}
+
+
+// The same walk from a packed program (templates.h XProgHalf, eight words already in registers): every X's reference
+// base is fetched before the first draw is made, so the loads overlap instead of alternating with the draws.
+__device__ __forceinline__ uint32_t walk_mate_xp(LState &s, const DevGenome &g, const uint32_t (&w)[8], uint64_t gpos, uint64_t gend,
+                                                 bool has_n, const uint32_t *jt1, const uint32_t *jt2) {
+	const uint32_t nx = (w[5] >> 8) & 0xffu, tail = (w[5] >> 16) & 0xffu;
+	uint32_t codes = 0;
+#pragma unroll
+	for (int k = 0; k < 7; k++) {
+		if ((uint32_t)k < nx) {
+			const uint32_t rf = (w[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+			codes |= rs_fetch_code(g, gpos + rf, gend, has_n) << (3 * k);
+		}
+	}
+	uint32_t len = 0;
+#pragma unroll
+	for (int k = 0; k < 7; k++) {
+		if ((uint32_t)k < nx) {
+			const uint32_t sk = (w[(14 + k) >> 2] >> (8 * ((14 + k) & 3))) & 0xffu;
+			if (sk) {
+				s = jump_tbl(s, sk, jt1, jt2);
+				len += sk;
+			}
+			const uint32_t ref = (codes >> (3 * k)) & 7u;
+			uint32_t code;
+			do {
+				s = lstep(s);
+				len++;
+				code = lbase_code_z(lout(s));
+			} while (code == ref);
+		}
+	}
+	if (tail) {
+		s = jump_tbl(s, tail, jt1, jt2);
+		len += tail;
 	}
 	return len;
 }

@@ -132,6 +132,32 @@ bool add_mate(Category &c, MateDesc &m, HostMateProg &hp, const char *qual, cons
 
 }  // namespace
 
+void Category::finish_xprog() {
+	xprog.assign(t.size(), XProgRec{});
+	for (size_t i = 0; i < t.size(); i++) {
+		for (int m = 0; m < 2; m++) {
+			XProgHalf &hf = xprog[i].h[m];
+			const HostMateProg &hp = prog[2 * i + m];
+			const uint32_t nx = hp.xs_end - hp.xs_begin;
+			bool fits = nx <= 7 && hp.tail_skip <= 255;
+			for (uint32_t k = 0; fits && k < nx; k++) fits = xsteps[hp.xs_begin + k].rf <= 65535u && xsteps[hp.xs_begin + k].skip <= 255u;
+			if (!fits) {
+				hf.nx = 0xff;
+			} else {
+				hf.nx = (uint8_t)nx;
+				hf.tail = (uint8_t)hp.tail_skip;
+				for (uint32_t k = 0; k < nx; k++) {
+					hf.rf[k] = (uint16_t)xsteps[hp.xs_begin + k].rf;
+					hf.skip[k] = (uint8_t)xsteps[hp.xs_begin + k].skip;
+				}
+			}
+		}
+		xprog[i].h[0].extra0 = t[i].opp_len;
+		xprog[i].h[0].extra1 = t[i].delta[0];
+		xprog[i].h[1].extra0 = t[i].delta[1];
+	}
+}
+
 int TemplateStore::set_unpaired(int ci, const qtipsim_tmpl_unp *v, size_t kept, uint64_t added, std::string &err) {
 	if (ci != CAT_U && ci != CAT_B) {
 		err = "set_templates_unpaired: category must be U or B";
@@ -203,6 +229,7 @@ int TemplateStore::set_unpaired(int ci, const qtipsim_tmpl_unp *v, size_t kept, 
 		c.draw_m1 = dsum / kept;
 		c.draw_v1 = std::max(0.0, dsq / kept - c.draw_m1 * c.draw_m1);
 	}
+	c.finish_xprog();
 	return QTIPSIM_OK;
 }
 
@@ -265,6 +292,7 @@ int TemplateStore::set_paired(int ci, const qtipsim_tmpl_pair *v, size_t kept, u
 		c.draw_m1 = dsum / kept;
 		c.draw_v1 = std::max(0.0, dsq / kept - c.draw_m1 * c.draw_m1);
 	}
+	c.finish_xprog();
 	return QTIPSIM_OK;
 }
 

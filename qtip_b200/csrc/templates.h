@@ -25,6 +25,23 @@ struct HostMateProg {
 	uint32_t tail_skip = 0;             // I/S draws after the last X
 };
 
+// One mate's draw program packed for the device resolvers: everything read_len needs about a template in one
+// 32-byte load (the XStep lists cost one dependent load per X).  nx = 0xff: the mate does not fit (more than 7 X, a
+// reference offset over 65535 or more than 255 skipped draws) and the XStep list is walked instead.
+struct alignas(32) XProgHalf {
+	uint16_t rf[7];    // reference offset of each X, relative to the mate's leftmost base
+	uint8_t skip[7];   // I/S draws before each X
+	uint8_t nx;
+	uint8_t tail;      // I/S draws after the last X
+	uint8_t pad;
+	uint32_t extra0;   // half 0: opp_len (B);  half 1: delta[1]
+	uint32_t extra1;   // half 0: delta[0]
+};
+struct alignas(64) XProgRec {
+	XProgHalf h[2];
+};
+static_assert(sizeof(XProgHalf) == 32 && sizeof(XProgRec) == 64, "XProg layout");
+
 struct Category {
 	std::vector<TmplDesc> t;
 	std::string qual;                 // arena
@@ -39,6 +56,8 @@ struct Category {
 	uint32_t max_rflen = 0;           // longest reference span of a mate
 	std::vector<XStep> xsteps;        // host-side draw programs (replay planner)
 	std::vector<HostMateProg> prog;   // 2 per template
+	std::vector<XProgRec> xprog;      // 1 per template (built by finish_xprog)
+	void finish_xprog();
 	uint64_t added = 0;               // num_added(), input_model.h:68-70
 	uint64_t max_len = 0;             // max_len(), input_model.h:82-84 / :155-157
 	bool valid = true;                // all transcripts well-formed

@@ -98,6 +98,16 @@ def test_ignbin_table_sampler_matches_oracle():
         assert (s1.value, s2.value) == (st.cg1, st.cg2)
 
 
+def test_draw_base_integer_thresholds():
+    """lbase_code_z (three integer comparisons on i4_uni's output) == draw_base through r4_uni_01 (simplesim.h:26-28,
+    rnglib.cpp:1502): the thresholds are re-derived by bisection and the two forms compared on +-200 000 around each
+    and on a stride of 977 over the whole range."""
+    L = util.hosttest()
+    t = (C.c_int32 * 3)()
+    assert L.qthost_base_thresholds(t, 200000, 977) == 0
+    assert list(t) == [536870865, 1073741729, 1610612672]
+
+
 def test_logf_matches_libm_sampled():
     """logf_glibc == host logf on a stride over all positive normal floats, and densely over
     (0, 1] where ignbin's arguments live.  (Exhaustive: tests/test_logf_exhaustive.py, -m slow.)"""
