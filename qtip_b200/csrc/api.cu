@@ -803,7 +803,20 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 		a2.band_sigma = e && *e ? (float)atof(e) : 4.0f;
 	}
 	uint32_t K = std::min<uint32_t>(R2_KMAX, std::max<uint32_t>(1u, envu("QTIPSIM_R2_K", (uint32_t)nsm)));
-	// windows whose reads cannot fit one dense table are resolved one per stage in exact mode: no point in speculating
+	// How many windows ahead can be speculated before the band (which widens with the square root of the distance)
+	// plus one window's reads outgrow the largest dense table?  Workloads where that is only a handful -- many reads per
+	// window, or bad-end reads whose ~150 skipped draws each make the position noise large -- are left to the
+	// first-generation resolver, which walks them round by round on a cluster (QTIPSIM_R2_FORCE=1 keeps them here: tests).
+	{
+		const double room = (double)a2.rcap - reach_max * 1.1 - 64.0;
+		double kfit = 0;
+		if (room > 0 && vmax > 0) {
+			const double r = (room / 2.2 - 16.0) / ((double)a2.band_sigma * sqrt(vmax));
+			kfit = r > 0 ? r * r + 1.0 : 1.0;
+		}
+		if (kfit < (double)K) K = kfit < 1.0 ? 1u : (uint32_t)kfit;
+		if (K < 16 && !getenv("QTIPSIM_R2_FORCE") && !getenv("QTIPSIM_R2_K")) return QTIPSIM_OK;
+	}
 	if (typical + 64.0 > (double)a2.rcap) K = 1;
 	if (na && K > na) K = na;
 	if (K > 1 && !getenv("QTIPSIM_R2_RCAP")) {
