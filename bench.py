@@ -4,10 +4,15 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scale S]
 
 One "step" = one pass of the hot path over the workload: (pack the FASTA), resolve the
-reference's draw chain, simulate + emit FASTQ for every read.  Workload at N=1 is
-BASELINE.json configs[2] (the one quoted for 1 B200): GRCh38-sized synthetic 3.1 Gbp
-reference, 10 M unpaired 250 bp reads; at N>1 it is configs[3] (3.1 Gbp, mixed c/d/b pairs,
-12.5 M pairs per GPU, sharded by FASTA window range; weak scaling).
+reference's draw chain, simulate + emit FASTQ for every read.
+
+Primary workload, at every N: BASELINE.json configs[2] (the one quoted for 1 B200): GRCh38-sized synthetic
+3.1 Gbp reference, 10 M unpaired 250 bp reads PER GPU (weak scaling: windows sharded by rank), native
+(Philox) RNG.  The same JSON line carries two more first-class blocks, each with its own value,
+step-level and kernel-level roofline and e2e:
+  "replay" : the same workload in REPLAY mode (bit-exact with the reference), same number of steps;
+  "c4"     : BASELINE.json configs[3] -- 3.1 Gbp, 12.5 M pairs per GPU (100 M on 8), 70/15/15
+             concordant / discordant / bad-end 2x150 -- native mode, plus its own "replay" block.
 
 Prints ONE JSON line on rank 0.  `value` = reads (or pairs) per second with the inputs
 resident in HBM; `e2e` = the same through the C ABI with host buffers (FASTA text and
@@ -195,10 +200,11 @@ def main():
     ap.add_argument("--mode", default="native", choices=["replay", "native"],
                     help="RNG mode of the primary numbers; the other mode is measured too (1 step) and reported alongside")
     ap.add_argument("--workload", default="auto", choices=["auto", "c3", "c4"],
-                    help="auto / c3: BASELINE config 3 (10M unpaired 250 bp reads per GPU, weak scaling); c4: the pair mix of "
-                         "config 4 (12.5M pairs per GPU), a secondary measurement")
+                    help="primary workload.  auto / c3: BASELINE config 3 (10M unpaired 250 bp reads per GPU, weak scaling), with "
+                         "config 4 (12.5M pairs per GPU, 70/15/15 c/d/b) as the \"c4\" block; c4: config 4 as the primary (diagnostic)")
     ap.add_argument("--cats", default="bcd", help="diagnostic: pair categories kept in the C4 mix (subset of 'bcd')")
-    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the replay-mode blocks")
+    ap.add_argument("--no-c4", action="store_true", help="skip the config-4 block")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -211,13 +217,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        res, why = run_reference_steps(wl, args.steps, max(1, min(args.warmup, 1)))
+        ref_warm = max(1, min(args.warmup, 1))  # one warm-up: a CPU timing does not need more, and each costs ~20 s
+        res, why = run_reference_steps(wl, args.steps, ref_warm)
         if res is None:
             print(json.dumps({"impl": "reference", "unavailable": why}))
             return 0
         line = {
             "impl": "reference", "metric": METRIC, "value": res["reads_per_s"], "unit": wl["unit"], "n_gpus": n_gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["sec_per_step"] * 1e3,
+            "steps": args.steps, "warmup": ref_warm, "ms_per_step": res["sec_per_step"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl["name"], "sample": res["sample"]},
             "output_gb_per_s": res["gb_per_s"],
@@ -292,18 +299,19 @@ def main():
 
     if world > 1:
         replicate_genome()
-    added = wl.get("added") or (len(wl["tu"]), len(wl["tb"]), len(wl["tc"]), len(wl["td"]))
+    cur = {"wl": wl}  # the workload being measured (the config-4 block swaps the templates in, same genome)
 
     def set_templates():
-        eng.set_unpaired(0, wl["tu"], added[0])
-        eng.set_unpaired(1, wl["tb"], added[1])
-        eng.set_paired(2, wl["tc"], added[2])
-        eng.set_paired(3, wl["td"], added[3])
+        w = cur["wl"]
+        added = w.get("added") or (len(w["tu"]), len(w["tb"]), len(w["tc"]), len(w["td"]))
+        eng.set_unpaired(0, w["tu"], added[0])
+        eng.set_unpaired(1, w["tb"], added[1])
+        eng.set_paired(2, w["tc"], added[2])
+        eng.set_paired(3, w["td"], added[3])
 
     set_templates()
     setup_s = time.perf_counter() - t_setup
 
-    kw = wl["kw"]
     state_buf = torch.zeros(2, dtype=torch.int64, device="cuda")
     host_out = [None] * _abi.NOUT
 
@@ -312,6 +320,7 @@ def main():
 
     def one_step(seed, rng_mode, e2e=False):
         """Runs one step on this rank's shard; returns stats."""
+        kw = cur["wl"]["kw"]
         tr0 = time.perf_counter()
         if e2e and world == 1 and stream_ready[0] and os.environ.get("QTIP_BENCH_STREAM") == "1":
             # opt-in (QTIP_BENCH_STREAM=1): the streaming path -- chunked upload, record-by-record pack + simulate,
@@ -369,8 +378,9 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def measure(rng_mode, steps, warmup, with_clocks):
-        """Device-resident arm + end-to-end arm for one RNG mode; returns a dict (rank 0) of reduced numbers."""
+    def measure(rng_mode, steps, warmup, with_clocks, do_e2e=True):
+        """Device-resident arm + end-to-end arm for one RNG mode of the current workload; returns a dict of reduced numbers."""
+        wl = cur["wl"]
         # clocks / throttle reasons are sampled (nvidia-smi, every 100 ms) from the warm-up through the
         # end-to-end arm: the device-timed region alone lasts only a few milliseconds per step
         sampler = ClockSampler(local_rank) if with_clocks else None
@@ -398,22 +408,23 @@ def main():
         ev_ms = ev0.elapsed_time(ev1)
         barrier()
         # end-to-end arm (host buffers; H2D of the FASTA text and templates, D2H of the FASTQ bytes inside)
-        one_step(300, rng_mode, e2e=True)  # warm (allocates the pinned result buffers)
-        stream_ready[0] = True
-        if os.environ.get("QTIP_BENCH_STREAM") == "1":
-            one_step(301, rng_mode, e2e=True)  # warm (the path the timed steps take)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        e2e_reads, e2e_d2h, e2e_launch = 0, 0, 0
+        e2e_reads, e2e_d2h, e2e_ms = 0, 0, 0.0
         e2e_steps = max(1, min(steps, 2))
-        for i in range(e2e_steps):
-            st = one_step(400 + i, rng_mode, e2e=True)
-            e2e_reads += sum(st.wrote)
-            e2e_d2h += sum(st.bytes)
-        e1.record()
-        torch.cuda.synchronize()
-        e2e_ms = e0.elapsed_time(e1)
+        if do_e2e:
+            one_step(300, rng_mode, e2e=True)  # warm (allocates the pinned result buffers)
+            stream_ready[0] = True
+            if os.environ.get("QTIP_BENCH_STREAM") == "1":
+                one_step(301, rng_mode, e2e=True)  # warm (the path the timed steps take)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(e2e_steps):
+                st = one_step(400 + i, rng_mode, e2e=True)
+                e2e_reads += sum(st.wrote)
+                e2e_d2h += sum(st.bytes)
+            e1.record()
+            torch.cuda.synchronize()
+            e2e_ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if sampler else None
         barrier()
         t = torch.tensor([ev_ms, e2e_ms, wall_ms], dtype=torch.float64, device="cuda")
@@ -428,18 +439,42 @@ def main():
         achieved = alg_step_rank0 / (sim_ms_step * 1e-3) / 1e9 if sim_ms_step > 0 else 0.0
         # FASTA text bytes: uploaded by rank 0 every e2e step (N > 1: then broadcast GPU to GPU as packed arrays)
         h2d = sum(l for _, l in wl["records"]) * 71 // 70 + 64 * len(wl["records"])
+        e2e = None
+        if do_e2e:
+            e2e = {"value": e2e_reads / (e2e_ms * 1e-3), "unit": wl["unit"], "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(e2e_d2h / e2e_steps), "ms_per_step": e2e_ms / e2e_steps,
+                   "output_gb_per_s": e2e_d2h / (e2e_ms * 1e-3) / 1e9, "steps": e2e_steps}
         return dict(value=reads / (ev_ms * 1e-3), ms_per_step=ev_ms / steps, wall_ms_per_step=wall_ms / steps,
                     output_gb_per_s=obytes / (ev_ms * 1e-3) / 1e9, reads_per_step=reads / steps,
                     phase={"plan": agg["ms_plan"] / steps, "simulate": sim_ms_step, "total": agg["ms_total"] / steps},
-                    achieved=achieved, alg_step=alg_step_rank0, launches=int(launches), clocks=clocks,
-                    e2e={"value": e2e_reads / (e2e_ms * 1e-3), "unit": wl["unit"], "h2d_bytes_per_step": int(h2d),
-                         "d2h_bytes_per_step": int(e2e_d2h / e2e_steps), "ms_per_step": e2e_ms / e2e_steps,
-                         "output_gb_per_s": e2e_d2h / (e2e_ms * 1e-3) / 1e9})
+                    achieved=achieved, alg_step=alg_step_rank0, alg_all=alg / steps, launches=int(launches), clocks=clocks,
+                    e2e=e2e, steps=steps, warmup=warmup)
 
     primary_mode = _abi.RNG_PHILOX if args.mode == "native" else _abi.RNG_REPLAY
     other_mode = _abi.RNG_REPLAY if args.mode == "native" else _abi.RNG_PHILOX
+    other = "replay" if args.mode == "native" else "native"
+    names = {"native": "philox (native counter-based RNG: the product default)",
+             "replay": "replay (consumes the reference's rnglib/ranlib stream: bit-exact with the reference)"}
+    sec_steps = max(3, args.steps)  # the other RNG mode is measured like the primary one, never on a single sample
     m = measure(primary_mode, args.steps, args.warmup, True)
-    m2 = None if args.no_secondary else measure(other_mode, 1, 1, False)
+    m2 = None if args.no_secondary else measure(other_mode, sec_steps, max(1, min(args.warmup, 3)), False)
+    # ---- BASELINE configs[3] on the same genome: 12.5 M pairs per GPU, 70/15/15 concordant / discordant / bad-end ----
+    m4 = m4r = wl4 = None
+    if args.workload in ("auto", "c3") and not args.no_c4:
+        wl4 = workload(n_gpus, args.scale, "c4", args.cats)
+        cur["wl"] = wl4
+        set_templates()
+        host_out[:] = [None] * _abi.NOUT  # the primary workload's pinned result buffers go back to the system
+        try:
+            torch._C._host_emptyCache()
+        except Exception:
+            pass
+        stream_ready[0] = False
+        m4 = measure(primary_mode, args.steps, args.warmup, False)
+        # the replay chain of this mix is long (~150 skipped draws per bad-end pair) and sequential across ranks: timed on
+        # the device-resident arm only
+        m4r = None if args.no_secondary else measure(other_mode, 3, 1, False, do_e2e=False)
+        cur["wl"] = wl
 
     if rank == 0:
         peaks = {}
@@ -450,42 +485,63 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-        # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture (same workload only)
-        traffic = None
-        if args.scale == 1.0 and args.workload in ("auto", "c3") and args.mode == "native":
+
+        def traffic_of(fname):
+            # DRAM bytes of one launch of the dominant kernel from the committed ncu --set full capture (same workload only)
+            if args.scale != 1.0:
+                return None
             try:
-                with open(os.path.join(ROOT, "profiles", "r01_k_simulate_direct_traffic.json")) as fh:
-                    traffic = json.load(fh)["traffic_bytes_per_launch"]
+                with open(os.path.join(ROOT, "profiles", fname)) as fh:
+                    return json.load(fh)["traffic_bytes_per_launch"]
             except Exception:
-                traffic = None
-        names = {"native": "philox (native counter-based RNG: the product default)",
-                 "replay": "replay (consumes the reference's rnglib/ranlib stream: bit-exact with the reference)"}
-        other = "replay" if args.mode == "native" else "native"
+                return None
+
+        def block(mm, w, mode, traffic=None):
+            """One measured (workload, RNG mode): throughput, where the step's time goes, the dominant kernel against the HBM
+            roofline and the whole step against it, and the end-to-end arm."""
+            step_gbs = mm["alg_step"] / (mm["ms_per_step"] * 1e-3) / 1e9 if mm["ms_per_step"] > 0 else 0.0
+            out = {"rng_mode": names[mode], "workload": w["name"], "value": mm["value"], "unit": w["unit"], "steps": mm["steps"],
+                   "warmup": mm["warmup"], "ms_per_step": mm["ms_per_step"], "reads_per_step": mm["reads_per_step"],
+                   "output_gb_per_s": mm["output_gb_per_s"], "phase_ms_per_step_rank0": mm["phase"],
+                   "roofline": {"bound": "hbm", "kernel": "k_simulate_direct", "achieved": mm["achieved"], "peak": peak, "unit": "GB/s",
+                                "frac": mm["achieved"] / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                                "algorithmic_bytes_per_step": mm["alg_step"]},
+                   "roofline_step": {"what": "algorithmic bytes of rank 0's step / rank 0's whole step (plan + offsets + simulate)",
+                                     "achieved": mm["alg_step"] / (mm["phase"]["total"] * 1e-3) / 1e9 if mm["phase"]["total"] > 0 else None,
+                                     "frac": (mm["alg_step"] / (mm["phase"]["total"] * 1e-3) / 1e9 / peak) if mm["phase"]["total"] > 0 and peak else None,
+                                     "achieved_all_ranks_wall": step_gbs},
+                   "gpu_launches": mm["launches"]}
+            if mm["e2e"] is not None:
+                out["e2e"] = mm["e2e"]
+            return out
+
+        tr_native = traffic_of("r02_k_simulate_direct_traffic.json") or traffic_of("r01_k_simulate_direct_traffic.json")
+        b = block(m, wl, args.mode, tr_native if (args.workload in ("auto", "c3") and args.mode == "native") else None)
         line = {
             "metric": METRIC, "value": m["value"], "unit": wl["unit"], "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": wl["name"], "rng_mode": names[args.mode], "chunksz": CHUNKSZ, "scale": args.scale,
                        "l2": "per-step working set (packed genome + FASTQ output) is GBs, far larger than the 126 MB L2",
-                       "parallelism": f"windows sharded across {world} rank(s); packed genome broadcast over NCCL"},
+                       "parallelism": f"windows sharded across {world} rank(s); packed genome broadcast over NCCL",
+                       "blocks": "replay = the same workload in REPLAY (bit-exact) mode; c4 = BASELINE configs[3], 12.5M pairs per GPU"},
             "output_gb_per_s": m["output_gb_per_s"],
             "reads_per_step": m["reads_per_step"],
             "wall_ms_per_step": m["wall_ms_per_step"],
             "phase_ms_per_step_rank0": m["phase"],
-            "roofline": {"bound": "hbm", "kernel": "k_simulate_direct", "achieved": m["achieved"], "peak": peak, "unit": "GB/s",
-                         "frac": m["achieved"] / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_step": m["alg_step"]},
+            "roofline": b["roofline"],
+            "roofline_step": b["roofline_step"],
             "e2e": m["e2e"],
-            "gpu_launches": m["launches"],
+            "gpu_launches": m["launches"] + (m2["launches"] if m2 else 0) + (m4["launches"] if m4 else 0) + (m4r["launches"] if m4r else 0),
             "clocks": m["clocks"],
             "setup_s": setup_s,
         }
         if m2 is not None:
-            line[other] = {"rng_mode": names[other], "value": m2["value"], "unit": wl["unit"], "ms_per_step": m2["ms_per_step"],
-                           "phase_ms_per_step_rank0": m2["phase"], "steps": 1, "warmup": 1,
-                           "roofline": {"achieved": m2["achieved"], "frac": m2["achieved"] / peak if peak else None,
-                                        "kernel": "k_simulate_direct"},
-                           "e2e": m2["e2e"], "output_gb_per_s": m2["output_gb_per_s"]}
+            line[other] = block(m2, wl, other)
+        if m4 is not None:
+            line["c4"] = block(m4, wl4, args.mode)
+            if m4r is not None:
+                line["c4"][other] = block(m4r, wl4, other)
         if n_gpus == 1 and not args.no_cpu_baseline:
             res, why = run_reference_steps(wl, 1, 0)
             if res is not None:
