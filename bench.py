@@ -322,12 +322,15 @@ def main():
         """Runs one step on this rank's shard; returns stats."""
         kw = cur["wl"]["kw"]
         tr0 = time.perf_counter()
-        if e2e and world == 1 and stream_ready[0] and os.environ.get("QTIP_BENCH_STREAM") == "1":
-            # opt-in (QTIP_BENCH_STREAM=1): the streaming path -- chunked upload, record-by-record pack + simulate,
-            # download of earlier records' reads while later text is still uploading.  Bit-exact with the one-shot
-            # path but not faster yet on this box (DESIGN.md section 8), so the default e2e arm stays one-shot.
+        if e2e and world == 1 and stream_ready[0] and os.environ.get("QTIP_BENCH_STREAM", "1") == "1":
+            # the streaming path (default at N = 1; QTIP_BENCH_STREAM=0 selects the one-shot calls): chunked upload,
+            # record-by-record pack + simulate, download of earlier records' reads while later text is still uploading.
+            # Same bytes as the one-shot path (tests/test_gpu_parity.py::test_streaming_path_equals_one_shot_path).
             eng.stream_begin(fa_pinned.numpy())
+            tr1 = time.perf_counter()
             set_templates()                                    # the host compiles the templates while the text uploads
+            if trace:
+                print(f"[trace] stream_begin {1e3 * (tr1 - tr0):.1f} ms, set_templates {1e3 * (time.perf_counter() - tr1):.1f} ms", file=sys.stderr)
             p = sim.make_params(CHUNKSZ, kw["fraction"], kw["function"], kw["min_u"], kw["min_c"], kw["min_d"], kw["min_b"],
                                 rng_mode, cg=cli_seed(seed), philox_seed=seed, shard_rank=0, shard_count=1)
             st = eng.stream_run(p, [t.data_ptr() if t is not None else 0 for t in host_out],
@@ -340,12 +343,13 @@ def main():
                 eng.load_fasta_bytes_async(fa_pinned.numpy())  # H2D of the FASTA text + device pack ...
             tr1 = time.perf_counter()
             set_templates()                                    # ... while the host compiles the templates
+            tr1b = time.perf_counter()
             eng.wait_genome()
             if world > 1:
                 replicate_genome()                             # N > 1: rank 0's packed genome to every GPU (NCCL)
             if trace:
-                print(f"[trace] load_fasta {1e3 * (tr1 - tr0):.1f} ms, set_templates {1e3 * (time.perf_counter() - tr1):.1f} ms",
-                      file=sys.stderr)
+                print(f"[trace] load_fasta {1e3 * (tr1 - tr0):.1f} ms, set_templates {1e3 * (tr1b - tr1):.1f} ms, genome resident after "
+                      f"{1e3 * (time.perf_counter() - tr0):.1f} ms", file=sys.stderr)
         cg = cli_seed(seed)
         chain = world > 1 and rng_mode == _abi.RNG_REPLAY
         if chain and rank > 0:
@@ -413,7 +417,7 @@ def main():
         if do_e2e:
             one_step(300, rng_mode, e2e=True)  # warm (allocates the pinned result buffers)
             stream_ready[0] = True
-            if os.environ.get("QTIP_BENCH_STREAM") == "1":
+            if world == 1 and os.environ.get("QTIP_BENCH_STREAM", "1") == "1":
                 one_step(301, rng_mode, e2e=True)  # warm (the path the timed steps take)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -131,6 +131,20 @@ struct qtipsim {
 	std::atomic<int> bulk_err{0};
 	double stream_t0 = 0;
 
+	// Control data (tables of a few KB to a few MB, counts read back) while bulk copies are in flight on the copy engines
+	// (streaming path): the copy engine of a direction serves copies in issue order, and pageable copies are staged
+	// synchronously, so a small copy would wait behind megabytes of text or FASTQ.  Instead the data crosses the link
+	// inside a kernel that reads / writes a pinned, mapped ring (no copy engine involved).
+	unsigned char *ctl_ring = nullptr;
+	size_t ctl_cap = 0, ctl_pos = 0;
+	bool ctl_zero_copy = false;
+	struct CtlPending {
+		void *dst;
+		const void *src;
+		size_t n;
+	};
+	std::vector<CtlPending> ctl_pending;  // device-to-host results to move out of the ring at the next stream sync
+
 	int fail(int code, const std::string &m) {
 		err = m;
 		return code;
@@ -147,6 +161,41 @@ struct qtipsim {
 		cudaError_t e__ = (call);                                \
 		if (e__ != cudaSuccess) return h->cuda_fail(e__, #call); \
 	} while (0)
+
+// synchronises the handle's stream and delivers the read-backs that went through the control ring
+static cudaError_t ctl_sync(qtipsim *h) {
+	const cudaError_t e = cudaStreamSynchronize(h->st);
+	if (e == cudaSuccess)
+		for (const auto &pd : h->ctl_pending) memcpy(pd.dst, pd.src, pd.n);
+	h->ctl_pending.clear();
+	h->ctl_pos = 0;
+	return e;
+}
+
+static void *ctl_alloc(qtipsim *h, size_t n) {
+	const size_t need = (n + 255) & ~(size_t)255;
+	if (!h->ctl_ring || need > h->ctl_cap) return nullptr;
+	if (h->ctl_pos + need > h->ctl_cap && ctl_sync(h) != cudaSuccess) return nullptr;  // everything in the ring has been consumed now
+	void *p = h->ctl_ring + h->ctl_pos;
+	h->ctl_pos += need;
+	return p;
+}
+
+static cudaError_t ctl_h2d(qtipsim *h, void *dst, const void *src, size_t n) {
+	void *p = h->ctl_zero_copy && n ? ctl_alloc(h, n) : nullptr;
+	if (!p) return cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, h->st);
+	memcpy(p, src, n);
+	launch_ctl_copy(dst, p, n, h->st);
+	return cudaGetLastError();
+}
+
+static cudaError_t ctl_d2h(qtipsim *h, void *dst, const void *src, size_t n) {
+	void *p = h->ctl_zero_copy && n ? ctl_alloc(h, n) : nullptr;
+	if (!p) return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, h->st);
+	launch_ctl_copy(p, src, n, h->st);
+	h->ctl_pending.push_back(qtipsim::CtlPending{dst, p, n});
+	return cudaGetLastError();
+}
 
 extern "C" {
 
@@ -192,6 +241,7 @@ void qtipsim_destroy(qtipsim_t *h) {
 	if (!h) return;
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->st);
+	if (h->ctl_ring) cudaFreeHost(h->ctl_ring);
 	DevBuf *all[] = {&h->d_tabs, &h->d_jh1, &h->d_jh2, &h->d_r2_aw, &h->d_r2_cum, &h->d_r2_anchor, &h->d_r2_counter, &h->d_r2_slot, &h->d_r2_end, &h->d_r2_cn,
 	                 &h->d_r2_wres, &h->d_r2_cnt, &h->d_r2_off, &h->d_r2_misc, &h->d_setups, &h->d_pclass, &h->d_rsresult, &h->d_text, &h->d_pk_a, &h->d_pk_b, &h->d_pk_c, &h->d_pk_d, &h->d_pk_e, &h->d_bases, &h->d_nmask, &h->d_nblk, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
 	                 &h->d_ncount, &h->d_cum, &h->d_len0, &h->d_len1, &h->d_scan_tmp, &h->d_small};
@@ -242,14 +292,14 @@ static int upload_genome(qtipsim *h) {
 	CK(h->d_names.ensure(g.names.size() + 16));
 	CK(cudaMemcpyAsync(h->d_bases.p, g.bases.data(), g.bases.size() * 4, cudaMemcpyHostToDevice, h->st));
 	CK(cudaMemcpyAsync(h->d_nmask.p, g.nmask.data(), g.nmask.size() * 4, cudaMemcpyHostToDevice, h->st));
-	CK(cudaMemcpyAsync(h->d_recs.p, g.recs.data(), g.recs.size() * sizeof(RecDev), cudaMemcpyHostToDevice, h->st));
+	CK(ctl_h2d(h, h->d_recs.p, g.recs.data(), g.recs.size() * sizeof(RecDev)));
 	if (!g.names.empty())
-		CK(cudaMemcpyAsync(h->d_names.p, g.names.data(), g.names.size(), cudaMemcpyHostToDevice, h->st));
+		CK(ctl_h2d(h, h->d_names.p, g.names.data(), g.names.size()));
 	{
 		const int rc = build_nblock(h, g.nmask.size());
 		if (rc) return rc;
 	}
-	CK(cudaStreamSynchronize(h->st));
+	CK(ctl_sync(h));
 	h->have_genome = true;
 	h->win_cache_ok = false;
 	h->setup_cache_ok = false;
@@ -338,8 +388,8 @@ static int find_headers_chunk(qtipsim *h, const uint8_t *text, uint64_t c0, uint
 	CK(cudaMemsetAsync(h->d_small.p, 0, 16 * 8, h->st));
 	launch_find_gt(h->d_text.as<uint8_t>() + c0, c1 - c0, h->d_pk_a.as<uint64_t>(), cap, h->d_small.as<uint32_t>(), h->st);
 	uint32_t ngt = 0;
-	CK(cudaMemcpyAsync(&ngt, h->d_small.p, 4, cudaMemcpyDeviceToHost, h->st));
-	CK(cudaStreamSynchronize(h->st));
+	CK(ctl_d2h(h, &ngt, h->d_small.p, 4));
+	CK(ctl_sync(h));
 	if (ngt > cap) {  // pathological: fall back to a host scan for '>'
 		for (const uint8_t *q0 = text + c0, *e = text + c1; q0 < e;) {
 			const uint8_t *q = (const uint8_t *)memchr(q0, '>', (size_t)(e - q0));
@@ -371,17 +421,17 @@ static int pack_records(qtipsim *h, bool presized) {
 	if (nunits) {
 		CK(h->d_pk_b.ensure((size_t)(3 * nseg + 1) * 8 + 16));
 		uint64_t *d_ss = h->d_pk_b.as<uint64_t>(), *d_se = d_ss + nseg, *d_ub = d_se + nseg;
-		CK(cudaMemcpyAsync(d_ss, seg_start, nseg * 8, cudaMemcpyHostToDevice, h->st));
-		CK(cudaMemcpyAsync(d_se, seg_end, nseg * 8, cudaMemcpyHostToDevice, h->st));
-		CK(cudaMemcpyAsync(d_ub, unit_base.data(), ((size_t)nseg + 1) * 8, cudaMemcpyHostToDevice, h->st));
+		CK(ctl_h2d(h, d_ss, seg_start, nseg * 8));
+		CK(ctl_h2d(h, d_se, seg_end, nseg * 8));
+		CK(ctl_h2d(h, d_ub, unit_base.data(), ((size_t)nseg + 1) * 8));
 		CK(h->d_pk_c.ensure((size_t)nunits * 4 + 16));                   // counts
 		CK(h->d_pk_d.ensure(((size_t)nunits + 1) * 8 + 16));             // exclusive prefix
 		CK(h->d_pk_e.ensure(((size_t)nunits / 1024 + 4) * 8));           // scan scratch
 		launch_count_bases(h->d_text.as<uint8_t>(), d_ss, d_se, d_ub, nseg, nunits, h->d_pk_c.as<uint32_t>(), h->st);
 		launch_scan(h->d_pk_c.as<uint32_t>(), h->d_pk_d.as<uint64_t>(), nunits, h->d_pk_e.as<uint64_t>(),
 		            h->d_pk_d.as<uint64_t>() + nunits, h->st);
-		CK(cudaMemcpyAsync(unit_pref.data(), h->d_pk_d.p, ((size_t)nunits + 1) * 8, cudaMemcpyDeviceToHost, h->st));
-		CK(cudaStreamSynchronize(h->st));
+		CK(ctl_d2h(h, unit_pref.data(), h->d_pk_d.p, ((size_t)nunits + 1) * 8));
+		CK(ctl_sync(h));
 	}
 	// ---- genome coordinates: 64 N in front, every record 64-aligned with an N gap behind it ----
 	std::vector<int64_t> seg_gbase(nseg);
@@ -415,7 +465,7 @@ static int pack_records(qtipsim *h, bool presized) {
 	}
 	if (nunits) {
 		CK(h->d_pk_a.ensure((size_t)nseg * 8 + 16));
-		CK(cudaMemcpyAsync(h->d_pk_a.p, seg_gbase.data(), nseg * 8, cudaMemcpyHostToDevice, h->st));
+		CK(ctl_h2d(h, h->d_pk_a.p, seg_gbase.data(), nseg * 8));
 		uint64_t *d_ss = h->d_pk_b.as<uint64_t>(), *d_se = d_ss + nseg, *d_ub = d_se + nseg;
 		launch_pack_units(h->d_text.as<uint8_t>(), d_ss, d_se, d_ub, nseg, nunits, h->d_pk_d.as<uint64_t>(),
 		                  h->d_pk_a.as<int64_t>(), h->d_bases.as<uint32_t>(), h->d_nmask.as<uint32_t>(), h->st);
@@ -424,8 +474,8 @@ static int pack_records(qtipsim *h, bool presized) {
 		const uint32_t np = (uint32_t)pad_lo.size();
 		CK(h->d_pk_c.ensure((size_t)np * 16 + 16));
 		uint64_t *d_lo = h->d_pk_c.as<uint64_t>(), *d_hi = d_lo + np;
-		CK(cudaMemcpyAsync(d_lo, pad_lo.data(), np * 8, cudaMemcpyHostToDevice, h->st));
-		CK(cudaMemcpyAsync(d_hi, pad_hi.data(), np * 8, cudaMemcpyHostToDevice, h->st));
+		CK(ctl_h2d(h, d_lo, pad_lo.data(), np * 8));
+		CK(ctl_h2d(h, d_hi, pad_hi.data(), np * 8));
 		launch_fill_n(d_lo, d_hi, np, h->d_nmask.as<uint32_t>(), h->st);
 	}
 	{
@@ -436,9 +486,9 @@ static int pack_records(qtipsim *h, bool presized) {
 	CK(h->d_recs.ensure(g.recs.size() * sizeof(RecDev) + 16));
 	CK(h->d_names.ensure(g.names.size() + 16));
 	if (!g.recs.empty())
-		CK(cudaMemcpyAsync(h->d_recs.p, g.recs.data(), g.recs.size() * sizeof(RecDev), cudaMemcpyHostToDevice, h->st));
+		CK(ctl_h2d(h, h->d_recs.p, g.recs.data(), g.recs.size() * sizeof(RecDev)));
 	if (!g.names.empty())
-		CK(cudaMemcpyAsync(h->d_names.p, g.names.data(), g.names.size(), cudaMemcpyHostToDevice, h->st));
+		CK(ctl_h2d(h, h->d_names.p, g.names.data(), g.names.size()));
 	h->recs_packed = r1;
 	h->win_cache_ok = false;
 	h->setup_cache_ok = false;
@@ -464,7 +514,7 @@ static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
 	rc = pack_records(h, false);
 	if (rc) return rc;
 	CK(cudaEventRecord(e1, h->st));
-	CK(cudaStreamSynchronize(h->st));
+	CK(ctl_sync(h));
 	CK(cudaGetLastError());
 	float ms = 0;
 	cudaEventElapsedTime(&ms, e0, e1);
@@ -483,7 +533,7 @@ static int ensure_host_packed(qtipsim *h) {
 	h->hg.nmask.resize(mw);
 	CK(cudaMemcpyAsync(h->hg.bases.data(), h->d_bases.p, bw * 4, cudaMemcpyDeviceToHost, h->st));
 	CK(cudaMemcpyAsync(h->hg.nmask.data(), h->d_nmask.p, mw * 4, cudaMemcpyDeviceToHost, h->st));
-	CK(cudaStreamSynchronize(h->st));
+	CK(ctl_sync(h));
 	h->host_packed = true;
 	return QTIPSIM_OK;
 }
@@ -569,13 +619,13 @@ int qtipsim_genome_adopt(qtipsim_t *h, const void *blob, uint64_t blob_bytes, co
 		const int rc = build_nblock(h, need_n / 4);
 		if (rc) return rc;
 	}
-	CK(cudaMemcpyAsync(h->d_recs.p, h->hg.recs.data(), h->hg.recs.size() * sizeof(RecDev), cudaMemcpyHostToDevice, h->st));
+	CK(ctl_h2d(h, h->d_recs.p, h->hg.recs.data(), h->hg.recs.size() * sizeof(RecDev)));
 	if (!h->hg.names.empty())
-		CK(cudaMemcpyAsync(h->d_names.p, h->hg.names.data(), h->hg.names.size(), cudaMemcpyHostToDevice, h->st));
+		CK(ctl_h2d(h, h->d_names.p, h->hg.names.data(), h->hg.names.size()));
 	// (the host replay planner fetches a host copy of the packed arrays on demand: ensure_host_packed)
 	h->hg.bases.clear();
 	h->hg.nmask.clear();
-	CK(cudaStreamSynchronize(h->st));
+	CK(ctl_sync(h));
 	h->have_genome = true;
 	h->win_cache_ok = false;
 	h->setup_cache_ok = false;
@@ -608,29 +658,29 @@ static int upload_templates(qtipsim *h) {
 		CK(h->d_qual[c].ensure(cg.qual.size() + 16));
 		CK(h->d_xs[c].ensure(cg.xs.size() + 16));
 		if (!cg.t.empty()) {
-			CK(cudaMemcpyAsync(h->d_t[c].p, cg.t.data(), cg.t.size() * sizeof(TmplDesc), cudaMemcpyHostToDevice, h->st));
-			CK(cudaMemcpyAsync(h->d_qual[c].p, cg.qual.data(), cg.qual.size(), cudaMemcpyHostToDevice, h->st));
-			CK(cudaMemcpyAsync(h->d_xs[c].p, cg.xs.data(), cg.xs.size(), cudaMemcpyHostToDevice, h->st));
+			CK(ctl_h2d(h, h->d_t[c].p, cg.t.data(), cg.t.size() * sizeof(TmplDesc)));
+			CK(ctl_h2d(h, h->d_qual[c].p, cg.qual.data(), cg.qual.size()));
+			CK(ctl_h2d(h, h->d_xs[c].p, cg.xs.data(), cg.xs.size()));
 			// compiled form; the quality arena is read with aligned 4-byte loads up to 16 bytes past an entry
 			CK(h->d_qual_out[c].ensure(cg.qual_out.size() + 64));
 			CK(h->d_ops[c].ensure(cg.ops.size() * 4 + 64));
 			CK(h->d_segs[c].ensure(cg.segs.size() * sizeof(SegDev) + 16));
 			CK(cudaMemsetAsync(h->d_qual_out[c].p, 0, cg.qual_out.size() + 64, h->st));
-			CK(cudaMemcpyAsync(h->d_qual_out[c].p, cg.qual_out.data(), cg.qual_out.size(), cudaMemcpyHostToDevice, h->st));
+			CK(ctl_h2d(h, h->d_qual_out[c].p, cg.qual_out.data(), cg.qual_out.size()));
 			if (!cg.ops.empty())
-				CK(cudaMemcpyAsync(h->d_ops[c].p, cg.ops.data(), cg.ops.size() * 4, cudaMemcpyHostToDevice, h->st));
+				CK(ctl_h2d(h, h->d_ops[c].p, cg.ops.data(), cg.ops.size() * 4));
 			if (!cg.segs.empty())
-				CK(cudaMemcpyAsync(h->d_segs[c].p, cg.segs.data(), cg.segs.size() * sizeof(SegDev), cudaMemcpyHostToDevice, h->st));
+				CK(ctl_h2d(h, h->d_segs[c].p, cg.segs.data(), cg.segs.size() * sizeof(SegDev)));
 			// draw programs for the device-side replay resolver
 			CK(h->d_xsteps[c].ensure(cg.xsteps.size() * sizeof(XStep) + 16));
 			CK(h->d_prog[c].ensure(cg.prog.size() * sizeof(HostMateProg) + 16));
 			if (!cg.xsteps.empty())
-				CK(cudaMemcpyAsync(h->d_xsteps[c].p, cg.xsteps.data(), cg.xsteps.size() * sizeof(XStep), cudaMemcpyHostToDevice, h->st));
+				CK(ctl_h2d(h, h->d_xsteps[c].p, cg.xsteps.data(), cg.xsteps.size() * sizeof(XStep)));
 			if (!cg.prog.empty())
-				CK(cudaMemcpyAsync(h->d_prog[c].p, cg.prog.data(), cg.prog.size() * sizeof(HostMateProg), cudaMemcpyHostToDevice, h->st));
+				CK(ctl_h2d(h, h->d_prog[c].p, cg.prog.data(), cg.prog.size() * sizeof(HostMateProg)));
 			CK(h->d_xprog[c].ensure(cg.xprog.size() * sizeof(XProgRec) + 64));
 			if (!cg.xprog.empty())
-				CK(cudaMemcpyAsync(h->d_xprog[c].p, cg.xprog.data(), cg.xprog.size() * sizeof(XProgRec), cudaMemcpyHostToDevice, h->st));
+				CK(ctl_h2d(h, h->d_xprog[c].p, cg.xprog.data(), cg.xprog.size() * sizeof(XProgRec)));
 		}
 		h->tmpl_dirty[c] = false;
 	}
@@ -643,8 +693,8 @@ static int upload_templates(qtipsim *h) {
 		}
 		CK(h->d_jt1.ensure(JUMP_TBL * 4));
 		CK(h->d_jt2.ensure(JUMP_TBL * 4));
-		CK(cudaMemcpyAsync(h->d_jt1.p, j1.data(), JUMP_TBL * 4, cudaMemcpyHostToDevice, h->st));
-		CK(cudaMemcpyAsync(h->d_jt2.p, j2.data(), JUMP_TBL * 4, cudaMemcpyHostToDevice, h->st));
+		CK(ctl_h2d(h, h->d_jt1.p, j1.data(), JUMP_TBL * 4));
+		CK(ctl_h2d(h, h->d_jt2.p, j2.data(), JUMP_TBL * 4));
 		// a^(4096 k): the high digit of a two-level jump (resolve2.cu)
 		std::vector<uint32_t> g1(JUMP_TBL), g2(JUMP_TBL);
 		const uint32_t b1 = mulmod1(j1[JUMP_TBL - 1], LA1), b2 = mulmod2(j2[JUMP_TBL - 1], LA2);
@@ -655,9 +705,9 @@ static int upload_templates(qtipsim *h) {
 		}
 		CK(h->d_jh1.ensure(JUMP_TBL * 4));
 		CK(h->d_jh2.ensure(JUMP_TBL * 4));
-		CK(cudaMemcpyAsync(h->d_jh1.p, g1.data(), JUMP_TBL * 4, cudaMemcpyHostToDevice, h->st));
-		CK(cudaMemcpyAsync(h->d_jh2.p, g2.data(), JUMP_TBL * 4, cudaMemcpyHostToDevice, h->st));
-		CK(cudaStreamSynchronize(h->st));  // the vectors are stack-lifetime
+		CK(ctl_h2d(h, h->d_jh1.p, g1.data(), JUMP_TBL * 4));
+		CK(ctl_h2d(h, h->d_jh2.p, g2.data(), JUMP_TBL * 4));
+		CK(ctl_sync(h));  // the vectors are stack-lifetime
 		h->have_jt = true;
 	}
 	return QTIPSIM_OK;
@@ -703,11 +753,11 @@ static int ensure_setups(qtipsim *h, const std::vector<Window> &win, uint64_t ol
 	h->tab_cache.resize(h->setup_cache.size());
 	for (size_t i = 0; i < h->setup_cache.size(); i++) binom_tables(h->setup_cache[i], h->tab_cache[i]);
 	CK(h->d_tabs.ensure(h->tab_cache.size() * sizeof(BinomTables)));
-	CK(cudaMemcpyAsync(h->d_tabs.p, h->tab_cache.data(), h->tab_cache.size() * sizeof(BinomTables), cudaMemcpyHostToDevice, h->st));
+	CK(ctl_h2d(h, h->d_tabs.p, h->tab_cache.data(), h->tab_cache.size() * sizeof(BinomTables)));
 	CK(h->d_pclass.ensure(nwin * 4 + 16));
-	CK(cudaMemcpyAsync(h->d_setups.p, h->setup_cache.data(), h->setup_cache.size() * sizeof(BinomSetup), cudaMemcpyHostToDevice, h->st));
-	if (nwin) CK(cudaMemcpyAsync(h->d_pclass.p, h->pclass_cache.data(), nwin * 4, cudaMemcpyHostToDevice, h->st));
-	CK(cudaStreamSynchronize(h->st));  // the cache vectors may be rebuilt by the next call
+	CK(ctl_h2d(h, h->d_setups.p, h->setup_cache.data(), h->setup_cache.size() * sizeof(BinomSetup)));
+	if (nwin) CK(ctl_h2d(h, h->d_pclass.p, h->pclass_cache.data(), nwin * 4));
+	CK(ctl_sync(h));  // the cache vectors may be rebuilt by the next call
 	memcpy(h->setup_key, key, sizeof(key));
 	h->setup_cache_ok = true;
 	return QTIPSIM_OK;
@@ -847,8 +897,8 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 	CK(h->d_r2_off.ensure((size_t)NCAT * ((size_t)na + 1) * 8));
 	CK(h->d_r2_misc.ensure(64));
 	CK(h->d_scan_tmp.ensure(((size_t)na / 1024 + 4) * 8));
-	CK(cudaMemcpyAsync(h->d_r2_aw.p, aw.data(), (size_t)na * 4, cudaMemcpyHostToDevice, h->st));
-	CK(cudaMemcpyAsync(h->d_r2_cum.p, cum.data(), cum.size() * 8, cudaMemcpyHostToDevice, h->st));
+	CK(ctl_h2d(h, h->d_r2_aw.p, aw.data(), (size_t)na * 4));
+	CK(ctl_h2d(h, h->d_r2_cum.p, cum.data(), cum.size() * 8));
 	CK(cudaMemsetAsync(h->d_r2_counter.p, 0, (size_t)max_launch * 4, h->st));
 	CK(cudaMemsetAsync(h->d_r2_misc.p, 0, 64, h->st));
 	StageAnchor a0;
@@ -856,7 +906,7 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 	a0.s1 = (uint32_t)p->cg1;
 	a0.s2 = (uint32_t)p->cg2;
 	a0.status = R2_RUNNING;
-	CK(cudaMemcpyAsync(h->d_r2_anchor.p, &a0, sizeof(a0), cudaMemcpyHostToDevice, h->st));
+	CK(ctl_h2d(h, h->d_r2_anchor.p, &a0, sizeof(a0)));
 	a2.jh1 = h->d_jh1.as<uint32_t>();
 	a2.jh2 = h->d_jh2.as<uint32_t>();
 	a2.tabs = h->d_tabs.as<BinomTables>();
@@ -883,8 +933,8 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 		if (!batch) return h->fail(QTIPSIM_ERANGE, "replay resolver made no progress");
 		for (uint32_t b = 0; b < batch; b++) launch_resolve2_stage(a2, launched + b, K, h->st);
 		launched += batch;
-		CK(cudaMemcpyAsync(&fin, a2.anchor + launched, sizeof(fin), cudaMemcpyDeviceToHost, h->st));
-		CK(cudaStreamSynchronize(h->st));
+		CK(ctl_d2h(h, &fin, a2.anchor + launched, sizeof(fin)));
+		CK(ctl_sync(h));
 		if (fin.status != R2_RUNNING) break;
 	}
 	h->r2_stages_last = launched;
@@ -907,9 +957,9 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 	uint64_t tot[NCAT];
 	uint32_t errw = 0;
 	for (int c = 0; c < NCAT; c++)
-		CK(cudaMemcpyAsync(&tot[c], offs.p[c] + na, 8, cudaMemcpyDeviceToHost, h->st));
-	CK(cudaMemcpyAsync(&errw, d_err, 4, cudaMemcpyDeviceToHost, h->st));
-	CK(cudaStreamSynchronize(h->st));
+		CK(ctl_d2h(h, &tot[c], offs.p[c] + na, 8));
+	CK(ctl_d2h(h, &errw, d_err, 4));
+	CK(ctl_sync(h));
 	if (errw) return QTIPSIM_OK;  // the first-generation kernel reports the reference's error for it
 	for (int c = 0; c < NCAT; c++) {
 		if (tot[c]) CK(h->d_plan[c].ensure(tot[c] * sizeof(PlanRec)));
@@ -917,8 +967,8 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 		a2.ra.cap[c] = tot[c];
 	}
 	launch_resolve2_emit(a2, d_cnt, d_start, offs, d_err, h->st);
-	CK(cudaMemcpyAsync(&errw, d_err, 4, cudaMemcpyDeviceToHost, h->st));
-	CK(cudaStreamSynchronize(h->st));
+	CK(ctl_d2h(h, &errw, d_err, 4));
+	CK(ctl_sync(h));
 	if (errw) return QTIPSIM_OK;
 	for (int c = 0; c < NCAT; c++) nreads[c] = tot[c];
 	p->cg1 = (int32_t)fin.s1;
@@ -987,10 +1037,10 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 			dg0.nrecs = (uint32_t)h->hg.recs.size();
 			CK(h->d_win.ensure(nw * sizeof(Window)));
 			CK(h->d_ncount.ensure(nw * 4));
-			CK(cudaMemcpyAsync(h->d_win.p, h->win_cache.data(), nw * sizeof(Window), cudaMemcpyHostToDevice, h->st));
+			CK(ctl_h2d(h, h->d_win.p, h->win_cache.data(), nw * sizeof(Window)));
 			launch_window_ncount(dg0, h->d_win.as<Window>(), nw, h->d_ncount.as<uint32_t>(), h->st);
-			CK(cudaMemcpyAsync(h->ncount_cache.data(), h->d_ncount.p, nw * 4, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaStreamSynchronize(h->st));
+			CK(ctl_d2h(h, h->ncount_cache.data(), h->d_ncount.p, nw * 4));
+			CK(ctl_sync(h));
 		}
 		h->win_cache_chunksz = p->chunksz;
 		h->win_cache_olap = olap;
@@ -1072,8 +1122,8 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 				ra.result = h->d_rsresult.as<unsigned long long>();
 				launch_resolve_replay(ra, h->st);
 				unsigned long long res[8];
-				CK(cudaMemcpyAsync(res, h->d_rsresult.p, sizeof(res), cudaMemcpyDeviceToHost, h->st));
-				CK(cudaStreamSynchronize(h->st));
+				CK(ctl_d2h(h, res, h->d_rsresult.p, sizeof(res)));
+				CK(ctl_sync(h));
 				if (res[7] == 3 && attempt < 6) {  // plan buffer too small: retry larger
 					grow *= 2.0;
 					continue;
@@ -1099,7 +1149,7 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 			CK(h->d_plan[c].ensure(nreads[c] * sizeof(PlanRec)));
 			CK(cudaMemcpyAsync(h->d_plan[c].p, plan.recs[c].data(), nreads[c] * sizeof(PlanRec), cudaMemcpyHostToDevice, h->st));
 		}
-		CK(cudaStreamSynchronize(h->st));  // plan vectors die at scope end
+		CK(ctl_sync(h));  // plan vectors die at scope end
 		p->cg1 = (int32_t)plan.rng_out.s1;
 		p->cg2 = (int32_t)plan.rng_out.s2;
 		draws = plan.draws;
@@ -1120,10 +1170,10 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 			                     h->d_setups.as<BinomSetup>(), nwin, olap, pp.target[c], p->philox_seed, c,
 			                     h->d_len0.as<uint32_t>(), h->st);
 			launch_scan(h->d_len0.as<uint32_t>(), cum, nwin, h->d_scan_tmp.as<uint64_t>(), cum + nwin, h->st);
-			CK(cudaMemcpyAsync(&edge[c][0], cum + pp.win_lo, 8, cudaMemcpyDeviceToHost, h->st));
-			CK(cudaMemcpyAsync(&edge[c][1], cum + pp.win_hi, 8, cudaMemcpyDeviceToHost, h->st));
+			CK(ctl_d2h(h, &edge[c][0], cum + pp.win_lo, 8));
+			CK(ctl_d2h(h, &edge[c][1], cum + pp.win_hi, 8));
 		}
-		CK(cudaStreamSynchronize(h->st));
+		CK(ctl_sync(h));
 		for (int c = 0; c < NCAT; c++) {
 			nreads[c] = edge[c][1] - edge[c][0];
 			read_base[c] = edge[c][0];
@@ -1187,8 +1237,8 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 		a.off1 = c != CAT_U ? h->d_off1[c].as<uint64_t>() : nullptr;
 	}
 	uint64_t small[16];
-	CK(cudaMemcpyAsync(small, h->d_small.p, sizeof(small), cudaMemcpyDeviceToHost, h->st));
-	CK(cudaStreamSynchronize(h->st));
+	CK(ctl_d2h(h, small, h->d_small.p, sizeof(small)));
+	CK(ctl_sync(h));
 	for (int s = 0; s < NOUT; s++) {
 		h->out_bytes[s] = small[s];
 		CK(h->d_out[s].ensure(small[s] + 64));
@@ -1231,12 +1281,12 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 	{
 		extern void qt_direct_debug_report();
 		extern void qt_warp_debug_report();
-		cudaStreamSynchronize(h->st);
+		ctl_sync(h);
 		qt_direct_debug_report();
 		qt_warp_debug_report();
 	}
 #endif
-	CK(cudaStreamSynchronize(h->st));
+	CK(ctl_sync(h));
 	CK(cudaGetLastError());
 	h->have_result = true;
 
@@ -1279,7 +1329,7 @@ int qtipsim_result_copy(qtipsim_t *h, int stream, void *dst, uint64_t cap) {
 	if (!dst) return QTIPSIM_EINVAL;
 	CK(cudaSetDevice(h->device));
 	CK(cudaMemcpyAsync(dst, h->d_out[stream].p, h->out_bytes[stream], cudaMemcpyDeviceToHost, h->st));
-	CK(cudaStreamSynchronize(h->st));
+	CK(ctl_sync(h));
 	return QTIPSIM_OK;
 }
 
@@ -1343,7 +1393,7 @@ int qtipsim_result_write_fds(qtipsim_t *h, const int fds[QTIPSIM_NOUT]) {
 			written += len_in_slot[slot];
 			slot ^= 1;
 		}
-		cudaStreamSynchronize(h->st);
+		ctl_sync(h);
 	}
 	cudaEventDestroy(done[0]);
 	cudaEventDestroy(done[1]);
@@ -1362,7 +1412,7 @@ int qtipsim_run_to_host(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stat
 		if (h->out_bytes[s])
 			CK(cudaMemcpyAsync(dst[s], h->d_out[s].p, h->out_bytes[s], cudaMemcpyDeviceToHost, h->st));
 	}
-	CK(cudaStreamSynchronize(h->st));
+	CK(ctl_sync(h));
 	return QTIPSIM_OK;
 }
 
@@ -1387,7 +1437,16 @@ int qtipsim_stream_begin(qtipsim_t *h, const void *bytes, size_t nbytes) {
 	CK(cudaSetDevice(h->device));
 	if (!h->st_h2d) CK(cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
 	if (!h->st_d2h) CK(cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
-	CK(cudaStreamSynchronize(h->st));
+	CK(ctl_sync(h));
+	if (!h->ctl_ring) {
+		const size_t cap = (size_t)env_u64("QTIPSIM_CTL_RING", 64ull << 20);
+		if (cudaHostAlloc((void **)&h->ctl_ring, cap, cudaHostAllocMapped) == cudaSuccess) h->ctl_cap = cap;
+		else {
+			h->ctl_ring = nullptr;
+			cudaGetLastError();  // no ring: control data goes through the copy engines as in the one-shot path
+		}
+	}
+	h->ctl_zero_copy = h->ctl_ring != nullptr && !getenv("QTIPSIM_NO_CTL_RING");
 	const uint64_t n = nbytes;
 	genome_reset(h, n);
 	h->stream_text = (const uint8_t *)bytes;
@@ -1416,7 +1475,7 @@ int qtipsim_stream_begin(qtipsim_t *h, const void *bytes, size_t nbytes) {
 	// control upload of the pack / plan steps would wait behind it.  A feeder thread issues the text in pieces (32 MB) and keeps three in flight; stream_ev[i] fires when chunk i (the unit of the header scan) has arrived.
 	h->chunks_issued.store(0);
 	h->bulk_err.store(0);
-	const uint64_t piece = std::max<uint64_t>(env_u64("QTIPSIM_STREAM_PIECE", 32ull << 20) & ~(uint64_t)15, 16);
+	const uint64_t piece = std::max<uint64_t>(env_u64("QTIPSIM_STREAM_PIECE", 8ull << 20) & ~(uint64_t)15, 16);
 	h->feeder = std::thread([h, bytes, n, piece]() {
 		if (cudaSetDevice(h->device) != cudaSuccess) h->bulk_err.store(1);
 		constexpr int DEPTH = 3;
@@ -1452,11 +1511,19 @@ int qtipsim_stream_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats
 	if (p->shard_count > 1) return h->fail(QTIPSIM_EINVAL, "the streaming path runs all windows on one GPU (shard_count must be 1)");
 	CK(cudaSetDevice(h->device));
 	h->stream_open = false;
+	struct CtlGuard {  // control data goes back to the copy engines when the streaming run is over, however it ends
+		qtipsim *h;
+		~CtlGuard() {
+			ctl_sync(h);
+			h->ctl_zero_copy = false;
+		}
+	} ctl_guard{h};
 	{
 		// templates go up now, while the first records are still arriving, not inside the first part's run
 		const int rc0 = upload_templates(h);
 		if (rc0) return rc0;
 	}
+	if (getenv("QTIPSIM_STREAM_TRACE")) fprintf(stderr, "[stream] stream_run entered at %.1f ms, templates up at %.1f ms\n", 0.0, now_ms() - h->stream_t0);
 	const uint8_t *text = h->stream_text;
 	const uint64_t n = h->stream_n;
 	const uint64_t min_part = env_u64("QTIPSIM_STREAM_MIN_PART", 512ull << 20);
@@ -1474,7 +1541,7 @@ int qtipsim_stream_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats
 	std::condition_variable dcv;
 	bool drain_stop = false;
 	int parts_home = 0;
-	const uint64_t dpiece = std::max<uint64_t>(env_u64("QTIPSIM_STREAM_PIECE", 32ull << 20), 4096);
+	const uint64_t dpiece = std::max<uint64_t>(env_u64("QTIPSIM_STREAM_PIECE", 8ull << 20), 4096);
 	std::thread drain([&]() {
 		if (cudaSetDevice(h->device) != cudaSuccess) h->bulk_err.store(1);
 		constexpr int DEPTH = 3;
@@ -1534,8 +1601,12 @@ int qtipsim_stream_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats
 					break;
 				}
 			}
+			const double t_arr = now_ms();
 			rc = find_headers_chunk(h, text, c0, c1, gts);
 			if (rc) break;
+			if (trace_parts)
+				fprintf(stderr, "[stream]   chunk %zu arrived %.1f ms, headers found %.1f ms (%zu)\n", i, t_arr - h->stream_t0,
+				        now_ms() - h->stream_t0, gts.size());
 		} else {
 			gts.clear();
 		}
@@ -1612,7 +1683,7 @@ int qtipsim_stream_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats
 	if (h->feeder.joinable()) h->feeder.join();
 	cudaStreamSynchronize(h->st_h2d);
 	cudaStreamSynchronize(h->st_d2h);
-	cudaStreamSynchronize(h->st);
+	ctl_sync(h);
 	for (cudaEvent_t e : h->stream_ev) cudaEventDestroy(e);
 	h->stream_ev.clear();
 	if (rc) return rc;

@@ -16,6 +16,28 @@ static int g_launches = 0;
 int kernels_launch_count() { return g_launches; }
 void kernels_count_launch() { g_launches++; }
 
+__global__ void __launch_bounds__(256) k_ctl_copy(unsigned char *dst, const unsigned char *src, size_t n, int vec) {
+	const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+	size_t done = 0;
+	if (vec) {  // both 16-byte aligned
+		const size_t n16 = n / 16;
+		const uint4 *s = (const uint4 *)src;
+		uint4 *d = (uint4 *)dst;
+		for (size_t i = tid; i < n16; i += nth) d[i] = s[i];
+		done = n16 * 16;
+	}
+	for (size_t i = done + tid; i < n; i += nth) dst[i] = src[i];
+}
+
+void launch_ctl_copy(void *dst, const void *src, size_t n, cudaStream_t st) {
+	if (!n) return;
+	const int vec = (((uintptr_t)dst | (uintptr_t)src) & 15) == 0;
+	const size_t work = vec ? n / 16 + 16 : n;
+	unsigned blocks = (unsigned)std::min<size_t>((work + 255) / 256, 592);
+	k_ctl_copy<<<blocks, 256, 0, st>>>((unsigned char *)dst, (const unsigned char *)src, n, vec);
+	kernels_count_launch();
+}
+
 // ------------------------------------------------------------------ helpers --
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }

@@ -77,6 +77,8 @@ bool launch_simulate_warp(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max
 bool launch_simulate_direct(const SimArgs &a, uint32_t max_name, uint32_t min_body, uint32_t max_body, cudaStream_t st);
 void launch_nblock(const uint32_t *nmask, uint64_t mask_words, uint32_t *nblk, uint64_t nblk_words, cudaStream_t st);
 void kernels_count_launch();
+// plain copy done by a kernel (either side may be pinned, mapped host memory): control data of the streaming path
+void launch_ctl_copy(void *dst, const void *src, size_t n, cudaStream_t st);
 
 // PHILOX planning: per-window counts on the device
 void launch_philox_counts(const Window *win, const uint32_t *ncount, const uint32_t *pclass, const BinomSetup *setups,

@@ -2,7 +2,9 @@
 #include "templates.h"
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
+#include <thread>
 
 namespace qt {
 
@@ -158,39 +160,34 @@ void Category::finish_xprog() {
 	}
 }
 
-int TemplateStore::set_unpaired(int ci, const qtipsim_tmpl_unp *v, size_t kept, uint64_t added, std::string &err) {
-	if (ci != CAT_U && ci != CAT_B) {
-		err = "set_templates_unpaired: category must be U or B";
-		return QTIPSIM_EINVAL;
-	}
-	Category &c = cat[ci];
-	c.clear();
-	c.added = added;
-	c.t.resize(kept);
-	c.prog.resize(2 * kept);
-	if (kept) {  // arenas sized from the first template: one allocation instead of a doubling chain
+namespace {
+
+// templates [0, n) of v into a fresh category (arena offsets from zero; sums instead of means)
+void fill_unpaired(Category &c, int ci, const qtipsim_tmpl_unp *v, size_t n) {
+	c.t.resize(n);
+	c.prog.resize(2 * n);
+	if (n) {  // arenas sized from the first template: one allocation instead of a doubling chain
 		const size_t l0 = v[0].qual ? strlen(v[0].qual) : 0;
-		c.qual.reserve(kept * (l0 + 8));
-		c.xs.reserve(kept * (l0 + 8));
-		c.qual_out.reserve(kept * (l0 + 24) + 64);
+		c.qual.reserve(n * (l0 + 8));
+		c.xs.reserve(n * (l0 + 8));
+		c.qual_out.reserve(n * (l0 + 24) + 64);
 	}
-	double bytes = 0, draws = 0, dsum = 0, dsq = 0;
 	auto draw_stats = [&](double fixed, double nx) {  // per template: mean fixed + 4/3 nx, variance 4/9 nx
 		const double m = fixed + nx * (4.0 / 3.0);
-		dsum += m;
-		dsq += m * m + nx * (4.0 / 9.0);
+		c.sum_dm += m;
+		c.sum_dsq += m * m + nx * (4.0 / 9.0);
 		c.draw_max_fixed = std::max<uint32_t>(c.draw_max_fixed, (uint32_t)(fixed + nx));
 	};
-	for (size_t i = 0; i < kept; i++) {
+	for (size_t i = 0; i < n; i++) {
 		TmplDesc &t = c.t[i];
 		memset(&t, 0, sizeof(t));
 		std::string why;
-		if (!add_mate(c, t.m[0], c.prog[2 * i], v[i].qual, v[i].xscript, v[i].fw_flag == 'T',
-		              v[i].best_score, why) && c.valid) {
+		if (!add_mate(c, t.m[0], c.prog[2 * i], v[i].qual, v[i].xscript, v[i].fw_flag == 'T', v[i].best_score, why) && c.valid) {
 			c.valid = false;
 			c.why = why;
 		}
 		t.nmates = 1;
+		const double nx = c.prog[2 * i].xs_end - c.prog[2 * i].xs_begin;
 		if (ci == CAT_B) {
 			t.aligned_is_mate1 = (v[i].mate_flag == '1');
 			t.opp_len = v[i].opp_len > 0 ? (uint32_t)v[i].opp_len : 0;
@@ -205,59 +202,35 @@ int TemplateStore::set_unpaired(int ci, const qtipsim_tmpl_unp *v, size_t kept, 
 			t.typ[1] = t.aligned_is_mate1 ? '1' : '2';
 			t.typ_len = 2;
 			// name (both scores) on both files + two bodies
-			bytes += 2.0 * (7 + 2 * (5 + t.m[0].score_len) + 2 + 1) + 2.0 * t.m[0].len + 2.0 * t.opp_len + 8;
-			draws += 2 + t.m[0].ndraw + t.opp_len;
-			{
-				const double nx = c.prog[2 * i].xs_end - c.prog[2 * i].xs_begin;
-				draw_stats(2.0 + t.m[0].ndraw - nx + t.opp_len, nx);
-			}
+			c.sum_bytes += 2.0 * (7 + 2 * (5 + t.m[0].score_len) + 2 + 1) + 2.0 * t.m[0].len + 2.0 * t.opp_len + 8;
+			c.sum_draws += 2 + t.m[0].ndraw + t.opp_len;
+			draw_stats(2.0 + t.m[0].ndraw - nx + t.opp_len, nx);
 		} else {
 			t.typ[0] = 'u';
 			t.typ_len = 1;
-			bytes += 7 + 5 + t.m[0].score_len + 1 + 1 + 2.0 * t.m[0].len + 4;
-			draws += 2 + t.m[0].ndraw;
-			{
-				const double nx = c.prog[2 * i].xs_end - c.prog[2 * i].xs_begin;
-				draw_stats(2.0 + t.m[0].ndraw - nx, nx);
-			}
+			c.sum_bytes += 7 + 5 + t.m[0].score_len + 1 + 1 + 2.0 * t.m[0].len + 4;
+			c.sum_draws += 2 + t.m[0].ndraw;
+			draw_stats(2.0 + t.m[0].ndraw - nx, nx);
 		}
 		c.max_len = std::max<uint64_t>(c.max_len, t.m[0].rflen);  // input_model.h:38-41
 	}
-	if (kept) {
-		c.mean_bytes = bytes / kept;
-		c.mean_draws = draws / kept;
-		c.draw_m1 = dsum / kept;
-		c.draw_v1 = std::max(0.0, dsq / kept - c.draw_m1 * c.draw_m1);
-	}
-	c.finish_xprog();
-	return QTIPSIM_OK;
 }
 
-int TemplateStore::set_paired(int ci, const qtipsim_tmpl_pair *v, size_t kept, uint64_t added, std::string &err) {
-	if (ci != CAT_C && ci != CAT_D) {
-		err = "set_templates_paired: category must be C or D";
-		return QTIPSIM_EINVAL;
-	}
-	Category &c = cat[ci];
-	c.clear();
-	c.added = added;
-	c.t.resize(kept);
-	c.prog.resize(2 * kept);
-	if (kept) {
+void fill_paired(Category &c, int ci, const qtipsim_tmpl_pair *v, size_t n) {
+	c.t.resize(n);
+	c.prog.resize(2 * n);
+	if (n) {
 		const size_t l0 = (v[0].qual_1 ? strlen(v[0].qual_1) : 0) + (v[0].qual_2 ? strlen(v[0].qual_2) : 0);
-		c.qual.reserve(kept * (l0 + 16));
-		c.xs.reserve(kept * (l0 + 16));
-		c.qual_out.reserve(kept * (l0 + 48) + 64);
+		c.qual.reserve(n * (l0 + 16));
+		c.xs.reserve(n * (l0 + 16));
+		c.qual_out.reserve(n * (l0 + 48) + 64);
 	}
-	double bytes = 0, draws = 0, dsum = 0, dsq = 0;
-	for (size_t i = 0; i < kept; i++) {
+	for (size_t i = 0; i < n; i++) {
 		TmplDesc &t = c.t[i];
 		memset(&t, 0, sizeof(t));
 		std::string why;
-		bool ok = add_mate(c, t.m[0], c.prog[2 * i], v[i].qual_1, v[i].xscript_1, v[i].fw_flag_1 == 'T',
-		                   v[i].score_1, why);
-		ok = ok && add_mate(c, t.m[1], c.prog[2 * i + 1], v[i].qual_2, v[i].xscript_2,
-		                    v[i].fw_flag_2 == 'T', v[i].score_2, why);
+		bool ok = add_mate(c, t.m[0], c.prog[2 * i], v[i].qual_1, v[i].xscript_1, v[i].fw_flag_1 == 'T', v[i].score_1, why);
+		ok = ok && add_mate(c, t.m[1], c.prog[2 * i + 1], v[i].qual_2, v[i].xscript_2, v[i].fw_flag_2 == 'T', v[i].score_2, why);
 		if (!ok && c.valid) {
 			c.valid = false;
 			c.why = why;
@@ -275,24 +248,119 @@ int TemplateStore::set_paired(int ci, const qtipsim_tmpl_pair *v, size_t kept, u
 			t.delta[0] = (uint32_t)(std::max<uint64_t>(fl, t.m[0].rflen) - t.m[0].rflen);
 		}
 		c.max_len = std::max<uint64_t>(c.max_len, fl);  // input_model.h:112-115
-		bytes += 2.0 * (7 + 9 + t.m[0].score_len + t.m[1].score_len + 2) + 2.0 * t.m[0].len + 2.0 * t.m[1].len + 8;
-		draws += 2 + t.m[0].ndraw + t.m[1].ndraw;
-		{
-			const double nx = (double)(c.prog[2 * i].xs_end - c.prog[2 * i].xs_begin) + (double)(c.prog[2 * i + 1].xs_end - c.prog[2 * i + 1].xs_begin);
-			const double fixed = 2.0 + t.m[0].ndraw + t.m[1].ndraw - nx;
-			const double m = fixed + nx * (4.0 / 3.0);
-			dsum += m;
-			dsq += m * m + nx * (4.0 / 9.0);
-			c.draw_max_fixed = std::max<uint32_t>(c.draw_max_fixed, (uint32_t)(fixed + nx));
+		c.sum_bytes += 2.0 * (7 + 9 + t.m[0].score_len + t.m[1].score_len + 2) + 2.0 * t.m[0].len + 2.0 * t.m[1].len + 8;
+		c.sum_draws += 2 + t.m[0].ndraw + t.m[1].ndraw;
+		const double nx = (double)(c.prog[2 * i].xs_end - c.prog[2 * i].xs_begin) + (double)(c.prog[2 * i + 1].xs_end - c.prog[2 * i + 1].xs_begin);
+		const double fixed = 2.0 + t.m[0].ndraw + t.m[1].ndraw - nx;
+		const double m = fixed + nx * (4.0 / 3.0);
+		c.sum_dm += m;
+		c.sum_dsq += m * m + nx * (4.0 / 9.0);
+		c.draw_max_fixed = std::max<uint32_t>(c.draw_max_fixed, (uint32_t)(fixed + nx));
+	}
+}
+
+// appends part p (built from offset zero) to c: every arena offset of p's descriptors moves by the arena's size so far
+void append_part(Category &c, Category &p) {
+	while (c.ops.size() % 4) c.ops.push_back(0u);  // draw-op lists stay 16-byte aligned
+	const uint32_t bq = (uint32_t)c.qual.size(), bx = (uint32_t)c.xs.size(), bo = (uint32_t)c.qual_out.size();
+	const uint32_t bops = (uint32_t)c.ops.size(), bseg = (uint32_t)c.segs.size(), bxs = (uint32_t)c.xsteps.size();
+	for (TmplDesc &t : p.t)
+		for (int m = 0; m < 2; m++) {
+			MateDesc &md = t.m[m];
+			if (m >= t.nmates) continue;
+			md.qual_off += bq;
+			md.xs_off += bx;
+			md.qual_out_off += bo;
+			md.ops_off += bops;
+			md.seg_off += bseg;
 		}
+	for (HostMateProg &hp : p.prog) {
+		hp.xs_begin += bxs;
+		hp.xs_end += bxs;
+	}
+	c.t.insert(c.t.end(), p.t.begin(), p.t.end());
+	c.prog.insert(c.prog.end(), p.prog.begin(), p.prog.end());
+	c.qual += p.qual;
+	c.xs += p.xs;
+	c.qual_out += p.qual_out;
+	c.ops.insert(c.ops.end(), p.ops.begin(), p.ops.end());
+	c.segs.insert(c.segs.end(), p.segs.begin(), p.segs.end());
+	c.xsteps.insert(c.xsteps.end(), p.xsteps.begin(), p.xsteps.end());
+	c.compiled_ok = c.compiled_ok && p.compiled_ok;
+	c.max_body = std::max(c.max_body, p.max_body);
+	c.min_body = std::min(c.min_body, p.min_body);
+	c.max_score_len = std::max(c.max_score_len, p.max_score_len);
+	c.max_rflen = std::max(c.max_rflen, p.max_rflen);
+	c.max_len = std::max(c.max_len, p.max_len);
+	c.draw_max_fixed = std::max(c.draw_max_fixed, p.draw_max_fixed);
+	if (c.valid && !p.valid) {  // parts are appended in template order: the first problem found stays the reported one
+		c.valid = false;
+		c.why = p.why;
+	}
+	c.sum_bytes += p.sum_bytes;
+	c.sum_draws += p.sum_draws;
+	c.sum_dm += p.sum_dm;
+	c.sum_dsq += p.sum_dsq;
+}
+
+// The per-template work (transcript scans, output-oriented quality copies, segment / draw-op compilation) is
+// independent between templates: large models are compiled in slices by a few threads and the slices concatenated.
+template <class V, class Fill>
+void build_category(Category &c, int ci, const V *v, size_t kept, uint64_t added, Fill fill) {
+	c.clear();
+	c.added = added;
+	unsigned nt = 1;
+	if (kept >= 4096) {
+		const char *e = getenv("QTIPSIM_TEMPLATE_THREADS");
+		nt = e && *e ? (unsigned)atoi(e) : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+		if (nt < 1) nt = 1;
+	}
+	if (nt == 1) {
+		fill(c, ci, v, kept);
+	} else {
+		std::vector<Category> parts(nt);
+		std::vector<std::thread> th;
+		for (unsigned k = 0; k < nt; k++) {
+			const size_t lo = kept * k / nt, hi = kept * (k + 1) / nt;
+			th.emplace_back([&, k, lo, hi]() { fill(parts[k], ci, v + lo, hi - lo); });
+		}
+		for (auto &t : th) t.join();
+		size_t q = 0, x = 0, o = 0;
+		for (auto &p : parts) q += p.qual.size(), x += p.xs.size(), o += p.qual_out.size();
+		c.qual.reserve(q);
+		c.xs.reserve(x);
+		c.qual_out.reserve(o + 64);
+		c.t.reserve(kept);
+		c.prog.reserve(2 * kept);
+		c.added = added;
+		for (auto &p : parts) append_part(c, p);
 	}
 	if (kept) {
-		c.mean_bytes = bytes / kept;
-		c.mean_draws = draws / kept;
-		c.draw_m1 = dsum / kept;
-		c.draw_v1 = std::max(0.0, dsq / kept - c.draw_m1 * c.draw_m1);
+		c.mean_bytes = c.sum_bytes / kept;
+		c.mean_draws = c.sum_draws / kept;
+		c.draw_m1 = c.sum_dm / kept;
+		c.draw_v1 = std::max(0.0, c.sum_dsq / kept - c.draw_m1 * c.draw_m1);
 	}
 	c.finish_xprog();
+}
+
+}  // namespace
+
+int TemplateStore::set_unpaired(int ci, const qtipsim_tmpl_unp *v, size_t kept, uint64_t added, std::string &err) {
+	if (ci != CAT_U && ci != CAT_B) {
+		err = "set_templates_unpaired: category must be U or B";
+		return QTIPSIM_EINVAL;
+	}
+	build_category(cat[ci], ci, v, kept, added, fill_unpaired);
+	return QTIPSIM_OK;
+}
+
+int TemplateStore::set_paired(int ci, const qtipsim_tmpl_pair *v, size_t kept, uint64_t added, std::string &err) {
+	if (ci != CAT_C && ci != CAT_D) {
+		err = "set_templates_paired: category must be C or D";
+		return QTIPSIM_EINVAL;
+	}
+	build_category(cat[ci], ci, v, kept, added, fill_paired);
 	return QTIPSIM_OK;
 }
 

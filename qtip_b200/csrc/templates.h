@@ -68,6 +68,7 @@ struct Category {
 	// (resolve2.cu): 2 index draws + one per I/S (+ opp_len) + Geometric(3/4) per X (simplesim.cpp:45-50)
 	double draw_m1 = 0, draw_v1 = 0;  // mean and variance over a uniformly drawn template
 	uint32_t draw_max_fixed = 0;      // most draws of a template when every X takes one draw
+	double sum_bytes = 0, sum_draws = 0, sum_dm = 0, sum_dsq = 0;  // running sums behind the four means above
 	void clear() { *this = Category(); }
 };
 

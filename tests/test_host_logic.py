@@ -354,3 +354,24 @@ def test_swar_pack_whole_fasta_matches_host_packer(name):
         assert seq == hs.unpack(gs, ln), nm
         assert not np.any((codes != 0) & (isn == 1)), nm  # N positions carry code 0, as the kernels expect
     hs.close()
+
+
+def test_template_compilation_in_slices_equals_single_thread(workdir, monkeypatch):
+    """Large models are compiled by several threads in slices that are concatenated (templates.cpp build_category):
+    the host plan -- every read's template, position and generator state -- is the one the single-threaded build gives."""
+    from qtip_b200 import synth
+    fa = synth.make_fasta([("a", 300000)], seed=909)
+    case = dict(fasta=fa, tu=synth.templates_unpaired(5000, 100, 910, indel=True, len_jitter=10),
+                tb=synth.templates_badend(4500, 80, 911, opp_len=30),
+                tc=synth.templates_paired(4200, 100, 912, frag_mean=300, frag_sd=30, indel=True),
+                td=synth.templates_paired(4100, 60, 913, discordant=True, max_fraglen=3000))
+    kw = dict(fraction=2000.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=(34, 2619), chunksz=128 * 1024)
+    res = []
+    for nt in ("1", "5"):
+        monkeypatch.setenv("QTIPSIM_TEMPLATE_THREADS", nt)
+        hs = util.HostSide(case)
+        rc, cg, draws, n = hs.plan(kw)
+        assert rc == 0
+        res.append((cg, draws, n, [hs.plan_recs(c, min(n[c], 400)) for c in range(4)], int(hs.L.qthost_olap(hs.h))))
+        hs.close()
+    assert res[0] == res[1]
