@@ -194,6 +194,18 @@ int qtipsim_stream_begin(qtipsim_t *h, const void *bytes, size_t nbytes);
 int qtipsim_stream_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats,
                        void *const dst[QTIPSIM_NOUT], const uint64_t cap[QTIPSIM_NOUT]);
 
+/* Tandem-SAM correctness labelling: Alignment::set_correctness (qtip_parse.cpp:519-713, called at :823, :944-945)
+ * for a batch of ALIGNED records of the SAM the aligner produced from the tandem reads -- the consumer of the read
+ * names the simulator emits.  qnames / rnames: the records' QNAME / RNAME strings, NUL-terminated, concatenated
+ * (qnames_bytes / rnames_bytes in total, terminators included); q_off[i] / r_off[i]: where record i's strings start;
+ * flag[i], pos[i]: its SAM FLAG and 1-based POS; wiggle: qtip_parse.cpp:797 (default 30).  correct[i] = 1 if the
+ * alignment lies within `wiggle` of the origin the name records (reference, strand and offset of the mate the FLAG
+ * names), 0 if not, -1 if the name is in neither simulated-read format (the reference leaves its field at -1).  All
+ * pointers are host memory; the labels are computed on the device. */
+int qtipsim_label_correctness(qtipsim_t *h, const char *qnames, uint64_t qnames_bytes, const uint64_t *q_off,
+                              const char *rnames, uint64_t rnames_bytes, const uint64_t *r_off, const int32_t *flag,
+                              const uint64_t *pos, uint64_t n, int32_t wiggle, int8_t *correct);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,7 @@ ORACLE_SO = os.path.join(HERE, "liboracle.so")
 REF_DIR = os.path.join(HERE, "_ref")
 REF_SO = os.path.join(REF_DIR, "libref.so")
 REF_PARSE = os.path.join(REF_DIR, "qtip-parse")
+REF_LABEL_SO = os.path.join(REF_DIR, "libreflabel.so")
 
 import sys
 
@@ -98,6 +99,8 @@ def orc() -> C.CDLL:
             C.c_float, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
             C.POINTER(OrcRng), C.POINTER(OrcOut)]
         lib.orc_simulate.restype = C.c_int
+        lib.orc_set_correctness.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint64, C.c_int]
+        lib.orc_set_correctness.restype = C.c_int
         _orc = lib
     return _orc
 
@@ -128,6 +131,20 @@ def ref() -> C.CDLL:
         lib.ref_initialize()
         _ref = lib
     return _ref
+
+
+_reflabel = None
+
+
+def ref_label() -> C.CDLL:
+    """The unmodified reference's Alignment::set_correctness (oracle/ref_label_wrap.cpp -> _ref/libreflabel.so)."""
+    global _reflabel
+    if _reflabel is None:
+        lib = C.CDLL(REF_LABEL_SO)
+        lib.ref_set_correctness.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint64, C.c_int]
+        lib.ref_set_correctness.restype = C.c_int
+        _reflabel = lib
+    return _reflabel
 
 
 class SimResult:

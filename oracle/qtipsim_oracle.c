@@ -678,3 +678,94 @@ int orc_simulate(
 	free(rd2.seq); free(rd2.qual_own);
 	return rc;
 }
+
+/* ---------------------------------------------------------------------------
+ * Tandem-SAM correctness labelling: Alignment::set_correctness, qtip_parse.cpp:519-713.
+ * flag / pos: SAM FLAG and 1-based POS of an aligned record; returns the value the reference leaves in
+ * `correct`: 1, 0, or -1 (name in neither simulated-read format).  Reads past a string's end (which the
+ * reference can do on malformed names) are cut short and count as "incorrect".
+ * ------------------------------------------------------------------------- */
+static int lab_abs_int(uint64_t a, uint64_t b) {  /* abs((int)(a - b)) on size_t operands */
+	int32_t d = (int32_t)(uint32_t)(a - b);
+	return d < 0 ? (int32_t)(0u - (uint32_t)d) : d;
+}
+
+int orc_set_correctness(const char *qname, const char *rname, int flag, uint64_t pos, int wiggle) {
+	const size_t rname_len = strlen(rname);
+	const int is_fw = (flag & 16) == 0;                                      /* :134-136 */
+	const char mate_flag = (flag & 64) ? '1' : ((flag & 128) ? '2' : '0');   /* :146-148 */
+	const char *startswith = "qtip!";                                        /* simplesim.h:20-24 */
+	if (strncmp(qname, startswith, 5) == 0) {                                /* :522 */
+		const char *cur = qname + 5;
+		const char *end = qname + strlen(qname);
+		if (*cur != ':') return 0;                                           /* assert(*qname_cur == sim_sep), :526 */
+		cur++;
+		if (mate_flag != '2' && strncmp(cur, rname, rname_len) != 0) return 0;   /* :528-532 */
+		if ((size_t)(end - cur) < rname_len) return 0;
+		cur += rname_len;
+		if (*(cur++) != ':') return 0;                                       /* :534 */
+		if (mate_flag != '2' && cur[0] != (is_fw ? '+' : '-')) return 0;     /* :539 */
+		if (cur >= end) return 0;
+		cur++;
+		if (*(cur++) != ':') return 0;
+		uint64_t refoff = 0;                                                 /* :547-551 */
+		while (isdigit((unsigned char)*cur)) refoff = refoff * 10 + (uint64_t)(*cur++ - '0');
+		if (mate_flag != '2' && lab_abs_int(refoff, pos - 1) >= wiggle) return 0;   /* :552 */
+		if (*(cur++) != ':') return 0;
+		if (*cur == '-') cur++;                                              /* score1, :559-571 */
+		while (isdigit((unsigned char)*cur)) cur++;
+		if (*(cur++) != ':') return 0;
+		if (cur[0] == 'u' && (cur[1] == '\0' || isspace((unsigned char)cur[1]))) return 1;   /* :575-578 */
+		if (mate_flag != '2') return 1;                                      /* :580-583 */
+		if (strncmp(cur, rname, rname_len) != 0) return 0;                   /* :585-588 */
+		if ((size_t)(end - cur) < rname_len) return 0;
+		cur += rname_len;
+		if (*(cur++) != ':') return 0;
+		if (cur[0] != (is_fw ? '+' : '-')) return 0;                         /* :594 */
+		cur++;
+		if (*(cur++) != ':') return 0;
+		refoff = 0;
+		while (isdigit((unsigned char)*cur)) refoff = refoff * 10 + (uint64_t)(*cur++ - '0');
+		if (lab_abs_int(refoff, pos - 1) >= wiggle) return 0;                /* :607 */
+		if (*(cur++) != ':') return 0;
+		if (*cur == '-') cur++;                                              /* score2 */
+		while (isdigit((unsigned char)*cur)) cur++;
+		if (*(cur++) != ':') return 0;
+		return 1;                                                            /* :631 */
+	}
+	/* wgsim-style names of simulated input reads, :634-712 */
+	const size_t qname_len = strlen(qname);
+	int nund = 0, ncolon = 0;
+	for (size_t i = 0; i < qname_len; i++) {
+		if (qname[i] == '_') nund++;
+		else if (qname[i] == ':' && nund >= 3) ncolon++;
+	}
+	if (!(nund >= 8 && ncolon == 4)) return -1;
+	const char *cur = qname, *end = qname + qname_len;
+	if (strncmp(cur, rname, rname_len) != 0) return 0;
+	if ((size_t)(end - cur) < rname_len) return 0;
+	cur += rname_len;
+	if (*cur++ != '_') return 0;
+	uint64_t frag_start = 0, frag_end = 0;
+	while (isdigit((unsigned char)*cur)) frag_start = frag_start * 10 + (uint64_t)(*cur++ - '0');
+	if (*cur++ != '_') return 0;
+	while (isdigit((unsigned char)*cur)) frag_end = frag_end * 10 + (uint64_t)(*cur++ - '0');
+	if (*cur++ != '_') return 0;
+	while (ncolon > 0) {                                                     /* :681-685 */
+		if (cur >= end) return 0;
+		if (*cur++ == ':') ncolon--;
+	}
+	while (cur < end && isdigit((unsigned char)*cur)) cur++;                  /* while(isdigit(*qname_cur++)); :686 */
+	if (cur >= end) return 0;
+	cur++;
+	int len1 = 0, len2 = 0;
+	while (isdigit((unsigned char)*cur)) len1 = len1 * 10 + (int)(*cur++ - '0');
+	if (*cur++ != '_') return 0;
+	while (isdigit((unsigned char)*cur)) len2 = len2 * 10 + (int)(*cur++ - '0');
+	if (*cur++ != '_') return 0;
+	const int flip = *cur == '1';
+	const int mate1 = mate_flag != '2';
+	const int len = mate1 ? len1 : len2;
+	if ((!flip) == mate1) return lab_abs_int(pos, frag_start) < wiggle;       /* left end of fragment, :704-706 */
+	return lab_abs_int(pos, frag_end - (uint64_t)(int64_t)len + 1) < wiggle;  /* right end, :707-709 */
+}

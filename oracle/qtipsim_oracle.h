@@ -113,6 +113,8 @@ void orc_out_free(orc_out *o);
 enum { ORC_FUNC_LINEAR = 1, ORC_FUNC_SQRT = 2, ORC_FUNC_CONST = 3 }; /* simplesim.h:197-201 */
 
 uint64_t orc_apply_function(float fraction, int function, uint64_t mn, uint64_t n); /* simplesim.cpp:177-190 */
+/* Alignment::set_correctness, qtip_parse.cpp:519-713: 1 / 0 / -1 */
+int orc_set_correctness(const char *qname, const char *rname, int flag, uint64_t pos, int wiggle);
 uint64_t orc_xscript_rflen(const char *xs);                                         /* edit_xscript.h:15-25 */
 
 /* StreamingSimulator ctor + simulate_batch (simplesim.h:214-245, simplesim.cpp:195-407).

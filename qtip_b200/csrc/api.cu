@@ -100,6 +100,7 @@ struct qtipsim {
 	std::vector<BinomSetup> setup_cache;
 	std::vector<BinomTables> tab_cache;  // BTPE acceptance bounds per set-up (lecuyer.h), for the band resolver
 	DevBuf d_tabs;
+	DevBuf d_label;  // qtipsim_label_correctness scratch
 	std::vector<uint32_t> pclass_cache;
 	uint64_t setup_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	bool setup_cache_ok = false;
@@ -242,7 +243,7 @@ void qtipsim_destroy(qtipsim_t *h) {
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->st);
 	if (h->ctl_ring) cudaFreeHost(h->ctl_ring);
-	DevBuf *all[] = {&h->d_tabs, &h->d_jh1, &h->d_jh2, &h->d_r2_aw, &h->d_r2_cum, &h->d_r2_anchor, &h->d_r2_counter, &h->d_r2_slot, &h->d_r2_end, &h->d_r2_cn,
+	DevBuf *all[] = {&h->d_label, &h->d_tabs, &h->d_jh1, &h->d_jh2, &h->d_r2_aw, &h->d_r2_cum, &h->d_r2_anchor, &h->d_r2_counter, &h->d_r2_slot, &h->d_r2_end, &h->d_r2_cn,
 	                 &h->d_r2_wres, &h->d_r2_cnt, &h->d_r2_off, &h->d_r2_misc, &h->d_setups, &h->d_pclass, &h->d_rsresult, &h->d_text, &h->d_pk_a, &h->d_pk_b, &h->d_pk_c, &h->d_pk_d, &h->d_pk_e, &h->d_bases, &h->d_nmask, &h->d_nblk, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
 	                 &h->d_ncount, &h->d_cum, &h->d_len0, &h->d_len1, &h->d_scan_tmp, &h->d_small};
 	for (DevBuf *b : all) b->release();
@@ -1699,5 +1700,36 @@ int qtipsim_stream_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats
 	return QTIPSIM_OK;
 }
 
+int qtipsim_label_correctness(qtipsim_t *h, const char *qnames, uint64_t qnames_bytes, const uint64_t *q_off, const char *rnames,
+                              uint64_t rnames_bytes, const uint64_t *r_off, const int32_t *flag, const uint64_t *pos, uint64_t n,
+                              int32_t wiggle, int8_t *correct) {
+	if (!h) return QTIPSIM_EINVAL;
+	if (!n) return QTIPSIM_OK;
+	if (!qnames || !q_off || !rnames || !r_off || !flag || !pos || !correct || !qnames_bytes || !rnames_bytes) return QTIPSIM_EINVAL;
+	// every string must end inside its arena: the kernel scans to the terminator
+	if (qnames[qnames_bytes - 1] != '\0' || rnames[rnames_bytes - 1] != '\0') return h->fail(QTIPSIM_EINVAL, "label_correctness: string arenas must end with a NUL");
+	for (uint64_t i = 0; i < n; i++)
+		if (q_off[i] >= qnames_bytes || r_off[i] >= rnames_bytes) return h->fail(QTIPSIM_EINVAL, "label_correctness: string offset outside its arena");
+	CK(cudaSetDevice(h->device));
+	const size_t qa = (qnames_bytes + 15) & ~(size_t)15, ra = (rnames_bytes + 15) & ~(size_t)15, na8 = (n * 8 + 15) & ~(size_t)15,
+	             na4 = (n * 4 + 15) & ~(size_t)15;
+	CK(h->d_label.ensure(qa + ra + 3 * na8 + na4 + n + 64));
+	char *d = h->d_label.as<char>();
+	char *d_q = d, *d_r = d_q + qa;
+	uint64_t *d_qo = (uint64_t *)(d_r + ra), *d_ro = (uint64_t *)((char *)d_qo + na8), *d_pos = (uint64_t *)((char *)d_ro + na8);
+	int32_t *d_flag = (int32_t *)((char *)d_pos + na8);
+	int8_t *d_out = (int8_t *)((char *)d_flag + na4);
+	CK(cudaMemcpyAsync(d_q, qnames, qnames_bytes, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemcpyAsync(d_r, rnames, rnames_bytes, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemcpyAsync(d_qo, q_off, n * 8, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemcpyAsync(d_ro, r_off, n * 8, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemcpyAsync(d_pos, pos, n * 8, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemcpyAsync(d_flag, flag, n * 4, cudaMemcpyHostToDevice, h->st));
+	launch_label_correctness(d_q, d_qo, d_r, d_ro, d_flag, d_pos, n, wiggle, d_out, h->st);
+	CK(cudaMemcpyAsync(correct, d_out, n, cudaMemcpyDeviceToHost, h->st));
+	CK(ctl_sync(h));
+	CK(cudaGetLastError());
+	return QTIPSIM_OK;
+}
 
 }  // extern "C"

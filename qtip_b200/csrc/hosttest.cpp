@@ -8,6 +8,7 @@
 #include <vector>
 #include "../../include/qtipsim.h"
 #include "genome.h"
+#include "label.h"
 #include "lecuyer.h"
 #include "pack_swar.h"
 #include "planner.h"
@@ -167,6 +168,10 @@ uint64_t qthost_base_thresholds(int32_t *t, int32_t span, int32_t stride) {
 	for (int64_t z = 1; z <= 2147483562; z += stride)
 		if (lbase_code_z((int32_t)z) != lbase_code(lfloat((int32_t)z))) bad++;
 	return bad;
+}
+// the product's labelling function (label.h), host build
+int qthost_label(const char *qname, const char *rname, int flag, uint64_t pos, int wiggle) {
+	return label_correctness(qname, rname, flag, pos, wiggle);
 }
 float qthost_logf(float x) { return logf_glibc(x); }
 // compares logf_glibc with the host libm over [lo, hi) bit patterns; returns mismatches

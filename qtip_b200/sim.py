@@ -202,6 +202,27 @@ class Engine:
     def results(self, st: _abi.Stats) -> List[bytes]:
         return [self.result(s, int(st.bytes[s])).tobytes() for s in range(NOUT)]
 
+    def label_correctness(self, qnames: Sequence[bytes], rnames: Sequence[bytes], flags: Sequence[int], pos: Sequence[int],
+                          wiggle: int = 30) -> np.ndarray:
+        """Alignment::set_correctness (qtip_parse.cpp:519-713) for a batch of aligned tandem-SAM records; returns int8
+        labels (1 correct, 0 incorrect, -1 not a simulated-read name)."""
+        n = len(qnames)
+        out = np.zeros(n, dtype=np.int8)
+        if not n:
+            return out
+        qa = b"".join(q + b"\0" for q in qnames)
+        ra = b"".join(r + b"\0" for r in rnames)
+        qo = np.zeros(n, dtype=np.uint64)
+        ro = np.zeros(n, dtype=np.uint64)
+        qo[1:] = np.cumsum([len(q) + 1 for q in qnames[:-1]], dtype=np.uint64)
+        ro[1:] = np.cumsum([len(r) + 1 for r in rnames[:-1]], dtype=np.uint64)
+        fl = np.ascontiguousarray(flags, dtype=np.int32)
+        ps = np.ascontiguousarray(pos, dtype=np.uint64)
+        P64, P32, P8 = C.POINTER(C.c_uint64), C.POINTER(C.c_int32), C.POINTER(C.c_int8)
+        self.check(self.lib.qtipsim_label_correctness(self.h, qa, len(qa), qo.ctypes.data_as(P64), ra, len(ra), ro.ctypes.data_as(P64),
+                                                      fl.ctypes.data_as(P32), ps.ctypes.data_as(P64), n, wiggle, out.ctypes.data_as(P8)))
+        return out
+
     def result_device_ptr(self, stream: int):
         p = C.c_void_p()
         n = C.c_uint64()

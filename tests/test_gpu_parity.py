@@ -201,6 +201,112 @@ def test_native_reads_are_consistent_with_genome(name, workdir):
     assert n == len(recs)
 
 
+def _xscript_matches(xs: bytes, read: bytes, ref: bytes, off: int) -> bool:
+    """read = transcript xs applied to ref at off (simplesim.cpp:38-62): '=' copies, X differs (any base over an N),
+    I / S are free draws, D skips a reference base.  ref is padded with N past the record end."""
+    rd = rf = 0
+    for op in xs:
+        c = chr(op)
+        if c == "=":
+            if read[rd] != ref[off + rf]:
+                return False
+            rd += 1; rf += 1
+        elif c == "X":
+            if read[rd] == ref[off + rf] or read[rd] not in b"ACGT":
+                return False
+            rd += 1; rf += 1
+        elif c == "I":
+            if read[rd] not in b"ACGT":
+                return False
+            rd += 1
+        elif c == "D":
+            rf += 1
+        elif c == "S":
+            if read[rd] not in b"ACGT":
+                return False
+            rd += 1; rf += 1
+    return rd == len(read)
+
+
+def _reflen(xs: bytes) -> int:
+    return sum(xs.count(c) for c in (b"S", b"=", b"X", b"D"))
+
+
+def _check_pairs_against_genome(case, cat, recs1, recs2, genome):
+    """Native-mode pairs against the genome at the offsets their (shared) name claims.
+    c / d (simplesim.cpp:342-397): mate 1 in file _1 and mate 2 in file _2 are some template's two transcripts applied at
+    off_1 / off_2, and the two offsets obey SURVEY Q9 (simplesim.cpp:354-363): upstream1 => off_2 - off_1 =
+    max(fraglen, rflen_2) - rflen_2, else the mirror image.  b (simplesim.cpp:279-334, simplesim.h:89-117): the aligned
+    mate (file _1 for b1, _2 for b2) is a template applied at the named offset; the other mate is opp_len random ACGT with
+    quality 'I' throughout; both halves of the name repeat the aligned mate's origin."""
+    assert len(recs1) == len(recs2) > 0
+    pad = {k: v + b"N" * 70000 for k, v in genome.items()}
+    orient = lambda q, fw: q if fw else q[::-1]  # noqa: E731
+    if cat == "b":
+        by = {}
+        for t in case["tb"]:
+            by.setdefault((t.fw_flag == "T", t.best_score, orient(t.qual, t.fw_flag == "T"), t.mate_flag), []).append(t)
+    else:
+        by = {}
+        for t in case["tc" if cat == "c" else "td"]:
+            f1, f2 = t.fw_flag_1 == "T", t.fw_flag_2 == "T"
+            by.setdefault((f1, t.score_1, orient(t.qual_1, f1), f2, t.score_2, orient(t.qual_2, f2)), []).append(t)
+    for (n1, s1, q1), (n2, s2, q2) in zip(recs1, recs2):
+        assert n1 == n2, (n1, n2)  # write_pair prints the same name on both mates (simplesim.cpp:132-171)
+        f = n1.split(b":")
+        assert f[0] == b"@qtip!" and len(f) == 10, n1
+        ref1, fw1, off1, sc1 = f[1], f[2] == b"+", int(f[3]), int(f[4])
+        ref2, fw2, off2, sc2 = f[5], f[6] == b"+", int(f[7]), int(f[8])
+        typ = f[9]
+        if cat == "b":
+            assert typ in (b"b1", b"b2") and (ref1, fw1, off1, sc1) == (ref2, fw2, off2, sc2), n1
+            aligned_is_1 = typ == b"b1"
+            sa, qa = (s1, q1) if aligned_is_1 else (s2, q2)
+            sr, qr = (s2, q2) if aligned_is_1 else (s1, q1)
+            cands = by.get((fw1, sc1, qa, "1" if aligned_is_1 else "2"))
+            assert cands, n1
+            read = sa if fw1 else _revcomp(sa)
+            assert any(_xscript_matches(t.edit_xscript, read, pad[ref1], off1) and len(sr) == t.opp_len for t in cands), n1
+            assert qr == b"I" * len(sr) and set(sr) <= set(b"ACGT"), n1
+        else:
+            assert typ == cat.encode() and ref1 == ref2, n1
+            cands = by.get((fw1, sc1, q1, fw2, sc2, q2))
+            assert cands, n1
+            r1 = s1 if fw1 else _revcomp(s1)
+            r2 = s2 if fw2 else _revcomp(s2)
+            ok = False
+            for t in cands:
+                rl1, rl2 = _reflen(t.edit_xscript_1), _reflen(t.edit_xscript_2)
+                if t.upstream1:
+                    if off2 - off1 != max(t.fraglen, rl2) - rl2:
+                        continue
+                elif off1 - off2 != max(t.fraglen, rl1) - rl1:
+                    continue
+                if _xscript_matches(t.edit_xscript_1, r1, pad[ref1], off1) and _xscript_matches(t.edit_xscript_2, r2, pad[ref2], off2):
+                    ok = True
+                    break
+            assert ok, n1
+    return len(recs1)
+
+
+@pytest.mark.parametrize("name", ["c4_mix_small", "mixed_small", "short_reads", "long_refid"])
+def test_native_pairs_are_consistent_with_genome(name, workdir):
+    """Every native-mode bad-end / concordant / discordant pair, both files, against the genome and the templates."""
+    case = cases.CASES[name]()
+    streams, st, _ = util.run_cuda(case, workdir, name, rng_mode=1, philox_seed=424242)
+    genome = _genome_dict(case, workdir, name)
+    checked = 0
+    for cat, i1, ci in (("b", 1, 1), ("c", 3, 2), ("d", 5, 3)):
+        if not st.wrote[ci]:
+            continue
+        r1, r2 = _parse_fastq(streams[i1]), _parse_fastq(streams[i1 + 1])
+        assert len(r1) == st.wrote[ci]
+        checked += _check_pairs_against_genome(case, cat, r1, r2, genome)
+    assert checked > 0
+    if st.wrote[0]:
+        assert _check_records_against_genome(case, _parse_fastq(streams[0]), genome, b"u") == st.wrote[0]
+
+
 def test_native_is_deterministic_and_seed_sensitive(workdir):
     case = cases.CASES["mixed_small"]()
     a, _, _ = util.run_cuda(case, workdir, "mixed_small", rng_mode=1, philox_seed=7)
@@ -276,6 +382,57 @@ def test_native_distributionally_equivalent_to_replay(workdir):
             alt = np.delete(f[4][r], r)
             from scipy import stats
             assert stats.chisquare(alt).pvalue > 1e-4
+
+
+def test_native_pair_mix_distributionally_equivalent_to_replay(workdir):
+    """north_star's chi-square criterion on the pair categories (BASELINE config 4 shape, 70/15/15 c/d/b): category counts,
+    fragment length, strand combination, position, mismatches per mate, which mate of a bad-end pair is the aligned one and
+    the base composition of its random mate -- native (Philox) against replay (the reference's own stream)."""
+    from scipy import stats
+    case = cases.CASES["c4_mix_small"]()
+    case["kw"] = dict(case["kw"], fraction=5.0)  # linear function: 5 x added => ~50 k pairs
+    rep, st_r, _ = util.run_cuda(case, workdir, "c4_mix_small")
+    nat, st_n, _ = util.run_cuda(case, workdir, "c4_mix_small", rng_mode=1, philox_seed=777)
+    for c in range(4):  # counts ~ sum over windows of Binomial(target, p_w) in both modes
+        assert abs(st_r.wrote[c] - st_n.wrote[c]) <= 5 * np.sqrt(st_r.wrote[c] + st_n.wrote[c] + 1)
+    genome = _genome_dict(case, workdir, "c4_mix_small")
+    names = sorted(genome)
+
+    def pair_feats(streams, i1, cat):
+        r1, r2 = _parse_fastq(streams[i1]), _parse_fastq(streams[i1 + 1])
+        frag, strands, rec, pos, mm, typ, comp = [], [], [], [], [], [], np.zeros(4)
+        for (n1, s1, _), (_, s2, _) in zip(r1, r2):
+            f = n1.split(b":")
+            fw1, off1, fw2, off2 = f[2] == b"+", int(f[3]), f[6] == b"+", int(f[7])
+            ref = genome[f[1]]
+            rec.append(names.index(f[1]))
+            pos.append(min(9, off1 * 10 // max(1, len(ref))))
+            strands.append(2 * int(fw1) + int(fw2))
+            if cat == "b":
+                aligned_is_1 = f[9] == b"b1"
+                typ.append(int(aligned_is_1))
+                sa, sr = (s1, s2) if aligned_is_1 else (s2, s1)
+                a = np.frombuffer(sa if fw1 else _revcomp(sa), np.uint8)
+                b = np.frombuffer((ref + b"N" * 1000)[off1:off1 + len(a)], np.uint8)
+                mm.append(int((a != b).sum()))
+                comp += np.array([sr.count(x) for x in (b"A", b"C", b"G", b"T")])
+            else:
+                frag.append(min(79, (max(off1, off2) + 150 - min(off1, off2)) // (10 if cat == "c" else 300)))
+                for sq, fw, off in ((s1, fw1, off1), (s2, fw2, off2)):  # these templates carry X only: mismatches = X columns
+                    a = np.frombuffer(sq if fw else _revcomp(sq), np.uint8)
+                    b = np.frombuffer((ref + b"N" * 70000)[off:off + len(a)], np.uint8)
+                    mm.append(int((a != b).sum()))
+        return dict(frag=np.bincount(frag, minlength=80) if frag else np.zeros(2), strands=np.bincount(strands, minlength=4),
+                    rec=np.bincount(rec, minlength=len(names)), pos=np.bincount(pos, minlength=10),
+                    mm=np.bincount(np.minimum(mm, 9), minlength=10), typ=np.bincount(typ, minlength=2) if typ else np.zeros(2), comp=comp)
+
+    for cat, i1 in (("b", 1), ("c", 3), ("d", 5)):
+        fr, fn = pair_feats(rep, i1, cat), pair_feats(nat, i1, cat)
+        for k in ("frag", "strands", "rec", "pos", "mm", "typ"):
+            assert _chi2_ok(fr[k], fn[k]), (cat, k)
+        if cat == "b":  # init_random draws uniform bases in both modes (simplesim.h:108-113)
+            for f in (fr, fn):
+                assert stats.chisquare(f["comp"]).pvalue > 1e-4
 
 
 @pytest.mark.parametrize("name", ["mixed_small", "c5_indel", "long_refid"])
@@ -402,3 +559,65 @@ def test_replay_bit_exact_random_configs(seed, workdir):
         assert got[i] == o.streams[i], (seed, i)
     assert (p.cg1, p.cg2) == tuple(o.cg)
     assert list(st.wrote) == list(o.wrote)
+
+
+# ------------------------------------------------------------------ tandem-SAM correctness labelling --
+
+def test_labelling_kernel_on_our_own_read_names(workdir):
+    """The read names the simulate kernels emit, fed back -- as the aligner's SAM would -- to k_label_correctness
+    through the C ABI: an alignment at the named origin is labelled correct for every read type and both mates, shifted
+    / flipped / moved ones are labelled like the reference's Alignment::set_correctness (qtip_parse.cpp:519-713) labels
+    them (oracle restatement always, the unmodified reference where oracle/_ref/libreflabel.so is present)."""
+    import random
+    from oracle import pyoracle as po
+    from qtip_b200 import sim
+    case = cases.CASES["mixed_small"]()
+    streams, st, _ = util.run_cuda(case, workdir, "mixed_small")
+    rnd = random.Random(3)
+    q, r, fl, ps, truth = [], [], [], [], []
+    for si, mate in ((0, 0), (1, 1), (2, 2), (3, 1), (4, 2), (5, 1), (6, 2)):
+        for name, _, _ in _parse_fastq(streams[si])[:600]:
+            f = name[1:].split(b":")
+            h = 0 if mate != 2 else 4  # which half of the name describes this mate
+            ref, fw, off = f[1 + h], f[2 + h] == b"+", int(f[3 + h])
+            base = (0 if mate == 0 else (1 | (64 if mate == 1 else 128)))
+            for variant in ("true", "shift", "flip", "other"):
+                pos, afw, aref = off + 1, fw, ref
+                if variant == "shift":
+                    pos = max(1, off + 1 + rnd.choice([-31, -30, -29, 29, 30, 31, 5000]))
+                elif variant == "flip":
+                    afw = not fw
+                elif variant == "other":
+                    aref = b"chrB" if ref != b"chrB" else b"chrA"
+                q.append(name[1:]); r.append(aref); fl.append(base | (0 if afw else 16)); ps.append(pos); truth.append(variant == "true")
+    eng = sim.Engine()
+    try:
+        got = eng.label_correctness(q, r, fl, ps, wiggle=30)
+    finally:
+        eng.close()
+    o = po.orc()
+    want = np.array([o.orc_set_correctness(a, b, c, d, 30) for a, b, c, d in zip(q, r, fl, ps)], dtype=np.int8)
+    assert (got == want).all()
+    assert all(got[i] == 1 for i in range(len(q)) if truth[i])  # the wire format round-trips
+    assert (got == 0).sum() > len(q) // 3
+    if os.path.exists(po.REF_LABEL_SO):
+        rl = po.ref_label()
+        ref = np.array([rl.ref_set_correctness(a, b, c, d, 30) for a, b, c, d in zip(q, r, fl, ps)], dtype=np.int8)
+        assert (got == ref).all()
+
+
+def test_labelling_kernel_matches_oracle_on_generated_records():
+    from oracle import pyoracle as po
+    from qtip_b200 import sim
+    from test_oracle_pin import label_cases
+    recs = label_cases(seed=21, n=20000)
+    eng = sim.Engine()
+    try:
+        for wiggle in (30, 2):
+            got = eng.label_correctness([x[0] for x in recs], [x[1] for x in recs], [x[2] for x in recs], [x[3] for x in recs], wiggle)
+            o = po.orc()
+            want = np.array([o.orc_set_correctness(a, b, c, d, wiggle) for a, b, c, d in recs], dtype=np.int8)
+            assert (got == want).all()
+            assert set(np.unique(got)) == {-1, 0, 1}
+    finally:
+        eng.close()

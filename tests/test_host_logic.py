@@ -375,3 +375,17 @@ def test_template_compilation_in_slices_equals_single_thread(workdir, monkeypatc
         res.append((cg, draws, n, [hs.plan_recs(c, min(n[c], 400)) for c in range(4)], int(hs.L.qthost_olap(hs.h))))
         hs.close()
     assert res[0] == res[1]
+
+
+def test_labelling_function_matches_oracle():
+    """label.h::label_correctness (the function k_label_correctness runs per alignment), host build, against the oracle's
+    restatement of Alignment::set_correctness (qtip_parse.cpp:519-713) on the shared record generator."""
+    from test_oracle_pin import label_cases
+    L, o = util.hosttest(), po.orc()
+    n1 = 0
+    for wiggle in (30, 3):
+        for q, rn, flag, pos in label_cases(seed=9, n=3000):
+            a = L.qthost_label(q, rn, flag, pos, wiggle)
+            assert a == o.orc_set_correctness(q, rn, flag, pos, wiggle), (q, rn, flag, pos, wiggle)
+            n1 += a == 1
+    assert n1 > 500

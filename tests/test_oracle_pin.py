@@ -196,3 +196,76 @@ def test_oracle_matches_reference_random_configs(seed, workdir):
     assert a.rc == 0 and b.rc == 0
     assert a.streams == b.streams
     assert a.cg == b.cg
+
+
+# ---- tandem-SAM correctness labelling: the oracle's restatement against the reference's own code ----
+
+def label_cases(seed=5, n=4000):
+    """(qname, rname, flag, pos) records: names in the simulator's wire format (simplesim.cpp:102-171) for every read
+    type, aligned where they came from or somewhere else, plus wgsim-style and foreign names.  None trips one of the
+    reference's asserts (an unpaired FLAG on a pair's name, a name that stops after 'qtip!')."""
+    import random
+    rnd = random.Random(seed)
+    refs = [b"chr1", b"chr10", b"chrX", b"contig_7", b"r", b"chr1_alt"]
+    out = []
+    for _ in range(n):
+        kind = rnd.choice(["u", "u", "c", "d", "b1", "b2", "wgsim", "junk"])
+        ref = rnd.choice(refs)
+        off = rnd.choice([0, 1, 29, 30, 31, rnd.randint(0, 10**6), rnd.randint(0, 3 * 10**9), 4294967295 + rnd.randint(0, 99)])
+        fw = rnd.random() < 0.5
+        score = rnd.randint(-300, 60)
+        dpos = rnd.choice([0, 0, 0, 1, -1, 29, -29, 30, -30, 31, rnd.randint(-10**5, 10**5)])
+        aref = ref if rnd.random() < 0.85 else rnd.choice(refs)
+        afw = fw if rnd.random() < 0.85 else not fw
+        if kind == "u":
+            q = b"qtip!:%s:%s:%d:%d:u" % (ref, b"+" if fw else b"-", off, score)
+            if rnd.random() < 0.1:
+                q += b" extra"
+            flag = 0 if afw else 16
+            out.append((q, aref, flag, max(0, off + 1 + dpos)))
+        elif kind in ("c", "d", "b1", "b2"):
+            off2 = off + rnd.randint(-400, 400) if kind != "b1" and kind != "b2" else off
+            off2 = max(0, off2)
+            fw2 = (not fw) if kind == "c" else (rnd.random() < 0.5)
+            if kind in ("b1", "b2"):
+                fw2 = fw
+            q = b"qtip!:%s:%s:%d:%d:%s:%s:%d:%d:%s" % (ref, b"+" if fw else b"-", off, score, ref, b"+" if fw2 else b"-", off2,
+                                                         rnd.randint(-300, 60), kind.encode())
+            mate2 = rnd.random() < 0.5
+            want_fw = fw2 if mate2 else fw
+            afw = want_fw if rnd.random() < 0.85 else not want_fw
+            flag = 1 | (128 if mate2 else 64) | (0 if afw else 16) | (2 if kind == "c" else 0)
+            base = off2 if mate2 else off
+            out.append((q, aref, flag, max(0, base + 1 + dpos)))
+        elif kind == "wgsim":
+            fs, l1, l2 = rnd.randint(1, 10**7), rnd.randint(30, 250), rnd.randint(30, 250)
+            fe = fs + rnd.randint(250, 800)
+            flip = rnd.randint(0, 1)
+            q = b"%s_%d_%d_0:0:0_0:0:0_%d_%d_%d_%x" % (ref, fs, fe, l1, l2, flip, rnd.randint(0, 255))
+            mate2 = rnd.random() < 0.5
+            left = (not flip) == (not mate2)
+            truth = fs if left else fe - (l2 if mate2 else l1) + 1
+            flag = 1 | (128 if mate2 else 64) | (16 if rnd.random() < 0.5 else 0)
+            out.append((q, aref, flag, max(1, truth + dpos)))
+        else:
+            q = rnd.choice([b"read_17", b"SRR1.55", b"qtip", b"a_b_c_d_e_f_g_h_i", b"x_1_2_3:4:5_6:7:8_9_10_1_a"])
+            out.append((q, aref, rnd.choice([0, 16, 65, 129]), rnd.randint(1, 10**6)))
+    return out
+
+
+def test_oracle_labelling_matches_reference_set_correctness():
+    """orc_set_correctness == the UNMODIFIED reference's Alignment::set_correctness (oracle/_ref/libreflabel.so) on 4000
+    records covering every read type, both mates, strand / reference / position disagreements around the wiggle, wgsim
+    names and foreign names, for three wiggle values."""
+    if not os.path.exists(po.REF_LABEL_SO):
+        pytest.skip("oracle/_ref/libreflabel.so not built (no /root/reference here)")
+    o, r = po.orc(), po.ref_label()
+    recs = label_cases()
+    seen = set()
+    for wiggle in (30, 1, 1000):
+        for q, rn, flag, pos in recs:
+            a = o.orc_set_correctness(q, rn, flag, pos, wiggle)
+            b = r.ref_set_correctness(q, rn, flag, pos, wiggle)
+            assert a == b, (q, rn, flag, pos, wiggle, a, b)
+            seen.add(a)
+    assert seen == {-1, 0, 1}
