@@ -206,6 +206,22 @@ int qtipsim_label_correctness(qtipsim_t *h, const char *qnames, uint64_t qnames_
                               const char *rnames, uint64_t rnames_bytes, const uint64_t *r_off, const int32_t *flag,
                               const uint64_t *pos, uint64_t n, int32_t wiggle, int8_t *correct);
 
+/* SAM alignment fields -> edit transcripts, the first half of the input model's template construction
+ * (qtip_parse.cpp: parse_cigar :223-253, mdz_to_list :258-300, cigar_to_edit_xscript :307-319,
+ * cigar_and_mdz_to_edit_xscript :326-401, lpos / rpos :164-186), for a batch of aligned records.
+ * cigars / mdzs: NUL-terminated strings, concatenated; c_off[i] / m_off[i]: record i's CIGAR / MD:Z (m_off[i] =
+ * UINT64_MAX: the record has no MD:Z tag); pos[i]: 1-based POS.  Out: xscripts (cap bytes) receives the transcripts,
+ * NUL-terminated, record i's at x_off[i] (x_off has n + 1 entries; x_off[n] = bytes used); left_clip / right_clip;
+ * lpos / rpos (the reference's, incl. rpos skipping the op after the leading soft clip), from which the
+ * caller derives a pair's fraglen = min(max-allowed-fraglen, dn.rpos - up.lpos + 1) and upstream1 (:154-158, :955-957);
+ * status[i] = 0, or why the reference would have asserted / thrown on the record (1 bad CIGAR, 2 unsupported op,
+ * 3 neither extended CIGAR nor MD:Z, 4 MD:Z does not fit the CIGAR): such records get an empty transcript.
+ * Returns QTIPSIM_ERANGE if cap is too small (x_off[n] then holds the bytes needed).  Host pointers throughout. */
+int qtipsim_edit_xscripts(qtipsim_t *h, const char *cigars, uint64_t cigars_bytes, const uint64_t *c_off, const char *mdzs,
+                          uint64_t mdzs_bytes, const uint64_t *m_off, const uint64_t *pos, uint64_t n, char *xscripts,
+                          uint64_t cap, uint64_t *x_off, int32_t *left_clip, int32_t *right_clip, uint64_t *lpos,
+                          uint64_t *rpos, int32_t *status);
+
 #ifdef __cplusplus
 }
 #endif

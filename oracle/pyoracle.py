@@ -101,6 +101,9 @@ def orc() -> C.CDLL:
         lib.orc_simulate.restype = C.c_int
         lib.orc_set_correctness.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint64, C.c_int]
         lib.orc_set_correctness.restype = C.c_int
+        lib.orc_edit_xscript.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.orc_edit_xscript.restype = C.c_int
         _orc = lib
     return _orc
 
@@ -143,8 +146,20 @@ def ref_label() -> C.CDLL:
         lib = C.CDLL(REF_LABEL_SO)
         lib.ref_set_correctness.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint64, C.c_int]
         lib.ref_set_correctness.restype = C.c_int
+        lib.ref_edit_xscript.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.ref_edit_xscript.restype = C.c_int
         _reflabel = lib
     return _reflabel
+
+
+def edit_xscript(lib_fn, cigar: bytes, mdz, pos: int, cap: int = 1 << 16):
+    """Calls orc_edit_xscript / ref_edit_xscript; returns (status, transcript, left_clip, right_clip, lpos, rpos)."""
+    out = C.create_string_buffer(cap)
+    lc, rc_ = C.c_int(), C.c_int()
+    lp, rp = C.c_uint64(), C.c_uint64()
+    st = lib_fn(cigar, mdz, pos, out, cap, C.byref(lc), C.byref(rc_), C.byref(lp), C.byref(rp))
+    return (st, out.value if st == 0 else b"", lc.value, rc_.value, lp.value if st == 0 else 0, rp.value if st == 0 else 0)
 
 
 class SimResult:

@@ -769,3 +769,111 @@ int orc_set_correctness(const char *qname, const char *rname, int flag, uint64_t
 	if ((!flip) == mate1) return lab_abs_int(pos, frag_start) < wiggle;       /* left end of fragment, :704-706 */
 	return lab_abs_int(pos, frag_end - (uint64_t)(int64_t)len + 1) < wiggle;  /* right end, :707-709 */
 }
+
+/* ---------------------------------------------------------------------------
+ * SAM fields -> edit transcript: parse_cigar (qtip_parse.cpp:223-253), mdz_to_list (:258-300),
+ * cigar_to_edit_xscript (:307-319), cigar_and_mdz_to_edit_xscript (:326-401), lpos / rpos (:164-186).
+ * Like the reference this builds the run / op lists and the MD:Z element list first.  Returns 0 and fills
+ * out (NUL-terminated, cap bytes) or a status > 0 where the reference asserts / throws.
+ * ------------------------------------------------------------------------- */
+int orc_edit_xscript(const char *cigar, const char *mdz, uint64_t pos, char *out, size_t cap, int *left_clip,
+                     int *right_clip, uint64_t *lpos, uint64_t *rpos) {
+	const size_t clen = strlen(cigar);
+	int *crun = (int *)malloc((clen + 1) * sizeof(int));
+	char *cops = (char *)malloc(clen + 1);
+	size_t nc = 0, i = 0;
+	int eqx = 0, rc = 0;
+	*left_clip = *right_clip = 0;
+	while (i < clen) {                                                       /* parse_cigar */
+		if (!isdigit((unsigned char)cigar[i])) { rc = 1; goto done; }
+		int run = 0;
+		do { run = run * 10 + (cigar[i] - '0'); i++; } while (isdigit((unsigned char)cigar[i]));
+		if (!(isalpha((unsigned char)cigar[i]) || cigar[i] == '=')) { rc = 1; goto done; }
+		if (nc == 0 && cigar[i] == 'S') *left_clip = run;
+		else if (i + 1 >= clen && cigar[i] == 'S') *right_clip = run;
+		if (cigar[i] == 'X' || cigar[i] == '=') eqx = 1;
+		cops[nc] = cigar[i];
+		crun[nc++] = run;
+		i++;
+	}
+	size_t n = 0;
+#define PUSH(ch) do { if (n + 1 < cap) out[n] = (ch); n++; } while (0)
+	if (eqx) {                                                               /* cigar_to_edit_xscript */
+		for (size_t k = 0; k < nc; k++) {
+			if (cops[k] == 'M' || cops[k] == 'P') { rc = 2; goto done; }
+			for (int j = 0; j < crun[k]; j++) PUSH(cops[k]);
+		}
+	} else {
+		if (!mdz) { rc = 3; goto done; }
+		const size_t mlen = strlen(mdz);                                     /* mdz_to_list */
+		int *mop = (int *)malloc((mlen + 1) * sizeof(int)), *mrun = (int *)malloc((mlen + 1) * sizeof(int));
+		size_t nm = 0, j = 0;
+		while (j < mlen) {
+			if (isdigit((unsigned char)mdz[j])) {
+				int run = 0;
+				do { run = run * 10 + (mdz[j] - '0'); j++; } while (j < mlen && isdigit((unsigned char)mdz[j]));
+				if (run > 0) { mop[nm] = 0; mrun[nm++] = run; }
+			} else if (isalpha((unsigned char)mdz[j])) {
+				int run = 0;
+				do { j++; run++; } while (j < mlen && isalpha((unsigned char)mdz[j]));
+				mop[nm] = 1; mrun[nm++] = run;
+			} else if (mdz[j] == '^') {
+				j++;
+				int run = 0;
+				while (j < mlen && isalpha((unsigned char)mdz[j])) { j++; run++; }
+				mop[nm] = 2; mrun[nm++] = run;
+			} else {
+				j++;
+			}
+		}
+		size_t mdo = 0;                                                      /* cigar_and_mdz_to_edit_xscript */
+		for (size_t k = 0; k < nc && !rc; k++) {
+			const char cop = cops[k];
+			if (cop == 'M') {
+				int left = crun[k];
+				while (left > 0 && mdo < nm) {
+					if (mop[mdo] == 2) { rc = 4; break; }
+					const int comb = left < mrun[mdo] ? left : mrun[mdo];
+					left -= comb;
+					if (mop[mdo] == 0) {
+						for (int t = 0; t < comb; t++) PUSH('=');
+					} else {
+						if (mrun[mdo] != comb) { rc = 4; break; }
+						for (int t = 0; t < comb; t++) PUSH('X');
+					}
+					if (comb < mrun[mdo]) mrun[mdo] -= comb;
+					else mdo++;
+				}
+			} else if (cop == 'I') { for (int t = 0; t < crun[k]; t++) PUSH('I'); }
+			else if (cop == 'D') {
+				if (mdo >= nm || mop[mdo] != 2 || mrun[mdo] != crun[k]) { rc = 4; break; }
+				mdo++;
+				for (int t = 0; t < crun[k]; t++) PUSH('D');
+			} else if (cop == 'N') { for (int t = 0; t < crun[k]; t++) PUSH('N'); }
+			else if (cop == 'S') { for (int t = 0; t < crun[k]; t++) PUSH('S'); }
+			else if (cop == 'H') { }
+			else rc = 2;
+		}
+		if (!rc && mdo != nm) rc = 4;
+		free(mop);
+		free(mrun);
+	}
+#undef PUSH
+	if (!rc) {
+		if (n + 1 > cap) rc = 5;
+		else {
+			out[n] = '\0';
+			*lpos = pos - (uint64_t)(int64_t)*left_clip;                     /* lpos, :164-167 */
+			size_t k = 0;                                                    /* rpos, :173-186 */
+			while (k < n && out[k] == 'S') k++;
+			k++;
+			uint64_t mv = 0;
+			for (; k < n; k++) mv += (out[k] == 'S' || out[k] == 'D' || out[k] == 'X' || out[k] == '=');
+			*rpos = pos + mv - 1;
+		}
+	}
+done:
+	free(crun);
+	free(cops);
+	return rc;
+}

@@ -113,6 +113,9 @@ void orc_out_free(orc_out *o);
 enum { ORC_FUNC_LINEAR = 1, ORC_FUNC_SQRT = 2, ORC_FUNC_CONST = 3 }; /* simplesim.h:197-201 */
 
 uint64_t orc_apply_function(float fraction, int function, uint64_t mn, uint64_t n); /* simplesim.cpp:177-190 */
+/* CIGAR (+ MD:Z) -> edit transcript, clips, lpos / rpos: qtip_parse.cpp:164-186, :223-401; 0 or a status */
+int orc_edit_xscript(const char *cigar, const char *mdz, uint64_t pos, char *out, size_t cap, int *left_clip,
+                     int *right_clip, uint64_t *lpos, uint64_t *rpos);
 /* Alignment::set_correctness, qtip_parse.cpp:519-713: 1 / 0 / -1 */
 int orc_set_correctness(const char *qname, const char *rname, int flag, uint64_t pos, int wiggle);
 uint64_t orc_xscript_rflen(const char *xs);                                         /* edit_xscript.h:15-25 */

@@ -23,6 +23,7 @@ RNG_REPLAY, RNG_PHILOX = 0, 1
 # every symbol include/qtipsim.h declares (tests/test_abi.py checks header <-> this list <-> .so)
 SYMBOLS = (
     "qtipsim_label_correctness",
+    "qtipsim_edit_xscripts",
     "qtipsim_abi_version",
     "qtipsim_create",
     "qtipsim_destroy",
@@ -121,6 +122,10 @@ def load() -> C.CDLL:
     lib.qtipsim_stream_begin.argtypes = [H, C.c_void_p, C.c_size_t]
     lib.qtipsim_label_correctness.argtypes = [H, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64),
                                               C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.c_uint64, C.c_int32, C.POINTER(C.c_int8)]
+    P64 = C.POINTER(C.c_uint64)
+    P32 = C.POINTER(C.c_int32)
+    lib.qtipsim_edit_xscripts.argtypes = [H, C.c_char_p, C.c_uint64, P64, C.c_char_p, C.c_uint64, P64, P64, C.c_uint64, C.c_void_p, C.c_uint64,
+                                          P64, P32, P32, P64, P64, P32]
     lib.qtipsim_stream_run.argtypes = [H, C.POINTER(RunParams), C.POINTER(Stats), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     _lib = lib
     return lib

@@ -100,7 +100,8 @@ struct qtipsim {
 	std::vector<BinomSetup> setup_cache;
 	std::vector<BinomTables> tab_cache;  // BTPE acceptance bounds per set-up (lecuyer.h), for the band resolver
 	DevBuf d_tabs;
-	DevBuf d_label;  // qtipsim_label_correctness scratch
+	DevBuf d_label;  // qtipsim_label_correctness / qtipsim_edit_xscripts scratch
+	DevBuf d_xs_out;
 	std::vector<uint32_t> pclass_cache;
 	uint64_t setup_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	bool setup_cache_ok = false;
@@ -243,7 +244,7 @@ void qtipsim_destroy(qtipsim_t *h) {
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->st);
 	if (h->ctl_ring) cudaFreeHost(h->ctl_ring);
-	DevBuf *all[] = {&h->d_label, &h->d_tabs, &h->d_jh1, &h->d_jh2, &h->d_r2_aw, &h->d_r2_cum, &h->d_r2_anchor, &h->d_r2_counter, &h->d_r2_slot, &h->d_r2_end, &h->d_r2_cn,
+	DevBuf *all[] = {&h->d_xs_out, &h->d_label, &h->d_tabs, &h->d_jh1, &h->d_jh2, &h->d_r2_aw, &h->d_r2_cum, &h->d_r2_anchor, &h->d_r2_counter, &h->d_r2_slot, &h->d_r2_end, &h->d_r2_cn,
 	                 &h->d_r2_wres, &h->d_r2_cnt, &h->d_r2_off, &h->d_r2_misc, &h->d_setups, &h->d_pclass, &h->d_rsresult, &h->d_text, &h->d_pk_a, &h->d_pk_b, &h->d_pk_c, &h->d_pk_d, &h->d_pk_e, &h->d_bases, &h->d_nmask, &h->d_nblk, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
 	                 &h->d_ncount, &h->d_cum, &h->d_len0, &h->d_len1, &h->d_scan_tmp, &h->d_small};
 	for (DevBuf *b : all) b->release();
@@ -1727,6 +1728,61 @@ int qtipsim_label_correctness(qtipsim_t *h, const char *qnames, uint64_t qnames_
 	CK(cudaMemcpyAsync(d_flag, flag, n * 4, cudaMemcpyHostToDevice, h->st));
 	launch_label_correctness(d_q, d_qo, d_r, d_ro, d_flag, d_pos, n, wiggle, d_out, h->st);
 	CK(cudaMemcpyAsync(correct, d_out, n, cudaMemcpyDeviceToHost, h->st));
+	CK(ctl_sync(h));
+	CK(cudaGetLastError());
+	return QTIPSIM_OK;
+}
+
+int qtipsim_edit_xscripts(qtipsim_t *h, const char *cigars, uint64_t cigars_bytes, const uint64_t *c_off, const char *mdzs,
+                          uint64_t mdzs_bytes, const uint64_t *m_off, const uint64_t *pos, uint64_t n, char *xscripts, uint64_t cap,
+                          uint64_t *x_off, int32_t *left_clip, int32_t *right_clip, uint64_t *lpos, uint64_t *rpos, int32_t *status) {
+	if (!h || !x_off) return QTIPSIM_EINVAL;
+	x_off[0] = 0;
+	if (!n) return QTIPSIM_OK;
+	if (!cigars || !cigars_bytes || !c_off || !m_off || !pos || !left_clip || !right_clip || !lpos || !rpos || !status) return QTIPSIM_EINVAL;
+	if (cigars[cigars_bytes - 1] != '\0' || (mdzs_bytes && (!mdzs || mdzs[mdzs_bytes - 1] != '\0')))
+		return h->fail(QTIPSIM_EINVAL, "edit_xscripts: string arenas must end with a NUL");
+	for (uint64_t i = 0; i < n; i++)
+		if (c_off[i] >= cigars_bytes || (m_off[i] != ~0ull && m_off[i] >= mdzs_bytes)) return h->fail(QTIPSIM_EINVAL, "edit_xscripts: string offset outside its arena");
+	CK(cudaSetDevice(h->device));
+	auto al = [](size_t b) { return (b + 15) & ~(size_t)15; };
+	const size_t in_bytes = al(cigars_bytes) + al(mdzs_bytes + 1) + 3 * al(n * 8) + al((n + 1) * 8) + 2 * al(n * 8) + 4 * al(n * 4) + 64;
+	CK(h->d_label.ensure(in_bytes));
+	CK(h->d_scan_tmp.ensure((n / 1024 + 4) * 8));
+	char *d = h->d_label.as<char>();
+	char *d_c = d;
+	char *d_m = d_c + al(cigars_bytes);
+	uint64_t *d_co = (uint64_t *)(d_m + al(mdzs_bytes + 1));
+	uint64_t *d_mo = (uint64_t *)((char *)d_co + al(n * 8));
+	uint64_t *d_pos = (uint64_t *)((char *)d_mo + al(n * 8));
+	uint64_t *d_xo = (uint64_t *)((char *)d_pos + al(n * 8));
+	uint64_t *d_lp = (uint64_t *)((char *)d_xo + al((n + 1) * 8));
+	uint64_t *d_rp = (uint64_t *)((char *)d_lp + al(n * 8));
+	uint32_t *d_len = (uint32_t *)((char *)d_rp + al(n * 8));
+	int32_t *d_lc = (int32_t *)((char *)d_len + al(n * 4));
+	int32_t *d_rc = (int32_t *)((char *)d_lc + al(n * 4));
+	int32_t *d_st = (int32_t *)((char *)d_rc + al(n * 4));
+	CK(cudaMemcpyAsync(d_c, cigars, cigars_bytes, cudaMemcpyHostToDevice, h->st));
+	if (mdzs_bytes) CK(cudaMemcpyAsync(d_m, mdzs, mdzs_bytes, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemcpyAsync(d_co, c_off, n * 8, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemcpyAsync(d_mo, m_off, n * 8, cudaMemcpyHostToDevice, h->st));
+	CK(cudaMemcpyAsync(d_pos, pos, n * 8, cudaMemcpyHostToDevice, h->st));
+	launch_xs_lengths(d_c, d_co, d_m, d_mo, d_pos, n, d_len, d_lc, d_rc, d_st, h->st);
+	launch_scan(d_len, d_xo, n, h->d_scan_tmp.as<uint64_t>(), d_xo + n, h->st);
+	uint64_t total = 0;
+	CK(cudaMemcpyAsync(&total, d_xo + n, 8, cudaMemcpyDeviceToHost, h->st));
+	CK(ctl_sync(h));
+	x_off[n] = total;
+	if (total > cap || !xscripts) return h->fail(QTIPSIM_ERANGE, "edit_xscripts: transcript arena too small");
+	CK(h->d_xs_out.ensure(total + 16));
+	launch_xs_fill(d_c, d_co, d_m, d_mo, d_pos, n, d_xo, d_st, h->d_xs_out.as<char>(), d_lp, d_rp, h->st);
+	CK(cudaMemcpyAsync(xscripts, h->d_xs_out.p, total, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(x_off, d_xo, (n + 1) * 8, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(left_clip, d_lc, n * 4, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(right_clip, d_rc, n * 4, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(lpos, d_lp, n * 8, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(rpos, d_rp, n * 8, cudaMemcpyDeviceToHost, h->st));
+	CK(cudaMemcpyAsync(status, d_st, n * 4, cudaMemcpyDeviceToHost, h->st));
 	CK(ctl_sync(h));
 	CK(cudaGetLastError());
 	return QTIPSIM_OK;

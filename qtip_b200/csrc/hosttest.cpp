@@ -12,6 +12,7 @@
 #include "lecuyer.h"
 #include "pack_swar.h"
 #include "planner.h"
+#include "xscript.h"
 #include "templates.h"
 
 using namespace qt;
@@ -172,6 +173,15 @@ uint64_t qthost_base_thresholds(int32_t *t, int32_t span, int32_t stride) {
 // the product's labelling function (label.h), host build
 int qthost_label(const char *qname, const char *rname, int flag, uint64_t pos, int wiggle) {
 	return label_correctness(qname, rname, flag, pos, wiggle);
+}
+// the product's transcript builder (xscript.h), host build
+int qthost_edit_xscript(const char *cigar, const char *mdz, uint64_t pos, char *out, uint32_t cap, int *lclip, int *rclip, uint64_t *lpos,
+                        uint64_t *rpos) {
+	const XsInfo r = xs_build(cigar, mdz, pos, out, cap);
+	*lclip = r.left_clip;
+	*rclip = r.right_clip;
+	if (r.status == XS_OK) xs_span(out, r.len, pos, r.left_clip, *lpos, *rpos);
+	return r.status;
 }
 float qthost_logf(float x) { return logf_glibc(x); }
 // compares logf_glibc with the host libm over [lo, hi) bit patterns; returns mismatches

@@ -102,6 +102,12 @@ void launch_plan_philox_lengths(const Window *win, const uint64_t *cum, uint32_t
 void launch_label_correctness(const char *qnames, const uint64_t *q_off, const char *rnames, const uint64_t *r_off, const int32_t *flag,
                               const uint64_t *pos, uint64_t n, int32_t wiggle, int8_t *correct, cudaStream_t st);
 
+// SAM fields -> edit transcripts (xscript.cu)
+void launch_xs_lengths(const char *cigars, const uint64_t *c_off, const char *mdzs, const uint64_t *m_off, const uint64_t *pos, uint64_t n,
+                       uint32_t *len1, int32_t *lclip, int32_t *rclip, int32_t *status, cudaStream_t st);
+void launch_xs_fill(const char *cigars, const uint64_t *c_off, const char *mdzs, const uint64_t *m_off, const uint64_t *pos, uint64_t n,
+                    const uint64_t *x_off, const int32_t *status, char *xs, uint64_t *lpos, uint64_t *rpos, cudaStream_t st);
+
 int kernels_launch_count();  // kernels launched through the wrappers above since process start
 
 }  // namespace qt

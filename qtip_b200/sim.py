@@ -223,6 +223,47 @@ class Engine:
                                                       fl.ctypes.data_as(P32), ps.ctypes.data_as(P64), n, wiggle, out.ctypes.data_as(P8)))
         return out
 
+    def edit_xscripts(self, cigars: Sequence[bytes], mdzs: Sequence[Optional[bytes]], pos: Sequence[int]):
+        """SAM CIGAR (+ MD:Z) -> edit transcripts on the device (qtip_parse.cpp:223-401); returns a list of
+        (status, transcript, left_clip, right_clip, lpos, rpos) per alignment."""
+        n = len(cigars)
+        if not n:
+            return []
+        ca = b"".join(c + b"\0" for c in cigars)
+        ma = b"".join(m + b"\0" for m in mdzs if m is not None)
+        co = np.zeros(n, dtype=np.uint64)
+        co[1:] = np.cumsum([len(c) + 1 for c in cigars[:-1]], dtype=np.uint64)
+        mo = np.full(n, np.iinfo(np.uint64).max, dtype=np.uint64)
+        acc = 0
+        for i, m in enumerate(mdzs):
+            if m is not None:
+                mo[i] = acc
+                acc += len(m) + 1
+        ps = np.ascontiguousarray(pos, dtype=np.uint64)
+        xo = np.zeros(n + 1, dtype=np.uint64)
+        lc, rc_, st = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros(n, np.int32)
+        lp, rp = np.zeros(n, np.uint64), np.zeros(n, np.uint64)
+        P64, P32 = C.POINTER(C.c_uint64), C.POINTER(C.c_int32)
+        cap = 1 << 16
+        for _ in range(2):  # the second call has the size the first one reported
+            buf = np.zeros(cap, dtype=np.uint8)
+            rc = self.lib.qtipsim_edit_xscripts(self.h, ca, len(ca), co.ctypes.data_as(P64), ma if ma else None, len(ma), mo.ctypes.data_as(P64),
+                                                ps.ctypes.data_as(P64), n, C.c_void_p(buf.ctypes.data), cap, xo.ctypes.data_as(P64),
+                                                lc.ctypes.data_as(P32), rc_.ctypes.data_as(P32), lp.ctypes.data_as(P64), rp.ctypes.data_as(P64),
+                                                st.ctypes.data_as(P32))
+            if rc == -6 and int(xo[n]) > cap:
+                cap = int(xo[n])
+                continue
+            self.check(rc)
+            break
+        raw = buf.tobytes()
+        out = []
+        for i in range(n):
+            xs = raw[int(xo[i]):int(xo[i + 1]) - 1]
+            ok = st[i] == 0
+            out.append((int(st[i]), xs if ok else b"", int(lc[i]), int(rc_[i]), int(lp[i]) if ok else 0, int(rp[i]) if ok else 0))
+        return out
+
     def result_device_ptr(self, stream: int):
         p = C.c_void_p()
         n = C.c_uint64()

@@ -621,3 +621,31 @@ def test_labelling_kernel_matches_oracle_on_generated_records():
             assert set(np.unique(got)) == {-1, 0, 1}
     finally:
         eng.close()
+
+
+# ------------------------------------------------------------------ SAM fields -> edit transcripts --
+
+def test_edit_xscript_kernels_match_oracle():
+    """k_xs_lengths / k_xs_fill through qtipsim_edit_xscripts against the oracle's restatement of the reference's CIGAR /
+    MD:Z parser on 6000 alignments (both CIGAR styles, indels, soft and hard clips, 64-bit positions) and on malformed
+    records; the transcripts of well-formed records are the ones their SAM fields were generated from."""
+    from oracle import pyoracle as po
+    from qtip_b200 import sim
+    from test_oracle_pin import xscript_cases
+    recs = xscript_cases(seed=44, n=6000)
+    bad = [(b"10M", None, 5, None), (b"5M2D5M", b"10", 9, None), (b"3P10M", b"10", 1, None), (b"M10", b"10", 1, None),
+           (b"4=1X5M", None, 3, None), (b"10M", b"5AC3", 1, None)]
+    allr = recs + bad
+    eng = sim.Engine()
+    try:
+        got = eng.edit_xscripts([r[0] for r in allr], [r[1] for r in allr], [r[2] for r in allr])
+    finally:
+        eng.close()
+    o = po.orc()
+    for (cigar, mdz, pos, xs), g in zip(allr, got):
+        want = po.edit_xscript(o.orc_edit_xscript, cigar, mdz, pos)
+        assert g[0] == want[0], (cigar, mdz, g, want)
+        if want[0] == 0:
+            assert g == want, (cigar, mdz, g, want)
+            assert xs is None or g[1] == xs
+    assert sum(1 for g in got if g[0] != 0) == len(bad)

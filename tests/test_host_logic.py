@@ -389,3 +389,23 @@ def test_labelling_function_matches_oracle():
             assert a == o.orc_set_correctness(q, rn, flag, pos, wiggle), (q, rn, flag, pos, wiggle)
             n1 += a == 1
     assert n1 > 500
+
+
+def test_edit_xscript_builder_matches_oracle():
+    """xscript.h::xs_build / xs_span (what k_xs_lengths / k_xs_fill run per alignment), host build, against the oracle's
+    restatement of the reference parser -- well-formed alignments and the malformed ones the reference asserts on."""
+    from test_oracle_pin import xscript_cases
+    L, o = util.hosttest(), po.orc()
+    recs = [(c, m, p) for c, m, p, _ in xscript_cases(seed=8)]
+    recs += [(b"10M", None, 5), (b"10M", b"4A6", 5), (b"10M", b"9", 5), (b"5M2D5M", b"5^A5", 9), (b"5M2D5M", b"10", 9), (b"3P10M", b"10", 1),
+             (b"M10", b"10", 1), (b"10", b"10", 1), (b"4=1X5M", None, 3), (b"10=", None, 3), (b"5S10=", None, 30), (b"20S", b"0", 4),
+             (b"10M5N10M", b"20", 100), (b"10M", b"5AC3", 1), (b"3M1I3M", b"2T3", 77)]
+    for cigar, mdz, pos in recs:
+        out = C.create_string_buffer(1 << 12)
+        lc, rc_ = C.c_int(), C.c_int()
+        lp, rp = C.c_uint64(), C.c_uint64()
+        st = L.qthost_edit_xscript(cigar, mdz, pos, out, 1 << 12, C.byref(lc), C.byref(rc_), C.byref(lp), C.byref(rp))
+        want = po.edit_xscript(o.orc_edit_xscript, cigar, mdz, pos, cap=1 << 12)
+        assert st == want[0], (cigar, mdz, st, want)
+        if st == 0:
+            assert (out.value, lc.value, rc_.value, lp.value, rp.value) == want[1:], (cigar, mdz)

@@ -269,3 +269,74 @@ def test_oracle_labelling_matches_reference_set_correctness():
             assert a == b, (q, rn, flag, pos, wiggle, a, b)
             seen.add(a)
     assert seen == {-1, 0, 1}
+
+
+# ---- SAM fields -> edit transcript: the oracle's restatement against the reference's own parser ----
+
+def sam_fields_from_xscript(xs: bytes, rnd):
+    """An M-style CIGAR + MD:Z and an extended (=/X) CIGAR that encode the transcript xs (ops = X I D S)."""
+    import itertools
+    runs = [(k, len(list(g))) for k, g in itertools.groupby(xs.decode())]
+    eqx = "".join(f"{n}{op}" for op, n in runs)
+    m_runs = []
+    for op, n in runs:
+        mop = "M" if op in "=X" else op
+        if m_runs and m_runs[-1][0] == mop:
+            m_runs[-1][1] += n
+        else:
+            m_runs.append([mop, n])
+    cigar = "".join(f"{n}{op}" for op, n in m_runs)
+    md, cnt = [], 0
+    for op, n in runs:
+        if op == "=":
+            cnt += n
+        elif op == "X":
+            for _ in range(n):
+                md.append(f"{cnt}{rnd.choice('ACGT')}")
+                cnt = 0
+        elif op == "D":
+            md.append(f"{cnt}^" + "".join(rnd.choice("ACGT") for _ in range(n)))
+            cnt = 0
+    md.append(str(cnt))
+    return cigar.encode(), "".join(md).encode(), eqx.encode()
+
+
+def xscript_cases(seed=3, n=1500):
+    """(cigar, mdz or None, pos, expected transcript) from synthetic templates: substitutions only, indels, soft clips,
+    hard clips, both CIGAR styles."""
+    import random
+    from qtip_b200 import synth
+    rnd = random.Random(seed)
+    ts = (synth.templates_unpaired(n // 3, 100, seed, max_x=5) + synth.templates_unpaired(n // 3, 150, seed + 1, indel=True, len_jitter=20) +
+          synth.templates_unpaired(n // 3, 60, seed + 2, indel=True))
+    out = []
+    for t in ts:
+        xs = t.edit_xscript
+        if rnd.random() < 0.3:  # soft clips at the ends
+            xs = b"S" * rnd.randint(1, 9) + xs + (b"S" * rnd.randint(1, 9) if rnd.random() < 0.5 else b"")
+        cigar, mdz, eqx = sam_fields_from_xscript(xs, rnd)
+        pos = rnd.choice([1, 7, rnd.randint(1, 10**6), rnd.randint(1, 3 * 10**9)])
+        if rnd.random() < 0.2:  # hard clips leave no trace in the transcript
+            cigar = b"%dH" % rnd.randint(1, 30) + cigar + b"%dH" % rnd.randint(1, 30)
+        if rnd.random() < 0.5:
+            out.append((cigar, mdz, pos, xs))
+        else:
+            out.append((eqx, mdz if rnd.random() < 0.5 else None, pos, xs))
+    return out
+
+
+def test_oracle_edit_xscript_matches_reference_parser():
+    """orc_edit_xscript == the UNMODIFIED reference's parse_cigar / mdz_to_list / cigar_and_mdz_to_edit_xscript / lpos /
+    rpos (qtip_parse.cpp:164-186, :223-401; oracle/_ref/libreflabel.so): transcript, clips and both positions, and the
+    transcript is the one the CIGAR / MD:Z pair was made from."""
+    if not os.path.exists(po.REF_LABEL_SO):
+        pytest.skip("oracle/_ref/libreflabel.so not built (no /root/reference here)")
+    o, r = po.orc(), po.ref_label()
+    n = 0
+    for cigar, mdz, pos, xs in xscript_cases():
+        a = po.edit_xscript(o.orc_edit_xscript, cigar, mdz, pos)
+        b = po.edit_xscript(r.ref_edit_xscript, cigar, mdz, pos)
+        assert a == b, (cigar, mdz, pos, a, b)
+        assert a[0] == 0 and a[1] == xs, (cigar, mdz, a)
+        n += 1
+    assert n >= 1400

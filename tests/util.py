@@ -73,6 +73,9 @@ def hosttest() -> C.CDLL:
         L.qthost_base_thresholds.restype = C.c_uint64
         L.qthost_label.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_uint64, C.c_int]
         L.qthost_label.restype = C.c_int
+        L.qthost_edit_xscript.argtypes = [C.c_char_p, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.qthost_edit_xscript.restype = C.c_int
         L.qthost_logf.argtypes = [C.c_float]
         L.qthost_logf.restype = C.c_float
         L.qthost_logf_sweep.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
