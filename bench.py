@@ -187,6 +187,32 @@ def run_reference_steps(wl, steps, warmup, threads_note="1 (the reference is sin
                 cores=1), None
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Pins this rank to the CPUs of its GPU's NUMA node before any pinned host memory is allocated, so that the rank's
+    FASTQ result buffers (GBs per step at N = 8) live in the memory next to its GPU's PCIe root.  No-op on single-node
+    hosts or where sysfs does not say."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node_path = f"/sys/bus/pci/devices/{bdf}/numa_node"
+        if not os.path.exists(node_path):
+            return
+        node = int(open(node_path).read().strip())
+        if node < 0:
+            return
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & ids
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+    except Exception:
+        pass
+
+
 # ---------------------------------------------------------------------- main --
 
 def main():
@@ -240,6 +266,7 @@ def main():
     from qtip_b200 import _abi, sim
 
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rng_mode = _abi.RNG_REPLAY if args.mode == "replay" else _abi.RNG_PHILOX
@@ -475,9 +502,10 @@ def main():
             pass
         stream_ready[0] = False
         m4 = measure(primary_mode, args.steps, args.warmup, False)
-        # the replay chain of this mix is long (~150 skipped draws per bad-end pair) and sequential across ranks: timed on
-        # the device-resident arm only
-        m4r = None if args.no_secondary else measure(other_mode, 3, 1, False, do_e2e=False)
+        # the replay chain of this mix is long (~150 skipped draws per bad-end pair: 3 s per 13.5 M pairs) and sequential
+        # across ranks, so N ranks would take N times as long for N times the pairs: timed at N = 1 only, on the
+        # device-resident arm
+        m4r = None if (args.no_secondary or world > 1) else measure(other_mode, 3, 1, False, do_e2e=False)
         cur["wl"] = wl
 
     if rank == 0:
