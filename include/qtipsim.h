@@ -156,6 +156,15 @@ int qtipsim_genome_adopt(qtipsim_t *h, const void *blob, uint64_t blob_bytes,
                          const void *d_bases, uint64_t bases_bytes,
                          const void *d_nmask, uint64_t nmask_bytes);
 
+/* Packed-genome cache: a trial after the first need not parse and pack the FASTA again -- the reference
+ * re-reads it byte by byte in every trial (fasta.cpp:42-127; 22 s of a 63 s run at 3.1 Gbp).  save: writes the loaded
+ * genome in packed form (record table, 2 bit/base, N mask: 0.375 byte per base) to `cache_path`, stamped with the FASTA's
+ * size and modification time.  load_cached: if `cache_path` holds a cache stamped with `fasta_path`'s current size and
+ * mtime, uploads it (1.17 GB instead of 3.13 GB of text at 3.1 Gbp, no pack kernels); otherwise loads and packs the
+ * FASTA and (re)writes the cache.  *hit (may be NULL) tells which happened. */
+int qtipsim_genome_save(qtipsim_t *h, const char *cache_path, const char *fasta_path);
+int qtipsim_load_fasta_cached(qtipsim_t *h, const char *fasta_path, const char *cache_path, int *hit);
+
 /* Input model: replaces InputModelUnpaired / InputModelPaired (input_model.h:26-42,
  * :100-116).  kept = templates in v[], added = alignments seen (num_added(), :68-70). */
 int qtipsim_set_templates_unpaired(qtipsim_t *h, int cat /* U or B */,
@@ -176,6 +185,17 @@ int qtipsim_result_device_ptr(qtipsim_t *h, int stream, const void **ptr, uint64
 /* Appends each stream to an open file descriptor (the shim passes fileno() of the
  * caller's FILE* after fflush; SimulatedRead::write/write_pair, simplesim.cpp:102-171). */
 int qtipsim_result_write_fds(qtipsim_t *h, const int fds[QTIPSIM_NOUT]);
+
+/* Output paths to the aligner that avoid the temporary-file round trip (the reference writes seven files and
+ * the driver concatenates / passes them on, qtip:378-409).
+ * stream_fds: like write_fds, but all seven streams are written CONCURRENTLY (one writer per descriptor, each with its
+ * own device-to-host pipeline): the descriptors may be FIFOs or pipes whose reader -- an aligner taking _1 and _2 files --
+ * consumes the paired files in lock step.
+ * interleaved: the two streams of a pair category (QTIPSIM_CAT_B, _C or _D) as ONE stream, mate 1's record followed by mate
+ * 2's for every pair (what `bowtie2 --interleaved` / `bwa mem -p` read, scripts/fastq_interleave.py): interleaved on the
+ * device, copied into dst (cap bytes); *nbytes = bytes[_1] + bytes[_2]. */
+int qtipsim_result_stream_fds(qtipsim_t *h, const int fds[QTIPSIM_NOUT]);
+int qtipsim_result_interleaved(qtipsim_t *h, int cat, void *dst, uint64_t cap, uint64_t *nbytes);
 
 /* Host-buffer convenience for end-to-end use: FASTA text + templates must already be
  * set; runs, then copies all seven streams into caller buffers dst[i] (cap[i] bytes). */

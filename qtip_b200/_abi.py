@@ -23,6 +23,10 @@ RNG_REPLAY, RNG_PHILOX = 0, 1
 # every symbol include/qtipsim.h declares (tests/test_abi.py checks header <-> this list <-> .so)
 SYMBOLS = (
     "qtipsim_label_correctness",
+    "qtipsim_result_stream_fds",
+    "qtipsim_result_interleaved",
+    "qtipsim_genome_save",
+    "qtipsim_load_fasta_cached",
     "qtipsim_edit_xscripts",
     "qtipsim_abi_version",
     "qtipsim_create",
@@ -122,6 +126,10 @@ def load() -> C.CDLL:
     lib.qtipsim_stream_begin.argtypes = [H, C.c_void_p, C.c_size_t]
     lib.qtipsim_label_correctness.argtypes = [H, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64),
                                               C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.c_uint64, C.c_int32, C.POINTER(C.c_int8)]
+    lib.qtipsim_result_stream_fds.argtypes = [H, C.POINTER(C.c_int)]
+    lib.qtipsim_result_interleaved.argtypes = [H, C.c_int, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.qtipsim_genome_save.argtypes = [H, C.c_char_p, C.c_char_p]
+    lib.qtipsim_load_fasta_cached.argtypes = [H, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]
     P64 = C.POINTER(C.c_uint64)
     P32 = C.POINTER(C.c_int32)
     lib.qtipsim_edit_xscripts.argtypes = [H, C.c_char_p, C.c_uint64, P64, C.c_char_p, C.c_uint64, P64, P64, C.c_uint64, C.c_void_p, C.c_uint64,

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <algorithm>
 #include <atomic>
@@ -108,6 +109,8 @@ struct qtipsim {
 	DevBuf d_plan[NCAT], d_len0, d_len1, d_off0[NCAT], d_off1[NCAT], d_scan_tmp, d_small;
 	DevBuf d_out[NOUT];
 	uint64_t out_bytes[NOUT] = {0, 0, 0, 0, 0, 0, 0};
+	uint64_t out_reads[NCAT] = {0, 0, 0, 0};  // reads / pairs per category in d_out (offsets in d_off0 / d_off1)
+	DevBuf d_inter;
 	bool have_result = false;
 
 	void *h_stage = nullptr;  // pinned staging for fd writes
@@ -244,7 +247,7 @@ void qtipsim_destroy(qtipsim_t *h) {
 	cudaSetDevice(h->device);
 	cudaStreamSynchronize(h->st);
 	if (h->ctl_ring) cudaFreeHost(h->ctl_ring);
-	DevBuf *all[] = {&h->d_xs_out, &h->d_label, &h->d_tabs, &h->d_jh1, &h->d_jh2, &h->d_r2_aw, &h->d_r2_cum, &h->d_r2_anchor, &h->d_r2_counter, &h->d_r2_slot, &h->d_r2_end, &h->d_r2_cn,
+	DevBuf *all[] = {&h->d_inter, &h->d_xs_out, &h->d_label, &h->d_tabs, &h->d_jh1, &h->d_jh2, &h->d_r2_aw, &h->d_r2_cum, &h->d_r2_anchor, &h->d_r2_counter, &h->d_r2_slot, &h->d_r2_end, &h->d_r2_cn,
 	                 &h->d_r2_wres, &h->d_r2_cnt, &h->d_r2_off, &h->d_r2_misc, &h->d_setups, &h->d_pclass, &h->d_rsresult, &h->d_text, &h->d_pk_a, &h->d_pk_b, &h->d_pk_c, &h->d_pk_d, &h->d_pk_e, &h->d_bases, &h->d_nmask, &h->d_nblk, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
 	                 &h->d_ncount, &h->d_cum, &h->d_len0, &h->d_len1, &h->d_scan_tmp, &h->d_small};
 	for (DevBuf *b : all) b->release();
@@ -634,6 +637,158 @@ int qtipsim_genome_adopt(qtipsim_t *h, const void *blob, uint64_t blob_bytes, co
 	h->host_packed = false;
 	h->have_result = false;
 	return QTIPSIM_OK;
+}
+
+// ---- packed-genome cache: [header][record-table blob][bases][nmask] ----
+namespace {
+struct CacheHeader {
+	char magic[8];  // "QTPG\1\0\0\0"
+	uint64_t fasta_size;
+	int64_t fasta_mtime_ns;
+	uint64_t blob_bytes, bases_bytes, nmask_bytes;
+};
+const char CACHE_MAGIC[8] = {'Q', 'T', 'P', 'G', 1, 0, 0, 0};
+bool fasta_stamp(const char *path, uint64_t &size, int64_t &mtime_ns) {
+	struct stat sb;
+	if (stat(path, &sb) != 0) return false;
+	size = (uint64_t)sb.st_size;
+	mtime_ns = (int64_t)sb.st_mtim.tv_sec * 1000000000ll + (int64_t)sb.st_mtim.tv_nsec;
+	return true;
+}
+}  // namespace
+
+static int ensure_stage(qtipsim *h) {
+	const size_t STAGE = 32u << 20;
+	if (!h->h_stage) {
+		CK(cudaHostAlloc(&h->h_stage, 2 * STAGE, cudaHostAllocDefault));
+		h->h_stage_cap = 2 * STAGE;
+	}
+	return QTIPSIM_OK;
+}
+
+int qtipsim_genome_save(qtipsim_t *h, const char *cache_path, const char *fasta_path) {
+	if (!h || !cache_path || !fasta_path) return QTIPSIM_EINVAL;
+	if (!h->have_genome) return h->fail(QTIPSIM_ESTATE, "genome_save: no genome loaded");
+	CK(cudaSetDevice(h->device));
+	CacheHeader hd;
+	memcpy(hd.magic, CACHE_MAGIC, 8);
+	if (!fasta_stamp(fasta_path, hd.fasta_size, hd.fasta_mtime_ns)) return h->fail(QTIPSIM_EIO, std::string("genome_save: cannot stat ") + fasta_path);
+	const std::string blob = h->hg.blob();
+	hd.blob_bytes = blob.size();
+	hd.bases_bytes = (h->hg.total_bases + 15) / 16 * 4 + 16;
+	hd.nmask_bytes = (h->hg.total_bases + 31) / 32 * 4 + 16;
+	int rc = ensure_stage(h);
+	if (rc) return rc;
+	const std::string tmp = std::string(cache_path) + ".tmp";
+	FILE *fh = fopen(tmp.c_str(), "wb");
+	if (!fh) return h->fail(QTIPSIM_EIO, std::string("genome_save: cannot write ") + tmp);
+	bool ok = fwrite(&hd, sizeof(hd), 1, fh) == 1 && (blob.empty() || fwrite(blob.data(), blob.size(), 1, fh) == 1);
+	const size_t STAGE = 32u << 20;
+	const void *src[2] = {h->d_bases.p, h->d_nmask.p};
+	const uint64_t len[2] = {hd.bases_bytes, hd.nmask_bytes};
+	for (int a = 0; a < 2 && ok; a++)
+		for (uint64_t off = 0; off < len[a] && ok; off += STAGE) {
+			const size_t n = (size_t)std::min<uint64_t>(STAGE, len[a] - off);
+			if (cudaMemcpyAsync(h->h_stage, (const char *)src[a] + off, n, cudaMemcpyDeviceToHost, h->st) != cudaSuccess || ctl_sync(h) != cudaSuccess) ok = false;
+			else ok = fwrite(h->h_stage, n, 1, fh) == 1;
+		}
+	ok = (fclose(fh) == 0) && ok;
+	if (!ok || rename(tmp.c_str(), cache_path) != 0) {
+		remove(tmp.c_str());
+		cudaGetLastError();
+		return h->fail(QTIPSIM_EIO, std::string("genome_save: writing ") + cache_path + " failed");
+	}
+	return QTIPSIM_OK;
+}
+
+// uploads a cache file whose stamp matches; false (with nothing changed on the handle's genome state) otherwise
+static int load_cache(qtipsim *h, const char *cache_path, uint64_t fsize, int64_t fmtime, bool &hit) {
+	hit = false;
+	FILE *fh = fopen(cache_path, "rb");
+	if (!fh) return QTIPSIM_OK;
+	CacheHeader hd;
+	bool ok = fread(&hd, sizeof(hd), 1, fh) == 1 && memcmp(hd.magic, CACHE_MAGIC, 8) == 0 && hd.fasta_size == fsize && hd.fasta_mtime_ns == fmtime &&
+	          hd.blob_bytes < (1ull << 32);
+	std::string blob;
+	if (ok) {
+		blob.resize((size_t)hd.blob_bytes);
+		ok = blob.empty() || fread(&blob[0], blob.size(), 1, fh) == 1;
+	}
+	HostGenome tmp;
+	ok = ok && tmp.from_blob(blob.data(), blob.size()) && hd.bases_bytes == (tmp.total_bases + 15) / 16 * 4 + 16 &&
+	     hd.nmask_bytes == (tmp.total_bases + 31) / 32 * 4 + 16;
+	if (!ok) {
+		fclose(fh);
+		return QTIPSIM_OK;  // absent, foreign or stale: the caller packs the FASTA
+	}
+	int rc = ensure_stage(h);
+	if (rc) {
+		fclose(fh);
+		return rc;
+	}
+	genome_reset(h, fsize);
+	if (h->d_bases.ensure(hd.bases_bytes) != cudaSuccess || h->d_nmask.ensure(hd.nmask_bytes) != cudaSuccess) {
+		fclose(fh);
+		return h->fail(QTIPSIM_ENOMEM, "genome cache: device allocation failed");
+	}
+	const size_t STAGE = 32u << 20;
+	void *dst[2] = {h->d_bases.p, h->d_nmask.p};
+	const uint64_t len[2] = {hd.bases_bytes, hd.nmask_bytes};
+	cudaEvent_t ev[2];
+	cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+	cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+	int slot = 0;
+	bool used[2] = {false, false};
+	for (int a = 0; a < 2 && ok; a++)
+		for (uint64_t off = 0; off < len[a] && ok; off += STAGE) {  // double-buffered: read slice k + 1 while slice k uploads
+			const size_t n = (size_t)std::min<uint64_t>(STAGE, len[a] - off);
+			char *hp = (char *)h->h_stage + (size_t)slot * STAGE;
+			if (used[slot]) cudaEventSynchronize(ev[slot]);
+			ok = fread(hp, n, 1, fh) == 1 && cudaMemcpyAsync((char *)dst[a] + off, hp, n, cudaMemcpyHostToDevice, h->st) == cudaSuccess;
+			cudaEventRecord(ev[slot], h->st);
+			used[slot] = true;
+			slot ^= 1;
+		}
+	fclose(fh);
+	cudaStreamSynchronize(h->st);
+	cudaEventDestroy(ev[0]);
+	cudaEventDestroy(ev[1]);
+	if (!ok) {
+		cudaGetLastError();
+		return h->fail(QTIPSIM_EIO, std::string("genome cache: reading ") + cache_path + " failed");
+	}
+	h->hg = tmp;
+	h->hg.fill_name16();
+	CK(h->d_recs.ensure(h->hg.recs.size() * sizeof(RecDev) + 16));
+	CK(h->d_names.ensure(h->hg.names.size() + 16));
+	rc = build_nblock(h, (size_t)(hd.nmask_bytes / 4));
+	if (rc) return rc;
+	CK(ctl_h2d(h, h->d_recs.p, h->hg.recs.data(), h->hg.recs.size() * sizeof(RecDev)));
+	if (!h->hg.names.empty()) CK(ctl_h2d(h, h->d_names.p, h->hg.names.data(), h->hg.names.size()));
+	CK(ctl_sync(h));
+	h->have_genome = true;
+	hit = true;
+	return QTIPSIM_OK;
+}
+
+int qtipsim_load_fasta_cached(qtipsim_t *h, const char *fasta_path, const char *cache_path, int *hit) {
+	if (!h || !fasta_path || !cache_path) return QTIPSIM_EINVAL;
+	if (hit) *hit = 0;
+	CK(cudaSetDevice(h->device));
+	uint64_t fsize = 0;
+	int64_t fmtime = 0;
+	if (!fasta_stamp(fasta_path, fsize, fmtime)) return h->fail(QTIPSIM_EIO, std::string("cannot open FASTA ") + fasta_path);
+	bool got = false;
+	int rc = load_cache(h, cache_path, fsize, fmtime, got);
+	if (rc) return rc;
+	if (got) {
+		if (hit) *hit = 1;
+		return QTIPSIM_OK;
+	}
+	const char *paths[1] = {fasta_path};
+	rc = qtipsim_load_fasta(h, paths, 1);
+	if (rc) return rc;
+	return qtipsim_genome_save(h, cache_path, fasta_path);
 }
 
 int qtipsim_set_templates_unpaired(qtipsim_t *h, int cat, const qtipsim_tmpl_unp *v, size_t kept, uint64_t added) {
@@ -1291,6 +1446,7 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 	CK(ctl_sync(h));
 	CK(cudaGetLastError());
 	h->have_result = true;
+	for (int c = 0; c < NCAT; c++) h->out_reads[c] = nreads[c];
 
 	if (stats) {
 		memset(stats, 0, sizeof(*stats));
@@ -1400,6 +1556,102 @@ int qtipsim_result_write_fds(qtipsim_t *h, const int fds[QTIPSIM_NOUT]) {
 	cudaEventDestroy(done[0]);
 	cudaEventDestroy(done[1]);
 	return rc;
+}
+
+int qtipsim_result_stream_fds(qtipsim_t *h, const int fds[QTIPSIM_NOUT]) {
+	if (!h || !fds) return QTIPSIM_EINVAL;
+	if (!h->have_result) return h->fail(QTIPSIM_ESTATE, "no result: call qtipsim_run first");
+	CK(cudaSetDevice(h->device));
+	CK(ctl_sync(h));
+	std::atomic<int> bad{0};
+	std::string first_err;
+	std::mutex em;
+	std::vector<std::thread> th;
+	for (int s = 0; s < NOUT; s++) {
+		if (!h->out_bytes[s] || fds[s] < 0) continue;
+		th.emplace_back([&, s]() {
+			// one writer per descriptor: double-buffered device-to-host slices on a stream of its own, then write()
+			const size_t SL = 8u << 20;
+			auto fail = [&](const std::string &m) {
+				std::lock_guard<std::mutex> lk(em);
+				if (!bad.exchange(1)) first_err = m;
+			};
+			if (cudaSetDevice(h->device) != cudaSuccess) return fail("cudaSetDevice");
+			cudaStream_t st;
+			void *hb = nullptr;
+			cudaEvent_t ev[2];
+			if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate");
+			if (cudaHostAlloc(&hb, 2 * SL, cudaHostAllocDefault) != cudaSuccess) {
+				cudaStreamDestroy(st);
+				return fail("cudaHostAlloc");
+			}
+			cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+			cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+			const char *src = h->d_out[s].as<char>();
+			const uint64_t n = h->out_bytes[s];
+			uint64_t issued = 0, written = 0, len_in[2] = {0, 0};
+			int slot = 0;
+			auto issue = [&](int sl) {
+				const uint64_t len = std::min<uint64_t>(SL, n - issued);
+				len_in[sl] = len;
+				cudaMemcpyAsync((char *)hb + (size_t)sl * SL, src + issued, len, cudaMemcpyDeviceToHost, st);
+				cudaEventRecord(ev[sl], st);
+				issued += len;
+			};
+			issue(0);
+			while (written < n && !bad.load()) {
+				if (issued < n) issue(slot ^ 1);
+				if (cudaEventSynchronize(ev[slot]) != cudaSuccess) {
+					fail("cudaEventSynchronize");
+					break;
+				}
+				const char *hp = (const char *)hb + (size_t)slot * SL;
+				uint64_t left = len_in[slot];
+				while (left) {
+					const ssize_t w = write(fds[s], hp, left);
+					if (w < 0) {
+						if (errno == EINTR) continue;
+						fail(std::string("write: ") + strerror(errno));
+						left = 0;
+						break;
+					}
+					hp += w;
+					left -= (uint64_t)w;
+				}
+				written += len_in[slot];
+				slot ^= 1;
+			}
+			cudaStreamSynchronize(st);
+			cudaEventDestroy(ev[0]);
+			cudaEventDestroy(ev[1]);
+			cudaFreeHost(hb);
+			cudaStreamDestroy(st);
+		});
+	}
+	for (auto &t : th) t.join();
+	if (bad.load()) {
+		cudaGetLastError();
+		return h->fail(QTIPSIM_EIO, "result_stream_fds: " + first_err);
+	}
+	return QTIPSIM_OK;
+}
+
+int qtipsim_result_interleaved(qtipsim_t *h, int cat, void *dst, uint64_t cap, uint64_t *nbytes) {
+	if (!h || !nbytes || cat < CAT_B || cat > CAT_D) return QTIPSIM_EINVAL;
+	if (!h->have_result) return h->fail(QTIPSIM_ESTATE, "no result: call qtipsim_run first");
+	const int s0 = cat_stream0(cat);
+	const uint64_t t0 = h->out_bytes[s0], t1 = h->out_bytes[s0 + 1], n = h->out_reads[cat];
+	*nbytes = t0 + t1;
+	if (!(t0 + t1)) return QTIPSIM_OK;
+	if (cap < t0 + t1 || !dst) return h->fail(QTIPSIM_ERANGE, "destination buffer too small");
+	CK(cudaSetDevice(h->device));
+	CK(h->d_inter.ensure(t0 + t1 + 16));
+	launch_interleave(h->d_out[s0].as<char>(), h->d_out[s0 + 1].as<char>(), h->d_off0[cat].as<uint64_t>(), h->d_off1[cat].as<uint64_t>(), n, t0, t1,
+	                  h->d_inter.as<char>(), h->st);
+	CK(cudaMemcpyAsync(dst, h->d_inter.p, t0 + t1, cudaMemcpyDeviceToHost, h->st));
+	CK(ctl_sync(h));
+	CK(cudaGetLastError());
+	return QTIPSIM_OK;
 }
 
 int qtipsim_run_to_host(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats, void *const dst[QTIPSIM_NOUT],

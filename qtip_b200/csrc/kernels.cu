@@ -29,6 +29,28 @@ __global__ void __launch_bounds__(256) k_ctl_copy(unsigned char *dst, const unsi
 	for (size_t i = done + tid; i < n; i += nth) dst[i] = src[i];
 }
 
+// Interleaves the two FASTQ streams of a pair category record by record (mate 1, mate 2, mate 1, ...): pair i's records are
+// src0[off0[i], end0) and src1[off1[i], end1) and go to dst[off0[i] + off1[i] ...).  One warp per pair, bytes.
+__global__ void __launch_bounds__(256) k_interleave(const char *src0, const char *src1, const uint64_t *off0, const uint64_t *off1, uint64_t n,
+                                                  uint64_t tot0, uint64_t tot1, char *dst) {
+	const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const uint32_t lane = threadIdx.x & 31;
+	if (i >= n) return;
+	const uint64_t a0 = off0[i], a1 = off1[i];
+	const uint64_t e0 = i + 1 < n ? off0[i + 1] : tot0, e1 = i + 1 < n ? off1[i + 1] : tot1;
+	char *d = dst + a0 + a1;
+	for (uint64_t k = lane; k < e0 - a0; k += 32) d[k] = src0[a0 + k];
+	d += e0 - a0;
+	for (uint64_t k = lane; k < e1 - a1; k += 32) d[k] = src1[a1 + k];
+}
+
+void launch_interleave(const char *src0, const char *src1, const uint64_t *off0, const uint64_t *off1, uint64_t n, uint64_t tot0, uint64_t tot1,
+                       char *dst, cudaStream_t st) {
+	if (!n) return;
+	k_interleave<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(src0, src1, off0, off1, n, tot0, tot1, dst);
+	kernels_count_launch();
+}
+
 void launch_ctl_copy(void *dst, const void *src, size_t n, cudaStream_t st) {
 	if (!n) return;
 	const int vec = (((uintptr_t)dst | (uintptr_t)src) & 15) == 0;

@@ -98,6 +98,9 @@ void launch_plan_philox_lengths(const Window *win, const uint64_t *cum, uint32_t
                                 const SimArgs &a, PlanRec *plan, uint32_t *len0, uint32_t *len1, unsigned long long *gbytes,
                                 cudaStream_t st);
 
+// mate 1 / mate 2 records of a pair category interleaved into one stream
+void launch_interleave(const char *src0, const char *src1, const uint64_t *off0, const uint64_t *off1, uint64_t n, uint64_t tot0, uint64_t tot1,
+                       char *dst, cudaStream_t st);
 // tandem-SAM correctness labelling (label.cu)
 void launch_label_correctness(const char *qnames, const uint64_t *q_off, const char *rnames, const uint64_t *r_off, const int32_t *flag,
                               const uint64_t *pos, uint64_t n, int32_t wiggle, int8_t *correct, cudaStream_t st);

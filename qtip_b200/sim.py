@@ -202,6 +202,30 @@ class Engine:
     def results(self, st: _abi.Stats) -> List[bytes]:
         return [self.result(s, int(st.bytes[s])).tobytes() for s in range(NOUT)]
 
+    def stream_fds(self, fds: Sequence[int]):
+        """All seven streams written concurrently (FIFO / pipe consumers that read paired files in lock step)."""
+        arr = (C.c_int * NOUT)(*fds)
+        self.check(self.lib.qtipsim_result_stream_fds(self.h, arr))
+
+    def result_interleaved(self, cat: int, st: _abi.Stats) -> bytes:
+        """Mate 1 / mate 2 records of a pair category as one interleaved FASTQ stream."""
+        s0 = 2 * cat - 1
+        cap = int(st.bytes[s0]) + int(st.bytes[s0 + 1])
+        out = np.empty(max(cap, 1), dtype=np.uint8)
+        n = C.c_uint64()
+        self.check(self.lib.qtipsim_result_interleaved(self.h, cat, C.c_void_p(out.ctypes.data), cap, C.byref(n)))
+        return out[:int(n.value)].tobytes()
+
+    def load_fasta_cached(self, fasta_path: str, cache_path: str) -> bool:
+        """Loads the genome from the packed cache if it is stamped with the FASTA's size and mtime, else packs the FASTA and
+        writes the cache; returns True on a cache hit."""
+        hit = C.c_int(0)
+        self.check(self.lib.qtipsim_load_fasta_cached(self.h, fasta_path.encode(), cache_path.encode(), C.byref(hit)))
+        return bool(hit.value)
+
+    def genome_save(self, cache_path: str, fasta_path: str):
+        self.check(self.lib.qtipsim_genome_save(self.h, cache_path.encode(), fasta_path.encode()))
+
     def label_correctness(self, qnames: Sequence[bytes], rnames: Sequence[bytes], flags: Sequence[int], pos: Sequence[int],
                           wiggle: int = 30) -> np.ndarray:
         """Alignment::set_correctness (qtip_parse.cpp:519-713) for a batch of aligned tandem-SAM records; returns int8

@@ -649,3 +649,113 @@ def test_edit_xscript_kernels_match_oracle():
             assert g == want, (cigar, mdz, g, want)
             assert xs is None or g[1] == xs
     assert sum(1 for g in got if g[0] != 0) >= 5  # the malformed records (one of the six above is in fact well-formed)
+
+
+# ------------------------------------------------------------------ packed-genome cache --
+
+def test_packed_genome_cache_round_trip(workdir):
+    """qtipsim_load_fasta_cached: the first load packs the FASTA and writes the cache, the second uploads the cache
+    (no parse, no pack kernels) and simulates the same bytes; a FASTA that changed on disk invalidates the cache."""
+    import time
+    from qtip_b200 import sim
+
+    def run(case, fa_path, cache):
+        eng = sim.Engine()
+        try:
+            hit = eng.load_fasta_cached(fa_path, cache)
+            added = case.get("added") or (len(case["tu"]), len(case["tb"]), len(case["tc"]), len(case["td"]))
+            eng.set_unpaired(0, case["tu"], added[0]); eng.set_unpaired(1, case["tb"], added[1])
+            eng.set_paired(2, case["tc"], added[2]); eng.set_paired(3, case["td"], added[3])
+            kw = case["kw"]
+            p = sim.make_params(case.get("chunksz", 128 * 1024), kw["fraction"], kw["function"], kw["min_u"], kw["min_c"], kw["min_d"],
+                                kw["min_b"], 0, cg=kw["cg"])
+            st = eng.run(p)
+            return hit, eng.results(st), st.kernel_launches
+        finally:
+            eng.close()
+
+    case = cases.CASES["mixed_small"]()
+    fa_path = os.path.join(workdir, "cache_case.fa")
+    cache = os.path.join(workdir, "cache_case.qtpg")
+    for p_ in (fa_path, cache):
+        if os.path.exists(p_):
+            os.unlink(p_)
+    case["fasta"].tofile(fa_path)
+    o = _oracle(case, workdir, "mixed_small")
+    hit1, s1, l1 = run(case, fa_path, cache)
+    assert not hit1 and os.path.getsize(cache) > 0
+    hit2, s2, l2 = run(case, fa_path, cache)
+    assert hit2 and s1 == s2 == o.streams
+    # another genome under the same name: the stamp (size, mtime) no longer matches
+    case2 = cases.CASES["edges"]()
+    time.sleep(0.01)
+    case2["fasta"].tofile(fa_path)
+    o2 = _oracle(case2, workdir, "edges")
+    hit3, s3, _ = run(case2, fa_path, cache)
+    assert not hit3 and s3 == o2.streams
+    hit4, s4, _ = run(case2, fa_path, cache)
+    assert hit4 and s4 == o2.streams
+
+
+# ------------------------------------------------------------------ output paths to the aligner (SURVEY 8f4) --
+
+@pytest.mark.timeout(180)
+def test_interleaved_and_fifo_outputs(workdir):
+    """qtipsim_result_interleaved: mate 1 / mate 2 records of every pair category alternate in one stream, byte for byte the
+    interleave of the two files.  qtipsim_result_stream_fds: all seven streams into pipes whose reader consumes each
+    category's _1 and _2 in lock step, record by record (what an aligner fed through FIFOs does) -- the sequential
+    writer would deadlock there -- and the bytes are the files'."""
+    import threading
+    from qtip_b200 import sim
+    case = cases.CASES["c4_mix_small"]()
+    case["kw"] = dict(case["kw"], fraction=3.0)
+    o = _oracle(case, workdir, "c4_mix_small")
+    eng = sim.Engine()
+    try:
+        eng.load_fasta_bytes(case["fasta"])
+        added = case.get("added")
+        eng.set_unpaired(0, case["tu"], added[0]); eng.set_unpaired(1, case["tb"], added[1])
+        eng.set_paired(2, case["tc"], added[2]); eng.set_paired(3, case["td"], added[3])
+        kw = case["kw"]
+        st = eng.run(sim.make_params(128 * 1024, kw["fraction"], kw["function"], kw["min_u"], kw["min_c"], kw["min_d"], kw["min_b"], 0, cg=kw["cg"]))
+        streams = eng.results(st)
+        assert streams == o.streams
+        for cat in (1, 2, 3):
+            a, b = _split_records(streams[2 * cat - 1]), _split_records(streams[2 * cat])
+            want = b"".join(x + y for x, y in zip(a, b))
+            assert eng.result_interleaved(cat, st) == want and len(want) > 100000
+        # FIFO-style consumers
+        pipes = [os.pipe() for _ in range(7)]
+        got = [bytearray() for _ in range(7)]
+
+        def lockstep(i1, i2):
+            f1, f2 = os.fdopen(pipes[i1][0], "rb"), os.fdopen(pipes[i2][0], "rb")
+            while True:
+                r1 = [f1.readline() for _ in range(4)]
+                r2 = [f2.readline() for _ in range(4)]
+                if not r1[0] and not r2[0]:
+                    break
+                got[i1] += b"".join(r1); got[i2] += b"".join(r2)
+            f1.close(); f2.close()
+
+        def single(i):
+            with os.fdopen(pipes[i][0], "rb") as f:
+                got[i] += f.read()
+
+        readers = [threading.Thread(target=single, args=(0,))] + [threading.Thread(target=lockstep, args=(i, i + 1)) for i in (1, 3, 5)]
+        for t in readers:
+            t.start()
+        eng.stream_fds([p[1] for p in pipes])
+        for p in pipes:
+            os.close(p[1])
+        for t in readers:
+            t.join(60)
+            assert not t.is_alive()
+        assert [bytes(g) for g in got] == streams
+    finally:
+        eng.close()
+
+
+def _split_records(b: bytes):
+    lines = b.split(b"\n")
+    return [b"\n".join(lines[4 * i:4 * i + 4]) + b"\n" for i in range((len(lines) - 1) // 4)]
