@@ -121,6 +121,7 @@ struct qtipsim {
 	std::vector<uint64_t> seg_start, seg_end;
 	uint64_t hdr_end = 0;
 	bool open_rec = false, open_is_leading = false;
+	bool names_overflow = false;  // the refid arena outgrew the 32-bit name offsets (loader fails with QTIPSIM_ERANGE)
 	RecDev open_desc{};
 	uint64_t open_start = 0;
 	uint32_t recs_packed = 0;
@@ -245,6 +246,10 @@ int qtipsim_create(qtipsim_t **out, int device) {
 void qtipsim_destroy(qtipsim_t *h) {
 	if (!h) return;
 	cudaSetDevice(h->device);
+	// an upload started by qtipsim_stream_begin and never consumed still writes into d_text: let it finish first
+	if (h->feeder.joinable()) h->feeder.join();
+	if (h->st_h2d) cudaStreamSynchronize(h->st_h2d);
+	if (h->st_d2h) cudaStreamSynchronize(h->st_d2h);
 	cudaStreamSynchronize(h->st);
 	if (h->ctl_ring) cudaFreeHost(h->ctl_ring);
 	DevBuf *all[] = {&h->d_inter, &h->d_xs_out, &h->d_label, &h->d_tabs, &h->d_jh1, &h->d_jh2, &h->d_r2_aw, &h->d_r2_cum, &h->d_r2_anchor, &h->d_r2_counter, &h->d_r2_slot, &h->d_r2_end, &h->d_r2_cn,
@@ -331,6 +336,7 @@ static void genome_reset(qtipsim *h, uint64_t n) {
 	h->seg_start.clear();
 	h->seg_end.clear();
 	h->hdr_end = 0;
+	h->names_overflow = false;
 	// sequence bytes before the first header form a record with an empty name (fasta.cpp:72-124)
 	h->open_rec = true;
 	h->open_is_leading = true;
@@ -373,6 +379,7 @@ static void resolve_headers(qtipsim *h, const uint8_t *text, uint64_t n, const s
 		uint64_t i = p + 1;
 		const uint64_t s0 = i;
 		while (i < n && !fa_is_sp(text[i])) i++;
+		if (g.names.size() + (i - s0) > 0xfffffff0ull) h->names_overflow = true;  // name offsets are 32-bit
 		h->open_desc = RecDev{0, 0, (uint32_t)g.names.size(), (uint32_t)(i - s0)};
 		g.names.append((const char *)text + s0, (size_t)(i - s0));
 		while (i < n && text[i] != '\n' && text[i] != '\r') i++;
@@ -516,6 +523,7 @@ static int device_pack(qtipsim *h, const uint8_t *text, uint64_t n) {
 	int rc = find_headers_chunk(h, text, 0, n, gts);
 	if (rc) return rc;
 	resolve_headers(h, text, n, gts, true);
+	if (h->names_overflow) return h->fail(QTIPSIM_ERANGE, "FASTA record names exceed 4 GiB in total");
 	rc = pack_records(h, false);
 	if (rc) return rc;
 	CK(cudaEventRecord(e1, h->st));
@@ -610,10 +618,13 @@ int qtipsim_genome_adopt(qtipsim_t *h, const void *blob, uint64_t blob_bytes, co
                          uint64_t bases_bytes, const void *d_nmask, uint64_t nmask_bytes) {
 	if (!h || !blob || !d_bases || !d_nmask) return QTIPSIM_EINVAL;
 	CK(cudaSetDevice(h->device));
-	if (!h->hg.from_blob(blob, blob_bytes)) return h->fail(QTIPSIM_EINVAL, "bad genome blob");
-	h->hg.fill_name16();
-	const uint64_t need_b = (h->hg.total_bases + 15) / 16 * 4 + 16, need_n = (h->hg.total_bases + 31) / 32 * 4 + 16;
+	HostGenome incoming;  // swapped in only after every check has passed: a failed adopt leaves the handle as it was
+	if (!incoming.from_blob(blob, blob_bytes)) return h->fail(QTIPSIM_EINVAL, "bad genome blob");
+	const uint64_t need_b = (incoming.total_bases + 15) / 16 * 4 + 16, need_n = (incoming.total_bases + 31) / 32 * 4 + 16;
 	if (bases_bytes < need_b || nmask_bytes < need_n) return h->fail(QTIPSIM_EINVAL, "packed genome buffers too small");
+	genome_reset(h, incoming.file_bytes);  // joins a pending streaming upload and clears the streaming / header-scan state
+	h->hg = incoming;
+	h->hg.fill_name16();
 	CK(h->d_bases.ensure(need_b));
 	CK(h->d_nmask.ensure(need_n));
 	CK(h->d_recs.ensure(h->hg.recs.size() * sizeof(RecDev) + 16));
@@ -1014,9 +1025,9 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 	// plus one window's reads outgrow the largest dense table?  Workloads where that is only a handful -- many reads per
 	// window, or bad-end reads whose ~150 skipped draws each make the position noise large -- are left to the
 	// first-generation resolver, which walks them round by round on a cluster (QTIPSIM_R2_FORCE=1 keeps them here: tests).
+	double kfit = 0;
 	{
 		const double room = (double)a2.rcap - reach_max * 1.1 - 64.0;
-		double kfit = 0;
 		if (room > 0 && vmax > 0) {
 			const double r = (room / 2.2 - 16.0) / ((double)a2.band_sigma * sqrt(vmax));
 			kfit = r > 0 ? r * r + 1.0 : 1.0;
@@ -1079,6 +1090,14 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 	a2.cnd = a2.cn + (size_t)K * a2.nbmax;
 	a2.wres = h->d_r2_wres.as<WinResolved>();
 
+	DevBuf dbgbuf;  // tracing only: per-phase time stamps of the CTAs of one stage
+	if (getenv("QTIPSIM_R2_DBG")) {
+		a2.dbg_stage = envu("QTIPSIM_R2_DBG", 50);
+		if (dbgbuf.ensure((size_t)K * 16 * 8) == cudaSuccess) {
+			cudaMemsetAsync(dbgbuf.p, 0, (size_t)K * 16 * 8, h->st);
+			a2.dbg = dbgbuf.as<unsigned long long>();
+		}
+	}
 	// ---- stages: launched in batches without host round trips; a batch ends with a look at the last anchor ----
 	uint32_t launched = 0;
 	StageAnchor fin;
@@ -1095,6 +1114,31 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 		if (fin.status != R2_RUNNING) break;
 	}
 	h->r2_stages_last = launched;
+	if (a2.dbg) {
+		std::vector<unsigned long long> st((size_t)K * 16);
+		cudaMemcpy(st.data(), a2.dbg, st.size() * 8, cudaMemcpyDeviceToHost);
+		unsigned long long t0 = ~0ull;
+		for (uint32_t c = 0; c < K; c++)
+			if (st[c * 16]) t0 = std::min(t0, st[c * 16]);
+		fprintf(stderr, "[resolve2 dbg] stage %u: per CTA us since the first CTA started: start | binomU advU | binomB advB | binomCD advC | built | walk-begin walk-end done\n", a2.dbg_stage);
+		for (uint32_t c = 0; c < K; c += (K > 16 ? K / 8 : 1)) {
+			fprintf(stderr, "  cta %3u:", c);
+			for (int k = 0; k < 12; k++) fprintf(stderr, " %7.1f", st[c * 16 + k] ? (double)(st[c * 16 + k] - t0) / 1e3 : -1.0);
+			fprintf(stderr, "\n");
+		}
+		uint32_t cl = K - 1;
+		fprintf(stderr, "  cta %3u:", cl);
+		for (int k = 0; k < 12; k++) fprintf(stderr, " %7.1f", st[cl * 16 + k] ? (double)(st[cl * 16 + k] - t0) / 1e3 : -1.0);
+		fprintf(stderr, "\n  cta %3u, inside the U region: reduce done %.1f, dense table %.1f, stride table %.1f, main orbit %.1f us\n", cl,
+		        (double)(st[cl * 16 + 12] - t0) / 1e3, (double)(st[cl * 16 + 13] - t0) / 1e3, (double)(st[cl * 16 + 14] - t0) / 1e3,
+		        (double)(st[cl * 16 + 15] - t0) / 1e3);
+		for (uint32_t c = 0; c < K; c++)
+			if (st[c * 16 + 11]) {
+				fprintf(stderr, "  walker was cta %u: walk %0.1f us, epilogue %0.1f us\n", c, (double)(st[c * 16 + 10] - st[c * 16 + 9]) / 1e3,
+				        (double)(st[c * 16 + 11] - st[c * 16 + 10]) / 1e3);
+			}
+		dbgbuf.release();
+	}
 	if (getenv("QTIPSIM_R2_TRACE"))
 		fprintf(stderr, "[resolve2] %u live windows, K = %u, rcap %u, %u stage launches, status %u, first %u, draws %llu\n", na, K, a2.rcap,
 		        launched, fin.status, fin.first, (unsigned long long)fin.abs);
@@ -1175,7 +1219,15 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 	int rc = upload_templates(h);
 	if (rc) return rc;
 
-	cudaEvent_t ev[4];
+	h->have_result = false;  // whatever the previous run left in d_out is about to be overwritten
+	struct Events {
+		cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+		~Events() {
+			for (auto &x : e)
+				if (x) cudaEventDestroy(x);
+		}
+	} evs;  // destroyed on every return path
+	cudaEvent_t(&ev)[4] = evs.e;
 	for (auto &e : ev) CK(cudaEventCreate(&e));
 	CK(cudaEventRecord(ev[0], h->st));
 
@@ -1473,7 +1525,6 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 		cudaEventElapsedTime(&ms, ev[0], ev[3]);
 		stats->ms_total = ms;
 	}
-	for (auto &e : ev) cudaEventDestroy(e);
 	return QTIPSIM_OK;
 }
 
@@ -1865,6 +1916,10 @@ int qtipsim_stream_run(qtipsim_t *h, qtipsim_run_params *p, qtipsim_stats *stats
 			gts.clear();
 		}
 		resolve_headers(h, text, n, gts, final);
+		if (h->names_overflow) {
+			rc = h->fail(QTIPSIM_ERANGE, "FASTA record names exceed 4 GiB in total");
+			break;
+		}
 		const double t_ready = now_ms();
 		const uint32_t r1 = (uint32_t)h->hg.recs.size();
 		if (r1 > h->recs_packed) {

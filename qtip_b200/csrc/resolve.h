@@ -82,6 +82,8 @@ struct Resolve2Args {
 	uint32_t *end;                // [NCAT][K][nbmax] candidate positions after each category
 	uint32_t *cn, *cnd;           // [K][nbmax] candidate counts
 	WinResolved *wres;            // [na]
+	unsigned long long *dbg;      // tracing only (QTIPSIM_R2_DBG): [K][16] globaltimer stamps of one stage's CTAs, or null
+	uint32_t dbg_stage;
 };
 
 void launch_resolve2_stage(const Resolve2Args &a, uint32_t s, uint32_t K, cudaStream_t st);

@@ -226,12 +226,22 @@ __device__ __forceinline__ uint64_t reach(const Resolve2Args &a, int cat, uint32
 	return (uint64_t)e;
 }
 
+__device__ __forceinline__ unsigned long long r2_now() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+#define R2_STAMP(k)                                                                                      \
+	do {                                                                                                 \
+		if (a2.dbg && s == a2.dbg_stage && threadIdx.x == 0) a2.dbg[(size_t)blockIdx.x * 16 + (k)] = r2_now(); \
+	} while (0)
+
 // All candidates of one window move over the reads of one category: P[i] = position (stage-relative) of candidate
 // i's next draw, N[i] = reads it still has to pass.  On return P[i] is the position after those reads, or INVALID.
 // exact (a single candidate, the true start): the dense table is extended round by round until the reads are done.
 __device__ __forceinline__ void advance_region(const Resolve2Args &a2, const WinCtx &wc, int cat, LState SA, uint32_t nb, bool exact,
                                                uint32_t *P, uint32_t *N, uint16_t *L1, uint16_t *TA, uint16_t *TB, uint32_t *red,
-                                               uint32_t *pts) {
+                                               uint32_t *pts, uint32_t s = 0xffffffffu) {
 	const ResolveArgs &a = a2.ra;
 	const uint32_t tid = threadIdx.x;
 	for (;;) {
@@ -259,9 +269,12 @@ __device__ __forceinline__ void advance_region(const Resolve2Args &a2, const Win
 		const uint64_t want = (uint64_t)(mx - rlo) + reach(a2, cat, mxn) + 1;
 		const uint32_t R = want < (uint64_t)a2.rcap ? (uint32_t)want : a2.rcap;
 		const LState S0 = jump2(SA, rlo, a.jt1, a.jt2, a2.jh1, a2.jh2);
+		R2_STAMP(12);
 		dense_eval<R2_T>(a, wc, cat, S0, R, L1, a2.jh1, a2.jh2);
 		__syncthreads();
+		R2_STAMP(13);
 		const uint16_t *LS = build_stride<R2_T>(L1, TA, TB, R);
+		R2_STAMP(14);
 		if (!exact) {
 			// ---- every candidate's orbit merges, within a few reads, with the orbit of the lowest position: that one
 			// is enumerated (rank in TB, positions in SEL), a candidate walks single reads until it meets it and looks
@@ -304,6 +317,7 @@ __device__ __forceinline__ void advance_region(const Resolve2Args &a2, const Win
 			}
 			__syncthreads();
 			const uint32_t olen = pts[R2_MAIN_PTS + 1];
+			R2_STAMP(15);
 			for (uint32_t i = tid; i < nb; i += R2_T) {
 				const uint32_t pos = P[i];
 				uint32_t n = N[i];
@@ -373,6 +387,9 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 	__shared__ uint32_t s_start[R2_KMAX];
 	__shared__ uint2 s_slot[R2_KMAX];
 	__shared__ uint32_t s_pts[R2_MAIN_PTS + 2];
+	// the window's four binomial set-ups and their BTPE tables: every candidate of the window samples from them
+	__shared__ __align__(16) BinomSetup s_su[NCAT];
+	__shared__ __align__(16) BinomTables s_tab[NCAT];
 
 	const ResolveArgs &a = a2.ra;
 	const uint32_t tid = threadIdx.x;
@@ -381,6 +398,7 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 		if (blockIdx.x == 0 && tid == 0) a2.anchor[s + 1] = an;
 		return;
 	}
+	R2_STAMP(0);
 	const LState SA{an.s1, an.s2};
 	const uint32_t K = gridDim.x;
 	const uint32_t j = blockIdx.x;
@@ -409,7 +427,20 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 		}
 		if (tid == 0) a2.slot[j] = make_uint2(lo, nb);
 		const uint32_t w = a2.aw[ai];
-		const WinCtx wc = make_winctx(a, w, a2.tabs);
+		WinCtx wc = make_winctx(a, w, a2.tabs);
+		{
+			const uint32_t *src = (const uint32_t *)wc.su;
+			uint32_t *dst = (uint32_t *)s_su;
+			for (uint32_t k = tid; k < NCAT * sizeof(BinomSetup) / 4; k += R2_T) dst[k] = __ldg(src + k);
+			if (wc.tab) {
+				src = (const uint32_t *)wc.tab;
+				dst = (uint32_t *)s_tab;
+				for (uint32_t k = tid; k < NCAT * sizeof(BinomTables) / 4; k += R2_T) dst[k] = __ldg(src + k);
+			}
+			__syncthreads();
+			wc.su = s_su;
+			if (wc.tab) wc.tab = s_tab;
+		}
 		uint32_t *endr[NCAT];
 		for (int r = 0; r < NCAT; r++) endr[r] = a2.end + ((size_t)r * K + j) * nbmax;
 		uint32_t *cn = a2.cn + (size_t)j * nbmax, *cnd = a2.cnd + (size_t)j * nbmax;
@@ -454,7 +485,9 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 					if (region == 2) cnd[i] = nd;
 				}
 				__syncthreads();
-				advance_region(a2, wc, cat0, SA, nb, exact, cur, cn, L1, TA, TB, s_red, s_pts);
+				R2_STAMP(1 + 2 * region);
+				advance_region(a2, wc, cat0, SA, nb, exact, cur, cn, L1, TA, TB, s_red, s_pts, region == 0 ? s : 0xffffffffu);
+				R2_STAMP(2 + 2 * region);
 				if (region == 2) {
 					uint32_t *ed = endr[CAT_D];
 					for (uint32_t i = tid; i < nb; i += R2_T) ed[i] = cur[i];
@@ -466,6 +499,7 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 	}
 
 	// ---- the last CTA to finish walks the chain through the stage's tables ----
+	R2_STAMP(8);
 	__threadfence();
 	__syncthreads();
 	if (tid == 0) {
@@ -475,9 +509,12 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 	__syncthreads();
 	if (!s_b[0]) return;
 	__threadfence();
+	R2_STAMP(9);
 	const uint32_t nstage = min(K, a2.na - an.first);
 	for (uint32_t jj = tid; jj < nstage; jj += R2_T) s_slot[jj] = __ldcg(&a2.slot[jj]);
 	__syncthreads();
+	// The walk: a chain of dependent look-ups, one per window (0.33 us each, measured; prefetching the neighbourhood of the
+	// rows ahead into shared memory or L1 did not shorten it, profiles/r02_k_resolve2_ncu_summary.md)
 	if (tid == 0) {
 		uint32_t pos = 0, nres = 0;
 		const uint32_t *eD = a2.end + (size_t)CAT_D * K * nbmax;
@@ -494,6 +531,7 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 		s_b[2] = pos;
 	}
 	__syncthreads();
+	R2_STAMP(10);
 	const uint32_t nres = s_b[1];
 	for (uint32_t jj = tid; jj < nres; jj += R2_T) {
 		WinResolved wr;
@@ -519,6 +557,7 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 		}
 		a2.anchor[s + 1] = nx;
 	}
+	R2_STAMP(11);
 }
 
 // Per resolved window: the four binomial counts, re-drawn at the region starts the walk established, and where each

@@ -335,6 +335,13 @@ void build_category(Category &c, int ci, const V *v, size_t kept, uint64_t added
 		c.added = added;
 		for (auto &p : parts) append_part(c, p);
 	}
+	// descriptor offsets into the arenas are 32-bit: a model whose arenas outgrow that is refused, not wrapped
+	if (c.qual.size() > 0xfffffff0ull || c.xs.size() > 0xfffffff0ull || c.qual_out.size() > 0xfffffff0ull || c.ops.size() > 0xfffffff0ull ||
+	    c.segs.size() > 0xfffffff0ull || c.xsteps.size() > 0xfffffff0ull) {
+		c.valid = false;
+		c.arena_overflow = true;
+		c.why = "input model too large: a template arena exceeds 4 GiB";
+	}
 	if (kept) {
 		c.mean_bytes = c.sum_bytes / kept;
 		c.mean_draws = c.sum_draws / kept;
@@ -352,6 +359,10 @@ int TemplateStore::set_unpaired(int ci, const qtipsim_tmpl_unp *v, size_t kept, 
 		return QTIPSIM_EINVAL;
 	}
 	build_category(cat[ci], ci, v, kept, added, fill_unpaired);
+	if (cat[ci].arena_overflow) {
+		err = cat[ci].why;
+		return QTIPSIM_ERANGE;
+	}
 	return QTIPSIM_OK;
 }
 
@@ -361,6 +372,10 @@ int TemplateStore::set_paired(int ci, const qtipsim_tmpl_pair *v, size_t kept, u
 		return QTIPSIM_EINVAL;
 	}
 	build_category(cat[ci], ci, v, kept, added, fill_paired);
+	if (cat[ci].arena_overflow) {
+		err = cat[ci].why;
+		return QTIPSIM_ERANGE;
+	}
 	return QTIPSIM_OK;
 }
 

@@ -60,6 +60,7 @@ struct Category {
 	void finish_xprog();
 	uint64_t added = 0;               // num_added(), input_model.h:68-70
 	uint64_t max_len = 0;             // max_len(), input_model.h:82-84 / :155-157
+	bool arena_overflow = false;      // an arena outgrew the 32-bit descriptor offsets
 	bool valid = true;                // all transcripts well-formed
 	std::string why;                  // first problem found
 	double mean_bytes = 0;            // expected FASTQ bytes per read, excluding refid/offset digits
