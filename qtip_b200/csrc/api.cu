@@ -1156,17 +1156,20 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 		offs.p[c] = off;
 	}
 	uint64_t tot[NCAT];
-	uint32_t errw = 0;
+	uint32_t errw2[2] = {0, 0};
 	for (int c = 0; c < NCAT; c++)
 		CK(ctl_d2h(h, &tot[c], offs.p[c] + na, 8));
-	CK(ctl_d2h(h, &errw, d_err, 4));
+	CK(ctl_d2h(h, errw2, d_err, 8));
 	CK(ctl_sync(h));
+	uint32_t errw = errw2[0];
 	if (errw) return QTIPSIM_OK;  // the first-generation kernel reports the reference's error for it
 	for (int c = 0; c < NCAT; c++) {
 		if (tot[c]) CK(h->d_plan[c].ensure(tot[c] * sizeof(PlanRec)));
 		a2.ra.plan[c] = h->d_plan[c].as<PlanRec>();
 		a2.ra.cap[c] = tot[c];
 	}
+	a2.walk_max = std::min<uint32_t>(4096u, envu("QTIPSIM_R2_WALK_MAX", 4096u));  // (k_resolve2_counts reports regions above 4096 reads)
+	a2.any_large = errw2[1] > a2.walk_max || a2.walk_max < 4096u;
 	launch_resolve2_emit(a2, d_cnt, d_start, offs, d_err, h->st);
 	CK(ctl_d2h(h, &errw, d_err, 4));
 	CK(ctl_sync(h));

@@ -82,6 +82,8 @@ struct Resolve2Args {
 	uint32_t *end;                // [NCAT][K][nbmax] candidate positions after each category
 	uint32_t *cn, *cnd;           // [K][nbmax] candidate counts
 	WinResolved *wres;            // [na]
+	uint32_t walk_max;            // regions of at most this many reads are emitted by one walking thread, the others by a CTA
+	uint32_t any_large;           // some region may exceed walk_max: launch the CTA version too
 	unsigned long long *dbg;      // tracing only (QTIPSIM_R2_DBG): [K][16] globaltimer stamps of one stage's CTAs, or null
 	uint32_t dbg_stage;
 };

@@ -592,6 +592,7 @@ __global__ void __launch_bounds__(128) k_resolve2_counts(Resolve2Args a2, uint32
 		cnt[(size_t)c * a2.na + i] = n[c];
 		start[(size_t)c * a2.na + i] = st[c];
 		if (n[c] && a.ntmpl[c] == 0) atomicMax(err, 2u);
+		if (n[c] > 4096u) atomicMax(err + 1, n[c]);  // err[1]: the largest region (the host picks the emit kernels by it)
 	}
 	if (n[CAT_U] && wc.nslots == 0) atomicMax(err, 1u);  // assert(nslots > 0), simplesim.cpp:252
 }
@@ -610,7 +611,7 @@ __global__ void __launch_bounds__(R2_TE) k_resolve2_emit(Resolve2Args a2, const 
 	const uint32_t i = blockIdx.x;
 	const int cat = (int)blockIdx.y;
 	uint32_t n = cnt[(size_t)cat * a2.na + i];
-	if (n == 0 || a.ntmpl[cat] == 0) return;
+	if (n == 0 || n <= a2.walk_max || a.ntmpl[cat] == 0) return;  // (few reads: k_resolve2_emit_walk has them)
 	const WinResolved wr = a2.wres[i];
 	const StageAnchor an = a2.anchor[wr.stage];
 	const LState SA{an.s1, an.s2};
@@ -700,6 +701,43 @@ __global__ void __launch_bounds__(R2_TE) k_resolve2_emit(Resolve2Args a2, const 
 	if (tid == 0 && n == 0 && pos != wr.end[cat]) atomicMax(err, 6u);
 }
 
+// The same plan records for the (window, category) pairs with few reads -- the usual case -- by simply WALKING the orbit:
+// one thread per window follows its n reads from the known start, evaluating only the reads that happen (the CTA version
+// above evaluates every stream position of the region to find them in parallel: ~6 x the work at 5 draws per read, worth
+// it only when one region holds thousands of reads).  Thousands of windows walk concurrently, so the per-read latency
+// does not matter.
+__global__ void __launch_bounds__(128) k_resolve2_emit_walk(Resolve2Args a2, int cat, const uint32_t *cnt, const uint32_t *start, const uint64_t *off,
+                                                          uint32_t walk_max, uint32_t *err) {
+	const ResolveArgs &a = a2.ra;
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= a2.na) return;
+	uint32_t n = cnt[(size_t)cat * a2.na + i];
+	if (n == 0 || n > walk_max || a.ntmpl[cat] == 0) return;
+	const WinResolved wr = a2.wres[i];
+	const StageAnchor an = a2.anchor[wr.stage];
+	const WinCtx wc = make_winctx(a, a2.aw[i]);
+	uint32_t pos = start[(size_t)cat * a2.na + i];
+	LState s = jump2(LState{an.s1, an.s2}, pos, a.jt1, a.jt2, a2.jh1, a2.jh2);
+	PlanRec *plan = a.plan[cat] + off[i];
+	for (uint32_t r = 0; r < n; r++) {
+		LState t = lstep(s);
+		const uint32_t ti = (uint32_t)lindex(lfloat(lout(t)), a.ntmpl[cat]);
+		t = lstep(t);
+		const uint64_t of = lindex(lfloat(lout(t)), wc.nslots);
+		PlanRec pr;
+		pr.tmpl = ti;
+		pr.record = wc.record;
+		pr.refoff = wc.refoff + of;
+		pr.s1 = t.s1;
+		pr.s2 = t.s2;
+		plan[r] = pr;
+		const uint32_t len = read_len(a, wc, cat, s);
+		s = jump2(s, len, a.jt1, a.jt2, a2.jh1, a2.jh2);
+		pos += len;
+	}
+	if (pos != wr.end[cat]) atomicMax(err, 6u);  // must end where the stage's table said
+}
+
 void launch_resolve2_stage(const Resolve2Args &a, uint32_t s, uint32_t K, cudaStream_t st) {
 	static bool attr = false;
 	if (!attr) {
@@ -722,9 +760,16 @@ void launch_resolve2_emit(const Resolve2Args &a, const uint32_t *cnt, const uint
 		cudaFuncSetAttribute(k_resolve2_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3u * R2_RCAP_MAX * 2u));
 		attr = true;
 	}
-	dim3 grid(a.na, NCAT);
-	k_resolve2_emit<<<grid, R2_TE, (size_t)3 * a.rcap_emit * 2, st>>>(a, cnt, start, offp, err);
-	kernels_count_launch();
+	for (int c = 0; c < NCAT; c++) {
+		if (!a.ra.cap[c] || !a.walk_max) continue;  // (cap[c] = reads of the category)
+		k_resolve2_emit_walk<<<(a.na + 127) / 128, 128, 0, st>>>(a, c, cnt, start, offp.p[c], a.walk_max, err);
+		kernels_count_launch();
+	}
+	if (a.any_large) {
+		dim3 grid(a.na, NCAT);
+		k_resolve2_emit<<<grid, R2_TE, (size_t)3 * a.rcap_emit * 2, st>>>(a, cnt, start, offp, err);
+		kernels_count_launch();
+	}
 }
 
 }  // namespace qt

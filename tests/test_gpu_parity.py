@@ -480,7 +480,8 @@ def test_first_generation_resolvers_equal_band_resolver(name, resolver, workdir,
 @pytest.mark.parametrize("knobs", [dict(QTIPSIM_R2_RCAP="1024", QTIPSIM_R2_RCAP_EMIT="1024"),      # many rounds per window
                                    dict(QTIPSIM_R2_SIGMA="0.3", QTIPSIM_R2_K="16"),                  # bands that miss
                                    dict(QTIPSIM_R2_NBMAX="64", QTIPSIM_R2_K="7"),                    # clipped bands
-                                   dict(QTIPSIM_R2_K="1"), dict(QTIPSIM_R2_K="400", QTIPSIM_R2_SIGMA="8")])
+                                   dict(QTIPSIM_R2_K="1"), dict(QTIPSIM_R2_K="400", QTIPSIM_R2_SIGMA="8"),
+                                   dict(QTIPSIM_R2_WALK_MAX="0"), dict(QTIPSIM_R2_WALK_MAX="40")])                   # which emit kernel takes a region
 @pytest.mark.parametrize("name", ["mixed_small", "c4_mix_small", "c3_shape_small", "edges", "long_reads", "c5_indel"])
 def test_band_resolver_is_exact_under_any_tuning(name, knobs, workdir, monkeypatch):
     """The band resolver's tables are exact or INVALID whatever the band width, the dense-table size or the stage
