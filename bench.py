@@ -508,6 +508,35 @@ def main():
         m4r = None if (args.no_secondary or world > 1) else measure(other_mode, 3, 1, False, do_e2e=False)
         cur["wl"] = wl
 
+    # ---- who limits the end-to-end arm at N > 1?  device-to-host copies of 2 GB into pinned memory: rank 0 alone, then every
+    # rank at once (the FASTQ bytes of a step go home that way: N x 5.8 GB) ----
+    d2h_probe = None
+    if world > 1:
+        nprobe = 2 << 30
+        dsrc = torch.empty(nprobe, dtype=torch.uint8, device="cuda")
+        hdst = torch.empty(nprobe, dtype=torch.uint8).pin_memory()
+
+        def d2h_once():
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            hdst.copy_(dsrc, non_blocking=True)
+            torch.cuda.synchronize()
+            return nprobe / (time.perf_counter() - t0) / 1e9
+
+        d2h_once()
+        barrier()
+        alone = d2h_once() if rank == 0 else 0.0
+        barrier()
+        together = d2h_once()
+        barrier()
+        tt = torch.tensor([alone, together, -together], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tsum = torch.tensor([together], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        d2h_probe = {"what": "2 GiB device-to-host into pinned memory: rank 0 alone, then all ranks at once", "alone_gb_per_s": float(tt[0]),
+                     "concurrent_per_rank_gb_per_s": {"max": float(tt[1]), "min": float(-tt[2])}, "concurrent_aggregate_gb_per_s": float(tsum[0])}
+        del dsrc, hdst
+
     if rank == 0:
         peaks = {}
         try:
@@ -568,6 +597,8 @@ def main():
             "clocks": m["clocks"],
             "setup_s": setup_s,
         }
+        if d2h_probe is not None and line["e2e"] is not None:
+            line["e2e"]["d2h_probe"] = d2h_probe
         if m2 is not None:
             line[other] = block(m2, wl, other)
         if m4 is not None:
