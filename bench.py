@@ -564,7 +564,7 @@ def main():
             out = {"rng_mode": names[mode], "workload": w["name"], "value": mm["value"], "unit": w["unit"], "steps": mm["steps"],
                    "warmup": mm["warmup"], "ms_per_step": mm["ms_per_step"], "reads_per_step": mm["reads_per_step"],
                    "output_gb_per_s": mm["output_gb_per_s"], "phase_ms_per_step_rank0": mm["phase"],
-                   "roofline": {"bound": "hbm", "kernel": "k_simulate_direct", "achieved": mm["achieved"], "peak": peak, "unit": "GB/s",
+                   "roofline": {"bound": "hbm", "kernel": "k_simulate_tile", "achieved": mm["achieved"], "peak": peak, "unit": "GB/s",
                                 "frac": mm["achieved"] / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
                                 "algorithmic_bytes_per_step": mm["alg_step"]},
                    "roofline_step": {"what": "algorithmic bytes of rank 0's step / rank 0's whole step (plan + offsets + simulate)",

@@ -1480,11 +1480,13 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 		                         2u * cg.max_body + 4u;
 		const char *force = getenv("QTIPSIM_KERNEL");
 		bool done = false;
-		// production: the direct kernel; categories it cannot take (a body under 17 bytes) use the staged kernel,
+		// production: the tile kernel (then its first generation, the direct kernel); categories they cannot take (a body under 17 bytes) use the staged kernel,
 		// records too large for either the generic warp-per-read kernel.  QTIPSIM_KERNEL forces one (tests).
-		const bool want_direct = !force || strcmp(force, "direct") == 0;
-		const bool want_staged = !force || strcmp(force, "direct") == 0 || strcmp(force, "staged") == 0;
-		if (cg.compiled_ok && want_direct) done = launch_simulate_direct(sa[c], max_rec - 2u * cg.max_body - 4u, cg.min_body, cg.max_body, h->st);
+		const bool want_tile = !force || strcmp(force, "tile") == 0;
+		const bool want_direct = !force || strcmp(force, "tile") == 0 || strcmp(force, "direct") == 0;
+		const bool want_staged = !force || strcmp(force, "tile") == 0 || strcmp(force, "direct") == 0 || strcmp(force, "staged") == 0;
+		if (cg.compiled_ok && want_tile) done = launch_simulate_tile(sa[c], max_rec - 2u * cg.max_body - 4u, cg.min_body, cg.max_body, h->st);
+		if (!done && cg.compiled_ok && want_direct) done = launch_simulate_direct(sa[c], max_rec - 2u * cg.max_body - 4u, cg.min_body, cg.max_body, h->st);
 		if (!done && cg.compiled_ok && want_staged) done = launch_simulate_warp(sa[c], max_rec, cg.max_body, h->st);
 		if (!done) launch_simulate(sa[c], h->st);
 	}
@@ -1492,9 +1494,11 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 #ifdef QT_BOUNDS
 	{
 		extern void qt_direct_debug_report();
+		extern void qt_tile_debug_report();
 		extern void qt_warp_debug_report();
 		ctl_sync(h);
 		qt_direct_debug_report();
+		qt_tile_debug_report();
 		qt_warp_debug_report();
 	}
 #endif

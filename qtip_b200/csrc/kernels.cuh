@@ -75,6 +75,9 @@ bool launch_simulate_warp(const SimArgs &a, uint32_t max_rec_bytes, uint32_t max
 // direct path (simulate_direct.cu): interior chunks go from registers to HBM, only a record's edge chunks are
 // staged.  max_name bounds the read name; returns false when the category cannot use it (caller falls back).
 bool launch_simulate_direct(const SimArgs &a, uint32_t max_name, uint32_t min_body, uint32_t max_body, cudaStream_t st);
+// tile path (simulate_tile.cu): second generation of the direct path and the production kernel -- one edge image per
+// record written whole by the chunk lanes, names appended as 16-byte pieces, one flat shipping loop.  Same contract.
+bool launch_simulate_tile(const SimArgs &a, uint32_t max_name, uint32_t min_body, uint32_t max_body, cudaStream_t st);
 void launch_nblock(const uint32_t *nmask, uint64_t mask_words, uint32_t *nblk, uint64_t nblk_words, cudaStream_t st);
 void kernels_count_launch();
 // plain copy done by a kernel (either side may be pinned, mapped host memory): control data of the streaming path

@@ -206,9 +206,13 @@ struct MateHot {
 	uint32_t score_len;
 	uint32_t score[3];
 };
+__device__ __forceinline__ MateHot mate_from_blocks(const uint4 &a, const uint4 &b, const uint4 &c);
 __device__ __forceinline__ MateHot load_mate(const MateDesc *m) {
 	const uint4 *p = (const uint4 *)m;
 	const uint4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+	return mate_from_blocks(a, b, c);
+}
+__device__ __forceinline__ MateHot mate_from_blocks(const uint4 &a, const uint4 &b, const uint4 &c) {
 	MateHot h;
 	h.qual_out_off = a.x;
 	h.ops_off = a.y;
@@ -230,8 +234,9 @@ struct TmplTail {
 	uint32_t delta[2], opp_len, typ, typ_len;
 	bool aligned_is_mate1;
 };
-__device__ __forceinline__ TmplTail load_tail(const TmplDesc *t) {
-	const uint4 a = __ldg((const uint4 *)t + 8);
+__device__ __forceinline__ TmplTail tail_from_block(const uint4 &a);
+__device__ __forceinline__ TmplTail load_tail(const TmplDesc *t) { return tail_from_block(__ldg((const uint4 *)t + 8)); }
+__device__ __forceinline__ TmplTail tail_from_block(const uint4 &a) {
 	TmplTail h;
 	h.delta[0] = a.x;
 	h.delta[1] = a.y;

@@ -464,6 +464,22 @@ def test_staged_kernel_path_still_bit_exact(name, workdir, monkeypatch):
     assert nat_s == nat_d  # both kernels consume the Philox stream identically
 
 
+@pytest.mark.parametrize("name", ["mixed_small", "c5_indel", "c4_mix_small", "edges", "long_refid", "c3_shape_small"])
+def test_direct_kernel_path_still_bit_exact(name, workdir, monkeypatch):
+    """The first-generation direct kernel (simulate_direct.cu: taken when a tile of 16 records does not fit the tile
+    kernel's shared-memory budget) stays covered on the ordinary cases, and consumes the Philox stream like the tile
+    kernel that replaced it as the default."""
+    monkeypatch.setenv("QTIPSIM_KERNEL", "direct")
+    case = cases.CASES[name]()
+    streams, st, p = util.run_cuda(case, workdir, name)
+    o = _oracle(case, workdir, name)
+    assert streams == o.streams
+    nat_d, _, _ = util.run_cuda(case, workdir, name, rng_mode=1, philox_seed=5)
+    monkeypatch.delenv("QTIPSIM_KERNEL")
+    nat_t, _, _ = util.run_cuda(case, workdir, name, rng_mode=1, philox_seed=5)
+    assert nat_d == nat_t
+
+
 @pytest.mark.parametrize("resolver", ["cluster", "cta"])
 @pytest.mark.parametrize("name", ["mixed_small", "c4_mix_small", "inversion", "edges", "c3_shape_small"])
 def test_first_generation_resolvers_equal_band_resolver(name, resolver, workdir, monkeypatch):
