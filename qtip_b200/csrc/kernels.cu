@@ -516,7 +516,7 @@ __device__ void emit_random_mate(uint32_t L, bool fw, const DrawSrc &ds, uint32_
 	for (uint32_t j = lane; j < L; j += 32) {
 		uint32_t code;
 		if (MODE == QTIPSIM_RNG_REPLAY) code = replay_code(ds, dcount + j);
-		else code = philox_bits16(ds, dcount + j) >> 14;
+		else code = philox_rmate_code(philox4x32((uint32_t)ds.gi, (uint32_t)(ds.gi >> 32), j >> 6, PHILOX_DOM_RMATE | (ds.dom & 0xffu), ds.k0, ds.k1), j);
 		if (fw) seq[j] = code_char(code);
 		else seq[L - 1 - j] = code_char_comp(code);
 		qual[j] = 'I';

@@ -22,6 +22,7 @@ struct Philox4 {
 static constexpr uint32_t PHILOX_DOM_PLAN = 0x100u;    // template + offset of a read
 static constexpr uint32_t PHILOX_DOM_BASE = 0x200u;    // base draws of a read
 static constexpr uint32_t PHILOX_DOM_WINDOW = 0x300u;  // per-window binomial counts
+static constexpr uint32_t PHILOX_DOM_RMATE = 0x400u;   // bases of a bad-end pair's random mate (below)
 
 QT_PHD uint32_t ph_mulhi(uint32_t a, uint32_t b) {
 #if defined(__CUDA_ARCH__)
@@ -49,5 +50,15 @@ QT_PHD Philox4 philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
 	}
 	return Philox4{{c0, c1, c2, c3}};
 }
+
+// The random mate of a bad-end pair (init_random, simplesim.h:89-117) needs opp_len uniform bases and nothing else:
+// two bits each.  Base j of the mate (in the order the reference draws them) is bits 2 (j mod 16) of word
+// (j / 16) mod 4 of block j / 64 -- so the blocks of a mate, laid end to end, ARE its 2-bit packed sequence in the
+// layout of the packed genome, and the simulate kernel prints it with the code that prints genome spans.
+QT_PHD Philox4 philox_rmate_block(uint64_t read_index, uint32_t block, int cat, uint64_t seed) {
+	return philox4x32((uint32_t)read_index, (uint32_t)(read_index >> 32), block, PHILOX_DOM_RMATE | (uint32_t)cat, (uint32_t)seed,
+	                  (uint32_t)(seed >> 32));
+}
+QT_PHD uint32_t philox_rmate_code(const Philox4 &blk, uint32_t j) { return (blk.v[(j >> 4) & 3u] >> (2u * (j & 15u))) & 3u; }
 
 }  // namespace qt

@@ -853,15 +853,14 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 #pragma unroll
 				for (int t = 0; t < 16; t++) {
 					if (t >= t_first && k0 + t < L) {
-						const uint32_t d = rd.r0 + (uint32_t)(fw ? k0 + t : L - 1 - (k0 + t));
-						if ((d >> 3) != curb) {
-							curb = d >> 3;
-							blk = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), curb, PHILOX_DOM_BASE | (uint32_t)CAT,
-							                 (uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32));
+						const uint32_t d = (uint32_t)(fw ? k0 + t : L - 1 - (k0 + t));  // two bits per base, 64 bases per block (philox.h)
+						if ((d >> 6) != curb) {
+							curb = d >> 6;
+							blk = philox_rmate_block(gi, curb, CAT, a.philox_seed);
 						}
-						const uint32_t wi = (d >> 1) & 3u;
+						const uint32_t wi = (d >> 4) & 3u;
 						const uint32_t x = wi == 0 ? blk.v[0] : wi == 1 ? blk.v[1] : wi == 2 ? blk.v[2] : blk.v[3];
-						const uint32_t code = ((d & 1u) ? (x >> 16) : (x & 0xffffu)) >> 14;
+						const uint32_t code = (x >> (2u * (d & 15u))) & 3u;
 						w[t >> 2] |= ((T >> (8u * code)) & 0xffu) << (8 * (t & 3));
 					}
 				}

@@ -403,13 +403,18 @@ k_simulate_tile(SimArgs a, int K, uint32_t kmagic, int PMAX, uint32_t pmagic, in
 			const int c_first = (int)(P >> 4), c_last = (int)((P + L - 1u) >> 4);
 			const int q_first = (int)(Pq >> 4), q_last = (int)((Pq + L - 1u) >> 4);
 			const uint32_t A0 = md.qual_out_off + 16u * (uint32_t)q_first - Pq;  // arena byte of the first quality chunk, >= 1
-			const uint64_t gadj = md.fw ? gpos + (uint64_t)(int64_t)md.ref0 - (P & 15u)
-			                            : gpos + (uint64_t)(int64_t)md.ref0 + (P & 15u) - 15u;
-			const uint32_t ns = random ? 0u : (uint32_t)(c_last - c_first + 1);
+			// A random mate drawn by the native generator is printed like a genome span: its row holds the mate's 2-bit
+			// codes from base 16 on (step A2r), read on the aligned mate's strand
+			const bool rnd_row = random && MODE == QTIPSIM_RNG_PHILOX;
+			const uint64_t gadj = rnd_row ? (md.fw ? 16u - (P & 15u) : 16u + (L - 1u) + (P & 15u) - 15u)
+			                    : md.fw   ? gpos + (uint64_t)(int64_t)md.ref0 - (P & 15u)
+			                              : gpos + (uint64_t)(int64_t)md.ref0 + (P & 15u) - 15u;
+			const uint32_t ns = random && !rnd_row ? 0u : (uint32_t)(c_last - c_first + 1);
+			const bool gen_s = general[mate] && !random;
 			const bool fast = !random && !general[mate];
 			// the read's row of packed genome words starts at a 16-byte unit of bases[]
 			const uint64_t wmin = md.fw ? (gadj >> 4) : (gadj >> 4) - (uint64_t)(ns ? ns - 1u : 0u);
-			const uint32_t gunit = (uint32_t)(wmin >> 2);
+			const uint32_t gunit = rnd_row ? 0u : (uint32_t)(wmin >> 2);
 			const uint32_t w0 = (uint32_t)((gadj >> 4) - 4ull * gunit);  // word of slot 0 in the read's row
 			const uint32_t wmax = md.fw ? w0 + ns : w0 + 1u;             // last word a chunk lane touches
 			uint32_t np = (wmax + 4u) >> 2;                              // 16-byte pieces staged
@@ -417,7 +422,7 @@ k_simulate_tile(SimArgs a, int K, uint32_t kmagic, int PMAX, uint32_t pmagic, in
 			const uint32_t ix = (uint32_t)(s * RW + lane);
 			tl_sts32(wb + LY::gunit + 4u * ix, fast ? (gunit | (np << 28)) : 0u);
 			tl_sts32(wb + LY::gb0 + 4u * ix, (uint32_t)(gpos - 64ull * gunit));
-			const uint32_t meta = (md.fw ? RF_FW : 0u) | (random ? RF_RANDOM : 0u) | (general[mate] ? RF_GENERAL : 0u) |
+			const uint32_t meta = (md.fw ? RF_FW : 0u) | (random ? RF_RANDOM : 0u) | (gen_s ? RF_GENERAL : 0u) |
 			                      ((uint32_t)(gadj & 15u) << 8) | ((A0 & 15u) << 12);
 			const uint32_t s0c = lane == 0 ? 0u : (rstart[s] - 2u) >> 4;
 			const uint32_t nS = (uint32_t)c_first - s0c + 1u;
@@ -430,7 +435,8 @@ k_simulate_tile(SimArgs a, int K, uint32_t kmagic, int PMAX, uint32_t pmagic, in
 			tl_sts64(wb + LY::pos + 8u * ix, make_uint2(P, L));
 			QT_CHK(ns <= (uint32_t)K && (uint32_t)(q_last - q_first + 1) <= (uint32_t)K && (!fast || np <= (uint32_t)PMAX), 9, ns, K);
 			QT_CHK(nS <= (uint32_t)hS && nS >= 2u && c_last > c_first && q_last > q_first, 5, nS, hS);
-			if (general[mate]) {
+			if (CAT == CAT_B && random) tl_sts32(wb + LY::rnd + 16u * (uint32_t)lane + 8u, (uint32_t)s | (md.fw ? 2u : 0u));  // TRnd::flags
+			if (gen_s) {
 				// (no packed genome is staged for a general-path read: its row holds the TGen record instead)
 				tl_sts128(gbuf0 + ix * row_bytes, make_uint4((uint32_t)gpos, (uint32_t)(gpos >> 32), (uint32_t)gend, (uint32_t)(gend >> 32)));
 				tl_sts64(gbuf0 + ix * row_bytes + 16u, make_uint2(md.seg_off, md.nseg));
@@ -459,6 +465,25 @@ k_simulate_tile(SimArgs a, int K, uint32_t kmagic, int PMAX, uint32_t pmagic, in
 		}
 	}
 	asm volatile("cp.async.commit_group;" ::: "memory");
+	if (CAT == CAT_B && MODE == QTIPSIM_RNG_PHILOX) {
+		// ---- step A2r (lane = 64 bases of a random mate): Philox blocks = the mate's packed codes, into its row from word 1 on ----
+		const int nbk = (K + 2) >> 2;  // blocks a mate can need
+		for (int b0 = 0; b0 < nbk; b0 += 4) {
+			for (int q = lane; q < 4 * nr; q += 32) {
+				const int i = q >> 2, b = b0 + (q & 3);
+				const uint32_t sr = tl_lds32(wb + LY::rnd + 16u * (uint32_t)i + 8u) & 1u;
+				const uint32_t L = tl_lds32(wb + LY::pos + 8u * (sr * RW + (uint32_t)i) + 4u);
+				if (64u * (uint32_t)b < L) {
+					const Philox4 blk = philox_rmate_block(a.read_index_base + r0 + (uint64_t)i, (uint32_t)b, CAT, a.philox_seed);
+					const uint32_t ra = gbuf0 + (sr * RW + (uint32_t)i) * row_bytes + 4u + 16u * (uint32_t)b;
+					tl_sts32(ra, blk.v[0]);
+					tl_sts32(ra + 4u, blk.v[1]);
+					tl_sts32(ra + 8u, blk.v[2]);
+					tl_sts32(ra + 12u, blk.v[3]);
+				}
+			}
+		}
+	}
 
 	// ---------------- the first draw ops of each read (lane = read): loaded now, put into shared memory after step Bq ----------------
 	uint4 op_a[NM];
@@ -702,17 +727,16 @@ k_simulate_tile(SimArgs a, int K, uint32_t kmagic, int PMAX, uint32_t pmagic, in
 				put_at(tb[s], simg, timg, c_first, c_last, P + outp, (T >> (8u * code)) & 0xffu);
 			}
 		}
-		if (CAT == CAT_B)
+		if (CAT == CAT_B && MODE == QTIPSIM_RNG_REPLAY)
 			// the random mate (init_random, simplesim.h:89-117) follows in the draw stream: hand the generator to step Br
-			tl_sts128(wb + LY::rnd + 16u * (uint32_t)lane, make_uint4(MODE == QTIPSIM_RNG_REPLAY ? st.s1 : dk, MODE == QTIPSIM_RNG_REPLAY ? st.s2 : 0u,
-			                                                         (s0_random ? 0u : 1u) | (mh[0].fw ? 2u : 0u), 0u));
+			tl_sts64(wb + LY::rnd + 16u * (uint32_t)lane, make_uint2(st.s1, st.s2));
 	}
-	if (CAT == CAT_B) {
+	if (CAT == CAT_B && MODE == QTIPSIM_RNG_REPLAY) {
 		__syncwarp();
-		// ---------------- step Br (lane = 16-byte chunk of a random mate): opp_len draws per read, 16 per lane ----------------
-		// Both generators are addressable: draw j of the mate is Philox draw (first + j), or the L'Ecuyer state
-		// (j + 1) steps past the handed-over one (jump tables), walked forwards for '+' mates and backwards -- a
-		// multiplication by a^-1 -- for '-' mates, whose bases are printed in reverse (simplesim.h:108-113).
+		// ---------------- step Br (REPLAY; lane = 16-byte chunk of a random mate): opp_len draws per read, 16 per lane ----------------
+		// The L'Ecuyer stream is addressable: draw j of the mate is the state (j + 1) steps past the handed-over one
+		// (jump tables), walked forwards for '+' mates and backwards -- a multiplication by a^-1 -- for '-' mates, whose
+		// bases are printed in reverse (simplesim.h:108-113).  (The native generator's random mates are rows: step A2r.)
 		const int nitems = nr * K;
 		for (int q = lane; q < nitems; q += 32) {
 			const int i = (int)__umulhi((uint32_t)q, kmagic), j = q - i * K;
@@ -727,7 +751,7 @@ k_simulate_tile(SimArgs a, int K, uint32_t kmagic, int PMAX, uint32_t pmagic, in
 			const int t_first = k0 < 0 ? -k0 : 0;        // first byte of the chunk inside the mate
 			const uint32_t T = fw ? TBL_FW : TBL_RC;
 			uint32_t w[4] = {0u, 0u, 0u, 0u};
-			if (MODE == QTIPSIM_RNG_REPLAY) {
+			{
 				const int jd0 = fw ? k0 + t_first : L - 1 - (k0 + t_first);  // draw of the first byte inside
 				LState st = ljump_tbl(LState{rd.x, rd.y}, (uint32_t)(fw ? jd0 : jd0 + 1), a.jt1, a.jt2);
 #pragma unroll
@@ -737,25 +761,6 @@ k_simulate_tile(SimArgs a, int K, uint32_t kmagic, int PMAX, uint32_t pmagic, in
 						const uint32_t code = lbase_code(lfloat(lout(st)));
 						w[t >> 2] |= ((T >> (8u * code)) & 0xffu) << (8 * (t & 3));
 						if (!fw) st = lstep_back(st);
-					}
-				}
-			} else {
-				const uint64_t gi = a.read_index_base + r0 + (uint64_t)i;
-				uint32_t curb = 0xffffffffu;
-				Philox4 blk{};
-#pragma unroll
-				for (int t = 0; t < 16; t++) {
-					if (t >= t_first && k0 + t < L) {
-						const uint32_t d = rd.x + (uint32_t)(fw ? k0 + t : L - 1 - (k0 + t));
-						if ((d >> 3) != curb) {
-							curb = d >> 3;
-							blk = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), curb, PHILOX_DOM_BASE | (uint32_t)CAT,
-							                 (uint32_t)a.philox_seed, (uint32_t)(a.philox_seed >> 32));
-						}
-						const uint32_t wi = (d >> 1) & 3u;
-						const uint32_t x = wi == 0 ? blk.v[0] : wi == 1 ? blk.v[1] : wi == 2 ? blk.v[2] : blk.v[3];
-						const uint32_t code = ((d & 1u) ? (x >> 16) : (x & 0xffffu)) >> 14;
-						w[t >> 2] |= ((T >> (8u * code)) & 0xffu) << (8 * (t & 3));
 					}
 				}
 			}

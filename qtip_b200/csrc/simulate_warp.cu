@@ -425,8 +425,14 @@ __global__ void __launch_bounds__(WT_MAX_WARPS * 32, QT_WT_MIN_BLOCKS) k_simulat
 				const uint32_t L = Lst[s];
 				const bool fw = mh[0].fw;
 				const uint32_t T = fw ? TBL_FW : TBL_RC;
+				Philox4 rb{};
 				for (uint32_t j = 0; j < L; j++) {
-					const uint32_t code = draw_code();
+					uint32_t code;
+					if (MODE == QTIPSIM_RNG_REPLAY) code = draw_code();
+					else {  // two bits per base, 64 bases per block (philox.h)
+						if ((j & 63u) == 0u) rb = philox_rmate_block(gi, j >> 6, CAT, a.philox_seed);
+						code = philox_rmate_code(rb, j);
+					}
 					seq[fw ? j : L - 1 - j] = (char)((T >> (8u * code)) & 0xffu);
 				}
 			}
