@@ -106,7 +106,7 @@ struct qtipsim {
 	std::vector<uint32_t> pclass_cache;
 	uint64_t setup_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	bool setup_cache_ok = false;
-	DevBuf d_plan[NCAT], d_len0, d_len1, d_off0[NCAT], d_off1[NCAT], d_scan_tmp, d_small;
+	DevBuf d_plan[NCAT], d_len0, d_len1, d_off0[NCAT], d_off1[NCAT], d_scan_tmp, d_scan_status, d_small;
 	DevBuf d_out[NOUT];
 	uint64_t out_bytes[NOUT] = {0, 0, 0, 0, 0, 0, 0};
 	uint64_t out_reads[NCAT] = {0, 0, 0, 0};  // reads / pairs per category in d_out (offsets in d_off0 / d_off1)
@@ -254,7 +254,7 @@ void qtipsim_destroy(qtipsim_t *h) {
 	if (h->ctl_ring) cudaFreeHost(h->ctl_ring);
 	DevBuf *all[] = {&h->d_inter, &h->d_xs_out, &h->d_label, &h->d_tabs, &h->d_jh1, &h->d_jh2, &h->d_r2_aw, &h->d_r2_cum, &h->d_r2_anchor, &h->d_r2_counter, &h->d_r2_slot, &h->d_r2_end, &h->d_r2_cn,
 	                 &h->d_r2_wres, &h->d_r2_cnt, &h->d_r2_off, &h->d_r2_misc, &h->d_setups, &h->d_pclass, &h->d_rsresult, &h->d_text, &h->d_pk_a, &h->d_pk_b, &h->d_pk_c, &h->d_pk_d, &h->d_pk_e, &h->d_bases, &h->d_nmask, &h->d_nblk, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
-	                 &h->d_ncount, &h->d_cum, &h->d_len0, &h->d_len1, &h->d_scan_tmp, &h->d_small};
+	                 &h->d_ncount, &h->d_cum, &h->d_len0, &h->d_len1, &h->d_scan_tmp, &h->d_scan_status, &h->d_small};
 	for (DevBuf *b : all) b->release();
 	for (int c = 0; c < NCAT; c++) {
 		h->d_t[c].release();
@@ -1404,6 +1404,7 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 	CK(h->d_len0.ensure(maxn * 4 + 16));
 	CK(h->d_len1.ensure(maxn * 4 + 16));
 	CK(h->d_scan_tmp.ensure((maxn / 1024 + 4) * 8));
+	CK(h->d_scan_status.ensure(plan_philox_scan_status_bytes(maxn)));
 	CK(h->d_small.ensure(16 * 8));
 	CK(cudaMemsetAsync(h->d_small.p, 0, 16 * 8, h->st));
 	uint64_t *d_tot = h->d_small.as<uint64_t>();           // [0..6] stream totals
@@ -1433,18 +1434,28 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 		const int s0 = cat_stream0(c);
 		CK(h->d_off0[c].ensure(nreads[c] * 8));
 		if (c != CAT_U) CK(h->d_off1[c].ensure(nreads[c] * 8));
-		if (p->rng_mode == QTIPSIM_RNG_PHILOX) {
-			// native plan and record lengths in one pass (the read's window by binary search over the cumulative counts)
+		const bool split_plan = getenv("QTIPSIM_PLAN_SPLIT") != nullptr;  // tests: plan + lengths, then separate scans
+		if (p->rng_mode == QTIPSIM_RNG_PHILOX && !split_plan) {
+			// native plan, record lengths and stream offsets in one pass (the read's window by binary search over the
+			// cumulative counts, the offsets by a single-pass prefix sum)
 			const uint64_t *cum = h->d_cum.as<uint64_t>() + (size_t)c * (nwin + 1);
-			launch_plan_philox_lengths(h->d_win.as<Window>() + pp.win_lo, cum + pp.win_lo, (uint32_t)(pp.win_hi - pp.win_lo), olap,
-			                           (uint32_t)h->ts.cat[c].t.size(), p->philox_seed, a, h->d_plan[c].as<PlanRec>(),
-			                           h->d_len0.as<uint32_t>(), c != CAT_U ? h->d_len1.as<uint32_t>() : nullptr, d_gb, h->st);
+			launch_plan_philox_scan(h->d_win.as<Window>() + pp.win_lo, cum + pp.win_lo, (uint32_t)(pp.win_hi - pp.win_lo), olap,
+			                        (uint32_t)h->ts.cat[c].t.size(), p->philox_seed, a, h->d_plan[c].as<PlanRec>(), h->d_off0[c].as<uint64_t>(),
+			                        c != CAT_U ? h->d_off1[c].as<uint64_t>() : nullptr, d_tot + s0, d_tot + s0 + 1, d_gb,
+			                        h->d_scan_status.as<unsigned long long>(), h->st);
 		} else {
-			launch_read_lengths(a, h->d_len0.as<uint32_t>(), c != CAT_U ? h->d_len1.as<uint32_t>() : nullptr, d_gb, h->st);
+			if (p->rng_mode == QTIPSIM_RNG_PHILOX) {
+				const uint64_t *cum = h->d_cum.as<uint64_t>() + (size_t)c * (nwin + 1);
+				launch_plan_philox_lengths(h->d_win.as<Window>() + pp.win_lo, cum + pp.win_lo, (uint32_t)(pp.win_hi - pp.win_lo), olap,
+				                           (uint32_t)h->ts.cat[c].t.size(), p->philox_seed, a, h->d_plan[c].as<PlanRec>(),
+				                           h->d_len0.as<uint32_t>(), c != CAT_U ? h->d_len1.as<uint32_t>() : nullptr, d_gb, h->st);
+			} else {
+				launch_read_lengths(a, h->d_len0.as<uint32_t>(), c != CAT_U ? h->d_len1.as<uint32_t>() : nullptr, d_gb, h->st);
+			}
+			launch_scan(h->d_len0.as<uint32_t>(), h->d_off0[c].as<uint64_t>(), nreads[c], h->d_scan_tmp.as<uint64_t>(), d_tot + s0, h->st);
+			if (c != CAT_U)
+				launch_scan(h->d_len1.as<uint32_t>(), h->d_off1[c].as<uint64_t>(), nreads[c], h->d_scan_tmp.as<uint64_t>(), d_tot + s0 + 1, h->st);
 		}
-		launch_scan(h->d_len0.as<uint32_t>(), h->d_off0[c].as<uint64_t>(), nreads[c], h->d_scan_tmp.as<uint64_t>(), d_tot + s0, h->st);
-		if (c != CAT_U)
-			launch_scan(h->d_len1.as<uint32_t>(), h->d_off1[c].as<uint64_t>(), nreads[c], h->d_scan_tmp.as<uint64_t>(), d_tot + s0 + 1, h->st);
 		a.off0 = h->d_off0[c].as<uint64_t>();
 		a.off1 = c != CAT_U ? h->d_off1[c].as<uint64_t>() : nullptr;
 	}

@@ -394,6 +394,209 @@ __global__ void __launch_bounds__(256) k_plan_philox_lengths(const Window *win, 
 	}
 }
 
+// The same plan, with the record lengths turned into stream offsets in the same pass: a single-pass prefix sum with
+// decoupled look-back over tiles of PS_THREADS reads (tile ids from a ticket counter, so a tile only ever waits for
+// tiles that have started).  status[s][tile] = flag << 62 | value: flag 1 = the tile's own sum, 2 = the sum of
+// everything up to and including the tile.  Replaces k_plan_philox_lengths + three scan kernels per stream and the
+// length arrays between them (28 bytes written and 8 read per read instead of 36 and 12).
+static constexpr int PS_THREADS = 256, PS_ITEMS = 4, PS_TILE = PS_THREADS * PS_ITEMS;  // consecutive reads per thread
+template <int NS>
+__global__ void __launch_bounds__(PS_THREADS) k_plan_philox_scan(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap,
+                                                                 uint32_t ntmpl, uint64_t seed, SimArgs a, PlanRec *plan, uint64_t *off0,
+                                                                 uint64_t *off1, uint64_t *tot0, uint64_t *tot1, unsigned long long *gbytes,
+                                                                 unsigned long long *status, unsigned int *ticket, uint32_t ntiles) {
+	__shared__ uint32_t s_tile, s_lo;
+	__shared__ uint32_t s_wsum[NS][PS_THREADS / 32];
+	__shared__ uint64_t s_prefix[NS];
+	__shared__ uint32_t s_gb[PS_THREADS / 32];
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+	if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+	__syncthreads();
+	const uint32_t tile = s_tile;
+	// window of the tile's first read: a 32-ary search by the first warp (three dependent probes for 32 k windows
+	// where a binary search takes fifteen), then every thread walks forward from there -- a tile's reads lie in the
+	// same or the next few windows (invariant: cum[lo] <= gi < cum[lo + 1])
+	if (wid == 0) {
+		const uint64_t g0 = a.read_index_base + (uint64_t)tile * PS_TILE;
+		uint32_t l = 0, h = nwin;
+		while (h - l > 1) {
+			const uint32_t step = (h - l + 31u) / 32u;
+			const uint32_t idx = l + (lane + 1u) * step;
+			const bool le = idx < h && cum[idx] <= g0;
+			const uint32_t n = (uint32_t)__popc(__ballot_sync(0xffffffffu, le));
+			const uint32_t nh = l + (n + 1u) * step;
+			l += n * step;
+			h = nh < h ? nh : h;
+		}
+		if (lane == 0) s_lo = l;
+	}
+	__syncthreads();
+	uint32_t lo = s_lo;
+	const uint64_t rbase = (uint64_t)tile * PS_TILE + (uint64_t)tid * PS_ITEMS;
+	uint32_t gb = 0, len[PS_ITEMS][NS];
+	// the plan records first: what follows gathers from the templates, and those loads then fly together
+	PlanRec pr[PS_ITEMS];
+#pragma unroll
+	for (int k = 0; k < PS_ITEMS; k++) {
+		const uint64_t r = rbase + k;
+		pr[k] = PlanRec{};
+		if (r < a.nreads) {
+			const uint64_t gi = a.read_index_base + r;
+			while (lo + 1 < nwin && cum[lo + 1] <= gi) lo++;
+			const Window w = win[lo];
+			const Philox4 x = philox4x32((uint32_t)gi, (uint32_t)(gi >> 32), 0u, PHILOX_DOM_PLAN | (uint32_t)a.cat, (uint32_t)seed,
+			                             (uint32_t)(seed >> 32));
+			const uint64_t nslots = (uint64_t)w.retsz - olap;
+			pr[k].tmpl = __umulhi(x.v[0], ntmpl);
+			pr[k].record = w.record;
+			pr[k].refoff = w.refoff + (nslots ? (uint64_t)__umulhi(x.v[1], (uint32_t)nslots) : 0);
+		}
+	}
+	if (rbase + PS_ITEMS <= a.nreads) {  // a thread's four records are 96 contiguous, 16-byte aligned bytes: six vector stores
+		static_assert(sizeof(PlanRec) == 24 && PS_ITEMS == 4, "plan store");
+		uint4 *pd = (uint4 *)(plan + rbase);
+		const uint32_t o0l = (uint32_t)pr[0].refoff, o0h = (uint32_t)(pr[0].refoff >> 32), o1l = (uint32_t)pr[1].refoff, o1h = (uint32_t)(pr[1].refoff >> 32);
+		const uint32_t o2l = (uint32_t)pr[2].refoff, o2h = (uint32_t)(pr[2].refoff >> 32), o3l = (uint32_t)pr[3].refoff, o3h = (uint32_t)(pr[3].refoff >> 32);
+		pd[0] = make_uint4(pr[0].tmpl, pr[0].record, o0l, o0h);
+		pd[1] = make_uint4(0u, 0u, pr[1].tmpl, pr[1].record);
+		pd[2] = make_uint4(o1l, o1h, 0u, 0u);
+		pd[3] = make_uint4(pr[2].tmpl, pr[2].record, o2l, o2h);
+		pd[4] = make_uint4(0u, 0u, pr[3].tmpl, pr[3].record);
+		pd[5] = make_uint4(o3l, o3h, 0u, 0u);
+	} else {
+#pragma unroll
+		for (int k = 0; k < PS_ITEMS; k++)
+			if (rbase + k < a.nreads) plan[rbase + k] = pr[k];
+	}
+#pragma unroll
+	for (int k = 0; k < PS_ITEMS; k++) {
+#pragma unroll
+		for (int s = 0; s < NS; s++) len[k][s] = 0u;
+		if (rbase + k < a.nreads) {
+			// what the lengths need of the template, as 16-byte blocks (common.h): block 1 of each mate (len, rflen, ...,
+			// score_len) and, for pairs, the block behind the mates (delta, opp_len, typ_len, aligned_is_mate1)
+			const uint4 *tp = (const uint4 *)(a.c.t + pr[k].tmpl);
+			const uint32_t rl = __ldg(&a.g.recs[pr[k].record].name_len);
+			const uint4 m0 = __ldg(tp + 1);
+			const uint32_t len_0 = m0.x, sl0 = (m0.w >> 16) & 0xffu;
+			gb += (m0.y + 3u) / 4u;
+			if (NS == 1) {
+				len[k][0] = 13u + rl + ndigits_u64(pr[k].refoff) + sl0 + 1u + 2u * len_0 + 4u;  // name_len_unp, typ "u"
+			} else {
+				const uint4 tl = __ldg(tp + 8);
+				const uint32_t typ_len = (tl.w >> 16) & 0xffu;
+				if (a.cat == CAT_B) {
+					const bool m1 = (tl.w >> 24) != 0;
+					const uint32_t nl = 18u + 2u * rl + 2u * ndigits_u64(pr[k].refoff) + 2u * sl0 + typ_len;
+					len[k][0] = nl + 2u * (m1 ? len_0 : tl.z) + 4u;
+					len[k][NS - 1] = nl + 2u * (m1 ? tl.z : len_0) + 4u;
+				} else {
+					const uint4 m1 = __ldg(tp + 5);
+					const uint32_t nl = 18u + 2u * rl + ndigits_u64(pr[k].refoff + tl.x) + ndigits_u64(pr[k].refoff + tl.y) + sl0 + ((m1.w >> 16) & 0xffu) + typ_len;
+					len[k][0] = nl + 2u * len_0 + 4u;
+					len[k][NS - 1] = nl + 2u * m1.x + 4u;
+					gb += (m1.y + 3u) / 4u;
+				}
+			}
+		}
+	}
+	// exclusive scan inside the tile (32-bit: a tile's records stay far below 4 GiB)
+	uint32_t tsum[NS], incl[NS];
+#pragma unroll
+	for (int s = 0; s < NS; s++) {
+		uint32_t v = 0;
+#pragma unroll
+		for (int k = 0; k < PS_ITEMS; k++) v += len[k][s];
+		tsum[s] = v;
+		for (int o = 1; o < 32; o <<= 1) {
+			const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+			if ((int)lane >= o) v += u;
+		}
+		incl[s] = v;
+		if (lane == 31) s_wsum[s][wid] = v;
+	}
+	for (int o = 16; o; o >>= 1) gb += __shfl_xor_sync(0xffffffffu, gb, o);
+	if (lane == 0) s_gb[wid] = gb;
+	__syncthreads();
+	if (wid == 0) {
+		uint32_t g = lane < PS_THREADS / 32 ? s_gb[lane] : 0u;
+		for (int o = 16; o; o >>= 1) g += __shfl_xor_sync(0xffffffffu, g, o);
+		if (lane == 0 && g) atomicAdd(gbytes, (unsigned long long)g);
+#pragma unroll
+		for (int s = 0; s < NS; s++) {
+			// warp sums -> exclusive warp offsets, tile sum
+			uint32_t v = lane < PS_THREADS / 32 ? s_wsum[s][lane] : 0u;
+			const uint32_t mine = v;
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t u = __shfl_up_sync(0xffffffffu, v, o);
+				if ((int)lane >= o) v += u;
+			}
+			const uint64_t agg = __shfl_sync(0xffffffffu, v, 31);
+			if (lane < PS_THREADS / 32) s_wsum[s][lane] = v - mine;
+			unsigned long long *st = status + (size_t)s * ntiles;
+			uint64_t excl = 0;
+			if (tile) {
+				if (lane == 0) *(volatile unsigned long long *)&st[tile] = (1ull << 62) | agg;
+				int pos = (int)tile - 1;
+				for (;;) {
+					const int idx = pos - (int)lane;
+					unsigned long long sv = 2ull << 62;  // in front of tile 0: an inclusive sum of zero
+					if (idx >= 0) {
+						do sv = *(volatile unsigned long long *)&st[idx];
+						while ((sv >> 62) == 0);
+					}
+					const uint32_t done = __ballot_sync(0xffffffffu, (sv >> 62) == 2);
+					const uint32_t upto = done ? (uint32_t)__ffs(done) - 1u : 31u;  // nearest tile whose inclusive sum is known
+					uint64_t part = lane <= upto ? (sv & ((1ull << 62) - 1)) : 0ull;
+					for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+					excl += part;
+					if (done) break;
+					pos -= 32;
+				}
+			}
+			if (lane == 0) {
+				*(volatile unsigned long long *)&st[tile] = (2ull << 62) | (excl + agg);
+				s_prefix[s] = excl;
+				if (tile == ntiles - 1) *(s ? tot1 : tot0) = excl + agg;
+			}
+		}
+	}
+	__syncthreads();
+#pragma unroll
+	for (int s = 0; s < NS; s++) {
+		uint64_t o = s_prefix[s] + s_wsum[s][wid] + (incl[s] - tsum[s]);
+		uint64_t *off = s ? off1 : off0;
+		if (rbase + PS_ITEMS <= a.nreads) {
+			const uint64_t o1 = o + len[0][s], o2 = o1 + len[1][s], o3 = o2 + len[2][s];
+			uint4 *od = (uint4 *)(off + rbase);
+			od[0] = make_uint4((uint32_t)o, (uint32_t)(o >> 32), (uint32_t)o1, (uint32_t)(o1 >> 32));
+			od[1] = make_uint4((uint32_t)o2, (uint32_t)(o2 >> 32), (uint32_t)o3, (uint32_t)(o3 >> 32));
+		} else {
+#pragma unroll
+			for (int k = 0; k < PS_ITEMS; k++) {
+				if (rbase + k < a.nreads) off[rbase + k] = o;
+				o += len[k][s];
+			}
+		}
+	}
+}
+
+// status: >= 2 * ntiles + 1 u64, zeroed by this call (the last word is the ticket counter)
+void launch_plan_philox_scan(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap, uint32_t ntmpl, uint64_t seed,
+                             const SimArgs &a, PlanRec *plan, uint64_t *off0, uint64_t *off1, uint64_t *tot0, uint64_t *tot1,
+                             unsigned long long *gbytes, unsigned long long *status, cudaStream_t st) {
+	if (!a.nreads) return;
+	const uint32_t ntiles = (uint32_t)((a.nreads + PS_TILE - 1) / PS_TILE);
+	cudaMemsetAsync(status, 0, ((size_t)2 * ntiles + 1) * 8, st);
+	unsigned int *ticket = (unsigned int *)(status + (size_t)2 * ntiles);
+	if (a.cat == CAT_U)
+		k_plan_philox_scan<1><<<ntiles, PS_THREADS, 0, st>>>(win, cum, nwin, olap, ntmpl, seed, a, plan, off0, off1, tot0, tot1, gbytes, status, ticket, ntiles);
+	else
+		k_plan_philox_scan<2><<<ntiles, PS_THREADS, 0, st>>>(win, cum, nwin, olap, ntmpl, seed, a, plan, off0, off1, tot0, tot1, gbytes, status, ticket, ntiles);
+	g_launches++;
+}
+size_t plan_philox_scan_status_bytes(uint64_t nreads) { return ((size_t)2 * ((nreads + PS_TILE - 1) / PS_TILE) + 2) * 8; }
+
 void launch_plan_philox_lengths(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap, uint32_t ntmpl, uint64_t seed,
                                 const SimArgs &a, PlanRec *plan, uint32_t *len0, uint32_t *len1, unsigned long long *gbytes,
                                 cudaStream_t st) {

@@ -101,6 +101,13 @@ void launch_plan_philox_lengths(const Window *win, const uint64_t *cum, uint32_t
                                 const SimArgs &a, PlanRec *plan, uint32_t *len0, uint32_t *len1, unsigned long long *gbytes,
                                 cudaStream_t st);
 
+// the same with the record lengths scanned into stream offsets in one pass (decoupled look-back); status: scratch of
+// plan_philox_scan_status_bytes(nreads) bytes
+void launch_plan_philox_scan(const Window *win, const uint64_t *cum, uint32_t nwin, uint64_t olap, uint32_t ntmpl, uint64_t seed,
+                             const SimArgs &a, PlanRec *plan, uint64_t *off0, uint64_t *off1, uint64_t *tot0, uint64_t *tot1,
+                             unsigned long long *gbytes, unsigned long long *status, cudaStream_t st);
+size_t plan_philox_scan_status_bytes(uint64_t nreads);
+
 // mate 1 / mate 2 records of a pair category interleaved into one stream
 void launch_interleave(const char *src0, const char *src1, const uint64_t *off0, const uint64_t *off1, uint64_t n, uint64_t tot0, uint64_t tot1,
                        char *dst, cudaStream_t st);

@@ -480,6 +480,18 @@ def test_direct_kernel_path_still_bit_exact(name, workdir, monkeypatch):
     assert nat_d == nat_t
 
 
+@pytest.mark.parametrize("name", ["mixed_small", "c4_mix_small", "c3_shape_small", "edges", "long_refid", "short_reads"])
+def test_native_single_pass_plan_equals_split_plan(name, workdir, monkeypatch):
+    """Native mode computes plan, record lengths and stream offsets in one kernel (single-pass prefix sum with
+    decoupled look-back, k_plan_philox_scan); QTIPSIM_PLAN_SPLIT=1 takes the plan + lengths kernel and the three-kernel
+    scans it replaced.  Same bytes, same counts."""
+    case = cases.CASES[name]()
+    a, sta, _ = util.run_cuda(case, workdir, name, rng_mode=1, philox_seed=11)
+    monkeypatch.setenv("QTIPSIM_PLAN_SPLIT", "1")
+    b, stb, _ = util.run_cuda(case, workdir, name, rng_mode=1, philox_seed=11)
+    assert a == b and list(sta.wrote) == list(stb.wrote)
+
+
 @pytest.mark.parametrize("resolver", ["cluster", "cta"])
 @pytest.mark.parametrize("name", ["mixed_small", "c4_mix_small", "inversion", "edges", "c3_shape_small"])
 def test_first_generation_resolvers_equal_band_resolver(name, resolver, workdir, monkeypatch):
