@@ -776,6 +776,25 @@ k_simulate_tile(SimArgs a, int K, uint32_t kmagic, int PMAX, uint32_t pmagic, in
 	// ---------------- step N (lane = read): '\n' of the previous record, name, separators ----------------
 	// Everything that stores whole chunks into the images is done; what follows only touches its own bytes.
 	if (act) {
+		// The name's inputs are loaded again (L1 / L2 hits) rather than held in registers across the chunk loops: the
+		// plan record, the template's mates and tail block, the record's name blocks
+		const PlanRec pr = a.plan[ri];
+		const TmplDesc *tp = a.c.t + pr.tmpl;
+		const uint4 *recp4 = (const uint4 *)(a.g.recs + pr.record);
+		const uint4 rec_b = __ldg(recp4 + 1), rec_c = __ldg(recp4 + 2);
+		TmplTail tt;
+		if (CAT == CAT_U) {
+			tt.delta[0] = tt.delta[1] = 0;
+			tt.opp_len = 0;
+			tt.typ = (uint32_t)'u';
+			tt.typ_len = 1;
+			tt.aligned_is_mate1 = false;
+		} else tt = load_tail(tp);
+		MateHot mh[NM];
+#pragma unroll
+		for (int m = 0; m < NM; m++) mh[m] = load_mate(&tp->m[m]);
+		const uint64_t ro[2] = {pr.refoff + tt.delta[0], pr.refoff + tt.delta[1]};
+		const bool s0_random = CAT == CAT_B && !tt.aligned_is_mate1;
 		const uint32_t rec_name_off = rec_b.x, rl = rec_b.y;
 		const char *refid = a.g.names + rec_name_off;
 		NameW<NS> w;
