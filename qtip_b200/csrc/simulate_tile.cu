@@ -773,64 +773,69 @@ k_simulate_tile(SimArgs a, int K, uint32_t kmagic, int PMAX, uint32_t pmagic, in
 	}
 	__syncwarp();
 
-	// ---------------- step N (lane = read): '\n' of the previous record, name, separators ----------------
-	// Everything that stores whole chunks into the images is done; what follows only touches its own bytes.
-	if (act) {
-		// The name's inputs are loaded again (L1 / L2 hits) rather than held in registers across the chunk loops: the
-		// plan record, the template's mates and tail block, the record's name blocks
-		const PlanRec pr = a.plan[ri];
-		const TmplDesc *tp = a.c.t + pr.tmpl;
-		const uint4 *recp4 = (const uint4 *)(a.g.recs + pr.record);
-		const uint4 rec_b = __ldg(recp4 + 1), rec_c = __ldg(recp4 + 2);
-		TmplTail tt;
-		if (CAT == CAT_U) {
-			tt.delta[0] = tt.delta[1] = 0;
-			tt.opp_len = 0;
-			tt.typ = (uint32_t)'u';
-			tt.typ_len = 1;
-			tt.aligned_is_mate1 = false;
-		} else tt = load_tail(tp);
-		MateHot mh[NM];
+	// ---------------- step N (lane = record): '\n' of the previous record, name, separators ----------------
+	// Everything that stores whole chunks into the images is done; what follows only touches its own bytes.  Pairs:
+	// lanes 0-15 print the first file's copy of the name, lanes 16-31 the second file's.
+	{
+		static_assert(RW == 16, "step N: two lanes per pair");
+		const int rl_ = NS == 2 ? (lane & 15) : lane, sx = NS == 2 ? (lane >> 4) : 0;
+		uint32_t rs = __shfl_sync(0xffffffffu, rstart[0], rl_);
+		if (NS == 2) {
+			const uint32_t rs1 = __shfl_sync(0xffffffffu, rstart[NS - 1], rl_);
+			rs = sx ? rs1 : rs;
+		}
+		const uint32_t nlx = __shfl_sync(0xffffffffu, nl, rl_);
+		if (rl_ < nr) {
+			// The name's inputs are loaded again (L1 / L2 hits) rather than held in registers across the chunk loops: the
+			// plan record, the template's mates and tail block, the record's name blocks
+			const PlanRec pr = a.plan[r0 + (uint64_t)rl_];
+			const TmplDesc *tp = a.c.t + pr.tmpl;
+			const uint4 *recp4 = (const uint4 *)(a.g.recs + pr.record);
+			const uint4 rec_b = __ldg(recp4 + 1), rec_c = __ldg(recp4 + 2);
+			TmplTail tt;
+			if (CAT == CAT_U) {
+				tt.delta[0] = tt.delta[1] = 0;
+				tt.opp_len = 0;
+				tt.typ = (uint32_t)'u';
+				tt.typ_len = 1;
+				tt.aligned_is_mate1 = false;
+			} else tt = load_tail(tp);
+			MateHot mh[NM];
 #pragma unroll
-		for (int m = 0; m < NM; m++) mh[m] = load_mate(&tp->m[m]);
-		const uint64_t ro[2] = {pr.refoff + tt.delta[0], pr.refoff + tt.delta[1]};
-		const bool s0_random = CAT == CAT_B && !tt.aligned_is_mate1;
-		const uint32_t rec_name_off = rec_b.x, rl = rec_b.y;
-		const char *refid = a.g.names + rec_name_off;
-		NameW<NS> w;
-		uint32_t s0c[NS];
-#pragma unroll
-		for (int s = 0; s < NS; s++) {
-			s0c[s] = lane == 0 ? 0u : (rstart[s] - 2u) >> 4;
+			for (int m = 0; m < NM; m++) mh[m] = load_mate(&tp->m[m]);
+			const uint64_t ro[2] = {pr.refoff + tt.delta[0], pr.refoff + tt.delta[1]};
+			const bool s0_random = CAT == CAT_B && !tt.aligned_is_mate1;
+			const uint32_t rec_name_off = rec_b.x, rl = rec_b.y;
+			const char *refid = a.g.names + rec_name_off;
+			const uint32_t imgx = img0 + (uint32_t)sx * img_stream + 16u * (uint32_t)(rl_ * STR);  // the record's image
+			const uint32_t s0c = rl_ == 0 ? 0u : (rs - 2u) >> 4;
+			NameW<1> w;
 			// byte rstart - 1 (for the tile's first record it may lie in the guard entry: never shipped)
-			name_begin<NS>(w, s, img0 + (uint32_t)s * img_stream + slot_off + (rstart[s] - 1u - 16u * s0c[s]));
-		}
-		name_append<NS, 2>(w, 0x7471400au, 0x3a217069u, 0u, 0u, 8u);  // "\n@qtip!:"
-		if (CAT == CAT_U) {
-			const uint32_t nd = nl - 13u - rl - mh[0].score_len - tt.typ_len;
-			name_origin<NS>(w, refid, rec_c, rl, ro[0], nd, mh[0]);
-		} else if (CAT == CAT_B) {
-			const uint32_t nd = (nl - 18u - 2u * rl - 2u * mh[0].score_len - tt.typ_len) >> 1;
-			name_origin<NS>(w, refid, rec_c, rl, ro[0], nd, mh[0]);
-			name_append<NS, 1>(w, 0x3au, 0u, 0u, 0u, 1u);
-			name_origin<NS>(w, refid, rec_c, rl, ro[0], nd, mh[0]);
-		} else {
-			const uint32_t nd0 = ndig64(ro[0]);
-			const uint32_t nd1 = nl - 18u - 2u * rl - mh[0].score_len - mh[NM - 1].score_len - tt.typ_len - nd0;
-			name_origin<NS>(w, refid, rec_c, rl, ro[0], nd0, mh[0]);
-			name_append<NS, 1>(w, 0x3au, 0u, 0u, 0u, 1u);
-			name_origin<NS>(w, refid, rec_c, rl, ro[1], nd1, mh[NM - 1]);
-		}
-		name_append<NS, 1>(w, 0x3au | (tt.typ << 8) | (0x0au << (8u + 8u * tt.typ_len)), 0u, 0u, 0u, 2u + tt.typ_len);  // ":<typ>\n"
-		name_flush<NS>(w);
-#pragma unroll
-		for (int s = 0; s < NS; s++) {
-			const bool random = CAT == CAT_B && ((s == 0) == s0_random);
-			const uint32_t L = random ? tt.opp_len : mh[CAT == CAT_B ? 0 : s].len;
-			const uint32_t P = rstart[s] + nl, Pq = P + L + 3u;
-			QT_CHK(w.wp[s] + w.f[s] == img0 + (uint32_t)s * img_stream + slot_off + (P - 16u * s0c[s]), 6, w.wp[s] + w.f[s], P);
+			name_begin<1>(w, 0, imgx + (rs - 1u - 16u * s0c));
+			name_append<1, 2>(w, 0x7471400au, 0x3a217069u, 0u, 0u, 8u);  // "\n@qtip!:"
+			if (CAT == CAT_U) {
+				const uint32_t nd = nlx - 13u - rl - mh[0].score_len - tt.typ_len;
+				name_origin<1>(w, refid, rec_c, rl, ro[0], nd, mh[0]);
+			} else if (CAT == CAT_B) {
+				const uint32_t nd = (nlx - 18u - 2u * rl - 2u * mh[0].score_len - tt.typ_len) >> 1;
+				name_origin<1>(w, refid, rec_c, rl, ro[0], nd, mh[0]);
+				name_append<1, 1>(w, 0x3au, 0u, 0u, 0u, 1u);
+				name_origin<1>(w, refid, rec_c, rl, ro[0], nd, mh[0]);
+			} else {
+				const uint32_t nd0 = ndig64(ro[0]);
+				const uint32_t nd1 = nlx - 18u - 2u * rl - mh[0].score_len - mh[NM - 1].score_len - tt.typ_len - nd0;
+				name_origin<1>(w, refid, rec_c, rl, ro[0], nd0, mh[0]);
+				name_append<1, 1>(w, 0x3au, 0u, 0u, 0u, 1u);
+				name_origin<1>(w, refid, rec_c, rl, ro[1], nd1, mh[NM - 1]);
+			}
+			name_append<1, 1>(w, 0x3au | (tt.typ << 8) | (0x0au << (8u + 8u * tt.typ_len)), 0u, 0u, 0u, 2u + tt.typ_len);  // ":<typ>\n"
+			name_flush<1>(w);
+			const bool random = CAT == CAT_B && ((sx == 0) == s0_random);
+			const uint32_t L = random ? tt.opp_len : (CAT == CAT_B || !sx ? mh[0].len : mh[NM - 1].len);
+			const uint32_t P = rs + nlx, Pq = P + L + 3u;
+			QT_CHK(w.wp[0] + w.f[0] == imgx + (P - 16u * s0c), 6, w.wp[0] + w.f[0], P);
 			const uint32_t c_last = (P + L - 1u) >> 4;
-			const uint32_t tseq = img0 + (uint32_t)s * img_stream + slot_off + 16u * (uint32_t)hS;
+			const uint32_t tseq = imgx + 16u * (uint32_t)hS;
 			// separators: each byte into T_seq when it lies in the chunk of the last sequence byte, else into T_qual
 			const uint32_t x0 = P + L, x1 = x0 + 1u, x2 = x0 + 2u;
 			tl_sts8(tseq + ((x0 >> 4) == c_last ? 0u : 16u) + (x0 & 15u), 0x0au);
@@ -851,9 +856,9 @@ k_simulate_tile(SimArgs a, int K, uint32_t kmagic, int PMAX, uint32_t pmagic, in
 				v.w = (v.w & m3) | (vq.w & ~m3);
 				tl_sts128(tseq, v);
 			}
-			if (lane == nr - 1) {  // no next record in this tile to print the record's last '\n'
+			if (rl_ == nr - 1) {  // no next record in this tile to print the record's last '\n'
 				const uint32_t q_last = (Pq + L - 1u) >> 4;
-				tl_sts8(img0 + (uint32_t)s * img_stream + slot_off + 16u * (uint32_t)STR + (Pq + L - 16u * q_last), 0x0au);
+				tl_sts8(imgx + 16u * (uint32_t)STR + (Pq + L - 16u * q_last), 0x0au);
 			}
 		}
 	}
