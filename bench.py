@@ -576,7 +576,7 @@ def main():
                 out["e2e"] = mm["e2e"]
             return out
 
-        tr_native = traffic_of("r02_k_simulate_direct_traffic.json") or traffic_of("r01_k_simulate_direct_traffic.json")
+        tr_native = traffic_of("r02_k_simulate_tile_traffic.json")
         b = block(m, wl, args.mode, tr_native if (args.workload in ("auto", "c3") and args.mode == "native") else None)
         line = {
             "metric": METRIC, "value": m["value"], "unit": wl["unit"], "n_gpus": n_gpus, "steps": args.steps,
