@@ -191,7 +191,7 @@ QT_HD LState ljump(LState s, uint64_t k) {
 // logf, bit-identical to glibc's (sysdeps/ieee754/flt-32/e_logf.c, the ARM
 // optimized-routines algorithm: 16-entry table, degree-3 polynomial in double).
 // Checked against the host libm over every positive normal float by
-// tests/test_logf_exhaustive.py (sampled in the default suite, exhaustive on demand);
+// tests/test_logf_exhaustive.py (and on a stride in tests/test_host_logic.py);
 // the fused and unfused evaluations agree after rounding to float on all of them.
 // Valid for positive normal x, which is all ignbin ever passes.
 // ---------------------------------------------------------------------------

@@ -110,7 +110,7 @@ def test_draw_base_integer_thresholds():
 
 def test_logf_matches_libm_sampled():
     """logf_glibc == host logf on a stride over all positive normal floats, and densely over
-    (0, 1] where ignbin's arguments live.  (Exhaustive: tests/test_logf_exhaustive.py, -m slow.)"""
+    (0, 1] where ignbin's arguments live.  (Every float: tests/test_logf_exhaustive.py.)"""
     L = util.hosttest()
     assert L.qthost_logf_sweep(0x00800000, 0x7f800000, 4099) == 0
     assert L.qthost_logf_sweep(0x30000000, 0x3f800001, 53) == 0
