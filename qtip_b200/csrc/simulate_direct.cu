@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(DT_MAX_WARPS * 32, CAT == CAT_U ? QT_DT_MIN_BL
 			hq.area = h.area;
 			s_hotq[s * RW + lane] = hq;
 			s_pos[s * RW + lane] = DPos{P, L};
-			QD_CHK(ns <= (uint32_t)K && (uint32_t)(q_last - q_first + 1) <= (uint32_t)K && (!fast || w0 + ns + 1 <= (uint32_t)(4 * PMAX)), 9, ns, K);
+			QD_CHK(ns <= (uint32_t)K && (uint32_t)(q_last - q_first + 1) <= (uint32_t)K && (!fast || (md.fw ? w0 + ns : w0 + 1u) < (uint32_t)(4 * PMAX)), 9, ns, K);  // last row word a chunk lane touches
 			if (general[mate]) {
 				DGen g;
 				g.gpos = gpos;
