@@ -921,8 +921,9 @@ static bool launch_cat(const SimArgs &a, uint32_t max_name, uint32_t max_body, c
 	const uint32_t strmagic = (uint32_t)((0x100000000ull + STR - 1) / STR);
 	const uint32_t wbytes = (LY::bytes(PMAX, STR) + 15u) & ~15u;
 	const uint32_t sm_budget = 216u * 1024u;
-	// resident warps per SM wanted: 24 (12 for concordant / discordant pairs); longer records go to the first-generation kernel
-	if (wbytes * ((CAT == CAT_C || CAT == CAT_D) ? 12u : 24u) > sm_budget) return false;
+	// resident warps per SM wanted: 24 (unpaired), 12 (pair categories: two images and rows per pair); longer records
+	// and names go to the first-generation kernel
+	if (wbytes * (CAT == CAT_U ? 24u : 12u) > sm_budget) return false;
 	if ((uint64_t)RW * (2ull * K + STR + 2ull) >= 65536u) return false;  // chunk numbers within a tile are 16-bit
 	if (16u * ((uint32_t)(RW + 1) * STR + 1u) >= 65536u) return false;   // image offsets are 16-bit
 	int warps = env_warps > 0 ? env_warps : (NS == 1 ? 1 : TL_MAX_WARPS);  // tiles per CTA: measured (QTIPSIM_WARPS overrides)

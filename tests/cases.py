@@ -127,6 +127,22 @@ def case_long_refid():
                 kw=dict(fraction=300.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(71)))
 
 
+def case_refid_lengths():
+    """Refids of 1 .. 47 characters (the simulate kernels print refids of up to 16 bytes from registers and longer
+    ones byte by byte; names decide how many edge chunks a record has), all categories, offsets of one to six digits."""
+    names = ["a", "chr7xyz", "chr8abcd", "contig_09", "NC_000001.11_xx", "NC_000001.11_xyz", "gi|568336023|gb|A",
+             "gi|568336023|gb|CM000663", "scaffold_0123456789_0123456789_01",
+             "very_long_contig_name_0123456789_0123456789_012"]
+    assert sorted(len(n) for n in names) == [1, 7, 8, 9, 15, 16, 17, 24, 33, 47]
+    fa = synth.make_fasta([(n + " some description", 9000 + 7000 * k) for k, n in enumerate(names)], seed=91, lead_n=30)
+    tu = synth.templates_unpaired(80, 100, 92, max_x=3)
+    tb = synth.templates_badend(60, 75, 93, opp_len=60)
+    tc = synth.templates_paired(80, 100, 94, frag_mean=320, frag_sd=30, max_x=3)
+    td = synth.templates_paired(40, 60, 95, discordant=True, max_fraglen=2500)
+    return dict(fasta=fa, tu=tu, tb=tb, tc=tc, td=td,
+                kw=dict(fraction=1500.0, function=3, min_u=1, min_c=1, min_d=1, min_b=1, cg=cli_seed(91)))
+
+
 def case_short_reads():
     """Bodies shorter than one 16-byte output chunk next to normal ones, all categories: the direct
     kernel declines the category (first / last chunk of a string could coincide) and the staged kernel
@@ -162,6 +178,7 @@ CASES = {
     "inversion": case_inversion,
     "long_refid": case_long_refid,
     "short_reads": case_short_reads,
+    "refid_lengths": case_refid_lengths,
     "long_reads": case_long_reads,
 }
 

@@ -464,7 +464,7 @@ def test_staged_kernel_path_still_bit_exact(name, workdir, monkeypatch):
     assert nat_s == nat_d  # both kernels consume the Philox stream identically
 
 
-@pytest.mark.parametrize("name", ["mixed_small", "c5_indel", "c4_mix_small", "edges", "long_refid", "c3_shape_small"])
+@pytest.mark.parametrize("name", ["mixed_small", "c5_indel", "c4_mix_small", "edges", "long_refid", "c3_shape_small", "refid_lengths"])
 def test_direct_kernel_path_still_bit_exact(name, workdir, monkeypatch):
     """The first-generation direct kernel (simulate_direct.cu: taken when a tile of 16 records does not fit the tile
     kernel's shared-memory budget) stays covered on the ordinary cases, and consumes the Philox stream like the tile
