@@ -1496,7 +1496,8 @@ static int run_impl(qtipsim *h, qtipsim_run_params *p, qtipsim_stats *stats, int
 		const bool want_tile = !force || strcmp(force, "tile") == 0;
 		const bool want_direct = !force || strcmp(force, "tile") == 0 || strcmp(force, "direct") == 0;
 		const bool want_staged = !force || strcmp(force, "tile") == 0 || strcmp(force, "direct") == 0 || strcmp(force, "staged") == 0;
-		if (cg.compiled_ok && want_tile) done = launch_simulate_tile(sa[c], max_rec - 2u * cg.max_body - 4u, cg.min_body, cg.max_body, h->st);
+		// (the tile kernel prints record offsets with a 32-bit decimal conversion: longer records take the first generation)
+		if (cg.compiled_ok && want_tile && max_reclen + p->chunksz <= 0xffffffffull) done = launch_simulate_tile(sa[c], max_rec - 2u * cg.max_body - 4u, cg.min_body, cg.max_body, h->st);
 		if (!done && cg.compiled_ok && want_direct) done = launch_simulate_direct(sa[c], max_rec - 2u * cg.max_body - 4u, cg.min_body, cg.max_body, h->st);
 		if (!done && cg.compiled_ok && want_staged) done = launch_simulate_warp(sa[c], max_rec, cg.max_body, h->st);
 		if (!done) launch_simulate(sa[c], h->st);

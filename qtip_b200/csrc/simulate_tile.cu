@@ -214,7 +214,7 @@ __device__ __forceinline__ void name_flush(NameW<NS> &w) {
 		}
 	}
 }
-// slow path (refids over 16 bytes, offsets over 32 bits): bytes one at a time
+// slow path (refids over 16 bytes): bytes one at a time
 template <int NS, class Get>
 __device__ __noinline__ void name_bytes(NameW<NS> &w, uint32_t n, Get get) {
 	name_flush<NS>(w);
@@ -261,20 +261,10 @@ __device__ __forceinline__ void name_origin(NameW<NS> &w, const char *__restrict
                                             uint32_t nd, const MateHot &m) {
 	if (rl <= 16u) name_append<NS, 4>(w, n16.x, n16.y, n16.z, n16.w, rl);
 	else name_bytes<NS>(w, rl, [&](uint32_t k) { return refid[k]; });
-	if (off <= 0xffffffffull) {
+	{  // (offsets fit 32 bits: the launcher sends genomes with longer records to the first-generation kernel)
 		uint32_t p0, p1, p2, p3;
 		name_dec_piece((uint32_t)off, nd, m.fw, p0, p1, p2, p3);
 		name_append<NS, 4>(w, p0, p1, p2, p3, 3u + nd);
-	} else {
-		name_append<NS, 1>(w, 0x3a003au | ((m.fw ? (uint32_t)'+' : (uint32_t)'-') << 8), 0u, 0u, 0u, 3u);
-		uint64_t pw = 1;
-		for (uint32_t k = 1; k < nd; k++) pw *= 10ull;
-		const uint64_t v = off;
-		name_bytes<NS>(w, nd, [&](uint32_t k) {
-			uint64_t d = pw;
-			for (uint32_t t = 0; t < k; t++) d /= 10ull;
-			return (char)('0' + (int)((v / d) % 10ull));
-		});
 	}
 	// ":<score>"
 	name_append<NS, 4>(w, 0x3au | (m.score[0] << 8), __funnelshift_l(m.score[0], m.score[1], 8u), __funnelshift_l(m.score[1], m.score[2], 8u),
