@@ -457,6 +457,39 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 		} else {
 			for (int region = 0; region < 3; region++) {  // U, B, then C and D (both counts are drawn before C's reads)
 				const int cat0 = region == 2 ? CAT_C : region;
+				if (region == 1 && wc.su[CAT_B].n == 0 && wc.su[CAT_C].n == 0 && wc.su[CAT_D].n == 0) {
+					// No targets for bad-end, concordant and discordant pairs (an unpaired-only model): the three counts are
+					// drawn one after the other from the end of the unpaired reads -- ignbin(0, p) takes one uniform, or more
+					// when it rounds to 1.0f -- and no reads follow: one jump per candidate instead of two, no empty advances
+					const uint32_t *prev = endr[CAT_U];
+					uint32_t *eB = endr[CAT_B], *eC = endr[CAT_C], *eDd = endr[CAT_D];
+					for (uint32_t i = tid; i < nb; i += R2_T) {
+						const uint32_t pos = prev[i];
+						uint32_t p1 = R2_INVALID, p2 = R2_INVALID;
+						if (pos != R2_INVALID) {
+							LState S = jump2(SA, pos, a.jt1, a.jt2, a2.jh1, a2.jh2);
+							uint32_t used = 0;
+							auto nx = [&]() {
+								S = lstep(S);
+								used++;
+								return lfloat(lout(S));
+							};
+							(void)binom_sample(wc.su[CAT_B], nx);
+							const uint32_t u1 = used;
+							(void)binom_sample(wc.su[CAT_C], nx);
+							(void)binom_sample(wc.su[CAT_D], nx);
+							if ((uint64_t)pos + used < (uint64_t)R2_POS_LIMIT) {
+								p1 = pos + u1;
+								p2 = pos + used;
+							}
+						}
+						eB[i] = p1;
+						eC[i] = p2;
+						eDd[i] = p2;
+					}
+					__syncthreads();
+					break;
+				}
 				uint32_t *cur = endr[cat0];
 				const uint32_t *prev = region == 0 ? nullptr : endr[cat0 - 1];
 				for (uint32_t i = tid; i < nb; i += R2_T) {
