@@ -88,7 +88,7 @@ struct qtipsim {
 	DevBuf d_jt1, d_jt2, d_jh1, d_jh2;
 	bool have_jt = false;
 	// band-speculative replay resolver (resolve2.cu)
-	DevBuf d_r2_aw, d_r2_cum, d_r2_anchor, d_r2_counter, d_r2_slot, d_r2_end, d_r2_cn, d_r2_wres, d_r2_cnt, d_r2_off, d_r2_misc;
+	DevBuf d_r2_aw, d_r2_cum, d_r2_anchor, d_r2_counter, d_r2_slot, d_r2_relay, d_r2_end, d_r2_cn, d_r2_wres, d_r2_cnt, d_r2_off, d_r2_misc;
 	uint32_t r2_stages_last = 0;  // stage launches of the last replay run (diagnostics)
 
 	DevBuf d_win, d_ncount, d_cum;
@@ -252,7 +252,7 @@ void qtipsim_destroy(qtipsim_t *h) {
 	if (h->st_d2h) cudaStreamSynchronize(h->st_d2h);
 	cudaStreamSynchronize(h->st);
 	if (h->ctl_ring) cudaFreeHost(h->ctl_ring);
-	DevBuf *all[] = {&h->d_inter, &h->d_xs_out, &h->d_label, &h->d_tabs, &h->d_jh1, &h->d_jh2, &h->d_r2_aw, &h->d_r2_cum, &h->d_r2_anchor, &h->d_r2_counter, &h->d_r2_slot, &h->d_r2_end, &h->d_r2_cn,
+	DevBuf *all[] = {&h->d_inter, &h->d_xs_out, &h->d_label, &h->d_tabs, &h->d_jh1, &h->d_jh2, &h->d_r2_aw, &h->d_r2_cum, &h->d_r2_anchor, &h->d_r2_counter, &h->d_r2_slot, &h->d_r2_relay, &h->d_r2_end, &h->d_r2_cn,
 	                 &h->d_r2_wres, &h->d_r2_cnt, &h->d_r2_off, &h->d_r2_misc, &h->d_setups, &h->d_pclass, &h->d_rsresult, &h->d_text, &h->d_pk_a, &h->d_pk_b, &h->d_pk_c, &h->d_pk_d, &h->d_pk_e, &h->d_bases, &h->d_nmask, &h->d_nblk, &h->d_recs, &h->d_names, &h->d_jt1, &h->d_jt2, &h->d_win,
 	                 &h->d_ncount, &h->d_cum, &h->d_len0, &h->d_len1, &h->d_scan_tmp, &h->d_scan_status, &h->d_small};
 	for (DevBuf *b : all) b->release();
@@ -1058,6 +1058,8 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 	CK(h->d_r2_anchor.ensure(((size_t)max_launch + 1) * sizeof(StageAnchor)));
 	CK(h->d_r2_counter.ensure((size_t)max_launch * 4));
 	CK(h->d_r2_slot.ensure((size_t)K * sizeof(uint2)));
+	CK(h->d_r2_relay.ensure(((size_t)K + 1) * 8));
+	CK(cudaMemsetAsync(h->d_r2_relay.p, 0, ((size_t)K + 1) * 8, h->st));
 	CK(h->d_r2_end.ensure((size_t)NCAT * K * a2.nbmax * 4));
 	CK(h->d_r2_cn.ensure((size_t)2 * K * a2.nbmax * 4));
 	CK(h->d_r2_wres.ensure((size_t)na * sizeof(WinResolved)));
@@ -1085,6 +1087,7 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 	a2.anchor = h->d_r2_anchor.as<StageAnchor>();
 	a2.counter = h->d_r2_counter.as<uint32_t>();
 	a2.slot = h->d_r2_slot.as<uint2>();
+	a2.relay = h->d_r2_relay.as<unsigned long long>();
 	a2.end = h->d_r2_end.as<uint32_t>();
 	a2.cn = h->d_r2_cn.as<uint32_t>();
 	a2.cnd = a2.cn + (size_t)K * a2.nbmax;

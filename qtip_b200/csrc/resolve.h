@@ -79,6 +79,7 @@ struct Resolve2Args {
 	StageAnchor *anchor;          // [launches + 1]
 	uint32_t *counter;            // [launches], zeroed
 	uint2 *slot;                  // [K] band of each CTA's window: {lo, nb}
+	unsigned long long *relay;    // [K + 1] (stage + 1) << 32 | exact start of window j of the stage (zeroed per run)
 	uint32_t *end;                // [NCAT][K][nbmax] candidate positions after each category
 	uint32_t *cn, *cnd;           // [K][nbmax] candidate counts
 	WinResolved *wres;            // [na]

@@ -405,6 +405,7 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 	const uint32_t ai = an.first + j;
 	const size_t nbmax = a2.nbmax;
 
+	uint32_t my_lo = 0, my_nb = 0;
 	if (ai < a2.na) {
 		// ---- this window's band of candidate starts, relative to the anchor ----
 		uint32_t lo = 0, nb = 1;
@@ -426,6 +427,8 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 			}
 		}
 		if (tid == 0) a2.slot[j] = make_uint2(lo, nb);
+		my_lo = lo;
+		my_nb = nb;
 		const uint32_t w = a2.aw[ai];
 		WinCtx wc = make_winctx(a, w, a2.tabs);
 		{
@@ -531,9 +534,30 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 		}
 	}
 
-	// ---- the last CTA to finish walks the chain through the stage's tables ----
+	// ---- the chain through the stage's tables, as a relay: window j + 1 starts where window j's table says, and CTA j
+	// looks that up itself as soon as its table is built and its own start has arrived from CTA j - 1 (which, with the
+	// narrower band, is usually done first): the chain is complete about one hop after the last table, instead of 148
+	// dependent L2 look-ups (0.33 us each) by one thread after everything else.  relay[j] = (stage + 1) << 32 | start of
+	// window j relative to the anchor, or R2_INVALID when the chain broke before it (band missed, table entry invalid).
+	// CTAs are dispatched in index order, so the CTA waited for is always resident or finished. ----
 	R2_STAMP(8);
 	__threadfence();
+	__syncthreads();
+	if (tid == 0 && ai < a2.na) {
+		const unsigned long long tag = (unsigned long long)(s + 1u) << 32;
+		uint32_t pos = 0;
+		if (j > 0) {
+			unsigned long long v;
+			do v = *(volatile unsigned long long *)&a2.relay[j];
+			while ((v >> 32) != (unsigned long long)(s + 1u));
+			pos = (uint32_t)v;
+		}
+		uint32_t e = R2_INVALID;
+		if (pos != R2_INVALID && pos >= my_lo && pos - my_lo < my_nb)
+			e = __ldcg(a2.end + ((size_t)CAT_D * K + j) * nbmax + (pos - my_lo));
+		*(volatile unsigned long long *)&a2.relay[j + 1] = tag | e;
+		__threadfence();
+	}
 	__syncthreads();
 	if (tid == 0) {
 		const uint32_t prev = atomicAdd(&a2.counter[s], 1u);
@@ -546,23 +570,14 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 	const uint32_t nstage = min(K, a2.na - an.first);
 	for (uint32_t jj = tid; jj < nstage; jj += R2_T) s_slot[jj] = __ldcg(&a2.slot[jj]);
 	__syncthreads();
-	// The walk: a chain of dependent look-ups, one per window (0.33 us each, measured; prefetching the neighbourhood of the
-	// rows ahead into shared memory or L1 did not shorten it, profiles/r02_k_resolve2_ncu_summary.md)
-	if (tid == 0) {
-		uint32_t pos = 0, nres = 0;
-		const uint32_t *eD = a2.end + (size_t)CAT_D * K * nbmax;
-		for (uint32_t jj = 0; jj < nstage; jj++) {
-			const uint2 sl = s_slot[jj];
-			if (pos < sl.x || pos - sl.x >= sl.y) break;  // the true start missed the band
-			const uint32_t e = __ldcg(eD + (size_t)jj * nbmax + (pos - sl.x));
-			if (e == R2_INVALID) break;
-			s_start[jj] = pos;
-			pos = e;
-			nres++;
-		}
-		s_b[1] = nres;
-		s_b[2] = pos;
-	}
+	// The last CTA to finish collects the relay: window jj resolved iff the chain reached window jj + 1
+	for (uint32_t jj = tid; jj < nstage; jj += R2_T) s_start[jj] = jj ? (uint32_t)__ldcg(&a2.relay[jj]) : 0u;
+	if (tid == 0) s_b[1] = nstage;
+	__syncthreads();
+	for (uint32_t jj = tid; jj < nstage; jj += R2_T)
+		if ((uint32_t)__ldcg(&a2.relay[jj + 1]) == R2_INVALID) atomicMin(&s_b[1], jj);
+	__syncthreads();
+	if (tid == 0) s_b[2] = s_b[1] ? (uint32_t)__ldcg(&a2.relay[s_b[1]]) : 0u;
 	__syncthreads();
 	R2_STAMP(10);
 	const uint32_t nres = s_b[1];
