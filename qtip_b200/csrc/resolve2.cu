@@ -495,13 +495,37 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 				}
 				uint32_t *cur = endr[cat0];
 				const uint32_t *prev = region == 0 ? nullptr : endr[cat0 - 1];
+				// Region 0: the candidates are CONSECUTIVE stream positions, and the uniform a draw at stream position q
+				// yields depends on q alone: the band's uniforms are tabulated once (one jump per thread, then a constant
+				// multiplier per 1024 positions) in the space the dense tables use later, and every candidate's sampler
+				// reads them instead of jumping to its own position and stepping the generator
+				float *F = (float *)r2_smem;
+				const uint32_t nF = nb + 96u;
+				const bool tab_u = region == 0 && nb > 1 && (size_t)nF * 4 <= (size_t)a2.rcap * 6;
+				if (tab_u) {
+					LState Sq = jump2(SA, lo + 1u + tid, a.jt1, a.jt2, a2.jh1, a2.jh2);
+					const uint32_t c1 = __ldg(&a.jt1[R2_T]), c2 = __ldg(&a.jt2[R2_T]);
+					for (uint32_t k = tid; k < nF; k += R2_T) {
+						F[k] = lfloat(lout(Sq));  // the uniform of the draw that takes the stream from lo + k to lo + k + 1
+						Sq.s1 = mulmod1(Sq.s1, c1);
+						Sq.s2 = mulmod2(Sq.s2, c2);
+					}
+					__syncthreads();
+				}
 				for (uint32_t i = tid; i < nb; i += R2_T) {
 					uint32_t pos = prev ? prev[i] : lo + i;
 					uint32_t n = 0, nd = 0;
 					if (pos != R2_INVALID) {
-						LState S = jump2(SA, pos, a.jt1, a.jt2, a2.jh1, a2.jh2);
+						LState S{0u, 0u};
+						if (!tab_u) S = jump2(SA, pos, a.jt1, a.jt2, a2.jh1, a2.jh2);
 						uint32_t used = 0;
 						auto nx = [&]() {
+							if (tab_u) {
+								const uint32_t k = i + used;
+								used++;
+								if (k < nF) return F[k];
+								return lfloat(lout(jump2(SA, pos + used, a.jt1, a.jt2, a2.jh1, a2.jh2)));  // (a sampler that ran past the table)
+							}
 							S = lstep(S);
 							used++;
 							return lfloat(lout(S));
