@@ -1018,7 +1018,10 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 	a2.nbmax = std::max<uint32_t>(64u, envu("QTIPSIM_R2_NBMAX", 24576u));
 	{
 		const char *e = getenv("QTIPSIM_R2_SIGMA");
-		a2.band_sigma = e && *e ? (float)atof(e) : 4.0f;
+		// 3 sigma: a stage's work grows with the band width, and a miss only ends the stage early (the window restarts the
+		// next one exactly): measured at C3, 4 sigma 34.6 ms / 162 stages, 3 sigma 30.3 ms / 162-170, 2.5 sigma 30.0 ms / 176-182,
+		// 2 sigma 34.0 ms / 215-234 (profiles/r02_k_resolve2_ncu_summary.md)
+		a2.band_sigma = e && *e ? (float)atof(e) : 3.0f;
 	}
 	uint32_t K = std::min<uint32_t>(R2_KMAX, std::max<uint32_t>(1u, envu("QTIPSIM_R2_K", (uint32_t)nsm)));
 	// How many windows ahead can be speculated before the band (which widens with the square root of the distance)
