@@ -1,5 +1,7 @@
-// simulate_direct.cu -- the production simulate+emit kernel (sm_100a): warp-autonomous tiles,
-// interior chunks straight from registers to HBM.
+// simulate_direct.cu -- the FIRST GENERATION of the simulate+emit kernel (sm_100a): warp-autonomous tiles,
+// interior chunks straight from registers to HBM.  simulate_tile.cu (one edge image per record, names appended as
+// 16-byte pieces, flat shipping loop) replaced it as the default; this one takes the categories whose tiles do not fit
+// the tile kernel's budget (long names or reads, records over 4 Gbp) and stays selectable with QTIPSIM_KERNEL=direct.
 //
 // Replaces SimulatedRead::init/mutate/init_random (simplesim.h:68-117, simplesim.cpp:31-71)
 // and SimulatedRead::write/write_pair (simplesim.cpp:102-171).  The reference produces a read

@@ -10,8 +10,7 @@
 //   * one edge IMAGE per record instead of an image plus four areas: the chunk lanes of steps Bq / Bs store a
 //     string's first and last 16-byte chunk WHOLE into the image entry of that chunk; the read name and the
 //     separators are written over them afterwards (step N), so nothing is merged under a byte mask at lane = read.
-//     The one chunk two strings can share (sequence tail, "\n+\n", quality head) keeps two entries and is merged by
-//     the lane that ships it
+//     The one chunk two strings can share (sequence tail, "\n+\n", quality head) keeps two entries, merged in step N
 //   * names are assembled from 16-byte PIECES held in registers ("\n@qtip!:", refid, ":<strand>:<offset>",
 //     ":<score>", ":<typ>\n") and appended with aligned 32-bit stores through a running accumulator -- about ten
 //     word stores per name instead of one byte store per character
@@ -24,8 +23,10 @@
 //   step Bs  lane = sequence chunk; general-path reads (N, past the record end, indel segments) in a second loop
 //   step C   lane = read (two lanes per read or pair in the native mode): the read's draws patched over image or
 //            HBM bytes (REPLAY: the reference's L'Ecuyer stream stepped from the plan's state; PHILOX: by index)
-//   step Br  bad-end pairs only, lane = chunk of the random mate: init_random's draws, 16 per lane
-//   step N   lane = read: '\n' of the previous record + name, separators
+//   step A2r bad-end pairs, native mode: the random mate's 2-bit codes (Philox blocks of 64 bases) into its row, to be
+//            printed by step Bs like a genome span
+//   step Br  bad-end pairs, REPLAY: lane = chunk of the random mate: init_random's draws, 16 per lane
+//   step N   one lane per record and file: '\n' of the previous record + name, separators, the shared chunk's merge
 //   step D   lane = image entry: images -> HBM, 16 bytes per lane; the tile's first and last chunk, shared with
 //            the neighbouring tiles, one byte per lane
 //
