@@ -1059,7 +1059,7 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 	CK(h->d_r2_aw.ensure((size_t)na * 4));
 	CK(h->d_r2_cum.ensure(cum.size() * 8));
 	CK(h->d_r2_anchor.ensure(((size_t)max_launch + 1) * sizeof(StageAnchor)));
-	CK(h->d_r2_counter.ensure((size_t)max_launch * 4));
+	CK(h->d_r2_counter.ensure((size_t)2 * max_launch * 4));
 	CK(h->d_r2_slot.ensure((size_t)K * sizeof(uint2)));
 	CK(h->d_r2_relay.ensure(((size_t)K + 1) * 8));
 	CK(cudaMemsetAsync(h->d_r2_relay.p, 0, ((size_t)K + 1) * 8, h->st));
@@ -1072,7 +1072,7 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 	CK(h->d_scan_tmp.ensure(((size_t)na / 1024 + 4) * 8));
 	CK(ctl_h2d(h, h->d_r2_aw.p, aw.data(), (size_t)na * 4));
 	CK(ctl_h2d(h, h->d_r2_cum.p, cum.data(), cum.size() * 8));
-	CK(cudaMemsetAsync(h->d_r2_counter.p, 0, (size_t)max_launch * 4, h->st));
+	CK(cudaMemsetAsync(h->d_r2_counter.p, 0, (size_t)2 * max_launch * 4, h->st));
 	CK(cudaMemsetAsync(h->d_r2_misc.p, 0, 64, h->st));
 	StageAnchor a0;
 	memset(&a0, 0, sizeof(a0));
@@ -1089,6 +1089,7 @@ static int resolve_replay_band(qtipsim *h, qtipsim_run_params *p, const PlanPara
 	a2.cumV = h->d_r2_cum.as<double>() + na + 1;
 	a2.anchor = h->d_r2_anchor.as<StageAnchor>();
 	a2.counter = h->d_r2_counter.as<uint32_t>();
+	a2.ticket = a2.counter + max_launch;
 	a2.slot = h->d_r2_slot.as<uint2>();
 	a2.relay = h->d_r2_relay.as<unsigned long long>();
 	a2.end = h->d_r2_end.as<uint32_t>();

@@ -77,7 +77,8 @@ struct Resolve2Args {
 	uint32_t rcap, rcap_emit;     // dense-table positions (stage / emit kernels)
 	uint32_t nbmax;               // most candidates per window
 	StageAnchor *anchor;          // [launches + 1]
-	uint32_t *counter;            // [launches], zeroed
+	uint32_t *counter;            // [launches], zeroed: CTAs of the launch that are done
+	uint32_t *ticket;             // [launches], zeroed: window slots of the launch handed out
 	uint2 *slot;                  // [K] band of each CTA's window: {lo, nb}
 	unsigned long long *relay;    // [K + 1] (stage + 1) << 32 | exact start of window j of the stage (zeroed per run)
 	uint32_t *end;                // [NCAT][K][nbmax] candidate positions after each category

@@ -401,7 +401,11 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 	R2_STAMP(0);
 	const LState SA{an.s1, an.s2};
 	const uint32_t K = gridDim.x;
-	const uint32_t j = blockIdx.x;
+	// which window of the stage this CTA takes: a ticket, not blockIdx -- the relay below waits for the CTA of window
+	// j - 1, which therefore has to have STARTED whenever this one has (tickets are handed out in starting order)
+	if (tid == 0) s_b[3] = atomicAdd(&a2.ticket[s], 1u);
+	__syncthreads();
+	const uint32_t j = s_b[3];
 	const uint32_t ai = an.first + j;
 	const size_t nbmax = a2.nbmax;
 
@@ -563,7 +567,7 @@ __global__ void __launch_bounds__(R2_T, 1) k_resolve2_stage(Resolve2Args a2, uin
 	// narrower band, is usually done first): the chain is complete about one hop after the last table, instead of 148
 	// dependent L2 look-ups (0.33 us each) by one thread after everything else.  relay[j] = (stage + 1) << 32 | start of
 	// window j relative to the anchor, or R2_INVALID when the chain broke before it (band missed, table entry invalid).
-	// CTAs are dispatched in index order, so the CTA waited for is always resident or finished. ----
+	// Window slots are taken by ticket, so the CTA waited for has always started. ----
 	R2_STAMP(8);
 	__threadfence();
 	__syncthreads();
