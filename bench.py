@@ -577,7 +577,12 @@ def main():
             return out
 
         tr_native = traffic_of("r02_k_simulate_tile_traffic.json")
-        b = block(m, wl, args.mode, tr_native if (args.workload in ("auto", "c3") and args.mode == "native") else None)
+        # config 4: the step's three launches (bad-end, concordant, discordant) together, like its `achieved`
+        tr_c4 = traffic_of("r02_k_simulate_tile_pairs_traffic.json") if (args.mode == "native" and args.cats == "bcd") else None
+        if args.workload in ("auto", "c3"):
+            b = block(m, wl, args.mode, tr_native if args.mode == "native" else None)
+        else:
+            b = block(m, wl, args.mode, tr_c4)
         line = {
             "metric": METRIC, "value": m["value"], "unit": wl["unit"], "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -602,7 +607,7 @@ def main():
         if m2 is not None:
             line[other] = block(m2, wl, other)
         if m4 is not None:
-            line["c4"] = block(m4, wl4, args.mode)
+            line["c4"] = block(m4, wl4, args.mode, tr_c4)
             if m4r is not None:
                 line["c4"][other] = block(m4r, wl4, other)
         if n_gpus == 1 and not args.no_cpu_baseline:
