@@ -302,12 +302,17 @@ def test_swar_pack_unit_arithmetic_matches_bytewise_pack():
         assert np.array_equal(bases, wb) and np.array_equal(nmask, wn), it
 
 
-@pytest.mark.parametrize("name", ["edges", "mixed_small"] + [f"rand{s}" for s in cases.RANDOM_SEEDS[:10]])
+@pytest.mark.parametrize("name", ["edges", "mixed_small"] + [f"rand{s}" for s in cases.RANDOM_SEEDS[:10]] +
+                         [f"fuzz{s}" for s in range(24)] + [f"fuzzeof{s}" for s in range(6)])
 def test_swar_pack_whole_fasta_matches_host_packer(name):
     """K0's unit arithmetic over whole FASTA files (4 KiB units cut anywhere in a line, CRLF, IUPAC, blank lines,
     headerless leading bases): every record's sequence lines packed unit by unit with the kernel's arithmetic on
     the host equal the host packer's record (which is pinned against the oracle above)."""
-    case = cases.random_case(int(name[4:])) if name.startswith("rand") else cases.CASES[name]()
+    if name.startswith("fuzz"):  # malformed-but-legal text (test_fasta_fuzz.py), incl. files that end inside a header line
+        import test_fasta_fuzz
+        case = test_fasta_fuzz.fuzz_case(int(name.lstrip("fuzeo")), eof_in_header=name.startswith("fuzzeof"))
+    else:
+        case = cases.random_case(int(name[4:])) if name.startswith("rand") else cases.CASES[name]()
     hs = util.HostSide(case)
     L = hs.L
     L.qthost_swar_pack_unit.restype = C.c_uint64
