@@ -242,6 +242,46 @@ int qtipsim_edit_xscripts(qtipsim_t *h, const char *cigars, uint64_t cigars_byte
                           uint64_t cap, uint64_t *x_off, int32_t *left_clip, int32_t *right_clip, uint64_t *lpos,
                           uint64_t *rpos, int32_t *status);
 
+/* The input model's reservoirs, fed with plain arrays: the second half of the template construction.  The
+ * reference's SAM pass offers every aligned record to one of four reservoirs -- unpaired and bad-end at
+ * qtip_parse.cpp:849-861, concordant and discordant at :1148-1166, ReservoirSampledEList::add_part1 ds.h:437-446 --
+ * and builds the four input models from what they kept (:1826-1829).  These three calls do the same for records
+ * handed over in batches, so the caller no longer builds TemplateUnpaired / TemplatePaired records one by one:
+ * begin(k): four empty reservoirs of capacity k[QTIPSIM_CAT_*] (input-model-size);
+ * add(batch, &cg1, &cg2): offers the batch's records in the order given (SAM order) and keeps what the reference
+ *   keeps -- including its habit of overwriting the LAST kept template, not a random one, once a reservoir is full (the
+ *   call sites write through list().back()) -- consuming one r4_uni_01 draw per record offered to a full reservoir from
+ *   the generator state cg1 / cg2 (get_state, rnglib.cpp:516), which is written back advanced (set_seed, :1674);
+ * commit(kept, added): the kept templates become the handle's four input models, as after qtipsim_set_templates_*
+ *   with added = records offered; kept / added (may be NULL) report list().size() / size() per category.
+ * A batch has two levels.  Alignment level, one entry per aligned SAM record, indexed by a1 / a2: best_score, len
+ * (Alignment::best_score, ::len), fw (1 = forward strand), QUAL strings and edit transcripts as NUL-terminated strings in
+ * one buffer each with their offsets -- xscripts / x_off exactly as qtipsim_edit_xscripts wrote them.  Record level, n
+ * entries: the category, the record's alignment(s), and mate_flag ('0' / '1' / '2') + opp_len for QTIPSIM_CAT_U / _B or
+ * upstream1 + fraglen for QTIPSIM_CAT_C / _D (the arrays of the other kind may be NULL if no such record is in the
+ * batch).  score_12 of a pair is best_score[a1] + best_score[a2] (:1151).  Host pointers, read during the call only. */
+typedef struct {
+	const int32_t *best_score;
+	const int32_t *len;
+	const uint8_t *fw;
+	const char *quals;
+	const uint64_t *q_off;
+	const char *xscripts;
+	const uint64_t *x_off;
+	uint64_t n;
+	const uint8_t *cat;
+	const uint64_t *a1;
+	const uint64_t *a2;
+	const uint8_t *mate_flag;
+	const int32_t *opp_len;
+	const uint8_t *upstream1;
+	const uint64_t *fraglen;
+} qtipsim_model_batch;
+
+int qtipsim_model_begin(qtipsim_t *h, const uint64_t k[4]);
+int qtipsim_model_add(qtipsim_t *h, const qtipsim_model_batch *batch, int32_t *cg1, int32_t *cg2);
+int qtipsim_model_commit(qtipsim_t *h, uint64_t kept[4], uint64_t added[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@
 //   ref_initialize/ref_set_seed/ref_get_state/ref_i4_uni/ref_r4_uni_01
 //        -> rnglib.cpp:941, :1674, :516, :573, :1444
 //   ref_ignbin            -> ranlib.cpp:1094
+//   ref_reservoir_offsets -> ReservoirSampledEList::add_part1, ds.h:437-446
 //   ref_simulate          -> StreamingSimulator ctor + simulate_batch
 //                            (simplesim.h:214-257, simplesim.cpp:195-407), fed by
 //                            InputModel{Unpaired,Paired} (input_model.h:26,100) built
@@ -58,6 +59,14 @@ void ref_set_seed(int a, int b) { set_seed(a, b); }
 void ref_get_state(int *a, int *b) { int x, y; get_state(x, y); *a = x; *b = y; }
 int ref_i4_uni() { return i4_uni(); }
 float ref_r4_uni_01() { return r4_uni_01(); }
+
+// ReservoirSampledEList<T>::add_part1 (ds.h:437-446) called n times on a reservoir of capacity k: the slot every call
+// returns (the call sites compare it with k(), qtip_parse.cpp:849-850, :1148-1149).  Consumes the global generator.
+uint64_t ref_reservoir_offsets(uint64_t k, uint64_t n, uint64_t *off) {
+	ReservoirSampledEList<int> r((size_t)k);
+	for (uint64_t i = 0; i < n; i++) off[i] = (uint64_t)r.add_part1();
+	return (uint64_t)r.list().size();
+}
 int ref_ignbin(int n, float p) { return ignbin(n, p); }
 
 // Runs the reference simulator.  paths[7] = u, b_1, b_2, c_1, c_2, d_1, d_2.

@@ -28,6 +28,9 @@ SYMBOLS = (
     "qtipsim_genome_save",
     "qtipsim_load_fasta_cached",
     "qtipsim_edit_xscripts",
+    "qtipsim_model_begin",
+    "qtipsim_model_add",
+    "qtipsim_model_commit",
     "qtipsim_abi_version",
     "qtipsim_create",
     "qtipsim_destroy",
@@ -84,6 +87,27 @@ class Stats(C.Structure):
     ]
 
 
+class ModelBatch(C.Structure):
+    """qtipsim_model_batch (include/qtipsim.h): alignment-level arrays indexed by a1 / a2, then n records."""
+    _fields_ = [
+        ("best_score", C.POINTER(C.c_int32)),
+        ("len", C.POINTER(C.c_int32)),
+        ("fw", C.POINTER(C.c_uint8)),
+        ("quals", C.c_char_p),
+        ("q_off", C.POINTER(C.c_uint64)),
+        ("xscripts", C.c_char_p),
+        ("x_off", C.POINTER(C.c_uint64)),
+        ("n", C.c_uint64),
+        ("cat", C.POINTER(C.c_uint8)),
+        ("a1", C.POINTER(C.c_uint64)),
+        ("a2", C.POINTER(C.c_uint64)),
+        ("mate_flag", C.POINTER(C.c_uint8)),
+        ("opp_len", C.POINTER(C.c_int32)),
+        ("upstream1", C.POINTER(C.c_uint8)),
+        ("fraglen", C.POINTER(C.c_uint64)),
+    ]
+
+
 _lib = None
 
 
@@ -134,6 +158,9 @@ def load() -> C.CDLL:
     P32 = C.POINTER(C.c_int32)
     lib.qtipsim_edit_xscripts.argtypes = [H, C.c_char_p, C.c_uint64, P64, C.c_char_p, C.c_uint64, P64, P64, C.c_uint64, C.c_void_p, C.c_uint64,
                                           P64, P32, P32, P64, P64, P32]
+    lib.qtipsim_model_begin.argtypes = [H, P64]
+    lib.qtipsim_model_add.argtypes = [H, C.POINTER(ModelBatch), P32, P32]
+    lib.qtipsim_model_commit.argtypes = [H, P64, P64]
     lib.qtipsim_stream_run.argtypes = [H, C.POINTER(RunParams), C.POINTER(Stats), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     _lib = lib
     return lib

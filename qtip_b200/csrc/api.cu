@@ -27,6 +27,7 @@
 #include "planner.h"
 #include "resolve.h"
 #include "templates.h"
+#include "model.h"
 
 using namespace qt;
 
@@ -81,6 +82,7 @@ struct qtipsim {
 	float ms_pack_pending = 0;
 
 	TemplateStore ts;
+	ModelBuilder model;  // the reservoirs of qtipsim_model_begin / _add / _commit
 	bool tmpl_dirty[NCAT] = {true, true, true, true};
 	DevBuf d_t[NCAT], d_qual[NCAT], d_xs[NCAT], d_qual_out[NCAT], d_ops[NCAT], d_segs[NCAT], d_xsteps[NCAT], d_prog[NCAT], d_xprog[NCAT];
 	DevBuf d_setups, d_pclass, d_rsresult;
@@ -817,6 +819,38 @@ int qtipsim_set_templates_paired(qtipsim_t *h, int cat, const qtipsim_tmpl_pair 
 }
 
 uint64_t qtipsim_olap(const qtipsim_t *h) { return h ? h->ts.olap() : 0; }
+
+// ---- the input model's reservoirs fed with plain arrays (model.h; qtip_parse.cpp:849-861, 1148-1166, ds.h:437-446) ----
+
+int qtipsim_model_begin(qtipsim_t *h, const uint64_t k[4]) {
+	if (!h || !k) return QTIPSIM_EINVAL;
+	h->model.begin(k);
+	return QTIPSIM_OK;
+}
+
+int qtipsim_model_add(qtipsim_t *h, const qtipsim_model_batch *batch, int32_t *cg1, int32_t *cg2) {
+	if (!h || !batch || !cg1 || !cg2) return QTIPSIM_EINVAL;
+	if (*cg1 < 1 || (uint32_t)*cg1 >= LM1 || *cg2 < 1 || (uint32_t)*cg2 >= LM2)
+		return h->fail(QTIPSIM_ERANGE, "rnglib state out of range (set_seed, rnglib.cpp:1714-1728)");
+	LState rng{(uint32_t)*cg1, (uint32_t)*cg2};
+	const int rc = h->model.add(*batch, rng, h->err);
+	if (rc) return rc;
+	*cg1 = (int32_t)rng.s1;
+	*cg2 = (int32_t)rng.s2;
+	return QTIPSIM_OK;
+}
+
+int qtipsim_model_commit(qtipsim_t *h, uint64_t kept[4], uint64_t added[4]) {
+	if (!h) return QTIPSIM_EINVAL;
+	for (int c = 0; c < NCAT; c++) {
+		if (kept) kept[c] = h->model.kept[c].size();
+		if (added) added[c] = h->model.n[c];
+	}
+	const int rc = h->model.commit(h->ts, h->err);
+	if (rc) return rc;
+	for (int c = 0; c < NCAT; c++) h->tmpl_dirty[c] = true;
+	return QTIPSIM_OK;
+}
 
 static int upload_templates(qtipsim *h) {
 	for (int c = 0; c < NCAT; c++) {

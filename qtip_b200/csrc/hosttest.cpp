@@ -14,6 +14,7 @@
 #include "planner.h"
 #include "xscript.h"
 #include "templates.h"
+#include "model.h"
 
 using namespace qt;
 
@@ -23,7 +24,9 @@ struct HostTest {
 	std::vector<Window> win;
 	std::vector<uint32_t> ncount;
 	Plan plan;
+	ModelBuilder model;
 	std::string err;
+	std::string scratch;
 };
 
 extern "C" {
@@ -57,6 +60,33 @@ int qthost_set_paired(HostTest *h, int cat, const qtipsim_tmpl_pair *v, size_t k
 	return h->ts.set_paired(cat, v, kept, added, h->err);
 }
 uint64_t qthost_olap(HostTest *h) { return h->ts.olap(); }
+
+// the input model's reservoirs (model.h): the same three steps as qtipsim_model_begin / _add / _commit
+int qthost_model_begin(HostTest *h, const uint64_t *k) {
+	h->model.begin(k);
+	return 0;
+}
+int qthost_model_add(HostTest *h, const qtipsim_model_batch *b, int32_t *cg1, int32_t *cg2) {
+	LState rng{(uint32_t)*cg1, (uint32_t)*cg2};
+	const int rc = h->model.add(*b, rng, h->err);
+	*cg1 = (int32_t)rng.s1;
+	*cg2 = (int32_t)rng.s2;
+	return rc;
+}
+uint64_t qthost_model_kept(HostTest *h, int cat) { return h->model.kept[cat].size(); }
+uint64_t qthost_model_offered(HostTest *h, int cat) { return h->model.n[cat]; }
+// kept record i of a category as one line of text (for comparison with the test's restatement)
+const char *qthost_model_record(HostTest *h, int cat, uint64_t i) {
+	const ModelBuilder::Rec &r = h->model.kept[cat][i];
+	std::string &o = h->scratch;
+	o.clear();
+	for (int m = 0; m < 2; m++) {
+		o += std::to_string(r.m[m].score) + "," + std::to_string(r.m[m].len) + "," + r.m[m].fw + "," + r.m[m].qual + "," + r.m[m].xs + "|";
+	}
+	o += std::string(1, r.mate_flag) + "," + std::to_string(r.opp_len) + "," + std::to_string(r.upstream1) + "," + std::to_string(r.fraglen);
+	return o.c_str();
+}
+int qthost_model_commit(HostTest *h) { return h->model.commit(h->ts, h->err); }
 int qthost_cat_valid(HostTest *h, int cat) { return h->ts.cat[cat].valid ? 1 : 0; }
 
 uint64_t qthost_windows(HostTest *h, uint64_t chunksz, uint64_t olap) {

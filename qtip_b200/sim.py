@@ -121,6 +121,22 @@ class Engine:
             a = np.ascontiguousarray(data, dtype=np.uint8)
             self.check(self.lib.qtipsim_load_fasta_bytes(self.h, C.c_void_p(a.ctypes.data), a.size))
 
+    def model_begin(self, k: Sequence[int]) -> None:
+        """Four empty reservoirs of capacity k[cat] (input-model-size); qtipsim_model_begin."""
+        self.check(self.lib.qtipsim_model_begin(self.h, (C.c_uint64 * 4)(*[int(x) for x in k])))
+
+    def model_add(self, batch: "_abi.ModelBatch", cg) -> tuple:
+        """Offers the batch's records (SAM order) to the reservoirs; cg = rnglib state in, returns the state out."""
+        cg1, cg2 = C.c_int32(int(cg[0])), C.c_int32(int(cg[1]))
+        self.check(self.lib.qtipsim_model_add(self.h, C.byref(batch), C.byref(cg1), C.byref(cg2)))
+        return cg1.value, cg2.value
+
+    def model_commit(self) -> tuple:
+        """The kept templates become the four input models; returns (kept[4], added[4])."""
+        kept, added = (C.c_uint64 * 4)(), (C.c_uint64 * 4)()
+        self.check(self.lib.qtipsim_model_commit(self.h, kept, added))
+        return list(kept), list(added)
+
     def stream_begin(self, data) -> None:
         """Streaming end-to-end path, step 1: starts the chunked upload of the FASTA text (a numpy uint8 array, pinned
         for asynchronous copies; it must stay alive until stream_run returns) and returns at once."""
