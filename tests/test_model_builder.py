@@ -243,3 +243,49 @@ def test_model_through_the_abi_gives_the_same_reads(workdir):
     o = po.oracle_simulate(util.write_fasta(case, workdir, "modelabi"), tu=case["tu"], tb=case["tb"], tc=case["tc"], td=case["td"],
                            **cases.sim_kwargs(case))
     assert o.rc == 0 and want == o.streams
+
+
+def test_sam_fields_to_input_model_pipeline():
+    """Both halves of the template construction chained on the host: CIGAR / MD:Z -> edit transcripts (xscript.h, what
+    k_xs_lengths / k_xs_fill run per alignment) written into one arena the way qtipsim_edit_xscripts lays it out
+    (NUL-terminated, x_off[i], x_off[n] = bytes used), that arena handed to the reservoirs as it is, commit: the model is
+    valid, holds the transcripts the SAM fields were made from, and its olap is the longest kept reference span."""
+    from test_oracle_pin import xscript_cases
+    L = hooks()
+    rnd = random.Random(3)
+    sam = xscript_cases(seed=21, n=600)
+    arena, x_off, score, ln, fw, quals, q_off = b"", [], [], [], [], b"", []
+    for cigar, mdz, pos, xs in sam:
+        out = C.create_string_buffer(1 << 12)
+        lc, rc_, lp, rp = C.c_int(), C.c_int(), C.c_uint64(), C.c_uint64()
+        assert L.qthost_edit_xscript(cigar, mdz, pos, out, 1 << 12, C.byref(lc), C.byref(rc_), C.byref(lp), C.byref(rp)) == 0
+        x_off.append(len(arena))
+        arena += out.value + b"\0"
+        rl = sum(out.value.count(c) for c in (b"=", b"X", b"I", b"S"))
+        score.append(-rnd.randint(0, 60)), ln.append(rl), fw.append(rnd.randint(0, 1))
+        q_off.append(len(quals))
+        quals += bytes(rnd.randint(45, 73) for _ in range(rl)) + b"\0"  # (no ',' : the record text below is split on it)
+    x_off.append(len(arena))
+    n = len(sam)
+    arrs = dict(best_score=np.array(score, np.int32), len=np.array(ln, np.int32), fw=np.array(fw, np.uint8),
+                q_off=np.array(q_off, np.uint64), x_off=np.array(x_off, np.uint64), cat=np.zeros(n, np.uint8),
+                a1=np.arange(n, dtype=np.uint64), mate_flag=np.full(n, ord("0"), np.uint8), opp_len=np.zeros(n, np.int32))
+    b = _abi.ModelBatch()
+    for k_, v in arrs.items():
+        setattr(b, k_, v.ctypes.data_as(dict(_abi.ModelBatch._fields_)[k_]))
+    b.quals, b.xscripts, b.n = quals, arena, n
+    h = C.c_void_p(L.qthost_create())
+    L.qthost_model_begin(h, (C.c_uint64 * 4)(100, 0, 0, 0))
+    cg1, cg2 = C.c_int32(11), C.c_int32(22)
+    assert L.qthost_model_add(h, C.byref(b), C.byref(cg1), C.byref(cg2)) == 0
+    assert (cg1.value, cg2.value) != (11, 22)  # 500 records were offered to the full reservoir
+    kept = [L.qthost_model_record(h, 0, i).decode().split("|")[0].split(",") for i in range(L.qthost_model_kept(h, 0))]
+    assert len(kept) == 100 and L.qthost_model_offered(h, 0) == n
+    made_from = {xs.decode() for _, _, _, xs in sam}
+    assert all(k_[4] in made_from for k_ in kept)
+    assert [k_[4] for k_ in kept[:99]] == [sam[i][3].decode() for i in range(99)]  # (only the last slot is ever replaced)
+    assert L.qthost_model_commit(h) == 0
+    assert L.qthost_cat_valid(h, 0) == 1
+    L.qthost_olap.restype = C.c_uint64
+    assert L.qthost_olap(h) == max(sum(k_[4].count(c) for c in "=XDS") for k_ in kept)
+    L.qthost_destroy(h)
