@@ -236,6 +236,9 @@ int qtipsim_label_correctness(qtipsim_t *h, const char *qnames, uint64_t qnames_
  * caller derives a pair's fraglen = min(max-allowed-fraglen, dn.rpos - up.lpos + 1) and upstream1 (:154-158, :955-957);
  * status[i] = 0, or why the reference would have asserted / thrown on the record (1 bad CIGAR, 2 unsupported op,
  * 3 neither extended CIGAR nor MD:Z, 4 MD:Z does not fit the CIGAR): such records get an empty transcript.
+ * Undefined in the reference and answered here: a transcript with at most one op after its leading soft clip (a one-column
+ * alignment, an all-S or an empty transcript) -- rpos() :173-186 steps over the leading S run and the op after it before
+ * its assert, so it aborts or reads past the terminator; such a record gets status 0 and rpos = pos + span - 1.
  * Returns QTIPSIM_ERANGE if cap is too small (x_off[n] then holds the bytes needed).  Host pointers throughout. */
 int qtipsim_edit_xscripts(qtipsim_t *h, const char *cigars, uint64_t cigars_bytes, const uint64_t *c_off, const char *mdzs,
                           uint64_t mdzs_bytes, const uint64_t *m_off, const uint64_t *pos, uint64_t n, char *xscripts,
