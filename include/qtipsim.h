@@ -271,6 +271,7 @@ typedef struct {
 	const uint64_t *q_off;
 	const char *xscripts;
 	const uint64_t *x_off;
+	uint64_t n_aln; /* entries in the alignment-level arrays: a1[i], a2[i] < n_aln */
 	uint64_t n;
 	const uint8_t *cat;
 	const uint64_t *a1;

@@ -97,6 +97,7 @@ class ModelBatch(C.Structure):
         ("q_off", C.POINTER(C.c_uint64)),
         ("xscripts", C.c_char_p),
         ("x_off", C.POINTER(C.c_uint64)),
+        ("n_aln", C.c_uint64),
         ("n", C.c_uint64),
         ("cat", C.POINTER(C.c_uint8)),
         ("a1", C.POINTER(C.c_uint64)),

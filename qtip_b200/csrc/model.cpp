@@ -42,6 +42,10 @@ int ModelBuilder::add(const qtipsim_model_batch &b, LState &rng, std::string &er
 			err = "qtipsim_model_add: missing array for this category";
 			return QTIPSIM_EINVAL;
 		}
+		if (b.a1[i] >= b.n_aln || (pair && b.a2[i] >= b.n_aln)) {
+			err = "qtipsim_model_add: alignment index out of range";
+			return QTIPSIM_EINVAL;
+		}
 		// add_part1, ds.h:437-446
 		n[c]++;
 		bool take;

@@ -73,7 +73,7 @@ def batch_of(recs):
     b = _abi.ModelBatch()
     for k, v in arrs.items():
         setattr(b, k, v.ctypes.data_as(dict(_abi.ModelBatch._fields_)[k]))
-    b.quals, b.xscripts, b.n = quals, xs, len(recs)
+    b.quals, b.xscripts, b.n, b.n_aln = quals, xs, len(recs), len(score)
     return b, (arrs, quals, xs)
 
 
@@ -200,6 +200,9 @@ def test_argument_errors():
     L.qthost_model_begin(h, (C.c_uint64 * 4)(5, 5, 5, 5))
     keep[0]["cat"][3] = 9
     assert L.qthost_model_add(h, C.byref(b), C.byref(cg1), C.byref(cg2)) == -1  # QTIPSIM_EINVAL
+    keep[0]["cat"][3] = 0
+    keep[0]["a1"][5] = b.n_aln
+    assert L.qthost_model_add(h, C.byref(b), C.byref(cg1), C.byref(cg2)) == -1  # alignment index out of range
     L.qthost_destroy(h)
 
 
@@ -273,7 +276,7 @@ def test_sam_fields_to_input_model_pipeline():
     b = _abi.ModelBatch()
     for k_, v in arrs.items():
         setattr(b, k_, v.ctypes.data_as(dict(_abi.ModelBatch._fields_)[k_]))
-    b.quals, b.xscripts, b.n = quals, arena, n
+    b.quals, b.xscripts, b.n, b.n_aln = quals, arena, n, n
     h = C.c_void_p(L.qthost_create())
     L.qthost_model_begin(h, (C.c_uint64 * 4)(100, 0, 0, 0))
     cg1, cg2 = C.c_int32(11), C.c_int32(22)
